@@ -1,0 +1,238 @@
+"""
+Generates tests/golden/*.npz by executing the UNMODIFIED reference (imported from
+/root/reference/src, CPU fp32) on deterministic synthetic inputs, and checks the CPU
+oracle against it on the spot.  Run in the build container only (the GPU box has no
+/root/reference):
+
+    python tests/golden/make_golden.py
+
+Weights are never shipped for the canonical (14.4 M parameter) config: both this script
+and the tests regenerate them with rcfd.synth.fill_state_dict_(state_dict, seed), which
+walks the state_dict in its own (reference-defined) order.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get('RCFD_REFERENCE', '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'radar-camera-fusion-depth_b200'))
+
+# the only missing import of the reference: log_utils.py:17 -> matplotlib
+for name in ('matplotlib', 'matplotlib.pyplot'):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+
+
+def _import_reference():
+    # The reference's module names (networks, net_utils, ...) collide with the product's
+    # flat modules, so import them with the reference's src dir FIRST on sys.path and
+    # keep handles.
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import fusionnet_model as ref_fm
+    import radarnet_model as ref_rm
+    import radarnet_main as ref_rmain
+    import net_utils as ref_nu
+    mods = dict(fusionnet_model=ref_fm, radarnet_model=ref_rm, radarnet_main=ref_rmain, net_utils=ref_nu)
+    sys.path[:] = saved
+    for m in ('fusionnet_model', 'radarnet_model', 'radarnet_main', 'net_utils', 'networks',
+              'fusionnet_losses', 'log_utils', 'radarnet_transforms', 'datasets', 'data_utils',
+              'eval_utils'):
+        sys.modules.pop(m, None)
+    return mods
+
+
+REFM = _import_reference()
+from rcfd import synth                      # noqa: E402
+import fusionnet_oracle as fo               # noqa: E402
+import radarnet_oracle as ro                # noqa: E402
+import scatter_oracle as so                 # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(8)
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def flat_state(model):
+    p = {}
+    for k, v in model.encoder.state_dict().items():
+        p['encoder.' + k] = v
+    for k, v in model.decoder.state_dict().items():
+        p['decoder.' + k] = v
+    return p
+
+
+def build_fusionnet(cfg, seed):
+    model = REFM['fusionnet_model'].FusionNetModel(device=torch.device('cpu'), **cfg)
+    p = flat_state(model)
+    synth.fill_state_dict_(p, seed)      # in place on the module's own storage
+    return model, p
+
+
+def fusionnet_case(name, cfg, n, h, w, seed, variant, save_weights, train=True):
+    model, p = build_fusionnet(cfg, seed)
+    image, depth = synth.fusionnet_inputs(n, h, w, seed, variant)
+    out = {}
+    # ---- eval mode
+    model.eval()
+    with torch.no_grad():
+        latent, skips = model.encoder(image=image, depth=depth)
+        logits = model.decoder(x=latent, skips=skips, shape=image.shape[-2:])[-1]
+        d_ref = model.forward(image, depth)
+        d_or, l_or = fo.fusionnet_forward(p, image, depth, n_levels=len(cfg['n_filters_encoder_image']))
+    assert relerr(l_or, logits) < 1e-5 and relerr(d_or, d_ref) < 1e-5, (relerr(l_or, logits), relerr(d_or, d_ref), float(logits.abs().max()))
+    out.update(eval_logits=logits.numpy(), eval_depth=d_ref.numpy(), eval_latent=latent.numpy(),
+               eval_skip1=skips[0].numpy()[:, :4], eval_skip3=skips[2].numpy()[:, :4])
+    if save_weights:
+        for k, v in p.items():
+            out['w::' + k] = v.numpy().copy()
+    out['meta'] = np.array([n, h, w, seed])
+    out['variant'] = np.array(variant)
+    if not train:
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'ok (eval only) depth range', float(d_ref.min()), float(d_ref.max()),
+              'logit range', float(logits.min()), float(logits.max()))
+        return
+    # ---- train mode: batch statistics, loss, grads, running-stat update
+    gt, lidar = synth.training_targets(n, h, w, seed)
+    p_before = {k: v.clone() for k, v in p.items()}
+    model.train()
+    for q in model.parameters():
+        q.grad = None
+    d_tr = model.forward(image, depth)
+    gt_clean = REFM['net_utils'].OutlierRemoval(7, 1.5).remove_outliers(gt)
+    loss, _ = model.compute_loss(image=image, output_depth=d_tr, ground_truth=gt_clean, lidar_map=lidar,
+                                 loss_func='l1', w_smoothness=0.0, loss_smoothness_kernel_size=-1,
+                                 validity_map_loss_smoothness=torch.ones_like(gt), w_lidar_loss=2.0)
+    loss.backward()
+    p_after = flat_state(model)
+    # oracle on the same
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in p_before.items()}
+    new_stats = {}
+    d_or, _ = fo.fusionnet_forward(po, image, depth, n_levels=len(cfg['n_filters_encoder_image']),
+                                   training=True, new_stats=new_stats)
+    gt_or = fo.outlier_removal(gt, 7, 1.5)
+    assert torch.equal(gt_or, gt_clean)
+    loss_or = fo.fusionnet_loss(d_or, gt_or, lidar, 2.0, 'l1')
+    loss_or.backward()
+    assert relerr(d_or.detach(), d_tr.detach()) < 1e-5
+    assert abs(float(loss_or.detach()) - float(loss.detach())) < 1e-5 * abs(float(loss.detach()))
+    names = [k for k in p_before if po[k].requires_grad]
+    ref_named = dict(list(('encoder.' + k, v) for k, v in model.encoder.named_parameters()) +
+                     list(('decoder.' + k, v) for k, v in model.decoder.named_parameters()))
+    gsum, gabs, ghead, gnone = [], [], [], []
+    for k in names:
+        g_ref = ref_named[k].grad
+        g_or = po[k].grad
+        assert (g_ref is None) == (g_or is None), k
+        if g_ref is None:
+            gnone.append(1); gsum.append(0.0); gabs.append(0.0); ghead.append(np.zeros(8, np.float32))
+            continue
+        assert relerr(g_or, g_ref) < 1e-4, (k, relerr(g_or, g_ref))
+        gnone.append(0)
+        gsum.append(float(g_ref.double().sum())); gabs.append(float(g_ref.double().abs().sum()))
+        ghead.append(g_ref.flatten()[:8].numpy().astype(np.float32).copy() if g_ref.numel() >= 8
+                     else np.resize(g_ref.flatten().numpy(), 8).astype(np.float32))
+    for k, v in new_stats.items():
+        assert relerr(v, p_after[k]) < 1e-5, k
+    rm_key = 'decoder.deconv0.conv.batch_norm.running_mean'
+    out.update(train_depth=d_tr.detach().numpy(), train_loss=np.float64(float(loss)),
+               grad_names=np.array(names), grad_sum=np.array(gsum), grad_abs=np.array(gabs),
+               grad_head=np.stack(ghead), grad_none=np.array(gnone),
+               train_running_mean_deconv0=p_after[rm_key].numpy(),
+               train_running_var_deconv0=p_after[rm_key.replace('mean', 'var')].numpy(),
+               gt_clean=gt_clean.numpy())
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok  loss', float(loss), 'depth range', float(d_ref.min()), float(d_ref.max()),
+          'logit range', float(logits.min()), float(logits.max()))
+
+
+def radarnet_case(name, cfg, n, h, w, k, seed):
+    model = REFM['radarnet_model'].RadarNetModel(device=torch.device('cpu'), **cfg)
+    p = flat_state(model)
+    synth.fill_state_dict_(p, seed)
+    model.eval()
+    ph, pw = cfg['input_patch_size_image']
+    pad = pw // 2
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(n, 3, h, w + 2 * pad, generator=g)       # already edge-padded size
+    pts, boxes = [], []
+    for b in range(n):
+        pt = synth.radar_points(k, h, w, seed + b)
+        pt[:, 0] += pad                                           # radarnet_main.py:980-983
+        bx = torch.stack([pt[:, 0] - pad, torch.zeros(k), pt[:, 0] + pad, torch.full((k,), float(h))], 1)
+        pts.append(pt); boxes.append(bx)
+    points = torch.cat(pts, 0)
+    with torch.no_grad():
+        logits = model.forward(image, points, boxes, return_logits=True)
+        l_or = ro.radarnet_forward(p, image, points, boxes, (ph, pw),
+                                   n_filters_image=cfg['n_filters_encoder_image'],
+                                   n_neuron_latent=cfg['n_neurons_encoder_depth'][-1])
+    assert relerr(l_or, logits) < 1e-5, relerr(l_or, logits)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), logits=logits.numpy(),
+                        meta=np.array([n, h, w, k, seed, ph, pw]))
+    print(name, 'ok  logits range', float(logits.min()), float(logits.max()))
+
+
+def roi_pool_case():
+    import torchvision
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(2, 3, 22, 62, generator=g)
+    boxes = [torch.tensor([[3.2, 0.0, 291.2, 352.0], [100.5, 0.0, 388.5, 352.0]]),
+             torch.tensor([[650.9, 0.0, 938.9, 352.0]])]
+    for scale, osz in ((1 / 16.0, (22, 18)), (1 / 32.0, (11, 9))):
+        f = feat if scale == 1 / 16.0 else feat[:, :, :11, :31].contiguous()
+        ref = torchvision.ops.roi_pool(f, boxes, spatial_scale=scale, output_size=osz)
+        mine = ro.roi_pool(f, boxes, scale, osz)
+        assert torch.equal(ref, mine), 'roi_pool oracle mismatch'
+    print('roi_pool oracle == torchvision')
+
+
+class _StubModel(object):
+    """Feeds pre-baked crops through the real radarnet_main.forward (S2 golden)."""
+    def __init__(self, crops, patch):
+        self.crops = crops
+        self.input_patch_size_image = patch
+
+    def forward(self, image, point, bounding_boxes, return_logits):
+        return self.crops
+
+
+def s2_case(name, h, w, patch, k, seed, zs=None):
+    g = torch.Generator().manual_seed(seed)
+    ph, pw = patch
+    pad = pw // 2
+    crops = torch.rand(k, 1, ph, pw, generator=g)
+    crops[:, :, : ph // 3] *= 0.4                      # plenty of sub-threshold pixels
+    pts = synth.radar_points(max(k, 8), h, w, seed)[:k].clone()
+    if zs is not None:
+        pts[:, 2] = torch.tensor(zs)
+    pts[:, 0] += pad
+    image = torch.zeros(1, 3, h, w)
+    depth, resp = REFM['radarnet_main'].forward(_StubModel(crops, patch), image, pts.clone(), None,
+                                                device=torch.device('cpu'))
+    d_or, r_or = so.s2_scatter(crops.numpy(), pts.numpy(), w, patch, compat=True)
+    assert np.array_equal(d_or, depth.numpy()) and np.array_equal(r_or, resp.numpy())
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), crops=crops.numpy(), points=pts.numpy(),
+                        depth=depth.numpy(), response=resp.numpy(), meta=np.array([h, w, ph, pw, k, seed]))
+    print(name, 'ok  nonzero', int((depth != 0).sum()), 'dtype', depth.dtype)
+
+
+if __name__ == '__main__':
+    fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
+    fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
+    fusionnet_case('fusionnet_canonical_2x96x160', synth.CANONICAL_FUSIONNET, 2, 96, 160, 1, 'quasi_dense', False)
+    roi_pool_case()
+    radarnet_case('radarnet_canonical_1x64x128_k3', dict(synth.CANONICAL_RADARNET, input_patch_size_image=(64, 64)),
+                  1, 64, 128, 3, 2)
+    s2_case('s2_compat_k6', 64, 160, (64, 64), 6, 11)
+    s2_case('s2_compat_alias_k3', 32, 96, (32, 32), 3, 12, zs=[2.7, 2.2, 1.9])
+    print('golden fixtures written to', OUT)

@@ -1,0 +1,204 @@
+/*
+ * rcfd.h -- C-ABI of librcfd_b200.so: the B200 (sm_100a) kernels behind the FusionNet /
+ * RadarNet hot path of nesl/radar-camera-fusion-depth.
+ *
+ * The reference has no FFI layer (its boundary is its Python module surface,
+ * SURVEY.md 8b); every arithmetic call it makes lands in torch / torchvision.  Each
+ * entry point below therefore cites the reference call site (file:line, relative to
+ * the reference repo) whose library call it replaces.  Plain pointers and sizes only:
+ * no torch types, no exceptions.  Every function returns 0 on success or a negative
+ * rcfd_status; rcfd_last_error() gives the message.  All pointers are DEVICE pointers
+ * unless stated; `stream` is a cudaStream_t passed as void*.  There is no CPU fallback.
+ *
+ * Tensors are NHWC ("pixels x channels") in the element type selected by `dtype`
+ * (RCFD_F32 = float, RCFD_BF16 = __nv_bfloat16); accumulation is always fp32.
+ */
+#ifndef RCFD_H_
+#define RCFD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum rcfd_status { RCFD_OK = 0, RCFD_EINVAL = -1, RCFD_ECUDA = -2, RCFD_EUNSUPPORTED = -3 };
+enum rcfd_dtype { RCFD_F32 = 0, RCFD_BF16 = 1 };
+enum rcfd_act { RCFD_ACT_NONE = 0, RCFD_ACT_LEAKY = 1, RCFD_ACT_SIGMOID = 2, RCFD_ACT_DEPTH_HEAD = 3 };
+enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN05 = 2 };
+
+const char* rcfd_version(void);
+const char* rcfd_arch(void);          /* "sm_100a" */
+const char* rcfd_last_error(void);
+
+/* ---------------------------------------------------------------------------------
+ * Convolution as implicit GEMM.  Replaces torch.nn.Conv2d(bias=False, padding=k//2)
+ * at src/net_utils.py:63-69,85 together with what surrounds it in the reference:
+ *   - nearest up-sampling of the input (src/net_utils.py:196) folded into addressing,
+ *   - channel concat of [up-sampled, skip] (src/net_utils.py:565) as a two-source K loop,
+ *   - eval-mode BatchNorm (src/net_utils.py:82,86) + activation (:15,:21,:88-91) and the
+ *     ResNet residual add + second activation (src/net_utils.py:323) in the epilogue,
+ *   - the bounded depth head min/(sigmoid(x)+min/max) (src/fusionnet_model.py:162-165),
+ *   - training-mode BatchNorm statistics (per-channel sum / sum of squares of the raw
+ *     conv output) accumulated by the epilogue.
+ * The same entry point computes dgrad (autograd of the call sites above): stride-1 with
+ * flipped/transposed weights, stride-2 with in_dilation = 2 (zero-inserted gradient).
+ * --------------------------------------------------------------------------------- */
+typedef struct rcfd_conv_desc {
+  int32_t n, ho, wo, cout;            /* output: n x ho x wo x cout                         */
+  int32_t kh, kw, stride, pad;
+  int32_t in_dilation;                /* 1, or 2 = input has zeros inserted between samples */
+  int32_t hin, win;                   /* logical input extent seen by the filter taps       */
+  const void* src0; int32_t h0, w0, c0;   /* source 0: n x h0 x w0 x c0; if (h0,w0)!=(hin,win)
+                                             it is nearest-up-sampled on load               */
+  const void* src1; int32_t c1;       /* optional source 1: n x hin x win x c1 (c1 = 0: none);
+                                         channels are ordered [src0 | src1] like torch.cat  */
+  const void* weight;                 /* packed [cout][kh*kw][c0+c1] (rcfd_pack_conv_weight) */
+  void* dst;                          /* n x ho x wo x cout, dtype (or float if dst_f32)    */
+  const float* scale;                 /* per-cout affine applied to the accumulator, or NULL */
+  const float* shift;
+  int32_t act;                        /* rcfd_act                                           */
+  float act_p0, act_p1;               /* DEPTH_HEAD: min_predict_depth, min/max             */
+  const void* residual;               /* optional n x ho x wo x cout: out = leaky(out + res) */
+  double* stats_sum;                  /* optional [cout]: += sum of raw accumulators         */
+  double* stats_sqsum;                /* optional [cout]: += sum of squares                  */
+  int32_t accumulate;                 /* dst += result (gradient accumulation)              */
+  int32_t dst_f32;                    /* store float regardless of dtype                     */
+  int32_t dtype;                      /* rcfd_dtype of src0/src1/weight/residual/dst         */
+  int32_t engine;                     /* rcfd_engine                                         */
+} rcfd_conv_desc;
+
+int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream);
+
+/* Weight gradient of the same convolution (autograd of src/net_utils.py:85):
+ * dw[cout][kh*kw][c0+c1] (float, packed like `weight`) = sum over pixels of
+ * dy[m][cout] * gathered_input[m][tap][c].  Uses d->src0/src1 geometry; d->dst is `dy`
+ * (n x ho x wo x cout, dtype).  `dw` is overwritten. */
+int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d);
+
+/* OIHW float (the reference's state_dict layout) <-> packed [cout][kh*kw][cin] dtype.
+ * mode 0: forward weights, channels [cin_off, cin_off+cin_cnt) of the OIHW tensor.
+ * mode 1: dgrad weights  out[ci][kh-1-r][kw-1-s][co] = w[co][cin_off+ci][r][s]
+ *         (rows = cin_cnt, K = kh*kw*cout). */
+int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh,
+                          int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t mode, int32_t dtype,
+                          void* stream);
+/* packed float [cout][kh*kw][cin_cnt] gradient -> OIHW float slice (+= if accumulate). */
+int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh,
+                           int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * BatchNorm2d, training mode (src/net_utils.py:82,86; torch.nn.BatchNorm2d eps 1e-5,
+ * momentum 0.1).  finalize: batch mean / biased var from the conv epilogue's sums ->
+ * scale = gamma*invstd, shift = beta - mean*scale; updates running stats in place
+ * (unbiased var); saves mean / invstd for backward.  count = n*h*w.
+ * --------------------------------------------------------------------------------- */
+int rcfd_bn_finalize(const double* sum, const double* sqsum, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float* scale, float* shift,
+                     float* save_mean, float* save_invstd, int32_t channels, int64_t count,
+                     float eps, float momentum, void* stream);
+/* eval mode: scale/shift from running statistics. */
+int rcfd_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                 const float* running_var, float* scale, float* shift, int32_t channels, float eps,
+                 void* stream);
+/* out = act(y*scale+shift); if residual: out = leaky(out + residual)  (src/net_utils.py:86-91,323) */
+int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* residual,
+                    void* out, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream);
+/* Backward of the above through act and batch statistics.
+ *   reduce: sums[0..C) += sum(dpre), sums[C..2C) += sum(dpre * xhat), dpre = dz * act'(pre)
+ *   apply : dy = scale * (dpre - sums[c]/count - xhat * sums[C+c]/count)
+ * dgamma = sums[C+c], dbeta = sums[c] (written by apply into dgamma/dbeta, += if accumulate). */
+int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, double* sums, int64_t pixels,
+                           int32_t channels, int32_t act, int32_t dtype, void* stream);
+int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const double* sums, void* dy,
+                          float* dgamma, float* dbeta, int64_t pixels, int32_t channels, int32_t act,
+                          int32_t dtype, void* stream);
+
+/* Gated fusion  fused = sigmoid(a) * b + img  with (a|b) = affine(y[:, :C] | y[:, C:2C])
+ * (src/networks.py:864-866 ... :973-975).  y: pixels x 2C; scale/shift: [2C] or NULL. */
+int rcfd_gate_fuse_fwd(const void* y, const float* scale, const float* shift, const void* img,
+                       void* out, int64_t pixels, int32_t channels, int32_t dtype, void* stream);
+/* dz_y (pixels x 2C) = grads wrt the affine outputs (a_pre | b); dimg is the incoming grad. */
+int rcfd_gate_fuse_bwd(const void* dout, const void* y, const float* scale, const float* shift,
+                       void* dz_y, int64_t pixels, int32_t channels, int32_t dtype, void* stream);
+
+/* MaxPool2d(3, 2, 1) (src/networks.py:71-74, :392-395), NHWC. bwd recomputes the arg-max
+ * (first maximum in window scan order, like ATen) and accumulates into dx (pre-zeroed). */
+int rcfd_maxpool3x3s2_fwd(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                          int32_t dtype, void* stream);
+int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, int32_t h, int32_t w,
+                          int32_t c, int32_t dtype, void* stream);
+
+/* Backward of nearest up-sampling (src/net_utils.py:196): dsrc[n,sy,sx,c] = sum of
+ * dup[n,y,x,c] over all (y,x) that map to (sy,sx). */
+int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs, int32_t ws,
+                              int32_t hu, int32_t wu, int32_t c, int32_t accumulate, int32_t dtype,
+                              void* stream);
+
+/* elementwise helpers used by backward */
+int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, int32_t dtype, void* stream);
+int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, void* stream);
+
+/* Layout / precision boundary: the reference API is NCHW float. */
+int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                      int32_t dtype, void* stream);
+int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                      int32_t dtype, void* stream);
+
+/* Depth head backward: dlogit = dd * (-d^2/min) * s(1-s), from the stored depth d
+ * (src/fusionnet_model.py:162-165). float in/out, count elements. */
+int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, float min_depth,
+                        float min_over_max, int64_t count, int32_t dtype, void* stream);
+
+/* Masked L1 loss of src/fusionnet_model.py:214-253,293 (loss_func 'l1'), sync-free:
+ *   gt' = gt * [lidar <= 0];  L = mean|out-gt'| over gt'>0  +  w_lidar * mean|out-lidar| over lidar>0
+ * accum: double[4] scratch (zeroed by the call); loss: float[1]; dout: float grad (may be NULL). */
+int rcfd_masked_l1_loss(const float* out, const float* gt, const float* lidar, float w_lidar,
+                        double* accum, float* loss, float* dout, int64_t count, void* stream);
+
+/* OutlierRemoval.remove_outliers (src/net_utils.py:591-638), float N x 1 x H x W. */
+int rcfd_outlier_removal(const float* depth, float* out, float* scratch_max, int32_t n, int32_t h,
+                         int32_t w, int32_t kernel_size, float threshold, void* stream);
+
+/* torch.optim.Adam step (src/fusionnet_main.py:307-312, weight_decay 0) over one flat
+ * float parameter / gradient / moment buffer. */
+int rcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+                   float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Radar point -> pixel scatters (integer index work, bit exact).
+ * S1: points_to_depth_map / merge z-buffer rule,
+ *     setup/setup_dataset_nuscenes_with_denseGT.py:814-840, :644-656, :699-713.
+ *     points_xy: 2 x npts doubles (x row then y row); depth: npts doubles;
+ *     img: h x w doubles (zeroed by the call when merge == 0). merge=0: ordered
+ *     last-writer-wins; merge=1: overwrite iff empty or closer (validity derived from img>0).
+ * S2: radarnet_main.forward paste/threshold/max/arg-max/fill, src/radarnet_main.py:563-591.
+ *     crops: k x ph x pw float; points: k x 3 float (x already shifted by +pad).
+ *     compat=1 reproduces the reference's int64 truncation + index aliasing; depth_i64 is
+ *     written in compat mode, depth_f32 otherwise (either may be NULL).
+ * --------------------------------------------------------------------------------- */
+int rcfd_scatter_points_to_depth_map(const double* points_xy, const double* depth, int32_t npts,
+                                     double* img, int32_t h, int32_t w, int32_t merge, void* stream);
+int rcfd_scatter_tiles_argmax(const float* crops, const float* points, int32_t k, int32_t ph,
+                              int32_t pw, int32_t h, int32_t w, int32_t compat, int64_t* depth_i64,
+                              float* depth_f32, float* response, void* stream);
+
+/* torchvision.ops.roi_pool as called at src/networks.py:1232-1247 (NHWC, max over the
+ * quantised bins; boxes: nbox x 5 float = (batch_index, x1, y1, x2, y2)). */
+int rcfd_roi_pool_fwd(const void* feat, const float* boxes, void* out, int32_t n, int32_t h, int32_t w,
+                      int32_t c, int32_t nbox, int32_t ph, int32_t pw, float spatial_scale,
+                      int32_t dtype, void* stream);
+
+/* FullyConnected stack (src/net_utils.py:201-247, src/networks.py:1033-1063):
+ * out[k][j] = leaky(sum_i x[k][i] * w[j][i] + b[j]); float weights (torch Linear layout). */
+int rcfd_linear_leaky_fwd(const float* x, const float* w, const float* b, float* out, int32_t rows,
+                          int32_t in_features, int32_t out_features, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCFD_H_ */

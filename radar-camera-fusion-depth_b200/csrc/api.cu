@@ -1,0 +1,61 @@
+// C-ABI entry points that dispatch between the convolution engines, plus version / error plumbing.
+#include <stdarg.h>
+#include <string.h>
+#include "conv_common.cuh"
+
+namespace rcfd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
+int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
+bool conv_tc_supported(const ConvKP& p, int dtype);
+int conv_tc_launch(const ConvKP& p, cudaStream_t st);
+
+}  // namespace rcfd
+
+using namespace rcfd;
+
+extern "C" {
+
+const char* rcfd_version(void) { return "rcfd-b200 0.1.0"; }
+const char* rcfd_arch(void) { return "sm_100a"; }
+const char* rcfd_last_error(void) { return g_err; }
+
+int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
+  ConvKP p;
+  int rc = make_conv_kp(d, &p);
+  if (rc != RCFD_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int engine = d->engine;
+  if (engine == RCFD_ENGINE_AUTO) engine = conv_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT;
+  if (engine == RCFD_ENGINE_TCGEN05) {
+    if (!conv_tc_supported(p, d->dtype)) {
+      set_error("conv: shape/dtype not supported by the tcgen05 engine (bf16, channels %% 8 == 0, cout %% 16 == 0, cout <= 256)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return conv_tc_launch(p, st);
+  }
+  if (engine != RCFD_ENGINE_SIMT) { set_error("conv: bad engine %d", engine); return RCFD_EINVAL; }
+  return conv_simt_launch(p, d->dtype, st);
+}
+
+int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d) { (void)d; return 0; }
+
+int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  ConvKP p;
+  int rc = make_conv_kp(d, &p);
+  if (rc != RCFD_OK) return rc;
+  RCFD_CHECK_ARG(dw != nullptr, "wgrad: null dw");
+  return conv_wgrad_simt_launch(p, dw, d->dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

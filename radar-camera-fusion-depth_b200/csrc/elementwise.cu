@@ -1,0 +1,743 @@
+// HBM-bound NHWC passes around the convolutions: BatchNorm finalize / apply / backward,
+// gated fusion, max-pool, nearest-upsample backward, layout conversion, depth head,
+// loss, outlier removal, Adam, weight packing.  All vectorised 4 channels per thread
+// where the channel count allows it (coalesced 16 B fp32 / 8 B bf16 accesses).
+#include "common.cuh"
+
+namespace rcfd {
+namespace {
+
+constexpr int NT = 256;
+
+inline int grid_for(int64_t work, int per_block = NT, int cap = 148 * 16) {
+  int64_t g = (work + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------ BatchNorm
+__global__ void bn_finalize_kernel(const double* sum, const double* sqsum, const float* gamma,
+                                   const float* beta, float* rmean, float* rvar, float* scale,
+                                   float* shift, float* smean, float* sinv, int C, double count,
+                                   float eps, float momentum) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sum[c] / count;
+  double var = sqsum[c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = 1.0 / sqrt(var + (double)eps);
+  float sc = (float)((double)gamma[c] * invstd);
+  scale[c] = sc;
+  shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+  if (smean) smean[c] = (float)mean;
+  if (sinv) sinv[c] = (float)invstd;
+  if (rmean) {
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * mean);
+    rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rmean,
+                               const float* rvar, float* scale, float* shift, int C, float eps) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float inv = 1.0f / sqrtf(rvar[c] + eps);
+  float sc = gamma[c] * inv;
+  scale[c] = sc;
+  shift[c] = beta[c] - rmean[c] * sc;
+}
+
+template <typename T>
+__global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const T* __restrict__ res,
+                                  T* __restrict__ out, int64_t nvec, int C, int act) {
+  const int CV = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    float4 v = Vec4<T>::ld(y + i * 4);
+    float4 s = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) {
+      s = *reinterpret_cast<const float4*>(scale + c);
+      b = *reinterpret_cast<const float4*>(shift + c);
+    }
+    v.x = apply_act(fmaf(v.x, s.x, b.x), act, 0.f, 0.f);
+    v.y = apply_act(fmaf(v.y, s.y, b.y), act, 0.f, 0.f);
+    v.z = apply_act(fmaf(v.z, s.z, b.z), act, 0.f, 0.f);
+    v.w = apply_act(fmaf(v.w, s.w, b.w), act, 0.f, 0.f);
+    if (res) {
+      float4 r = Vec4<T>::ld(res + i * 4);
+      v.x = leaky(v.x + r.x); v.y = leaky(v.y + r.y); v.z = leaky(v.z + r.z); v.w = leaky(v.w + r.w);
+    }
+    Vec4<T>::st(out + i * 4, v);
+  }
+}
+
+__device__ __forceinline__ float dact(float pre, float dz, int act) {
+  if (act == RCFD_ACT_LEAKY) return pre > 0.f ? dz : kLeakySlope * dz;
+  if (act == RCFD_ACT_SIGMOID) {
+    float s = sigmoid_precise(pre);
+    return dz * s * (1.f - s);
+  }
+  return dz;
+}
+
+// per-channel sums of dpre and dpre*xhat.  Thread t owns channel-vector (t % CVP); rows strided.
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ y,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     double* __restrict__ sums, int64_t pixels, int C, int CVP, int act,
+                                     int64_t rows_per_block) {
+  __shared__ float red[2][NT * 4];
+  const int CV = C >> 2;
+  const int cv = threadIdx.x % CVP;
+  const int r0 = threadIdx.x / CVP;
+  const int rstep = NT / CVP;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t pbeg = blockIdx.x * rows_per_block;
+  int64_t pend = pbeg + rows_per_block;
+  if (pend > pixels) pend = pixels;
+  if (cv < CV) {
+    const int c = cv * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    for (int64_t p = pbeg + r0; p < pend; p += rstep) {
+      const float4 g = Vec4<T>::ld(dz + p * C + c);
+      const float4 v = Vec4<T>::ld(y + p * C + c);
+      float d;
+      d = dact(fmaf(v.x, sc.x, sh.x), g.x, act); s[0] += d; q[0] += d * (v.x - mu.x) * is.x;
+      d = dact(fmaf(v.y, sc.y, sh.y), g.y, act); s[1] += d; q[1] += d * (v.y - mu.y) * is.y;
+      d = dact(fmaf(v.z, sc.z, sh.z), g.z, act); s[2] += d; q[2] += d * (v.z - mu.z) * is.z;
+      d = dact(fmaf(v.w, sc.w, sh.w), g.w, act); s[3] += d; q[3] += d * (v.w - mu.w) * is.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x * 4 + j] = s[j];
+    red[1][threadIdx.x * 4 + j] = q[j];
+  }
+  __syncthreads();
+  // thread t < C reduces channel t over the rstep row-groups
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const int v = c >> 2, j = c & 3;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < rstep; ++r) {
+      a += (double)red[0][(r * CVP + v) * 4 + j];
+      b += (double)red[1][(r * CVP + v) * 4 + j];
+    }
+    atomicAdd(sums + c, a);
+    atomicAdd(sums + C + c, b);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const double* __restrict__ sums, T* __restrict__ dy, int64_t nvec,
+                                    int C, int act, float inv_count) {
+  const int CV = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    const float4 g = Vec4<T>::ld(dz + i * 4);
+    const float4 v = Vec4<T>::ld(y + i * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    float4 o;
+    float d;
+    d = dact(fmaf(v.x, sc.x, sh.x), g.x, act);
+    o.x = sc.x * (d - (float)sums[c + 0] * inv_count - (v.x - mu.x) * is.x * (float)sums[C + c + 0] * inv_count);
+    d = dact(fmaf(v.y, sc.y, sh.y), g.y, act);
+    o.y = sc.y * (d - (float)sums[c + 1] * inv_count - (v.y - mu.y) * is.y * (float)sums[C + c + 1] * inv_count);
+    d = dact(fmaf(v.z, sc.z, sh.z), g.z, act);
+    o.z = sc.z * (d - (float)sums[c + 2] * inv_count - (v.z - mu.z) * is.z * (float)sums[C + c + 2] * inv_count);
+    d = dact(fmaf(v.w, sc.w, sh.w), g.w, act);
+    o.w = sc.w * (d - (float)sums[c + 3] * inv_count - (v.w - mu.w) * is.w * (float)sums[C + c + 3] * inv_count);
+    Vec4<T>::st(dy + i * 4, o);
+  }
+}
+
+__global__ void bn_bwd_params_kernel(const double* sums, float* dgamma, float* dbeta, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+// ------------------------------------------------------------------ gated fusion
+template <typename T>
+__global__ void gate_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const T* __restrict__ img,
+                                T* __restrict__ out, int64_t nvec, int C) {
+  const int CV = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / CV;
+    const int c = (int)(i - p * CV) * 4;
+    float4 a = Vec4<T>::ld(y + p * 2 * C + c);
+    float4 b = Vec4<T>::ld(y + p * 2 * C + C + c);
+    if (scale) {
+      const float4 sa = *reinterpret_cast<const float4*>(scale + c), ba = *reinterpret_cast<const float4*>(shift + c);
+      const float4 sb = *reinterpret_cast<const float4*>(scale + C + c), bb = *reinterpret_cast<const float4*>(shift + C + c);
+      a.x = fmaf(a.x, sa.x, ba.x); a.y = fmaf(a.y, sa.y, ba.y); a.z = fmaf(a.z, sa.z, ba.z); a.w = fmaf(a.w, sa.w, ba.w);
+      b.x = fmaf(b.x, sb.x, bb.x); b.y = fmaf(b.y, sb.y, bb.y); b.z = fmaf(b.z, sb.z, bb.z); b.w = fmaf(b.w, sb.w, bb.w);
+    }
+    const float4 im = Vec4<T>::ld(img + p * C + c);
+    float4 o;
+    o.x = fmaf(sigmoid_precise(a.x), b.x, im.x);
+    o.y = fmaf(sigmoid_precise(a.y), b.y, im.y);
+    o.z = fmaf(sigmoid_precise(a.z), b.z, im.z);
+    o.w = fmaf(sigmoid_precise(a.w), b.w, im.w);
+    Vec4<T>::st(out + p * C + c, o);
+  }
+}
+
+template <typename T>
+__global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                T* __restrict__ dzy, int64_t nvec, int C) {
+  const int CV = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / CV;
+    const int c = (int)(i - p * CV) * 4;
+    float4 a = Vec4<T>::ld(y + p * 2 * C + c);
+    float4 b = Vec4<T>::ld(y + p * 2 * C + C + c);
+    if (scale) {
+      const float4 sa = *reinterpret_cast<const float4*>(scale + c), ba = *reinterpret_cast<const float4*>(shift + c);
+      const float4 sb = *reinterpret_cast<const float4*>(scale + C + c), bb = *reinterpret_cast<const float4*>(shift + C + c);
+      a.x = fmaf(a.x, sa.x, ba.x); a.y = fmaf(a.y, sa.y, ba.y); a.z = fmaf(a.z, sa.z, ba.z); a.w = fmaf(a.w, sa.w, ba.w);
+      b.x = fmaf(b.x, sb.x, bb.x); b.y = fmaf(b.y, sb.y, bb.y); b.z = fmaf(b.z, sb.z, bb.z); b.w = fmaf(b.w, sb.w, bb.w);
+    }
+    const float4 g = Vec4<T>::ld(dout + p * C + c);
+    float4 da, db;
+    float s;
+    s = sigmoid_precise(a.x); da.x = g.x * b.x * s * (1.f - s); db.x = g.x * s;
+    s = sigmoid_precise(a.y); da.y = g.y * b.y * s * (1.f - s); db.y = g.y * s;
+    s = sigmoid_precise(a.z); da.z = g.z * b.z * s * (1.f - s); db.z = g.z * s;
+    s = sigmoid_precise(a.w); da.w = g.w * b.w * s * (1.f - s); db.w = g.w * s;
+    Vec4<T>::st(dzy + p * 2 * C + c, da);
+    Vec4<T>::st(dzy + p * 2 * C + C + c, db);
+  }
+}
+
+// ------------------------------------------------------------------ max-pool 3x3 s2 p1
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W,
+                                   int C, int HO, int WO) {
+  const int CV = C >> 2;
+  const int64_t total = (int64_t)N * HO * WO * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int ox = (int)(r % WO); r /= WO;
+    const int oy = (int)(r % HO);
+    const int n = (int)(r / HO);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = Vec4<T>::ld(x + ((size_t)(n * H + iy) * W + ix) * C + cv * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    Vec4<T>::st(out + i * 4, m);
+  }
+}
+
+// gather form: every input pixel looks at the <= 4 windows covering it and takes the
+// gradient of those whose FIRST maximum (row-major window scan, like ATen) it is.
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+                                   T* __restrict__ dx, int N, int H, int W, int C, int HO, int WO) {
+  const int64_t total = (int64_t)N * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    const float self = to_f<T>(x[i]);
+    float g = 0.f;
+    for (int oy = (iy + 1) / 2 - ((iy + 1) % 2 == 0 ? 1 : 0); oy <= (iy + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= HO) continue;
+      for (int ox = (ix + 1) / 2 - ((ix + 1) % 2 == 0 ? 1 : 0); ox <= (ix + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= WO) continue;
+        // is (iy, ix) the first maximum of window (oy, ox)?
+        bool win = true;
+        for (int dy = 0; dy < 3 && win; ++dy) {
+          const int yy = oy * 2 - 1 + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            const int xx = ox * 2 - 1 + dxx;
+            if (xx < 0 || xx >= W) continue;
+            if (yy == iy && xx == ix) continue;
+            const float v = to_f<T>(x[((size_t)(n * H + yy) * W + xx) * C + c]);
+            const bool before = (yy < iy) || (yy == iy && xx < ix);
+            if (v > self || (before && v == self)) { win = false; break; }
+          }
+        }
+        if (win) g += to_f<T>(dout[((size_t)(n * HO + oy) * WO + ox) * C + c]);
+      }
+    }
+    dx[i] = from_f<T>(g);
+  }
+}
+
+// ------------------------------------------------------------------ nearest upsample backward
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dup, T* __restrict__ dsrc, int N, int HS,
+                                    int WS, int HU, int WU, int C, float sch, float scw, int accumulate) {
+  const int64_t total = (int64_t)N * HS * WS * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int sx = (int)(r % WS); r /= WS;
+    const int sy = (int)(r % HS);
+    const int n = (int)(r / HS);
+    int y0 = (int)floorf((float)sy / sch) - 2, y1 = (int)ceilf((float)(sy + 1) / sch) + 2;
+    int x0 = (int)floorf((float)sx / scw) - 2, x1 = (int)ceilf((float)(sx + 1) / scw) + 2;
+    if (y0 < 0) y0 = 0;
+    if (x0 < 0) x0 = 0;
+    if (y1 > HU - 1) y1 = HU - 1;
+    if (x1 > WU - 1) x1 = WU - 1;
+    float g = 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      if (nearest_src(y, sch, HS) != sy) continue;
+      for (int x = x0; x <= x1; ++x) {
+        if (nearest_src(x, scw, WS) != sx) continue;
+        g += to_f<T>(dup[((size_t)(n * HU + y) * WU + x) * C + c]);
+      }
+    }
+    dsrc[i] = from_f<T>(accumulate ? to_f<T>(dsrc[i]) + g : g);
+  }
+}
+
+// ------------------------------------------------------------------ small elementwise
+template <typename T>
+__global__ void leaky_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ din, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = to_f<T>(dout[i]);
+    din[i] = from_f<T>(to_f<T>(out[i]) > 0.f ? g : kLeakySlope * g);
+  }
+}
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ acc, const T* __restrict__ x, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc[i] = from_f<T>(to_f<T>(acc[i]) + to_f<T>(x[i]));
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int H, int W) {
+  const int64_t total = (int64_t)N * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    dst[i] = from_f<T>(src[((size_t)(n * C + c) * H + y) * W + x]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W) {
+  const int64_t total = (int64_t)N * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    int64_t r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const int n = (int)(r / C);
+    dst[i] = to_f<T>(src[((size_t)(n * H + y) * W + x) * C + c]);
+  }
+}
+
+template <typename T>
+__global__ void depth_head_bwd_kernel(const float* __restrict__ dd, const float* __restrict__ d,
+                                      T* __restrict__ dl, float mn, float r, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float dv = d[i];
+    const float s = mn / dv - r;              // sigmoid(logit)
+    dl[i] = from_f<T>(-dd[i] * dv * dv / mn * s * (1.f - s));
+  }
+}
+
+// ------------------------------------------------------------------ masked L1 loss
+__global__ void l1_accum_kernel(const float* __restrict__ out, const float* __restrict__ gt,
+                                const float* __restrict__ lidar, double* __restrict__ accum, int64_t n) {
+  float sg = 0.f, cg = 0.f, sl = 0.f, cl = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float o = out[i], l = lidar[i];
+    const float g = l > 0.f ? 0.f : gt[i];
+    if (g > 0.f) { sg += fabsf(o - g); cg += 1.f; }
+    if (l > 0.f) { sl += fabsf(o - l); cl += 1.f; }
+  }
+  __shared__ double red[4][NT / 32];
+  float v[4] = {sg, cg, sl, cl};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = v[j];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = (double)x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(accum + threadIdx.x, t);
+  }
+}
+__global__ void l1_finish_kernel(const float* __restrict__ out, const float* __restrict__ gt,
+                                 const float* __restrict__ lidar, const double* __restrict__ accum,
+                                 float w_lidar, float* __restrict__ loss, float* __restrict__ dout, int64_t n) {
+  const float inv_g = (float)(1.0 / accum[1]);
+  const float inv_l = (float)(1.0 / accum[3]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float L = (float)(accum[0] / accum[1]);
+    if (w_lidar > 0.f) L += w_lidar * (float)(accum[2] / accum[3]);
+    loss[0] = L;
+  }
+  if (!dout) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float o = out[i], l = lidar[i];
+    const float g = (w_lidar > 0.f && l > 0.f) ? 0.f : gt[i];
+    float d = 0.f;
+    if (g > 0.f) d += (o > g ? 1.f : (o < g ? -1.f : 0.f)) * inv_g;
+    if (w_lidar > 0.f && l > 0.f) d += w_lidar * (o > l ? 1.f : (o < l ? -1.f : 0.f)) * inv_l;
+    dout[i] = d;
+  }
+}
+
+// ------------------------------------------------------------------ outlier removal
+__global__ void max_kernel(const float* __restrict__ x, float* __restrict__ mx, int64_t n) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, x[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(mx), __float_as_int(m));   // values >= 0
+}
+__global__ void outlier_kernel(const float* __restrict__ d, const float* __restrict__ mx,
+                               float* __restrict__ out, int N, int H, int W, int ks, float thr) {
+  const float fill = 10.f * mx[0];
+  const int pad = ks / 2;
+  const int64_t total = (int64_t)N * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    int64_t r = i / W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    float mn = fill;
+    for (int dy = -pad; dy <= pad; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -pad; dx <= pad; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const float v = d[((size_t)n * H + yy) * W + xx];
+        mn = fminf(mn, v > 0.f ? v : fill);
+      }
+    }
+    const float v = d[i];
+    out[i] = (mn < v - thr) ? v * 0.f : v;
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float step_size, float b1, float b2,
+                            float eps, float inv_sqrt_bc2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);         // torch lerp form
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
+// ------------------------------------------------------------------ weight (un)packing
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin,
+                                   int kh, int kw, int cin_off, int cin_cnt, int mode) {
+  const int taps = kh * kw;
+  const int64_t total = (int64_t)cout * taps * cin_cnt;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (mode == 0) {          // out[co][tap][ci]
+      const int ci = (int)(i % cin_cnt);
+      int64_t r = i / cin_cnt;
+      const int tap = (int)(r % taps);
+      const int co = (int)(r / taps);
+      out[i] = from_f<T>(w[((size_t)co * cin + cin_off + ci) * taps + tap]);
+    } else {                  // out[ci][flipped tap][co]
+      const int co = (int)(i % cout);
+      int64_t r = i / cout;
+      const int tap = (int)(r % taps);
+      const int ci = (int)(r / taps);
+      out[i] = from_f<T>(w[((size_t)co * cin + cin_off + ci) * taps + (taps - 1 - tap)]);
+    }
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout,
+                                    int cin, int kh, int kw, int cin_off, int cin_cnt, int accumulate) {
+  const int taps = kh * kw;
+  const int64_t total = (int64_t)cout * taps * cin_cnt;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_cnt);
+    int64_t r = i / cin_cnt;
+    const int tap = (int)(r % taps);
+    const int co = (int)(r / taps);
+    const size_t o = ((size_t)co * cin + cin_off + ci) * taps + tap;
+    g[o] = accumulate ? g[o] + packed[i] : packed[i];
+  }
+}
+
+}  // namespace
+}  // namespace rcfd
+
+using namespace rcfd;
+
+#define DISPATCH_T(dtype, ...)                                   \
+  if ((dtype) == RCFD_F32) { typedef float T; __VA_ARGS__; }     \
+  else if ((dtype) == RCFD_BF16) { typedef bf16 T; __VA_ARGS__; } \
+  else { set_error("bad dtype %d", (int)(dtype)); return RCFD_EINVAL; }
+
+extern "C" {
+
+int rcfd_bn_finalize(const double* sum, const double* sqsum, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float* scale, float* shift,
+                     float* save_mean, float* save_invstd, int32_t channels, int64_t count, float eps,
+                     float momentum, void* stream) {
+  RCFD_CHECK_ARG(sum && sqsum && gamma && beta && scale && shift && channels > 0 && count > 0, "bn_finalize: bad args");
+  RCFD_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must come together");
+  bn_finalize_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(
+      sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, channels,
+      (double)count, eps, momentum);
+  RCFD_CHECK_LAUNCH("bn_finalize");
+  return RCFD_OK;
+}
+
+int rcfd_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                 float* scale, float* shift, int32_t channels, float eps, void* stream) {
+  RCFD_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && channels > 0, "bn_fold: bad args");
+  bn_fold_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
+                                                                            scale, shift, channels, eps);
+  RCFD_CHECK_LAUNCH("bn_fold");
+  return RCFD_OK;
+}
+
+int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* residual, void* out,
+                    int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(y && out && pixels > 0 && channels > 0 && channels % 4 == 0, "bn_act_fwd: bad args (channels %% 4)");
+  RCFD_CHECK_ARG((scale == nullptr) == (shift == nullptr), "bn_act_fwd: scale/shift");
+  const int64_t nvec = pixels * channels / 4;
+  DISPATCH_T(dtype, (bn_act_fwd_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)y, scale, shift, (const T*)residual, (T*)out, nvec, channels, act)));
+  RCFD_CHECK_LAUNCH("bn_act_fwd");
+  return RCFD_OK;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, double* sums, int64_t pixels,
+                           int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && sums, "bn_bwd_reduce: null");
+  RCFD_CHECK_ARG(channels % 4 == 0 && channels <= 1024 && channels > 0 && pixels > 0, "bn_bwd_reduce: channels");
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("bn_bwd_reduce memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  const int CVP = next_pow2(channels / 4);
+  const int rstep = NT / CVP;
+  int blocks = (int)((pixels + rstep * 8 - 1) / (rstep * 8));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  int64_t rpb = (pixels + blocks - 1) / blocks;
+  blocks = (int)((pixels + rpb - 1) / rpb);
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, pixels, channels, CVP, act, rpb)));
+  RCFD_CHECK_LAUNCH("bn_bwd_reduce");
+  return RCFD_OK;
+}
+
+int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const double* sums, void* dy, float* dgamma,
+                          float* dbeta, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && sums && dy, "bn_bwd_apply: null");
+  RCFD_CHECK_ARG(channels % 4 == 0 && channels > 0 && pixels > 0, "bn_bwd_apply: channels");
+  const int64_t nvec = pixels * channels / 4;
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nvec, channels, act,
+                        (float)(1.0 / (double)pixels))));
+  RCFD_CHECK_LAUNCH("bn_bwd_apply");
+  if (dgamma || dbeta) {
+    bn_bwd_params_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(sums, dgamma, dbeta, channels);
+    RCFD_CHECK_LAUNCH("bn_bwd_params");
+  }
+  return RCFD_OK;
+}
+
+int rcfd_gate_fuse_fwd(const void* y, const float* scale, const float* shift, const void* img, void* out,
+                       int64_t pixels, int32_t channels, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(y && img && out && pixels > 0 && channels > 0 && channels % 4 == 0, "gate_fwd: bad args");
+  const int64_t nvec = pixels * channels / 4;
+  DISPATCH_T(dtype, (gate_fwd_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)y, scale, shift, (const T*)img, (T*)out, nvec, channels)));
+  RCFD_CHECK_LAUNCH("gate_fwd");
+  return RCFD_OK;
+}
+
+int rcfd_gate_fuse_bwd(const void* dout, const void* y, const float* scale, const float* shift, void* dz_y,
+                       int64_t pixels, int32_t channels, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dout && y && dz_y && pixels > 0 && channels > 0 && channels % 4 == 0, "gate_bwd: bad args");
+  const int64_t nvec = pixels * channels / 4;
+  DISPATCH_T(dtype, (gate_bwd_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, (const T*)y, scale, shift, (T*)dz_y, nvec, channels)));
+  RCFD_CHECK_LAUNCH("gate_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_maxpool3x3s2_fwd(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t dtype,
+                          void* stream) {
+  RCFD_CHECK_ARG(x && out && n > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_fwd: bad args");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * ho * wo * (c / 4);
+  DISPATCH_T(dtype, (maxpool_fwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, n, h,
+                                                                                           w, c, ho, wo)));
+  RCFD_CHECK_LAUNCH("maxpool_fwd");
+  return RCFD_OK;
+}
+
+int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
+                          int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(x && dout && dx && n > 0 && h > 0 && w > 0 && c > 0, "maxpool_bwd: bad args");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * h * w * c;
+  DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
+  RCFD_CHECK_LAUNCH("maxpool_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs, int32_t ws, int32_t hu,
+                              int32_t wu, int32_t c, int32_t accumulate, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dup && dsrc && n > 0 && hs > 0 && ws > 0 && hu > 0 && wu > 0 && c > 0, "upsample_bwd: bad args");
+  const int64_t total = (int64_t)n * hs * ws * c;
+  const float sch = (float)hs / (float)hu, scw = (float)ws / (float)wu;
+  DISPATCH_T(dtype, (upsample_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                        (const T*)dup, (T*)dsrc, n, hs, ws, hu, wu, c, sch, scw, accumulate)));
+  RCFD_CHECK_LAUNCH("upsample_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dout && out && din && count > 0, "leaky_bwd: bad args");
+  DISPATCH_T(dtype, (leaky_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out,
+                                                                                          (T*)din, count)));
+  RCFD_CHECK_LAUNCH("leaky_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(acc && x && count > 0, "add_inplace: bad args");
+  DISPATCH_T(dtype, (add_inplace_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((T*)acc, (const T*)x, count)));
+  RCFD_CHECK_LAUNCH("add_inplace");
+  return RCFD_OK;
+}
+
+int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t dtype,
+                      void* stream) {
+  RCFD_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad args");
+  const int64_t total = (int64_t)n * c * h * w;
+  DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w)));
+  RCFD_CHECK_LAUNCH("nchw_to_nhwc");
+  return RCFD_OK;
+}
+
+int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t dtype,
+                      void* stream) {
+  RCFD_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nhwc_to_nchw: bad args");
+  const int64_t total = (int64_t)n * c * h * w;
+  DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const T*)src, dst, n, c, h, w)));
+  RCFD_CHECK_LAUNCH("nhwc_to_nchw");
+  return RCFD_OK;
+}
+
+int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, float min_depth, float min_over_max,
+                        int64_t count, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(ddepth && depth && dlogit && count > 0 && min_depth > 0.f, "depth_head_bwd: bad args");
+  DISPATCH_T(dtype, (depth_head_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>(
+                        ddepth, depth, (T*)dlogit, min_depth, min_over_max, count)));
+  RCFD_CHECK_LAUNCH("depth_head_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_masked_l1_loss(const float* out, const float* gt, const float* lidar, float w_lidar, double* accum,
+                        float* loss, float* dout, int64_t count, void* stream) {
+  RCFD_CHECK_ARG(out && gt && lidar && accum && loss && count > 0, "masked_l1_loss: bad args");
+  RCFD_CHECK_ARG(w_lidar > 0.f, "masked_l1_loss: the fused kernel implements the w_lidar_loss > 0 branch");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(accum, 0, 4 * sizeof(double), st);
+  if (e != cudaSuccess) { set_error("masked_l1 memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  l1_accum_kernel<<<grid_for(count, NT, 148 * 4), NT, 0, st>>>(out, gt, lidar, accum, count);
+  RCFD_CHECK_LAUNCH("l1_accum");
+  l1_finish_kernel<<<grid_for(count), NT, 0, st>>>(out, gt, lidar, accum, w_lidar, loss, dout, count);
+  RCFD_CHECK_LAUNCH("l1_finish");
+  return RCFD_OK;
+}
+
+int rcfd_outlier_removal(const float* depth, float* out, float* scratch_max, int32_t n, int32_t h, int32_t w,
+                         int32_t kernel_size, float threshold, void* stream) {
+  RCFD_CHECK_ARG(depth && out && scratch_max && n > 0 && h > 0 && w > 0 && kernel_size > 0 && (kernel_size & 1),
+                 "outlier_removal: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)n * h * w;
+  cudaError_t e = cudaMemsetAsync(scratch_max, 0, sizeof(float), st);
+  if (e != cudaSuccess) { set_error("outlier memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  max_kernel<<<grid_for(total, NT, 148 * 2), NT, 0, st>>>(depth, scratch_max, total);
+  RCFD_CHECK_LAUNCH("outlier_max");
+  outlier_kernel<<<grid_for(total), NT, 0, st>>>(depth, scratch_max, out, n, h, w, kernel_size, threshold);
+  RCFD_CHECK_LAUNCH("outlier");
+  return RCFD_OK;
+}
+
+int rcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                   float beta1, float beta2, float eps, int32_t step, void* stream) {
+  RCFD_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && count > 0 && step > 0, "adam: bad args");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(count), NT, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count,
+                                                                (float)((double)lr / bc1), beta1, beta2, eps,
+                                                                (float)(1.0 / sqrt(bc2)));
+  RCFD_CHECK_LAUNCH("adam");
+  return RCFD_OK;
+}
+
+int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
+                          int32_t cin_off, int32_t cin_cnt, int32_t mode, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_weight: bad args");
+  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin && (mode == 0 || mode == 1), "pack_weight: range");
+  const int64_t total = (int64_t)cout * kh * kw * cin_cnt;
+  DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                        w_oihw, (T*)packed, cout, cin, kh, kw, cin_off, cin_cnt, mode)));
+  RCFD_CHECK_LAUNCH("pack_weight");
+  return RCFD_OK;
+}
+
+int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
+                           int32_t cin_off, int32_t cin_cnt, int32_t accumulate, void* stream) {
+  RCFD_CHECK_ARG(packed && g_oihw && cout > 0 && cin > 0 && kh > 0 && kw > 0, "unpack_wgrad: bad args");
+  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin, "unpack_wgrad: range");
+  const int64_t total = (int64_t)cout * kh * kw * cin_cnt;
+  unpack_wgrad_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(packed, g_oihw, cout, cin, kh, kw, cin_off,
+                                                                        cin_cnt, accumulate);
+  RCFD_CHECK_LAUNCH("unpack_wgrad");
+  return RCFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+// Radar point -> pixel scatters, the RadarNet ROI pooling and its point MLP.
+// Integer index work is bit exact with the reference (see include/rcfd.h for citations).
+#include "common.cuh"
+
+namespace rcfd {
+namespace {
+
+// ---- S1: np.round (half-to-even) -> ordered img[y, x] = z ; one thread per point.
+// Sequential "last writer wins" == point i writes iff no later point lands on its pixel.
+__global__ void s1_plot_kernel(const double* __restrict__ pts, const double* __restrict__ depth, int npts,
+                               double* __restrict__ img, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  const long long x = (long long)rint(pts[i]);            // rint: round-half-to-even like np.round
+  const long long y = (long long)rint(pts[npts + i]);
+  if (x < 0 || x >= W || y < 0 || y >= H) return;          // reference guarantees in-range (mask :195-200)
+  for (int j = i + 1; j < npts; ++j) {
+    if ((long long)rint(pts[j]) == x && (long long)rint(pts[npts + j]) == y) return;
+  }
+  img[(size_t)y * W + x] = depth[i];
+}
+
+// ---- S1 merge (z-buffer): sequentially "overwrite iff empty or closer" == the pixel ends with
+// min(existing if > 0, all new depths); the point achieving that min (lowest index on ties) writes.
+__global__ void s1_merge_kernel(const double* __restrict__ pts, const double* __restrict__ depth, int npts,
+                                double* __restrict__ img, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  const long long x = (long long)rint(pts[i]);
+  const long long y = (long long)rint(pts[npts + i]);
+  if (x < 0 || x >= W || y < 0 || y >= H) return;
+  const double z = depth[i];
+  for (int j = 0; j < npts; ++j) {
+    if (j == i) continue;
+    if ((long long)rint(pts[j]) == x && (long long)rint(pts[npts + j]) == y) {
+      const double zj = depth[j];
+      if (zj < z || (zj == z && j < i)) return;
+    }
+  }
+  const double cur = img[(size_t)y * W + x];
+  if (!(cur > 0.0) || z < cur) img[(size_t)y * W + x] = z;
+}
+
+// ---- S2: one thread per output pixel; running max / first arg-max over the K pasted crops.
+__global__ void s2_kernel(const float* __restrict__ crops, const float* __restrict__ points, int K, int ph, int pw,
+                          int H, int W, int compat, long long* __restrict__ depth_i64,
+                          float* __restrict__ depth_f32, float* __restrict__ response) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const int y = idx / W, x = idx - y * W;
+  const int pad = pw / 2;
+  const int cy = y - (H - ph);                 // row inside the crop (crop is pasted at the bottom)
+  const int xp = x + pad;                      // column in the padded canvas
+  float best = 0.f;
+  int arg = 0;
+  for (int k = 0; k < K; ++k) {
+    float v = 0.f;
+    if (cy >= 0) {
+      const int col = xp - ((int)points[k * 3] - pad);     // int() truncation, radarnet_main.py:568
+      if (col >= 0 && col < pw) {
+        v = crops[((size_t)k * ph + cy) * pw + col];
+        if (v < 0.5f) v = 0.f;
+      }
+    }
+    if (k == 0 || v > best) {
+      if (k == 0 || v > best) { best = v; arg = k; }
+    }
+  }
+  response[idx] = best;
+  if (compat) {
+    long long v = arg;
+    for (int k = 0; k < K; ++k)
+      if (v == k) v = (long long)points[k * 3 + 2];          // int64 fill truncates, later k re-match
+    if (depth_i64) depth_i64[idx] = best == 0.f ? 0 : v;
+  } else {
+    if (depth_f32) depth_f32[idx] = best == 0.f ? 0.f : points[arg * 3 + 2];
+  }
+}
+
+// ---- roi_pool (torchvision semantics), NHWC, thread per (box, bin, channel)
+template <typename T>
+__global__ void roi_pool_kernel(const T* __restrict__ feat, const float* __restrict__ boxes, T* __restrict__ out,
+                                int N, int H, int W, int C, int nbox, int PH, int PW, float scale) {
+  const int64_t total = (int64_t)nbox * PH * PW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int pw = (int)(r % PW); r /= PW;
+    const int ph = (int)(r % PH);
+    const int b = (int)(r / PH);
+    const float* box = boxes + (size_t)b * 5;
+    const int n = (int)box[0];
+    const int sw = (int)roundf(box[1] * scale), sh = (int)roundf(box[2] * scale);
+    const int ew = (int)roundf(box[3] * scale), eh = (int)roundf(box[4] * scale);
+    const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+    const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
+    int hs = (int)floorf((float)ph * bh), he = (int)ceilf((float)(ph + 1) * bh);
+    int ws = (int)floorf((float)pw * bw), we = (int)ceilf((float)(pw + 1) * bw);
+    hs = min(max(hs + sh, 0), H); he = min(max(he + sh, 0), H);
+    ws = min(max(ws + sw, 0), W); we = min(max(we + sw, 0), W);
+    const bool empty = (he <= hs) || (we <= ws);
+    float m = empty ? 0.f : -3.402823466e+38f;
+    if (n >= 0 && n < N) {
+      for (int yy = hs; yy < he; ++yy)
+        for (int xx = ws; xx < we; ++xx) m = fmaxf(m, to_f<T>(feat[((size_t)(n * H + yy) * W + xx) * C + c]));
+    }
+    out[i] = from_f<T>(m);
+  }
+}
+
+__global__ void linear_leaky_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ out, int rows, int fin, int fout) {
+  const int64_t total = (int64_t)rows * fout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % fout);
+    const int r = (int)(i / fout);
+    float acc = b[j];
+    const float* xr = x + (size_t)r * fin;
+    const float* wr = w + (size_t)j * fin;
+    for (int k = 0; k < fin; ++k) acc = fmaf(xr[k], wr[k], acc);
+    out[i] = leaky(acc);
+  }
+}
+
+}  // namespace
+}  // namespace rcfd
+
+using namespace rcfd;
+
+extern "C" {
+
+int rcfd_scatter_points_to_depth_map(const double* points_xy, const double* depth, int32_t npts, double* img,
+                                     int32_t h, int32_t w, int32_t merge, void* stream) {
+  RCFD_CHECK_ARG(img && h > 0 && w > 0 && npts >= 0, "scatter S1: bad args");
+  RCFD_CHECK_ARG(npts == 0 || (points_xy && depth), "scatter S1: null points");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!merge) {
+    cudaError_t e = cudaMemsetAsync(img, 0, sizeof(double) * (size_t)h * w, st);
+    if (e != cudaSuccess) { set_error("S1 memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  }
+  if (npts == 0) return RCFD_OK;
+  if (merge) s1_merge_kernel<<<ceil_div(npts, 128), 128, 0, st>>>(points_xy, depth, npts, img, h, w);
+  else s1_plot_kernel<<<ceil_div(npts, 128), 128, 0, st>>>(points_xy, depth, npts, img, h, w);
+  RCFD_CHECK_LAUNCH("scatter_s1");
+  return RCFD_OK;
+}
+
+int rcfd_scatter_tiles_argmax(const float* crops, const float* points, int32_t k, int32_t ph, int32_t pw, int32_t h,
+                              int32_t w, int32_t compat, int64_t* depth_i64, float* depth_f32, float* response,
+                              void* stream) {
+  RCFD_CHECK_ARG(crops && points && response && k > 0 && ph > 0 && pw > 0 && h >= ph && w > 0, "scatter S2: bad args");
+  RCFD_CHECK_ARG(compat ? depth_i64 != nullptr : depth_f32 != nullptr, "scatter S2: missing depth output for mode");
+  s2_kernel<<<ceil_div((int64_t)h * w, 256), 256, 0, (cudaStream_t)stream>>>(
+      crops, points, k, ph, pw, h, w, compat, reinterpret_cast<long long*>(depth_i64), depth_f32, response);
+  RCFD_CHECK_LAUNCH("scatter_s2");
+  return RCFD_OK;
+}
+
+int rcfd_roi_pool_fwd(const void* feat, const float* boxes, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                      int32_t nbox, int32_t ph, int32_t pw, float spatial_scale, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(feat && boxes && out && n > 0 && h > 0 && w > 0 && c > 0 && nbox > 0 && ph > 0 && pw > 0,
+                 "roi_pool: bad args");
+  const int64_t total = (int64_t)nbox * ph * pw * c;
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (dtype == RCFD_F32)
+    roi_pool_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)feat, boxes, (float*)out, n, h, w, c,
+                                                                     nbox, ph, pw, spatial_scale);
+  else if (dtype == RCFD_BF16)
+    roi_pool_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat, boxes, (bf16*)out, n, h, w, c, nbox,
+                                                                    ph, pw, spatial_scale);
+  else { set_error("roi_pool: bad dtype"); return RCFD_EINVAL; }
+  RCFD_CHECK_LAUNCH("roi_pool");
+  return RCFD_OK;
+}
+
+int rcfd_linear_leaky_fwd(const float* x, const float* w, const float* b, float* out, int32_t rows, int32_t in_features,
+                          int32_t out_features, void* stream) {
+  RCFD_CHECK_ARG(x && w && b && out && rows > 0 && in_features > 0 && out_features > 0, "linear: bad args");
+  const int64_t total = (int64_t)rows * out_features;
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  linear_leaky_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, rows, in_features, out_features);
+  RCFD_CHECK_LAUNCH("linear_leaky");
+  return RCFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""
+FusionNetModel with the reference's constructor / method surface (reference:
+src/fusionnet_model.py:7-401), executed on librcfd_b200.so.
+
+Tensors at the API are NCHW float32 like the reference; parameters keep the reference's
+names and OIHW float32 layout so ``state_dict`` / checkpoints / torch.optim interoperate.
+``forward`` returns a tensor that supports ``loss.backward()``: the whole network is one
+autograd node whose backward replays the engine's tape (dgrad / wgrad / BN backward
+kernels) and fills ``parameter.grad``.
+
+Extras that the reference does not have (all optional):
+  * ``set_precision('fp32' | 'bf16')`` -- storage precision of activations / weights inside
+    the kernels (accumulation is always fp32).  'fp32' is the parity mode.
+  * ``forward(..., return_logits=True)`` for tests.
+"""
+import torch
+
+import fusionnet_losses as losses
+import networks
+from rcfd import engine, ops
+
+
+class _FusionNetFunction(torch.autograd.Function):
+    """One autograd node for the whole encoder-decoder."""
+
+    @staticmethod
+    def forward(fctx, model, image, input_depth, *params):
+        record = torch.is_grad_enabled() and model.encoder.training and any(p.requires_grad for p in params)
+        out_nhwc, ectx = model._run(image, input_depth, record=record)
+        fctx.model, fctx.ectx, fctx.out_nhwc = model, ectx, out_nhwc
+        fctx.set_materialize_grads(False)
+        n, h, w, _ = out_nhwc.shape
+        return out_nhwc.view(n, 1, h, w)        # C == 1: NHWC and NCHW coincide
+
+    @staticmethod
+    def backward(fctx, grad_out):
+        ectx = fctx.ectx
+        n_in = 3 + len(list(fctx.model.parameters()))
+        if grad_out is None or ectx is None or ectx.tape is None:
+            return (None,) * n_in
+        tape = ectx.tape
+        tape.grads[id(fctx.out_nhwc)] = grad_out.contiguous().float().view(fctx.out_nhwc.shape)
+        tape.backward()
+        fctx.model._deliver_grads(tape.param_grads)
+        tape.param_grads = []
+        fctx.ectx = None
+        return (None,) * n_in
+
+
+class FusionNetModel(object):
+    """Image + radar depth fusion network (reference src/fusionnet_model.py:7)."""
+
+    def __init__(self, input_channels_image, input_channels_depth, encoder_type, n_filters_encoder_image,
+                 n_filters_encoder_depth, fusion_type, decoder_type, n_resolution_decoder, n_filters_decoder,
+                 deconv_type, activation_func, weight_initializer, min_predict_depth, max_predict_depth,
+                 device=torch.device('cuda')):
+        self.encoder_type = encoder_type
+        self.min_predict_depth = min_predict_depth
+        self.max_predict_depth = max_predict_depth
+        self.device = device
+        self.compute_dtype = torch.float32
+        self.conv_engine = ops.ENGINE_AUTO
+        self._cache = {}
+        self.grad_hook = None          # called with the list of (param, grad) after backward (DDP)
+
+        if fusion_type not in ('add', 'weight', 'weight_and_project', 'concat'):
+            raise ValueError('Unsupported fusion type: {}'.format(fusion_type))
+        if 'fusionnet18' in encoder_type or 'resnet18' in encoder_type:
+            n_layer = 18
+        elif 'fusionnet34' in encoder_type or 'resnet34' in encoder_type:
+            n_layer = 34
+        else:
+            raise ValueError('Unsupported encoder type: {}'.format(encoder_type))
+        if not ('fusionnet18' in encoder_type or 'fusionnet34' in encoder_type):
+            raise ValueError('Unsupported encoder type on the B200 path: {} (image-only resnet encoders are not '
+                             'used by any shipped FusionNet config)'.format(encoder_type))
+        self.encoder = networks.FusionNetEncoder(
+            n_layer=n_layer, input_channels_image=input_channels_image, input_channels_depth=input_channels_depth,
+            n_filters_encoder_image=n_filters_encoder_image, n_filters_encoder_depth=n_filters_encoder_depth,
+            weight_initializer=weight_initializer, activation_func=activation_func,
+            use_batch_norm='batch_norm' in encoder_type, fusion_type=fusion_type)
+        n_filters_encoder = list(n_filters_encoder_image)
+        n_skips = n_filters_encoder[:-1][::-1] + [0]
+        if 'multiscale' in decoder_type:
+            self.decoder = networks.MultiScaleDecoder(
+                input_channels=n_filters_encoder[-1], output_channels=1, n_resolution=n_resolution_decoder,
+                n_filters=n_filters_decoder, n_skips=n_skips, weight_initializer=weight_initializer,
+                activation_func=activation_func, output_func='linear', use_batch_norm='batch_norm' in decoder_type,
+                deconv_type=deconv_type)
+        else:
+            raise ValueError('Unsuported decoder type: {}'.format(decoder_type))
+        if not ('batch_norm' in encoder_type and 'batch_norm' in decoder_type):
+            raise ValueError('the B200 path implements the shipped batch_norm encoder / decoder variants')
+        self.to(self.device)
+
+    # ------------------------------------------------------------------ precision / engine knobs
+    def set_precision(self, precision):
+        self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[precision]
+        self._cache.clear()
+        return self
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, image, input_depth, record=False, return_logits=False, taps=None):
+        if not (image.is_cuda and input_depth.is_cuda):
+            raise RuntimeError('FusionNetModel runs on CUDA only (no CPU fallback)')
+        ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
+                              record=record, engine=self.conv_engine)
+        ectx.taps = taps
+        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype)
+        dep = ops.nchw_to_nhwc(input_depth.float(), self.compute_dtype)
+        latent, skips = engine.fusionnet_encoder(ectx, self.encoder, img, dep)
+        if taps is not None:
+            taps['latent'] = latent
+            for i, s in enumerate(skips):
+                taps['skip%d' % (i + 1)] = s
+        head = None if return_logits else (float(self.min_predict_depth),
+                                           float(self.min_predict_depth) / float(self.max_predict_depth))
+        out, _ = engine.multiscale_decoder(ectx, self.decoder, latent, skips, image.shape[-2:], head=head)
+        engine.finish_bn_counters(ectx)
+        return out, ectx
+
+    def forward(self, image, input_depth, return_multiscale=False, return_logits=False):
+        """N x 3 x H x W image, N x 2 x H x W (depth, response) -> N x 1 x H x W depth in
+        [min, max] metres (reference src/fusionnet_model.py:140-170)."""
+        if return_logits:
+            out, _ = self._run(image, input_depth, return_logits=True)
+            n, h, w, _ = out.shape
+            out = out.view(n, 1, h, w)
+        else:
+            out = _FusionNetFunction.apply(self, image, input_depth, *self.parameters())
+        return [out] if return_multiscale else out
+
+    def _deliver_grads(self, param_grads):
+        for p, g in param_grads:
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+        if self.grad_hook is not None:
+            self.grad_hook(param_grads)
+
+    # ------------------------------------------------------------------ loss
+    def compute_loss(self, image, output_depth, ground_truth, lidar_map, loss_func, w_smoothness,
+                     loss_smoothness_kernel_size, validity_map_loss_smoothness, w_lidar_loss):
+        """Reference src/fusionnet_model.py:172-302.  The canonical training configuration
+        (single scale, 'l1', w_lidar_loss > 0, w_smoothness == 0) is one fused, sync-free
+        masked-L1 kernel; every other combination follows the reference formula with tensor ops."""
+        single = not isinstance(output_depth, list)
+        if (single and loss_func == 'l1' and w_lidar_loss > 0.0 and not w_smoothness > 0.0
+                and output_depth.is_cuda and output_depth.shape == ground_truth.shape):
+            loss = losses.MaskedL1.apply(output_depth, ground_truth, lidar_map, float(w_lidar_loss))
+            return loss, {'loss': loss, 'loss_supervised': loss, 'loss_smoothness': 0.0, 'loss_lidar': 0.0}
+
+        loss_supervised, loss_smoothness, loss_lidar = 0.0, 0.0, 0.0
+        if w_lidar_loss > 0.0:
+            ground_truth = ground_truth * (lidar_map <= 0.0).to(ground_truth.dtype)
+        valid_gt = ground_truth > 0
+        valid_lidar = lidar_map > 0
+        outputs = output_depth if isinstance(output_depth, list) else [output_depth]
+        pick = {'l1': losses.l1_loss, 'l2': losses.l2_loss, 'smoothl1': losses.smooth_l1_loss}
+        if loss_func not in pick:
+            raise ValueError('No such loss: {}'.format(loss_func))
+        for scale, output in enumerate(outputs):
+            th, tw = ground_truth.shape[-2:]
+            if output.shape[-2] > th and output.shape[-1] > tw:
+                output = torch.nn.functional.interpolate(output, size=(th, tw), mode='bilinear', align_corners=True)
+            w_scale = 1.0 / (2 ** (len(outputs) - scale - 1))
+            loss_supervised = loss_supervised + w_scale * pick[loss_func](output[valid_gt], ground_truth[valid_gt])
+            if w_lidar_loss > 0.0:
+                loss_lidar = loss_lidar + w_scale * pick[loss_func](output[valid_lidar], lidar_map[valid_lidar])
+            if w_smoothness > 0.0:
+                if loss_smoothness_kernel_size <= 1:
+                    loss_smoothness = loss_smoothness + w_scale * losses.smoothness_loss_func(image=image, predict=output)
+                else:
+                    fs = [1, 1, loss_smoothness_kernel_size, loss_smoothness_kernel_size]
+                    loss_smoothness = loss_smoothness + w_scale * losses.sobel_smoothness_loss_func(
+                        image=image, predict=output, weights=validity_map_loss_smoothness, filter_size=fs)
+        loss = loss_supervised + w_smoothness * loss_smoothness + w_lidar_loss * loss_lidar
+        return loss, {'loss': loss, 'loss_supervised': loss_supervised, 'loss_smoothness': loss_smoothness,
+                      'loss_lidar': loss_lidar}
+
+    # ------------------------------------------------------------------ state management
+    def parameters(self):
+        """Encoder parameters then decoder parameters (reference :304-316; Adam state order)."""
+        return list(self.encoder.parameters()) + list(self.decoder.parameters())
+
+    def train(self):
+        self.encoder.train()
+        self.decoder.train()
+
+    def eval(self):
+        self.encoder.eval()
+        self.decoder.eval()
+
+    def to(self, device):
+        self.device = device
+        self.encoder.to(device)
+        self.decoder.to(device)
+        self._cache.clear()
+
+    def _modules_bare(self):
+        enc = self.encoder.module if isinstance(self.encoder, torch.nn.DataParallel) else self.encoder
+        dec = self.decoder.module if isinstance(self.decoder, torch.nn.DataParallel) else self.decoder
+        return enc, dec
+
+    def save_model(self, checkpoint_path, step, optimizer):
+        """Same checkpoint dictionary as the reference (:347-368)."""
+        torch.save({'train_step': step,
+                    'optimizer_state_dict': optimizer.state_dict(),
+                    'encoder_state_dict': self.encoder.state_dict(),
+                    'decoder_state_dict': self.decoder.state_dict()}, checkpoint_path)
+
+    @staticmethod
+    def _strip_module_prefix(state):
+        # the reference saves after data_parallel(), so its keys carry a 'module.' prefix
+        return {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in state.items()}
+
+    def restore_model(self, checkpoint_path, optimizer=None):
+        """Accepts both bare and 'module.'-prefixed (reference DataParallel) keys (:370-393)."""
+        checkpoint = torch.load(checkpoint_path, map_location=self.device, weights_only=False)
+        self.encoder.load_state_dict(self._strip_module_prefix(checkpoint['encoder_state_dict']))
+        self.decoder.load_state_dict(self._strip_module_prefix(checkpoint['decoder_state_dict']))
+        self._cache.clear()
+        if optimizer is not None:
+            optimizer.load_state_dict(checkpoint['optimizer_state_dict'])
+        return checkpoint['train_step'], optimizer
+
+    def data_parallel(self):
+        """The reference wraps encoder / decoder in torch.nn.DataParallel (:395-401).  Here
+        multi-GPU is one process per GPU (torchrun) with an NCCL gradient all-reduce:
+        see rcfd.parallel.DistributedGradSync.  Single process: nothing to do."""
+        from rcfd import parallel
+        parallel.attach_if_distributed(self)
+
+    def log_summary(self, *args, **kwargs):
+        """TensorBoard summaries are observability, out of scope for the hot path."""
+        return None

@@ -1,0 +1,105 @@
+"""
+ctypes binding of librcfd_b200.so (the C-ABI in include/rcfd.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  The library is built in-tree by build.py (nvcc, sm_100a).
+"""
+import ctypes
+import os
+from ctypes import c_int32, c_int64, c_float, c_void_p, c_char_p, POINTER, Structure
+
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_HERE, 'librcfd_b200.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+
+class ConvDesc(Structure):
+    _fields_ = [
+        ('n', c_int32), ('ho', c_int32), ('wo', c_int32), ('cout', c_int32),
+        ('kh', c_int32), ('kw', c_int32), ('stride', c_int32), ('pad', c_int32),
+        ('in_dilation', c_int32), ('hin', c_int32), ('win', c_int32),
+        ('src0', c_void_p), ('h0', c_int32), ('w0', c_int32), ('c0', c_int32),
+        ('src1', c_void_p), ('c1', c_int32),
+        ('weight', c_void_p), ('dst', c_void_p),
+        ('scale', c_void_p), ('shift', c_void_p),
+        ('act', c_int32), ('act_p0', c_float), ('act_p1', c_float),
+        ('residual', c_void_p),
+        ('stats_sum', c_void_p), ('stats_sqsum', c_void_p),
+        ('accumulate', c_int32), ('dst_f32', c_int32), ('dtype', c_int32), ('engine', c_int32),
+    ]
+
+
+# name -> argtypes (all return int32 status unless listed in _RESTYPE)
+_P = c_void_p
+_SIGS = {
+    'rcfd_conv2d_fwd': [POINTER(ConvDesc), _P],
+    'rcfd_conv2d_wgrad': [POINTER(ConvDesc), _P, _P, c_int64, _P],
+    'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
+    'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],
+    'rcfd_bn_act_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_act_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_act_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_gate_fuse_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
+    'rcfd_gate_fuse_bwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
+    'rcfd_maxpool3x3s2_fwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_maxpool3x3s2_bwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_upsample_nearest_bwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_leaky_bwd': [_P, _P, _P, c_int64, c_int32, _P],
+    'rcfd_add_inplace': [_P, _P, c_int64, c_int32, _P],
+    'rcfd_nchw_to_nhwc': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_nhwc_to_nchw': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_depth_head_bwd': [_P, _P, _P, c_float, c_float, c_int64, c_int32, _P],
+    'rcfd_masked_l1_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],
+    'rcfd_outlier_removal': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P],
+    'rcfd_adam_step': [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, _P],
+    'rcfd_scatter_points_to_depth_map': [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_scatter_tiles_argmax': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P],
+    'rcfd_roi_pool_fwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P],
+    'rcfd_linear_leaky_fwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
+    'rcfd_version': [], 'rcfd_arch': [], 'rcfd_last_error': [],
+}
+_RESTYPE = {'rcfd_version': c_char_p, 'rcfd_arch': c_char_p, 'rcfd_last_error': c_char_p,
+            'rcfd_conv2d_wgrad_workspace': c_int64}
+
+EXPORTED_SYMBOLS = sorted(_SIGS)
+
+_lib = None
+launch_count = 0      # number of C-ABI kernel-launching calls made (bench: gpu_launches evidence)
+
+
+class RcfdError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'librcfd_b200.so not found at %s -- build it with `python radar-camera-fusion-depth_b200/build.py` '
+            '(nvcc, sm_100a).  There is no CPU / PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, c_int32)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-status entry point; raise RcfdError(message) on failure."""
+    global launch_count
+    lib = _lib if _lib is not None else load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        raise RcfdError('%s failed (%d): %s' % (name, rc, lib.rcfd_last_error().decode()))

@@ -1,0 +1,420 @@
+"""
+Executor of the FusionNet / RadarNet graphs on librcfd_b200.so.
+
+The module trees in networks.py / net_utils.py hold parameters in the reference's layout;
+this file walks them and issues C-ABI calls (rcfd.ops).  Activations are NHWC in the
+compute dtype (float32 "parity" mode or bfloat16 "fast" mode), accumulation is fp32.
+
+What the reference does as separate library calls is fused here:
+  * eval mode:  conv + folded BN + activation (+ residual add + activation, + depth head)
+                = ONE kernel per conv (reference src/net_utils.py:84-91, :323);
+  * train mode: conv epilogue accumulates the BatchNorm batch statistics, then one
+                normalise+activation(+residual) pass;
+  * nearest up-sampling and channel concat are address maps of the consuming conv
+    (reference src/net_utils.py:196, :565), never materialised;
+  * the two 1x1 fusion convs of a level run as one stacked GEMM followed by one
+    gate kernel (reference src/networks.py:864-866).
+
+Training keeps a tape of closures (reverse-mode), so ``loss.backward()`` on the tensor
+returned by FusionNetModel.forward runs dgrad / wgrad / BN-backward kernels and writes
+parameter gradients (float32 OIHW, the reference's layout).
+"""
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD
+
+_ACT = {'linear': ACT_NONE, 'leaky_relu': ACT_LEAKY, 'sigmoid': ACT_SIGMOID}
+
+
+class Tape(object):
+    """Reverse-mode tape: forward ops append closures; grads are keyed by tensor identity."""
+
+    def __init__(self):
+        self.steps = []
+        self.grads = {}
+        self.keep = []
+        self.param_grads = []        # (parameter, grad tensor float32 in the parameter's layout)
+
+    def add_grad(self, t, g):
+        k = id(t)
+        if k in self.grads:
+            ops.add_(self.grads[k], g)
+        else:
+            self.grads[k] = g
+            self.keep.append(t)
+
+    def grad_of(self, t):
+        return self.grads.pop(id(t), None)
+
+    def backward(self):
+        for fn in reversed(self.steps):
+            fn()
+        self.steps = []
+        self.grads = {}
+        self.keep = []
+
+
+class Context(object):
+    """Per-forward state: dtype, mode, tape, BatchNorm scratch pool, packed-weight cache."""
+
+    def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO):
+        self.dtype = dtype
+        self.training = training
+        self.device = device
+        self.tape = Tape() if record else None
+        self.cache = cache if cache is not None else {}
+        self.engine = engine
+        self._pool_stats = None
+        self._pool_aff = None
+        self._off_stats = 0
+        self._off_aff = 0
+        self.bn_counters = []
+        self.taps = None
+
+    # -- scratch: stats are zero-initialised doubles, affine params are floats
+    def stats(self, c):
+        if self._pool_stats is None or self._off_stats + 2 * c > self._pool_stats.numel():
+            self._pool_stats = torch.zeros(max(65536, 2 * c), device=self.device, dtype=torch.float64)
+            self._off_stats = 0
+        s = self._pool_stats[self._off_stats:self._off_stats + 2 * c]
+        self._off_stats += 2 * c
+        return s[:c], s[c:]
+
+    def aff(self, c, k=4):
+        n = k * c
+        if self._pool_aff is None or self._off_aff + n > self._pool_aff.numel():
+            self._pool_aff = torch.empty(max(131072, n), device=self.device, dtype=torch.float32)
+            self._off_aff = 0
+        s = self._pool_aff[self._off_aff:self._off_aff + n]
+        self._off_aff += n
+        return [s[i * c:(i + 1) * c] for i in range(k)]
+
+    # -- weights: packed per forward in training (they change every step), cached by version in eval
+    def packed(self, key, params, fn):
+        ver = tuple(p._version for p in params) + (self.dtype,)
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = fn()
+        self.cache[key] = (ver, val)
+        return val
+
+    def weight(self, mod):
+        w = mod.conv.weight
+        return self.packed(('w', id(mod)), [w], lambda: ops.pack_weight(w.detach(), self.dtype))
+
+    def folded_bn(self, mod):
+        bn = mod.batch_norm
+        ps = [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def make():
+            scale = torch.empty(bn.num_features, device=self.device, dtype=torch.float32)
+            shift = torch.empty_like(scale)
+            ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift)
+            return scale, shift
+        return self.packed(('bn', id(mod)), ps, make)
+
+
+# ----------------------------------------------------------------------------- conv unit
+def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, want_input_grad=True):
+    """net_utils.Conv2d: conv -> BN? -> act? (-> residual add -> leaky).  head=(min, min/max)
+    turns the activation into the bounded depth head and stores float32."""
+    k, stride, cout = mod.kernel_size, mod.stride, mod.out_channels
+    act = _ACT[mod.act_kind]
+    w = ctx.weight(mod)
+    if head is not None:
+        out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=ACT_DEPTH_HEAD, act_params=head,
+                         out_f32=True, engine=ctx.engine)
+        if ctx.tape is not None:
+            _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad,
+                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype))
+        return out
+    if not mod.use_batch_norm:
+        out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=act, residual=residual, engine=ctx.engine)
+        if ctx.tape is not None:
+            assert act == ACT_NONE and residual is None
+            _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad)
+        return out
+    bn = mod.batch_norm
+    if not ctx.training:
+        scale, shift = ctx.folded_bn(mod)
+        return ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, scale=scale, shift=shift, act=act,
+                          residual=residual, engine=ctx.engine)
+    # training: raw conv + batch statistics -> finalize -> normalise/activate(/residual)
+    ssum, ssq = ctx.stats(cout)
+    y = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, stats=(ssum, ssq), engine=ctx.engine)
+    scale, shift, mean, invstd = ctx.aff(cout)
+    ops.bn_finalize(ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
+                    mean, invstd, y.numel() // cout)
+    ctx.bn_counters.append(bn.num_batches_tracked)
+    z = ops.bn_act(y, scale, shift, act, residual=residual)
+    if ctx.tape is not None:
+        _record_conv_backward(ctx, mod, x0, x1, in_size, z, (y, scale, shift, mean, invstd, act, residual),
+                              want_input_grad)
+    return z
+
+
+def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_grad, pre=None):
+    tape = ctx.tape
+    k, stride = mod.kernel_size, mod.stride
+    w_param = mod.conv.weight
+
+    def bwd():
+        dz = tape.grad_of(z)
+        if dz is None:
+            return
+        if pre is not None:
+            dz = pre(dz)
+        if bn_state is not None:
+            y, scale, shift, mean, invstd, act, residual = bn_state
+            if residual is not None:
+                dz = ops.leaky_bwd(dz, z)               # through the post-add activation
+                tape.add_grad(residual, dz)
+            bn = mod.batch_norm
+            dgamma = torch.empty_like(bn.weight)
+            dbeta = torch.empty_like(bn.bias)
+            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
+            tape.param_grads.append((bn.weight, dgamma))
+            tape.param_grads.append((bn.bias, dbeta))
+        else:
+            dy = dz
+        dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size)
+        gw = torch.empty_like(w_param)
+        ops.unpack_wgrad(dw, gw)
+        tape.param_grads.append((w_param, gw))
+        if not want_input_grad:
+            return
+        c0 = x0.shape[3]
+        hin, win = (x0.shape[1], x0.shape[2]) if in_size is None else in_size
+        pad_d = k - 1 - k // 2
+        for (src, off, cnt) in ((x0, 0, c0),) + (((x1, c0, x1.shape[3]),) if x1 is not None else ()):
+            wd = ops.pack_weight(w_param.detach(), ctx.dtype, cin_off=off, cin_cnt=cnt, dgrad=True)
+            dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine)
+            if src is x0 and (hin, win) != (x0.shape[1], x0.shape[2]):
+                dsrc = ops.upsample_nearest_bwd(dsrc, (x0.shape[1], x0.shape[2]))
+            tape.add_grad(src, dsrc)
+    tape.steps.append(bwd)
+
+
+# ----------------------------------------------------------------------------- gated fusion level
+def fusion_level(ctx, mod_w, mod_p, dep, img):
+    """fused = sigmoid(BN(Ww . d)) * BN(Wp . d) + img   (reference src/networks.py:864-866)"""
+    c = mod_w.out_channels
+    ww, wp = mod_w.conv.weight, mod_p.conv.weight
+    wcat = ctx.packed(('wcat', id(mod_w)), [ww, wp],
+                      lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype))
+    bw, bp = mod_w.batch_norm, mod_p.batch_norm
+    if not ctx.training:
+        def make():
+            scale = torch.empty(2 * c, device=ctx.device, dtype=torch.float32)
+            shift = torch.empty_like(scale)
+            ops.bn_fold(bw.weight.detach(), bw.bias.detach(), bw.running_mean, bw.running_var, scale[:c], shift[:c])
+            ops.bn_fold(bp.weight.detach(), bp.bias.detach(), bp.running_mean, bp.running_var, scale[c:], shift[c:])
+            return scale, shift
+        scale, shift = ctx.packed(('bncat', id(mod_w)),
+                                  [bw.weight, bw.bias, bw.running_mean, bw.running_var,
+                                   bp.weight, bp.bias, bp.running_mean, bp.running_var], make)
+        y = ops.conv2d(dep, wcat, 2 * c, 1, 1, scale=scale, shift=shift, engine=ctx.engine)
+        return ops.gate_fuse(y, None, None, img)
+    ssum, ssq = ctx.stats(2 * c)
+    y = ops.conv2d(dep, wcat, 2 * c, 1, 1, stats=(ssum, ssq), engine=ctx.engine)
+    scale, shift, mean, invstd = ctx.aff(2 * c)
+    count = y.numel() // (2 * c)
+    for bn, lo in ((bw, 0), (bp, c)):
+        ops.bn_finalize(ssum[lo:lo + c], ssq[lo:lo + c], bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                        bn.running_var, scale[lo:lo + c], shift[lo:lo + c], mean[lo:lo + c], invstd[lo:lo + c], count)
+        ctx.bn_counters.append(bn.num_batches_tracked)
+    out = ops.gate_fuse(y, scale, shift, img)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            dout = tape.grad_of(out)
+            if dout is None:
+                return
+            dzy = ops.gate_fuse_bwd(dout, y, scale, shift)
+            tape.add_grad(img, dout)
+            dg = torch.empty(2 * c, device=ctx.device, dtype=torch.float32)
+            db = torch.empty_like(dg)
+            dy = ops.bn_act_bwd(dzy, y, scale, shift, mean, invstd, ACT_NONE, dg, db)
+            for bn, lo in ((bw, 0), (bp, c)):
+                tape.param_grads.append((bn.weight, dg[lo:lo + c]))
+                tape.param_grads.append((bn.bias, db[lo:lo + c]))
+            dw = ops.conv2d_wgrad(dep, dy, 1, 1)                         # [2c, 1, cd]
+            for wparam, lo in ((ww, 0), (wp, c)):
+                g = torch.empty_like(wparam)
+                ops.unpack_wgrad(dw[lo:lo + c], g)
+                tape.param_grads.append((wparam, g))
+            wd = ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype, dgrad=True)
+            tape.add_grad(dep, ops.conv2d(dy, wd, dep.shape[3], 1, 1, engine=ctx.engine))
+        tape.steps.append(bwd)
+    return out
+
+
+def max_pool(ctx, x):
+    out = ops.maxpool3x3s2(x)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            d = tape.grad_of(out)
+            if d is not None:
+                tape.add_grad(x, ops.maxpool3x3s2_bwd(x, d))
+        tape.steps.append(bwd)
+    return out
+
+
+def res_block(ctx, blk, x):
+    """net_utils.ResNetBlock (reference src/net_utils.py:309-323)."""
+    c1 = conv_unit(ctx, blk.conv1, x)
+    if blk.stride != 1 or blk.in_channels != blk.out_channels:
+        sc = conv_unit(ctx, blk.projection, x)
+    else:
+        sc = x
+    return conv_unit(ctx, blk.conv2, c1, residual=sc)
+
+
+def res_stage(ctx, stage, x):
+    for blk in stage:
+        x = res_block(ctx, blk, x)
+    return x
+
+
+def decoder_block(ctx, blk, x, skip, shape):
+    """net_utils.DecoderBlock (reference src/net_utils.py:535-569)."""
+    if skip is not None:
+        shape = (skip.shape[1], skip.shape[2])
+    elif shape is None:
+        shape = (2 * x.shape[1], 2 * x.shape[2])
+    d = conv_unit(ctx, blk.deconv.conv, x, in_size=(int(shape[0]), int(shape[1])))
+    return conv_unit(ctx, blk.conv, d, x1=skip if blk.skip_channels > 0 else None)
+
+
+# ----------------------------------------------------------------------------- whole graphs
+def fusionnet_encoder(ctx, enc, image, depth):
+    """networks.FusionNetEncoder.forward (reference src/networks.py:840-1005); NHWC in / out."""
+    ci = conv_unit(ctx, enc.conv1_image, image, want_input_grad=False)
+    cd = conv_unit(ctx, enc.conv1_depth, depth, want_input_grad=False)
+    layers = [fusion_level(ctx, enc.conv1_weight, enc.conv1_project, cd, ci)]
+    xi, xd = max_pool(ctx, ci), max_pool(ctx, cd)
+    for level in range(2, 8):
+        si = getattr(enc, 'blocks%d_image' % level)
+        if si is None:
+            break
+        xi = res_stage(ctx, si, xi)
+        xd = res_stage(ctx, getattr(enc, 'blocks%d_depth' % level), xd)
+        layers.append(fusion_level(ctx, getattr(enc, 'conv%d_weight' % level), getattr(enc, 'conv%d_project' % level),
+                                   xd, xi))
+    return layers[-1], layers[:-1]
+
+
+def resnet_encoder(ctx, enc, x):
+    """networks.ResNetEncoder.forward (reference src/networks.py:232-268)."""
+    layers = [conv_unit(ctx, enc.conv1, x, want_input_grad=False)]
+    y = max_pool(ctx, layers[-1])
+    for level in range(2, 8):
+        stage = getattr(enc, 'blocks%d' % level)
+        if stage is None:
+            break
+        y = res_stage(ctx, stage, y)
+        layers.append(y)
+    return layers[-1], layers[:-1]
+
+
+def multiscale_decoder(ctx, dec, latent, skips, shape, head=None):
+    """networks.MultiScaleDecoder.forward, n_resolution == 1 (reference src/networks.py:1557-1657).
+    Returns (output, last feature map)."""
+    x = latent
+    n = len(skips) - 1
+    for b in range(dec.n_blocks - 1, -1, -1):
+        blk = getattr(dec, 'deconv%d' % b)
+        if n >= 0:
+            x = decoder_block(ctx, blk, x, skips[n], None)
+            n -= 1
+        else:
+            x = decoder_block(ctx, blk, x, None, shape)
+        if ctx.taps is not None:
+            ctx.taps['deconv%d' % b] = x
+    out = conv_unit(ctx, dec.output0, x, head=head) if head is not None else \
+        ops.conv2d(x, ctx.weight(dec.output0), dec.output0.out_channels, 3, 1, out_f32=True, engine=ctx.engine)
+    return out, x
+
+
+def finish_bn_counters(ctx):
+    if ctx.bn_counters:
+        torch._foreach_add_(ctx.bn_counters, 1)
+        ctx.bn_counters = []
+
+
+# ----------------------------------------------------------------------------- standalone module calls
+def _ctx_for(mod, x):
+    training = False      # standalone block calls are inference-only (training goes through the model wrappers)
+    return Context(torch.float32, training, x.device)
+
+
+def standalone_activation(x, kind):
+    flat = x.contiguous().view(-1, 4) if x.numel() % 4 == 0 else None
+    if flat is None:
+        raise ValueError('standalone activation needs numel % 4 == 0')
+    return ops.bn_act(flat, None, None, _ACT[kind]).view(x.shape)
+
+
+def standalone(mod, kind, x, **kw):
+    """Run one module of the tree by itself on NCHW float tensors (inference semantics of
+    ``mod.training`` is NOT honoured for BatchNorm statistics: eval-mode folding is used)."""
+    ctx = _ctx_for(mod, x)
+    to = lambda t: ops.nchw_to_nhwc(t.float(), ctx.dtype)
+    back = ops.nhwc_to_nchw
+    if kind == 'conv':
+        return back(conv_unit(ctx, mod, to(x)))
+    if kind == 'upconv':
+        return back(conv_unit(ctx, mod.conv, to(x), in_size=tuple(kw['shape'])))
+    if kind == 'resblock':
+        return back(res_block(ctx, mod, to(x)))
+    if kind == 'decoder_block':
+        skip = kw.get('skip')
+        return back(decoder_block(ctx, mod, to(x), to(skip) if skip is not None else None, kw.get('shape')))
+    if kind == 'resnet_encoder':
+        latent, skips = resnet_encoder(ctx, mod, to(x))
+        return back(latent), [back(s) for s in skips]
+    if kind == 'fusionnet_encoder':
+        latent, skips = fusionnet_encoder(ctx, mod, to(x), to(kw['depth']))
+        return back(latent), [back(s) for s in skips]
+    if kind == 'decoder':
+        out, _ = multiscale_decoder(ctx, mod, to(x), [to(s) for s in kw['skips']], kw.get('shape'))
+        return [out.view(out.shape[0], 1, out.shape[1], out.shape[2])]
+    if kind == 'radarnet_encoder':
+        latent, skips = radarnet_encoder(ctx, mod, to(x), kw['points'], kw['boxes'])
+        return back(latent), [back(s) for s in skips]
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------- RadarNet column
+def boxes_to_rois(boxes_list, device):
+    rows = []
+    for b, boxes in enumerate(boxes_list):
+        boxes = boxes.to(device=device, dtype=torch.float32)
+        rows.append(torch.cat([torch.full((boxes.shape[0], 1), float(b), device=device), boxes], dim=1))
+    return torch.cat(rows, dim=0).contiguous()
+
+
+def radarnet_encoder(ctx, enc, image, points, boxes_list):
+    """networks.RadarNetV1Encoder.forward (reference src/networks.py:1203-1256); image NHWC."""
+    ph, pw = enc.input_patch_size_image
+    lat_h, lat_w = int(ph // 32.0), int(pw // 32.0)
+    scales = [1 / 2.0, 1 / 4.0, 1 / 8.0, 1 / 16.0, 1 / 32.0, 1 / 64.0, 1 / 128.0]
+    latent_img, skips_img = resnet_encoder(ctx, enc.encoder_image, image)
+    rois = boxes_to_rois(boxes_list, image.device)
+    latent_pooled = ops.roi_pool(latent_img, rois, (lat_h, lat_w), 1 / 32.0)
+    skips = [ops.roi_pool(s, rois, (int(ph * scales[i]), int(pw * scales[i])), scales[i])
+             for i, s in enumerate(skips_img)]
+    x = points.to(device=image.device, dtype=torch.float32).contiguous()
+    for fc in enc.encoder_depth.mlp:
+        x = ops.linear_leaky(x, fc.fully_connected.weight.detach(), fc.fully_connected.bias.detach())
+    k = x.shape[0]
+    cl = enc.n_neuron_latent_depth
+    # reference views the MLP output as (K, C, h, w) NCHW (src/networks.py:1252) -> NHWC
+    lat_d = ops.nchw_to_nhwc(x.view(k, cl, lat_h, lat_w), ctx.dtype)
+    latent = torch.cat([latent_pooled, lat_d], dim=3).contiguous()      # channel concat of two small tensors
+    return latent, skips

@@ -1,0 +1,291 @@
+"""
+Tensor-level wrappers over the C-ABI: torch is used for device memory and streams only.
+Every function requires CUDA tensors and calls librcfd_b200.so; nothing here computes in
+PyTorch.  Activations are NHWC tensors [N, H, W, C] (float32 or bfloat16).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ConvDesc, F32, BF16, ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD,
+                   ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05)
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'rcfd ops need contiguous CUDA tensors'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def conv_out_size(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=None, shift=None,
+           act=ACT_NONE, act_params=(0.0, 0.0), residual=None, stats=None, out=None, out_f32=False,
+           accumulate=False, in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO):
+    """Implicit-GEMM convolution (see include/rcfd.h rcfd_conv2d_fwd).
+    x0: [N, h0, w0, c0]; in_size: logical (H, W) the taps see (x0 is nearest-up-sampled to it);
+    x1: optional [N, H, W, c1] concat partner; stats: (sum, sqsum) float64 [cout] tensors."""
+    n, h0, w0, c0 = x0.shape
+    hin, win = (h0, w0) if in_size is None else (int(in_size[0]), int(in_size[1]))
+    pad = k // 2 if pad is None else pad
+    if out_size is None:
+        if in_dilation == 1:
+            ho, wo = conv_out_size(hin, k, stride, pad), conv_out_size(win, k, stride, pad)
+        else:
+            raise ValueError('out_size is required with in_dilation')
+    else:
+        ho, wo = out_size
+    d = ConvDesc()
+    d.n, d.ho, d.wo, d.cout = n, ho, wo, cout
+    d.kh = d.kw = k
+    d.stride, d.pad, d.in_dilation = stride, pad, in_dilation
+    d.hin, d.win = hin, win
+    d.src0, d.h0, d.w0, d.c0 = x0.data_ptr(), h0, w0, c0
+    if x1 is not None:
+        assert x1.shape[0] == n and x1.shape[1] == hin and x1.shape[2] == win and x1.dtype == x0.dtype
+        d.src1, d.c1 = x1.data_ptr(), x1.shape[3]
+    else:
+        d.src1, d.c1 = None, 0
+    d.weight = weight_packed.data_ptr()
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), device=x0.device, dtype=torch.float32 if out_f32 else x0.dtype)
+    d.dst = out.data_ptr()
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.act, d.act_p0, d.act_p1 = act, act_params[0], act_params[1]
+    d.residual = residual.data_ptr() if residual is not None else None
+    if stats is not None:
+        d.stats_sum, d.stats_sqsum = stats[0].data_ptr(), stats[1].data_ptr()
+    d.accumulate = 1 if accumulate else 0
+    d.dst_f32 = 1 if out_f32 else 0
+    d.dtype = dt(x0)
+    d.engine = engine
+    _lib.call('rcfd_conv2d_fwd', ctypes.byref(d), _stream())
+    return out
+
+
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None):
+    """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above."""
+    n, h0, w0, c0 = x0.shape
+    hin, win = (h0, w0) if in_size is None else (int(in_size[0]), int(in_size[1]))
+    pad = k // 2 if pad is None else pad
+    _, ho, wo, cout = dy.shape
+    c1 = 0 if x1 is None else x1.shape[3]
+    d = ConvDesc()
+    d.n, d.ho, d.wo, d.cout = n, ho, wo, cout
+    d.kh = d.kw = k
+    d.stride, d.pad, d.in_dilation = stride, pad, 1
+    d.hin, d.win = hin, win
+    d.src0, d.h0, d.w0, d.c0 = x0.data_ptr(), h0, w0, c0
+    d.src1, d.c1 = (x1.data_ptr() if x1 is not None else None), c1
+    dw = torch.empty((cout, k * k, c0 + c1), device=x0.device, dtype=torch.float32)
+    d.weight = dw.data_ptr()       # unused by wgrad, must be non-null
+    d.dst = dy.data_ptr()
+    d.dtype = dt(x0)
+    _lib.call('rcfd_conv2d_wgrad', ctypes.byref(d), _p(dw), None, 0, _stream())
+    return dw
+
+
+def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None):
+    cout, cin, kh, kw = w_oihw.shape
+    cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
+    if out is None:
+        shape = (cin_cnt, kh * kw, cout) if dgrad else (cout, kh * kw, cin_cnt)
+        out = torch.empty(shape, device=w_oihw.device, dtype=dtype)
+    _lib.call('rcfd_pack_conv_weight', _p(w_oihw), _p(out), cout, cin, kh, kw, cin_off, cin_cnt,
+              1 if dgrad else 0, _DT[dtype], _stream())
+    return out
+
+
+def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False):
+    cout, cin, kh, kw = grad_oihw.shape
+    cin_cnt = dw_packed.shape[2]
+    _lib.call('rcfd_unpack_conv_wgrad', _p(dw_packed), _p(grad_oihw), cout, cin, kh, kw, cin_off, cin_cnt,
+              1 if accumulate else 0, _stream())
+
+
+def bn_finalize(ssum, ssq, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, count):
+    _lib.call('rcfd_bn_finalize', _p(ssum), _p(ssq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+              _p(scale), _p(shift), _p(save_mean), _p(save_invstd), gamma.numel(), int(count), BN_EPS, BN_MOMENTUM,
+              _stream())
+
+
+def bn_fold(gamma, beta, running_mean, running_var, scale, shift):
+    _lib.call('rcfd_bn_fold', _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(scale), _p(shift),
+              gamma.numel(), BN_EPS, _stream())
+
+
+def bn_act(y, scale, shift, act, residual=None, out=None):
+    c = y.shape[-1]
+    out = torch.empty_like(y) if out is None else out
+    _lib.call('rcfd_bn_act_fwd', _p(y), _p(scale), _p(shift), _p(residual), _p(out), y.numel() // c, c, act, dt(y),
+              _stream())
+    return out
+
+
+def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None):
+    c = y.shape[-1]
+    pixels = y.numel() // c
+    if sums is None:
+        sums = torch.empty(2 * c, device=y.device, dtype=torch.float64)
+    _lib.call('rcfd_bn_act_bwd_reduce', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), pixels, c,
+              act, dt(y), _stream())
+    dy = torch.empty_like(y)
+    _lib.call('rcfd_bn_act_bwd_apply', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), _p(dy),
+              _p(dgamma), _p(dbeta), pixels, c, act, dt(y), _stream())
+    return dy
+
+
+def gate_fuse(y2c, scale, shift, img):
+    c = img.shape[-1]
+    out = torch.empty_like(img)
+    _lib.call('rcfd_gate_fuse_fwd', _p(y2c), _p(scale), _p(shift), _p(img), _p(out), img.numel() // c, c, dt(img),
+              _stream())
+    return out
+
+
+def gate_fuse_bwd(dout, y2c, scale, shift):
+    c = dout.shape[-1]
+    dz = torch.empty_like(y2c)
+    _lib.call('rcfd_gate_fuse_bwd', _p(dout), _p(y2c), _p(scale), _p(shift), _p(dz), dout.numel() // c, c, dt(dout),
+              _stream())
+    return dz
+
+
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1), c), device=x.device, dtype=x.dtype)
+    _lib.call('rcfd_maxpool3x3s2_fwd', _p(x), _p(out), n, h, w, c, dt(x), _stream())
+    return out
+
+
+def maxpool3x3s2_bwd(x, dout):
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    _lib.call('rcfd_maxpool3x3s2_bwd', _p(x), _p(dout), _p(dx), n, h, w, c, dt(x), _stream())
+    return dx
+
+
+def upsample_nearest_bwd(dup, src_hw):
+    n, hu, wu, c = dup.shape
+    hs, ws = src_hw
+    dsrc = torch.empty((n, hs, ws, c), device=dup.device, dtype=dup.dtype)
+    _lib.call('rcfd_upsample_nearest_bwd', _p(dup), _p(dsrc), n, hs, ws, hu, wu, c, 0, dt(dup), _stream())
+    return dsrc
+
+
+def leaky_bwd(dout, out):
+    din = torch.empty_like(dout)
+    _lib.call('rcfd_leaky_bwd', _p(dout), _p(out), _p(din), dout.numel(), dt(dout), _stream())
+    return din
+
+
+def add_(acc, x):
+    _lib.call('rcfd_add_inplace', _p(acc), _p(x), acc.numel(), dt(acc), _stream())
+    return acc
+
+
+def nchw_to_nhwc(x, dtype):
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    out = torch.empty((n, h, w, c), device=x.device, dtype=dtype)
+    _lib.call('rcfd_nchw_to_nhwc', _p(x), _p(out), n, c, h, w, _DT[dtype], _stream())
+    return out
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    _lib.call('rcfd_nhwc_to_nchw', _p(x), _p(out), n, c, h, w, dt(x), _stream())
+    return out
+
+
+def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype):
+    dl = torch.empty(depth.shape, device=depth.device, dtype=dtype)
+    _lib.call('rcfd_depth_head_bwd', _p(ddepth.contiguous()), _p(depth), _p(dl), float(min_depth), float(min_over_max),
+              depth.numel(), _DT[dtype], _stream())
+    return dl
+
+
+def masked_l1_loss(out, gt, lidar, w_lidar, want_grad=True):
+    accum = torch.empty(4, device=out.device, dtype=torch.float64)
+    loss = torch.empty(1, device=out.device, dtype=torch.float32)
+    dout = torch.empty_like(out) if want_grad else None
+    _lib.call('rcfd_masked_l1_loss', _p(out.contiguous()), _p(gt.contiguous()), _p(lidar.contiguous()), float(w_lidar),
+              _p(accum), _p(loss), _p(dout), out.numel(), _stream())
+    return loss, dout
+
+
+def outlier_removal(depth, kernel_size=7, threshold=1.5):
+    depth = depth.contiguous()
+    n, _, h, w = depth.shape
+    out = torch.empty_like(depth)
+    scratch = torch.empty(1, device=depth.device, dtype=torch.float32)
+    _lib.call('rcfd_outlier_removal', _p(depth), _p(out), _p(scratch), n, h, w, kernel_size, float(threshold), _stream())
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    _lib.call('rcfd_adam_step', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(beta1),
+              float(beta2), float(eps), int(step), _stream())
+
+
+def scatter_points_to_depth_map(points_xy, depth, h, w, img=None):
+    """S1.  points_xy: [2, N] float64 CUDA, depth: [N] float64.  img given -> z-buffer merge into it."""
+    merge = img is not None
+    if img is None:
+        img = torch.empty((h, w), device=points_xy.device, dtype=torch.float64)
+    npts = points_xy.shape[1]
+    _lib.call('rcfd_scatter_points_to_depth_map', _p(points_xy.contiguous()), _p(depth.contiguous()), npts, _p(img), h,
+              w, 1 if merge else 0, _stream())
+    return img
+
+
+def scatter_tiles_argmax(crops, points, h, w, compat=True):
+    """S2.  crops: [K, 1, ph, pw] float32; points: [K, 3] float32 (x already shifted by +pad)."""
+    k, _, ph, pw = crops.shape
+    response = torch.empty((1, h, w), device=crops.device, dtype=torch.float32)
+    if compat:
+        depth = torch.empty((1, h, w), device=crops.device, dtype=torch.int64)
+        _lib.call('rcfd_scatter_tiles_argmax', _p(crops.contiguous()), _p(points.contiguous()), k, ph, pw, h, w, 1,
+                  _p(depth), None, _p(response), _stream())
+    else:
+        depth = torch.empty((1, h, w), device=crops.device, dtype=torch.float32)
+        _lib.call('rcfd_scatter_tiles_argmax', _p(crops.contiguous()), _p(points.contiguous()), k, ph, pw, h, w, 0,
+                  None, _p(depth), _p(response), _stream())
+    return depth, response
+
+
+def roi_pool(feat, boxes5, out_size, spatial_scale):
+    """feat: NHWC; boxes5: [nbox, 5] float32 (batch_index, x1, y1, x2, y2)."""
+    n, h, w, c = feat.shape
+    nbox = boxes5.shape[0]
+    out = torch.empty((nbox, out_size[0], out_size[1], c), device=feat.device, dtype=feat.dtype)
+    _lib.call('rcfd_roi_pool_fwd', _p(feat), _p(boxes5.contiguous()), _p(out), n, h, w, c, nbox, out_size[0],
+              out_size[1], float(spatial_scale), dt(feat), _stream())
+    return out
+
+
+def linear_leaky(x, w, b):
+    rows, fin = x.shape
+    fout = w.shape[0]
+    out = torch.empty((rows, fout), device=x.device, dtype=torch.float32)
+    _lib.call('rcfd_linear_leaky_fwd', _p(x.contiguous()), _p(w), _p(b), _p(out), rows, fin, fout, _stream())
+    return out

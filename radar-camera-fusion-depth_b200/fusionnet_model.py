@@ -24,8 +24,7 @@ class _FusionNetFunction(torch.autograd.Function):
     """One autograd node for the whole encoder-decoder."""
 
     @staticmethod
-    def forward(fctx, model, image, input_depth, *params):
-        record = torch.is_grad_enabled() and model.encoder.training and any(p.requires_grad for p in params)
+    def forward(fctx, model, record, image, input_depth, *params):
         out_nhwc, ectx = model._run(image, input_depth, record=record)
         fctx.model, fctx.ectx, fctx.out_nhwc = model, ectx, out_nhwc
         fctx.set_materialize_grads(False)
@@ -35,7 +34,7 @@ class _FusionNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(fctx, grad_out):
         ectx = fctx.ectx
-        n_in = 3 + len(list(fctx.model.parameters()))
+        n_in = 4 + len(list(fctx.model.parameters()))
         if grad_out is None or ectx is None or ectx.tape is None:
             return (None,) * n_in
         tape = ectx.tape
@@ -101,8 +100,7 @@ class FusionNetModel(object):
 
     # ------------------------------------------------------------------ execution
     def _run(self, image, input_depth, record=False, return_logits=False, taps=None):
-        if not (image.is_cuda and input_depth.is_cuda):
-            raise RuntimeError('FusionNetModel runs on CUDA only (no CPU fallback)')
+        # rcfd.ops refuses non-CUDA tensors: there is no CPU fallback behind this call
         ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
                               record=record, engine=self.conv_engine)
         ectx.taps = taps
@@ -127,7 +125,10 @@ class FusionNetModel(object):
             n, h, w, _ = out.shape
             out = out.view(n, 1, h, w)
         else:
-            out = _FusionNetFunction.apply(self, image, input_depth, *self.parameters())
+            params = self.parameters()
+            # grad mode is off inside autograd.Function.forward, so decide here whether to tape
+            record = torch.is_grad_enabled() and self.encoder.training and any(p.requires_grad for p in params)
+            out = _FusionNetFunction.apply(self, record, image, input_depth, *params)
         return [out] if return_multiscale else out
 
     def _deliver_grads(self, param_grads):

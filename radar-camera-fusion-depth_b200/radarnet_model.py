@@ -51,8 +51,6 @@ class RadarNetModel(object):
     def forward(self, image, point, bounding_boxes, return_logits=True):
         """image N x 3 x H x W (already edge-padded), point sum(K_i) x 3, bounding_boxes list of K_i x 4
         -> sum(K_i) x 1 x ph x pw logits or sigmoid responses (reference :102-124)."""
-        if not image.is_cuda:
-            raise RuntimeError('RadarNetModel runs on CUDA only (no CPU fallback)')
         if self.encoder.training and torch.is_grad_enabled():
             raise NotImplementedError('RadarNet training (backward) is not part of this round; call under '
                                       'torch.no_grad() / model.eval() for stage-1 inference')

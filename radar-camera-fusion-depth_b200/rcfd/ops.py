@@ -28,7 +28,8 @@ def _stream():
 def _p(t):
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), 'rcfd ops need contiguous CUDA tensors'
+    if not (t.is_cuda and t.is_contiguous()):
+        raise RuntimeError('rcfd ops need contiguous CUDA tensors (there is no CPU fallback)')
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -42,6 +43,8 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     """Implicit-GEMM convolution (see include/rcfd.h rcfd_conv2d_fwd).
     x0: [N, h0, w0, c0]; in_size: logical (H, W) the taps see (x0 is nearest-up-sampled to it);
     x1: optional [N, H, W, c1] concat partner; stats: (sum, sqsum) float64 [cout] tensors."""
+    for t in (x0, x1, weight_packed, scale, shift, residual, out):
+        _p(t)                                   # CUDA + contiguity check
     n, h0, w0, c0 = x0.shape
     hin, win = (h0, w0) if in_size is None else (int(in_size[0]), int(in_size[1]))
     pad = k // 2 if pad is None else pad
@@ -83,6 +86,8 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
 
 def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None):
     """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above."""
+    for t in (x0, x1, dy):
+        _p(t)
     n, h0, w0, c0 = x0.shape
     hin, win = (h0, w0) if in_size is None else (int(in_size[0]), int(in_size[1]))
     pad = k // 2 if pad is None else pad

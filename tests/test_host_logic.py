@@ -1,0 +1,169 @@
+"""CPU: host-side logic (engine graph wiring, reverse-mode tape, gradient delivery, checkpoint
+surface, data-parallel gradient sync) with the kernels replaced by tests/mock_ops.py, a torch-CPU
+emulation of the C-ABI semantics.  The real kernels are tested on the GPU (-m gpu)."""
+import os
+import sys
+
+import pytest
+import torch
+
+import fusionnet_oracle as fo
+from rcfd import synth
+from helpers import load_golden, relerr, synth_fusionnet_state
+import mock_ops
+
+
+@pytest.fixture
+def mocked(monkeypatch):
+    import rcfd
+    from rcfd import engine
+    import fusionnet_model, fusionnet_losses, net_utils
+    monkeypatch.setitem(sys.modules, 'rcfd.ops', mock_ops)
+    monkeypatch.setattr(rcfd, 'ops', mock_ops, raising=False)
+    for mod in (engine, fusionnet_model, fusionnet_losses):
+        monkeypatch.setattr(mod, 'ops', mock_ops)
+    return mock_ops
+
+
+def _model(cfg, p):
+    import fusionnet_model
+    m = fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg)
+    m.encoder.load_state_dict({k[8:]: v for k, v in p.items() if k.startswith('encoder.')})
+    m.decoder.load_state_dict({k[8:]: v for k, v in p.items() if k.startswith('decoder.')})
+    return m
+
+
+def test_engine_eval_graph_matches_golden(mocked):
+    g = load_golden('fusionnet_small_2x64x96')
+    p = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('w::')}
+    n, h, w, seed = [int(v) for v in g['meta']]
+    image, depth = synth.fusionnet_inputs(n, h, w, seed, str(g['variant']))
+    m = _model(synth.SMALL_FUSIONNET, p)
+    m.eval()
+    with torch.no_grad():
+        d = m.forward(image, depth)
+        l = m.forward(image, depth, return_logits=True)
+    assert relerr(d, g['eval_depth']) < 1e-4 and relerr(l, g['eval_logits']) < 1e-4
+
+
+def test_engine_train_step_tape_matches_golden(mocked):
+    g = load_golden('fusionnet_small_2x64x96')
+    p = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('w::')}
+    n, h, w, seed = [int(v) for v in g['meta']]
+    image, depth = synth.fusionnet_inputs(n, h, w, seed, str(g['variant']))
+    gt, lidar = synth.training_targets(n, h, w, seed)
+    import net_utils
+    m = _model(synth.SMALL_FUSIONNET, p)
+    m.train()
+    gt = net_utils.OutlierRemoval(7, 1.5).remove_outliers(gt)
+    d = m.forward(image, depth)
+    # is_cuda is False on the mock: the tensor-op branch of compute_loss is exercised here ...
+    loss, info = m.compute_loss(image=image, output_depth=d, ground_truth=gt, lidar_map=lidar, loss_func='l1',
+                                w_smoothness=0.0, loss_smoothness_kernel_size=-1,
+                                validity_map_loss_smoothness=torch.ones_like(gt), w_lidar_loss=2.0)
+    loss.backward()
+    assert relerr(d.detach(), g['train_depth']) < 1e-4
+    assert abs(float(loss) - float(g['train_loss'])) < 1e-4 * float(g['train_loss'])
+    named = dict([('encoder.' + k, v) for k, v in m.encoder.named_parameters()] +
+                 [('decoder.' + k, v) for k, v in m.decoder.named_parameters()])
+    for i, k in enumerate(g['grad_names']):
+        k = str(k)
+        if g['grad_none'][i]:
+            assert named[k].grad is None, k
+        else:
+            assert abs(float(named[k].grad.double().sum()) - g['grad_sum'][i]) <= 1e-3 * g['grad_abs'][i] + 1e-9, k
+            assert relerr(named[k].grad.flatten()[:8], g['grad_head'][i][:named[k].numel()]) < 5e-3 or \
+                float(named[k].grad.abs().max()) < 1e-6, k
+    sd = m.decoder.state_dict()
+    assert relerr(sd['deconv0.conv.batch_norm.running_mean'], g['train_running_mean_deconv0']) < 1e-4
+    assert int(sd['deconv0.conv.batch_norm.num_batches_tracked']) == 1
+    # ... and the fused masked-L1 autograd node gives the same loss / gradient
+    import fusionnet_losses
+    d2 = d.detach().clone().requires_grad_(True)
+    l2 = fusionnet_losses.MaskedL1.apply(d2, gt, lidar, 2.0)
+    l2.backward()
+    d3 = d.detach().clone().requires_grad_(True)
+    fo.fusionnet_loss(d3, gt, lidar, 2.0, 'l1').backward()
+    assert abs(float(l2) - float(loss)) < 1e-6 * float(loss) and relerr(d2.grad, d3.grad) < 1e-6
+
+
+def test_checkpoint_surface_roundtrip(tmp_path, mocked):
+    p = synth_fusionnet_state(synth.SMALL_FUSIONNET, 7)
+    m = _model(synth.SMALL_FUSIONNET, p)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    path = str(tmp_path / 'model-5.pth')
+    m.save_model(path, 5, opt)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {'train_step', 'optimizer_state_dict', 'encoder_state_dict', 'decoder_state_dict'}
+    # the reference saves after data_parallel(): 'module.'-prefixed keys must load too
+    ck['encoder_state_dict'] = {'module.' + k: v for k, v in ck['encoder_state_dict'].items()}
+    ck['decoder_state_dict'] = {'module.' + k: v for k, v in ck['decoder_state_dict'].items()}
+    torch.save(ck, path)
+    m2 = _model(synth.SMALL_FUSIONNET, synth_fusionnet_state(synth.SMALL_FUSIONNET, 8))
+    step, _ = m2.restore_model(path, torch.optim.Adam(m2.parameters(), lr=1e-3))
+    assert step == 5
+    for a, b in zip(m.parameters(), m2.parameters()):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        import fusionnet_model
+        fusionnet_model.FusionNetModel(device=torch.device('cpu'), **dict(synth.SMALL_FUSIONNET, fusion_type='nope'))
+    with pytest.raises(ValueError):
+        m.compute_loss(None, torch.ones(1, 1, 2, 2), torch.ones(1, 1, 2, 2), torch.ones(1, 1, 2, 2), 'bogus', 0.0, -1,
+                       None, 0.0)
+
+
+def _ddp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    for q in (here, os.path.join(root, 'oracle'), os.path.join(root, 'radar-camera-fusion-depth_b200')):
+        sys.path.insert(0, q)
+    import rcfd
+    from rcfd import engine, parallel
+    import fusionnet_model, fusionnet_losses
+    sys.modules['rcfd.ops'] = mock_ops
+    rcfd.ops = mock_ops
+    for mod in (engine, fusionnet_model, fusionnet_losses):
+        mod.ops = mock_ops
+    torch.manual_seed(100 + rank)                       # different init per rank: broadcast must fix it
+    cfg = dict(synth.SMALL_FUSIONNET)
+    m = fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg)
+    m.data_parallel()                                   # attaches DistributedGradSync, broadcasts rank 0's state
+    assert isinstance(m.grad_hook, parallel.DistributedGradSync)
+    m.train()
+    image, depth = synth.fusionnet_inputs(1, 64, 64, 50 + rank, 'quasi_dense')
+    gt, lidar = synth.training_targets(1, 64, 64, 50 + rank)
+    d = m.forward(image, depth)
+    loss, _ = m.compute_loss(image, d, gt, lidar, 'l1', 0.0, -1, torch.ones_like(gt), 2.0)
+    loss.backward()
+    torch.save({'grads': [None if q.grad is None else q.grad.clone() for q in m.parameters()],
+                'params': [q.detach().clone() for q in m.parameters()],
+                'payload': m.grad_hook.payload_bytes()}, os.path.join(tmp, 'rank%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_sync_gloo(tmp_path):
+    """world_size 2 over gloo: replicas start identical (rank-0 broadcast), every used gradient is
+    the average over ranks, never-used projections stay None and outside the buckets."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(str(tmp_path / 'rank0.pt'), weights_only=False)
+    r1 = torch.load(str(tmp_path / 'rank1.pt'), weights_only=False)
+    n_none = 0
+    for a, b in zip(r0['params'], r1['params']):
+        assert torch.equal(a, b)
+    for a, b in zip(r0['grads'], r1['grads']):
+        assert (a is None) == (b is None)
+        if a is None:
+            n_none += 1
+        else:
+            assert torch.equal(a, b)
+    # SMALL config: the 10 identity-shortcut blocks '*.1.projection' plus blocks2_image.0 (16 -> 16, stride 1)
+    assert n_none == 11
+    used = sum(p.numel() for p, g in zip(r0['params'], r0['grads']) if g is not None)
+    assert r0['payload'] == used * 4

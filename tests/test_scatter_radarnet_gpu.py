@@ -1,0 +1,117 @@
+"""GPU parity: radar scatters (bit exact), ROI pooling, point MLP and the RadarNet column."""
+import numpy as np
+import pytest
+import torch
+
+import radarnet_oracle as ro
+import scatter_oracle as so
+from rcfd import synth
+from helpers import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('k', [0, 1, 8, 64, 500])
+def test_s1_scatter_bit_exact(k):
+    from rcfd import ops
+    h, w = 64, 96
+    pts = synth.radar_points(max(k, 8), h, w, 5)[:k].double()
+    xy = pts[:, :2].t().contiguous()
+    z = pts[:, 2].contiguous()
+    ref = so.s1_points_to_depth_map(xy.numpy(), z.numpy(), h, w)
+    img = ops.scatter_points_to_depth_map(xy.to(DEV), z.to(DEV), h, w)
+    assert np.array_equal(img.cpu().numpy(), ref)
+    # z-buffer merge of a second sweep
+    pts2 = synth.radar_points(max(k, 8), h, w, 6)[:k].double()
+    if k >= 8:
+        pts2[:4, :2] = pts[:4, :2]                     # collisions with the main sweep
+        pts2[0, 2], pts2[1, 2] = pts[0, 2] - 0.5, pts[1, 2] + 0.5
+    xy2, z2 = pts2[:, :2].t().contiguous(), pts2[:, 2].contiguous()
+    ref2, ref_xy, ref_z = so.s1_merge([(xy.numpy(), z.numpy()), (xy2.numpy(), z2.numpy())], h, w)
+    ops.scatter_points_to_depth_map(xy2.to(DEV), z2.to(DEV), h, w, img=img)
+    assert np.array_equal(img.cpu().numpy(), ref2)
+    nz = torch.nonzero(img)                               # row-major, like np.nonzero (:771)
+    assert np.array_equal(nz[:, 1].cpu().numpy(), ref_xy[0]) and np.array_equal(nz[:, 0].cpu().numpy(), ref_xy[1])
+
+
+@pytest.mark.parametrize('name', ['s2_compat_k6', 's2_compat_alias_k3'])
+def test_s2_scatter_golden_bit_exact(name):
+    from rcfd import ops
+    g = load_golden(name)
+    h, w, ph, pw, k, seed = [int(v) for v in g['meta']]
+    crops, pts = torch.from_numpy(g['crops']).to(DEV), torch.from_numpy(g['points']).to(DEV)
+    depth, resp = ops.scatter_tiles_argmax(crops, pts, h, w, compat=True)
+    assert depth.dtype == torch.int64
+    assert np.array_equal(depth.cpu().numpy(), g['depth']) and np.array_equal(resp.cpu().numpy(), g['response'])
+    d2, r2 = ops.scatter_tiles_argmax(crops, pts, h, w, compat=False)
+    ref2, _ = so.s2_scatter(g['crops'], g['points'], w, (ph, pw), compat=False)
+    assert np.array_equal(d2.cpu().numpy(), ref2) and torch.equal(r2, resp)
+
+
+def test_s2_edge_cases():
+    from rcfd import ops
+    h, w, ph, pw = 48, 80, 32, 16                           # crop shorter than the image, K = 1, all below threshold
+    crops = torch.rand(1, 1, ph, pw) * 0.49
+    pts = torch.tensor([[20.0 + pw // 2, 5.0, 33.3]])
+    d, r = ops.scatter_tiles_argmax(crops.to(DEV), pts.to(DEV), h, w, compat=True)
+    assert int(d.abs().sum()) == 0 and float(r.abs().sum()) == 0.0
+    crops2 = torch.rand(5, 1, ph, pw)
+    pts2 = torch.tensor([[8.0 + k * 13.7, 3.0, 3.9 + k] for k in range(5)])
+    for compat in (True, False):
+        ref_d, ref_r = so.s2_scatter(crops2.numpy(), pts2.numpy(), w, (ph, pw), compat=compat)
+        full_d = np.zeros((1, h, w), ref_d.dtype); full_r = np.zeros((1, h, w), np.float32)
+        full_d[:, h - ph:] = ref_d; full_r[:, h - ph:] = ref_r
+        d, r = ops.scatter_tiles_argmax(crops2.to(DEV), pts2.to(DEV), h, w, compat=compat)
+        assert np.array_equal(d.cpu().numpy(), full_d) and np.array_equal(r.cpu().numpy(), full_r)
+
+
+def test_roi_pool_and_mlp():
+    from rcfd import ops
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(2, 4, 22, 62, generator=g)
+    boxes = [torch.tensor([[3.2, 0.0, 291.2, 352.0], [100.5, 0.0, 388.5, 352.0]]),
+             torch.tensor([[650.9, 0.0, 938.9, 352.0]])]
+    from rcfd import engine
+    rois = engine.boxes_to_rois(boxes, DEV)
+    for scale, osz in ((1 / 16.0, (22, 18)), (1 / 32.0, (11, 9))):
+        f = feat if scale == 1 / 16.0 else feat[:, :, :11, :31].contiguous()
+        ref = ro.roi_pool(f, boxes, scale, osz)
+        out = ops.roi_pool(f.permute(0, 2, 3, 1).contiguous().to(DEV), rois, osz, scale)
+        assert torch.equal(out.cpu().permute(0, 3, 1, 2), ref)
+    x, w, b = torch.randn(7, 3, generator=g), torch.randn(32, 3, generator=g), torch.randn(32, generator=g)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.linear(x, w, b), 0.2)
+    assert relerr(ops.linear_leaky(x.to(DEV), w.to(DEV), b.to(DEV)).cpu(), ref) < 1e-5
+
+
+def test_radarnet_forward_golden_and_s2():
+    import radarnet_model
+    import radarnet_main
+    g = load_golden('radarnet_canonical_1x64x128_k3')
+    n, h, w, k, seed, ph, pw = [int(v) for v in g['meta']]
+    cfg = dict(synth.CANONICAL_RADARNET, input_patch_size_image=(ph, pw))
+    m = radarnet_model.RadarNetModel(device=DEV, **cfg)
+    p = {}
+    for kk, v in m.encoder.state_dict().items():
+        p['encoder.' + kk] = v
+    for kk, v in m.decoder.state_dict().items():
+        p['decoder.' + kk] = v
+    synth.fill_state_dict_(p, seed)                 # in place on the CUDA parameters (same CPU generator values)
+    m.eval()
+    pad = pw // 2
+    gen = torch.Generator().manual_seed(seed)
+    image = torch.rand(n, 3, h, w + 2 * pad, generator=gen)
+    pt = synth.radar_points(k, h, w, seed)
+    pt[:, 0] += pad
+    boxes = [torch.stack([pt[:, 0] - pad, torch.zeros(k), pt[:, 0] + pad, torch.full((k,), float(h))], 1)]
+    with torch.no_grad():
+        logits = m.forward(image.to(DEV), pt.to(DEV), boxes, return_logits=True)
+    assert relerr(logits.cpu(), g['logits']) < 1e-3
+    # stage-1 entry point: edge pad + forward + S2 scatter, vs oracle composition
+    with torch.no_grad():
+        unpadded = image[:, :, :, pad:-pad].contiguous()
+        depth, resp = radarnet_main.forward(m, unpadded.to(DEV), pt.to(DEV), boxes, device=DEV)
+        crops = m.forward(torch.nn.functional.pad(unpadded, (pad, pad, 0, 0), mode='replicate').to(DEV), pt.to(DEV),
+                          boxes, return_logits=False)
+    ref_d, ref_r = so.s2_scatter(crops.cpu().numpy(), pt.numpy(), w, (ph, pw), compat=True)
+    assert np.array_equal(depth.cpu().numpy(), ref_d) and np.array_equal(resp.cpu().numpy(), ref_r)

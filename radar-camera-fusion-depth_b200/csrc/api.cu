@@ -18,6 +18,8 @@ int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
 int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
 bool conv_tc_supported(const ConvKP& p, int dtype);
 int conv_tc_launch(const ConvKP& p, cudaStream_t st);
+bool wgrad_tc_supported(const ConvKP& p, int dtype);
+int wgrad_tc_launch(const ConvKP& p, float* dw, cudaStream_t st);
 
 }  // namespace rcfd
 
@@ -55,6 +57,15 @@ int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64
   int rc = make_conv_kp(d, &p);
   if (rc != RCFD_OK) return rc;
   RCFD_CHECK_ARG(dw != nullptr, "wgrad: null dw");
+  int engine = d->engine;
+  if (engine == RCFD_ENGINE_AUTO) engine = wgrad_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT;
+  if (engine == RCFD_ENGINE_TCGEN05) {
+    if (!wgrad_tc_supported(p, d->dtype)) {
+      set_error("wgrad: shape/dtype not supported by the tcgen05 engine (bf16, channels %% 8 == 0)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return wgrad_tc_launch(p, dw, (cudaStream_t)stream);
+  }
   return conv_wgrad_simt_launch(p, dw, d->dtype, (cudaStream_t)stream);
 }
 

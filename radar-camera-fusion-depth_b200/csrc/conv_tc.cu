@@ -1,6 +1,321 @@
-// placeholder, replaced by the tcgen05 engine
-#include "conv_common.cuh"
+// tcgen05 engine of the implicit-GEMM convolution (bf16 operands, fp32 accumulation in TMEM).
+//
+// One CTA computes a 128-pixel x BN-channel output tile:
+//   * warps 0-3 (128 threads) are PRODUCERS: thread r owns output pixel m0+r and gathers its
+//     K = (tap, channel) row in 16-byte cp.async chunks straight into the canonical
+//     K-major SWIZZLE_128B shared-memory layout the tensor core reads -- the filter taps,
+//     zero padding, stride, nearest up-sampling, channel concat and zero insertion (dgrad of
+//     stride-2 convs) are all address arithmetic here; nothing is materialised in HBM.
+//     The same threads also stream the weight tile (B operand).
+//   * warp 4 is the MMA ISSUER: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) on
+//     shared-memory descriptors, accumulating in tensor memory; tcgen05.commit releases the
+//     smem stage back to the producers through an mbarrier.
+//   * after the K loop warps 0-3 become the EPILOGUE: tcgen05.ld their 32 TMEM lanes, then
+//     BatchNorm statistics (butterfly transpose-reduce) / folded BN + activation (+ residual)
+//     and 16-byte bf16 stores.
+// smem stages form an mbarrier ring (full: 128 producer arrivals after
+// cp.async.wait_group + fence.proxy.async; empty: tcgen05.commit).
+#include "tc_common.cuh"
+
 namespace rcfd {
-bool conv_tc_supported(const ConvKP&, int) { return false; }
-int conv_tc_launch(const ConvKP&, cudaStream_t) { set_error("tcgen05 engine not built"); return RCFD_EUNSUPPORTED; }
+namespace {
+
+using namespace tc;
+constexpr int BKE = 64;          // K elements per stage (128 bytes of bf16 = one swizzle row)
+constexpr int NPROD = 128;
+constexpr int NTHREADS = 160;
+constexpr int LAG = 2;           // cp.async groups in flight before a stage is published
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int A_BYTES = TM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
+  typedef TcCfg<BN> C;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + C::STAGES * C::A_BYTES;
+  const uint32_t sBar = sB + C::STAGES * C::B_BYTES;          // full[STAGES], empty[STAGES], accum
+  const uint32_t sTmem = sBar + 8 * (2 * C::STAGES + 1);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+  float* red = reinterpret_cast<float*>(gen_base);             // epilogue scratch aliases stage 0 (drained by then)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
+  const int num_kb = (p.K + BKE - 1) / BKE;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(sBar + 8 * s, NPROD);
+      mbar_init(sBar + 8 * (C::STAGES + s), 1);
+    }
+    mbar_init(sBar + 8 * (2 * C::STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== PRODUCER
+    const int r = tid;
+    const int gm = m0 + r;
+    const bool mvalid = gm < p.M;
+    int pn = 0, oy = 0, ox = 0;
+    if (mvalid) {
+      pn = gm / (p.ho * p.wo);
+      const int rem = gm - pn * p.ho * p.wo;
+      oy = rem / p.wo;
+      ox = rem - oy * p.wo;
+    }
+    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+    const bf16* S0 = reinterpret_cast<const bf16*>(p.src0);
+    const bf16* S1 = reinterpret_cast<const bf16*>(p.src1);
+    const bf16* Wt = reinterpret_cast<const bf16*>(p.weight);
+    const uint32_t rowA = (uint32_t)r * 128u, swz = (uint32_t)(r & 7);
+    int tr = 0, ts = 0, tc = 0;     // running (tap row, tap col, channel) of the next 8-channel chunk
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % C::STAGES;
+      if (kb >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((kb / C::STAGES) & 1) ^ 1);
+      const uint32_t a_st = sA + s * C::A_BYTES + rowA;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bf16* src = S0;
+        uint32_t nbytes = 0;
+        if (mvalid && tr < p.kh) {
+          int iy = iy0 + tr, ix = ix0 + ts;
+          bool ok = true;
+          if (p.dil == 2) {
+            ok = ((iy | ix) & 1) == 0;
+            iy >>= 1;
+            ix >>= 1;
+          }
+          if (ok && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
+            if (tc < p.c0) {
+              int sy = iy, sx = ix;
+              if (p.up) {
+                sy = nearest_src(iy, p.sch, p.h0);
+                sx = nearest_src(ix, p.scw, p.w0);
+              }
+              src = S0 + ((size_t)(pn * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
+            } else {
+              src = S1 + ((size_t)(pn * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
+            }
+            nbytes = 16;
+          }
+        }
+        cp_async16(a_st + (((uint32_t)j ^ swz) << 4), src, nbytes);
+        tc += 8;
+        if (tc >= p.ctot) {
+          tc = 0;
+          if (++ts == p.kw) {
+            ts = 0;
+            ++tr;
+          }
+        }
+      }
+      // weight tile: BN rows x 8 chunks
+      const uint32_t b_st = sB + s * C::B_BYTES;
+      const int kbase = kb * BKE;
+      for (int i = tid; i < BN * 8; i += NPROD) {
+        const int n = i >> 3, j = i & 7;
+        const int k = kbase + j * 8;
+        const bool ok = (n0 + n < p.cout) && (k < p.K);
+        const bf16* src = ok ? Wt + (size_t)(n0 + n) * p.K + k : Wt;
+        cp_async16(b_st + (uint32_t)n * 128u + (((uint32_t)j ^ (uint32_t)(n & 7)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (kb >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(sBar + 8 * ((kb - LAG) % C::STAGES));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (num_kb > LAG ? num_kb - LAG : 0); kb < num_kb; ++kb) mbar_arrive(sBar + 8 * (kb % C::STAGES));
+
+    // =========================================================== EPILOGUE (same warps)
+    mbar_wait(sBar + 8 * (2 * C::STAGES), 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool want_stats = p.ssum != nullptr;
+    const bf16* R = reinterpret_cast<const bf16*>(p.residual);
+    bf16* D = reinterpret_cast<bf16*>(p.dst);
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 16) {
+      float v[16];
+      tmem_ld16(trow + cb, v);
+      if (want_stats) {
+        // butterfly transpose-reduce: 16 columns x 32 lanes -> lanes 0..15 hold one column sum each
+        float s16[16], q16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          s16[i] = v[i];            // rows >= M gathered zeros -> contribute nothing
+          q16[i] = v[i] * v[i];
+        }
+        // step over lane bit 4 keeps all 16 columns (just halves the lanes), then halve columns
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
+          q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool hi = (lane & w) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const float send_s = hi ? s16[i] : s16[i + w];
+            const float keep_s = hi ? s16[i + w] : s16[i];
+            s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+            const float send_q = hi ? q16[i] : q16[i + w];
+            const float keep_q = hi ? q16[i + w] : q16[i];
+            q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+          }
+        }
+        // lane l (< 16) now holds column bitrev-free index: column = (lane & 15) by construction
+        if (lane < 16) {
+          red[(warp * BN + cb + lane) * 2 + 0] = s16[0];
+          red[(warp * BN + cb + lane) * 2 + 1] = q16[0];
+        }
+      }
+      if (mvalid) {
+        const int nb = n0 + cb;
+        const size_t o = (size_t)gm * p.cout + nb;
+        if (nb < p.cout) {
+          if (p.scale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
+          }
+          if (p.act == RCFD_ACT_LEAKY) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+          } else if (p.act == RCFD_ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
+          }
+          if (R) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+              v[2 * i] = leaky(v[2 * i] + f.x);
+              v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
+            }
+          }
+          if (p.accumulate) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+              v[2 * i] += f.x;
+              v[2 * i + 1] += f.y;
+            }
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    if (want_stats) {
+      // combine the 4 warps' partials, one double atomic per channel and CTA
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = tid; c < BN; c += NPROD) {
+        if (n0 + c < p.cout) {
+          double s = 0.0, q = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            s += (double)red[(w * BN + c) * 2 + 0];
+            q += (double)red[(w * BN + c) * 2 + 1];
+          }
+          atomicAdd(p.ssum + n0 + c, s);
+          atomicAdd(p.ssq + n0 + c, q);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================== MMA ISSUER (warp 4)
+    const uint32_t idesc = umma_idesc(BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % C::STAGES;
+      mbar_wait(sBar + 8 * s, (kb / C::STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_st = sA + s * C::A_BYTES, b_st = sB + s * C::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKE / 16; ++k) {
+          umma_f16(tmem_base, umma_desc_sw128(a_st + k * 32), umma_desc_sw128(b_st + k * 32), idesc,
+                   (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(sBar + 8 * (C::STAGES + s));                  // frees the smem stage when the MMAs retire
+        if (kb == num_kb - 1) umma_commit(sBar + 8 * (2 * C::STAGES));   // accumulator complete
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
 }
+
+template <int BN>
+int launch_tc(const ConvKP& p, cudaStream_t st) {
+  typedef TcCfg<BN> C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { set_error("conv_tc: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.M, TM), ceil_div(p.cout, BN));
+  conv_tc_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(p);
+  RCFD_CHECK_LAUNCH("conv_tc");
+  return RCFD_OK;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvKP& p, int dtype) {
+  if (dtype != RCFD_BF16) return false;
+  if (p.c0 % 8 != 0 || p.c1 % 8 != 0) return false;
+  if (p.cout % 32 != 0) return false;
+  if (p.dst_f32) return false;
+  if (p.act == RCFD_ACT_DEPTH_HEAD) return false;
+  return true;
+}
+
+int conv_tc_launch(const ConvKP& p, cudaStream_t st) {
+  if (p.cout % 128 == 0) return launch_tc<128>(p, st);
+  if (p.cout % 64 == 0) return launch_tc<64>(p, st);
+  return launch_tc<32>(p, st);
+}
+
+}  // namespace rcfd

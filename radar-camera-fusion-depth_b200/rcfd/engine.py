@@ -179,7 +179,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
             tape.param_grads.append((bn.bias, dbeta))
         else:
             dy = dz
-        dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size)
+        dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine)
         gw = torch.empty_like(w_param)
         ops.unpack_wgrad(dw, gw)
         tape.param_grads.append((w_param, gw))
@@ -241,7 +241,7 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
             for bn, lo in ((bw, 0), (bp, c)):
                 tape.param_grads.append((bn.weight, dg[lo:lo + c]))
                 tape.param_grads.append((bn.bias, db[lo:lo + c]))
-            dw = ops.conv2d_wgrad(dep, dy, 1, 1)                         # [2c, 1, cd]
+            dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine)                         # [2c, 1, cd]
             for wparam, lo in ((ww, 0), (wp, c)):
                 g = torch.empty_like(wparam)
                 ops.unpack_wgrad(dw[lo:lo + c], g)

@@ -84,7 +84,7 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     return out
 
 
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None):
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO):
     """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above."""
     for t in (x0, x1, dy):
         _p(t)
@@ -104,6 +104,7 @@ def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None):
     d.weight = dw.data_ptr()       # unused by wgrad, must be non-null
     d.dst = dy.data_ptr()
     d.dtype = dt(x0)
+    d.engine = engine
     _lib.call('rcfd_conv2d_wgrad', ctypes.byref(d), _p(dw), None, 0, _stream())
     return dw
 

@@ -77,7 +77,7 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
 
 
 @torch.enable_grad()
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None):
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO):
     a = _gather_input(x0, x1, in_size, 1)
     cout = dy.shape[3]
     w = torch.zeros(cout, a.shape[1], k, k, requires_grad=True)

@@ -1,0 +1,152 @@
+"""GPU parity of the tcgen05 engine (bf16 operands, fp32 accumulation in TMEM) against a torch
+CPU fp32 convolution of the SAME bf16-rounded operands (so only accumulation order and the
+bf16 rounding of the output differ: tolerance 1e-2 of the output range) and against the SIMT
+engine in bf16."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = 1e-2
+BF = torch.bfloat16
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _q(t):
+    return t.bfloat16().float()
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, BF)
+
+
+def _nchw(x):
+    return x.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+CASES = [
+    # n, cin, cout, h, w, k, stride
+    (1, 64, 64, 16, 24, 3, 1),        # K = 576 = 9 stages, M = 384 = 3 tiles
+    (2, 32, 32, 13, 19, 3, 1),        # M tail (494), two taps per 64-wide K chunk
+    (1, 16, 32, 12, 20, 3, 1),        # K = 144: padded last stage
+    (1, 24, 96, 9, 9, 3, 1),          # K = 216, cout = 3 x BN(32)
+    (1, 128, 128, 11, 22, 3, 1),      # BN = 128
+    (1, 256, 256, 6, 11, 3, 1),       # M = 66 < one tile, grid.y = 2
+    (1, 64, 128, 22, 44, 3, 2),       # stride 2
+    (2, 32, 64, 10, 14, 1, 1),        # 1x1 (gated fusion shape family)
+    (1, 64, 128, 11, 22, 1, 2),       # 1x1 stride 2 (projection shortcut)
+    (2, 8, 32, 20, 28, 7, 2),         # 7x7 stem with channels padded to 8
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_tc_conv_plain(case):
+    from rcfd import ops
+    n, cin, cout, h, w, k, s = case
+    x = _q(_rand(n, cin, h, w, seed=1))
+    wt = _q(_rand(cout, cin, k, k, seed=2) / (cin * k * k) ** 0.5)
+    ref = F.conv2d(x, wt, None, s, k // 2)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    out = ops.conv2d(_nhwc(x), wp, cout, k, s, engine=ops.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    assert relerr(_nchw(out), ref) < TOL
+    simt = ops.conv2d(_nhwc(x), wp, cout, k, s, engine=ops.ENGINE_SIMT)
+    assert relerr(_nchw(out), _nchw(simt)) < TOL
+
+
+@pytest.mark.parametrize('src_hw,dst_hw', [((6, 11), (11, 22)), ((8, 12), (16, 24))])
+def test_tc_upsample_concat_epilogue(src_hw, dst_hw):
+    from rcfd import ops
+    n, c0, c1, cout = 2, 64, 32, 64
+    x0, x1 = _q(_rand(n, c0, *src_hw, seed=3)), _q(_rand(n, c1, *dst_hw, seed=4))
+    wt = _q(_rand(cout, c0 + c1, 3, 3, seed=5) / 30.0)
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=6) * 0.1
+    res = _q(_rand(n, cout, *dst_hw, seed=7))
+    ref = F.conv2d(torch.cat([F.interpolate(x0, size=dst_hw), x1], 1), wt, None, 1, 1)
+    ref = F.leaky_relu(ref * scale[None, :, None, None] + shift[None, :, None, None], 0.2)
+    ref = F.leaky_relu(ref + res, 0.2)
+    out = ops.conv2d(_nhwc(x0), ops.pack_weight(wt.to(DEV), BF), cout, 3, 1, x1=_nhwc(x1), in_size=dst_hw,
+                     scale=scale.to(DEV), shift=shift.to(DEV), act=ops.ACT_LEAKY, residual=_nhwc(res),
+                     engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(out), ref) < TOL
+
+
+def test_tc_stats_sigmoid_accumulate():
+    from rcfd import ops
+    n, cin, cout, h, w = 2, 32, 64, 15, 17
+    x, wt = _q(_rand(n, cin, h, w, seed=8)), _q(_rand(cout, cin, 3, 3, seed=9) / 17.0)
+    ref = F.conv2d(x, wt, None, 1, 1)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    ssq = torch.zeros_like(ssum)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    out = ops.conv2d(_nhwc(x), wp, cout, 3, 1, stats=(ssum, ssq), engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(out), ref) < TOL
+    assert relerr(ssum.cpu(), ref.double().sum(dim=(0, 2, 3))) < 1e-4         # fp32 accumulators, before rounding
+    assert relerr(ssq.cpu(), (ref.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    sig = ops.conv2d(_nhwc(x), wp, cout, 3, 1, act=ops.ACT_SIGMOID, engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(sig), torch.sigmoid(ref)) < TOL
+    acc = _nhwc(_q(_rand(n, cout, h, w, seed=10)))
+    base = _nchw(acc).clone()
+    ops.conv2d(_nhwc(x), wp, cout, 3, 1, out=acc, accumulate=True, engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(acc), base + ref) < TOL
+
+
+@pytest.mark.parametrize('case', [(2, 32, 64, 12, 20, 3, 1), (1, 32, 64, 11, 22, 3, 2), (2, 32, 64, 9, 9, 1, 2)])
+def test_tc_dgrad(case):
+    from rcfd import ops
+    n, cin, cout, h, w, k, s = case
+    x = _q(_rand(n, cin, h, w, seed=11)).requires_grad_(True)
+    wt = _q(_rand(cout, cin, k, k, seed=12) / (cin * k * k) ** 0.5)
+    y = F.conv2d(x, wt, None, s, k // 2)
+    dy = _q(_rand(*y.shape, seed=13))
+    y.backward(dy)
+    wd = ops.pack_weight(wt.to(DEV), BF, dgrad=True)
+    dx = ops.conv2d(_nhwc(dy), wd, cin, k, 1, pad=k - 1 - k // 2, in_dilation=s, out_size=(h, w),
+                    engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(dx), x.grad) < TOL
+
+
+def test_tc_rejects_unsupported():
+    from rcfd import ops, _lib
+    x = torch.zeros(1, 4, 4, 8, device=DEV)          # fp32 -> not a tcgen05 case
+    w = torch.zeros(32, 9, 8, device=DEV)
+    with pytest.raises(_lib.RcfdError):
+        ops.conv2d(x, w, 32, 3, 1, engine=ops.ENGINE_TCGEN05)
+
+
+@pytest.mark.parametrize('case', [(2, 64, 64, 16, 24, 3, 1), (1, 32, 32, 13, 19, 3, 1), (1, 16, 32, 12, 20, 3, 1),
+                                  (1, 128, 256, 11, 22, 3, 2), (2, 32, 128, 10, 14, 1, 1), (1, 24, 96, 9, 9, 3, 1),
+                                  (1, 256, 512, 6, 11, 1, 1), (3, 64, 32, 40, 56, 3, 1)])
+def test_tc_wgrad(case):
+    """tcgen05 weight gradient (MN-major operands, split over pixels) vs autograd of F.conv2d."""
+    from rcfd import ops
+    n, cin, cout, h, w, k, s = case
+    x = _q(_rand(n, cin, h, w, seed=21))
+    wt = (_rand(cout, cin, k, k, seed=22) * 0.05).requires_grad_(True)
+    y = F.conv2d(x, wt, None, s, k // 2)
+    dy = _q(_rand(*y.shape, seed=23))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), k, s, engine=ops.ENGINE_TCGEN05)
+    gw = torch.empty(cout, cin, k, k, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3          # exact bf16 products, fp32 accumulation / atomics order
+
+
+def test_tc_wgrad_dual_source_upsampled():
+    from rcfd import ops
+    n, c0, c1, cout = 1, 64, 32, 64
+    x0, x1 = _q(_rand(n, c0, 8, 12, seed=24)), _q(_rand(n, c1, 16, 24, seed=25))
+    wt = (_rand(cout, c0 + c1, 3, 3, seed=26) * 0.05).requires_grad_(True)
+    y = F.conv2d(torch.cat([F.interpolate(x0, size=(16, 24)), x1], 1), wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=27))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x0), _nhwc(dy), 3, 1, x1=_nhwc(x1), in_size=(16, 24), engine=ops.ENGINE_TCGEN05)
+    gw = torch.empty(cout, c0 + c1, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3

@@ -223,7 +223,9 @@ def run_ours(args):
         model.train()
         if world > 1:
             model.data_parallel()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        from rcfd import optim, parallel
+        opt = optim.FusedAdam(model.parameters(), lr=1e-3)      # torch.optim.Adam semantics, one flat kernel
+        parallel.use_flat_gradients(model, opt)
         outlier = net_utils.OutlierRemoval(7, 1.5)
     else:
         model.eval()
@@ -240,7 +242,7 @@ def run_ours(args):
             loss, _ = model.compute_loss(image=image, output_depth=out, ground_truth=gt_c, lidar_map=lidar,
                                          loss_func='l1', w_smoothness=0.0, loss_smoothness_kernel_size=-1,
                                          validity_map_loss_smoothness=None, w_lidar_loss=2.0)
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad()
             loss.backward()
             opt.step()
             return loss

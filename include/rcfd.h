@@ -78,16 +78,19 @@ int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64
                       void* stream);
 int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d);
 
-/* OIHW float (the reference's state_dict layout) <-> packed [cout][kh*kw][cin] dtype.
- * mode 0: forward weights, channels [cin_off, cin_off+cin_cnt) of the OIHW tensor.
+/* OIHW float (the reference's state_dict layout) <-> packed [cout][kh*kw][cin_pad] dtype.
+ * mode 0: forward weights, channels [cin_off, cin_off+cin_cnt) of the OIHW tensor, zero-padded to
+ *         cin_pad >= cin_cnt channels per tap (the 3- / 2- / 1-channel inputs are stored with 8).
  * mode 1: dgrad weights  out[ci][kh-1-r][kw-1-s][co] = w[co][cin_off+ci][r][s]
- *         (rows = cin_cnt, K = kh*kw*cout). */
+ *         (rows = cin_cnt, K = kh*kw*cout_pad with cout zero-padded to `cin_pad` when it is larger). */
 int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh,
-                          int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t mode, int32_t dtype,
-                          void* stream);
-/* packed float [cout][kh*kw][cin_cnt] gradient -> OIHW float slice (+= if accumulate). */
+                          int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t mode,
+                          int32_t dtype, void* stream);
+/* packed float [>=cout][kh*kw][cin_pad] gradient -> OIHW float slice (+= if accumulate); only the
+ * first cin_cnt channels of every tap and the first cout rows are read. */
 int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh,
-                           int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t accumulate, void* stream);
+                           int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t accumulate,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------
  * BatchNorm2d, training mode (src/net_utils.py:82,86; torch.nn.BatchNorm2d eps 1e-5,
@@ -143,16 +146,17 @@ int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs
 int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, int32_t dtype, void* stream);
 int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, void* stream);
 
-/* Layout / precision boundary: the reference API is NCHW float. */
+/* Layout / precision boundary: the reference API is NCHW float.  cpad >= c: the NHWC
+ * destination has cpad channels per pixel, the extra ones zero (16-byte gathers need c % 8 == 0). */
 int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
-                      int32_t dtype, void* stream);
+                      int32_t cpad, int32_t dtype, void* stream);
 int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                       int32_t dtype, void* stream);
 
 /* Depth head backward: dlogit = dd * (-d^2/min) * s(1-s), from the stored depth d
- * (src/fusionnet_model.py:162-165). float in/out, count elements. */
+ * (src/fusionnet_model.py:162-165). float in; dlogit is count x cpad (channel 0 = value, rest 0). */
 int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, float min_depth,
-                        float min_over_max, int64_t count, int32_t dtype, void* stream);
+                        float min_over_max, int64_t count, int32_t cpad, int32_t dtype, void* stream);
 
 /* Masked L1 loss of src/fusionnet_model.py:214-253,293 (loss_func 'l1'), sync-free:
  *   gt' = gt * [lidar <= 0];  L = mean|out-gt'| over gt'>0  +  w_lidar * mean|out-lidar| over lidar>0

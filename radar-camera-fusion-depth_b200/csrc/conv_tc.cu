@@ -24,11 +24,11 @@ using namespace tc;
 constexpr int BKE = 64;          // K elements per stage (128 bytes of bf16 = one swizzle row)
 constexpr int NPROD = 128;
 constexpr int NTHREADS = 160;
-constexpr int LAG = 2;           // cp.async groups in flight before a stage is published
 
 template <int BN>
 struct TcCfg {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int LAG = STAGES - 1;   // cp.async groups in flight before a stage is published
   static constexpr int A_BYTES = TM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -72,88 +72,104 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
 
   if (warp < 4) {
     // =========================================================== PRODUCER
-    const int r = tid;
-    const int gm = m0 + r;
-    const bool mvalid = gm < p.M;
-    int pn = 0, oy = 0, ox = 0;
-    if (mvalid) {
-      pn = gm / (p.ho * p.wo);
-      const int rem = gm - pn * p.ho * p.wo;
-      oy = rem / p.wo;
-      ox = rem - oy * p.wo;
+    // Lane mapping chosen for the memory system: 8 consecutive lanes fetch the 8 16-byte chunks
+    // of ONE pixel's 128-byte K segment (a full line per 8 lanes instead of 32 scattered
+    // sectors per instruction); each thread serves chunk j of 8 different pixel rows.
+    const int j = tid & 7;
+    const int rbase = tid >> 3;                 // rows rbase + 16 * i
+    const uint32_t swz = (uint32_t)(rbase & 7); // (rbase + 16 i) & 7 is the same for every i
+    int pn_[8], iy0_[8], ix0_[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = m0 + rbase + 16 * i;
+      if (g < p.M) {
+        const int pn = g / (p.ho * p.wo);
+        const int rem = g - pn * p.ho * p.wo;
+        const int oy = rem / p.wo;
+        pn_[i] = pn;
+        iy0_[i] = oy * p.stride - p.pad;
+        ix0_[i] = (rem - oy * p.wo) * p.stride - p.pad;
+      } else {
+        pn_[i] = 0;
+        iy0_[i] = -(1 << 20);                   // fails every bounds test -> zero fill
+        ix0_[i] = -(1 << 20);
+      }
     }
-    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
     const bf16* S0 = reinterpret_cast<const bf16*>(p.src0);
     const bf16* S1 = reinterpret_cast<const bf16*>(p.src1);
     const bf16* Wt = reinterpret_cast<const bf16*>(p.weight);
-    const uint32_t rowA = (uint32_t)r * 128u, swz = (uint32_t)(r & 7);
-    int tr = 0, ts = 0, tc = 0;     // running (tap row, tap col, channel) of the next 8-channel chunk
+    // running (tap row, tap col, channel) of this thread's chunk: k = kb * 64 + j * 8
+    int tc = j * 8, ts = 0, tr = 0;
+    while (tc >= p.ctot) {
+      tc -= p.ctot;
+      if (++ts == p.kw) { ts = 0; ++tr; }
+    }
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % C::STAGES;
       if (kb >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((kb / C::STAGES) & 1) ^ 1);
-      const uint32_t a_st = sA + s * C::A_BYTES + rowA;
+      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)rbase * 128u + (((uint32_t)j ^ swz) << 4);
+      const bool kvalid = tr < p.kh;
+      const bool from0 = tc < p.c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int i = 0; i < 8; ++i) {
         const bf16* src = S0;
         uint32_t nbytes = 0;
-        if (mvalid && tr < p.kh) {
-          int iy = iy0 + tr, ix = ix0 + ts;
-          bool ok = true;
-          if (p.dil == 2) {
-            ok = ((iy | ix) & 1) == 0;
-            iy >>= 1;
-            ix >>= 1;
-          }
-          if (ok && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
-            if (tc < p.c0) {
-              int sy = iy, sx = ix;
-              if (p.up) {
-                sy = nearest_src(iy, p.sch, p.h0);
-                sx = nearest_src(ix, p.scw, p.w0);
-              }
-              src = S0 + ((size_t)(pn * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
-            } else {
-              src = S1 + ((size_t)(pn * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
+        int iy = iy0_[i] + tr, ix = ix0_[i] + ts;
+        bool ok = kvalid;
+        if (p.dil == 2) {
+          ok = ok && (((iy | ix) & 1) == 0);
+          iy >>= 1;
+          ix >>= 1;
+        }
+        if (ok && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
+          if (from0) {
+            int sy = iy, sx = ix;
+            if (p.up) {
+              sy = nearest_src(iy, p.sch, p.h0);
+              sx = nearest_src(ix, p.scw, p.w0);
             }
-            nbytes = 16;
+            src = S0 + ((size_t)(pn_[i] * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
+          } else {
+            src = S1 + ((size_t)(pn_[i] * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
           }
+          nbytes = 16;
         }
-        cp_async16(a_st + (((uint32_t)j ^ swz) << 4), src, nbytes);
-        tc += 8;
-        if (tc >= p.ctot) {
-          tc = 0;
-          if (++ts == p.kw) {
-            ts = 0;
-            ++tr;
-          }
-        }
+        cp_async16(a_st + (uint32_t)i * (16u * 128u), src, nbytes);
       }
-      // weight tile: BN rows x 8 chunks
+      tc += BKE;                                 // next k block: same chunk slot, 64 channels further
+      while (tc >= p.ctot) {
+        tc -= p.ctot;
+        if (++ts == p.kw) { ts = 0; ++tr; }
+      }
+      // weight tile: BN rows x 8 chunks (consecutive lanes -> consecutive chunks of a row)
       const uint32_t b_st = sB + s * C::B_BYTES;
       const int kbase = kb * BKE;
       for (int i = tid; i < BN * 8; i += NPROD) {
-        const int n = i >> 3, j = i & 7;
-        const int k = kbase + j * 8;
+        const int n = i >> 3, jj = i & 7;
+        const int k = kbase + jj * 8;
         const bool ok = (n0 + n < p.cout) && (k < p.K);
         const bf16* src = ok ? Wt + (size_t)(n0 + n) * p.K + k : Wt;
-        cp_async16(b_st + (uint32_t)n * 128u + (((uint32_t)j ^ (uint32_t)(n & 7)) << 4), src, ok ? 16u : 0u);
+        cp_async16(b_st + (uint32_t)n * 128u + (((uint32_t)jj ^ (uint32_t)(n & 7)) << 4), src, ok ? 16u : 0u);
       }
       cp_async_commit();
-      if (kb >= LAG) {
-        cp_async_wait<LAG>();
+      if (kb >= C::LAG) {
+        cp_async_wait<C::LAG>();
         fence_proxy_async();
-        mbar_arrive(sBar + 8 * ((kb - LAG) % C::STAGES));
+        mbar_arrive(sBar + 8 * ((kb - C::LAG) % C::STAGES));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int kb = (num_kb > LAG ? num_kb - LAG : 0); kb < num_kb; ++kb) mbar_arrive(sBar + 8 * (kb % C::STAGES));
+    for (int kb = (num_kb > C::LAG ? num_kb - C::LAG : 0); kb < num_kb; ++kb) mbar_arrive(sBar + 8 * (kb % C::STAGES));
 
     // =========================================================== EPILOGUE (same warps)
+    const int gm = m0 + tid;                      // TMEM lane == tile row == output pixel
+    const bool mvalid = gm < p.M;
     mbar_wait(sBar + 8 * (2 * C::STAGES), 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool want_stats = p.ssum != nullptr;
+    const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
     const bf16* R = reinterpret_cast<const bf16*>(p.residual);
     bf16* D = reinterpret_cast<bf16*>(p.dst);
 #pragma unroll 1
@@ -196,7 +212,26 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
       if (mvalid) {
         const int nb = n0 + cb;
         const size_t o = (size_t)gm * p.cout + nb;
-        if (nb < p.cout) {
+        if (!vector_epilogue) {
+          // generic path: cout not a multiple of 16 (e.g. the 1-channel output head), float
+          // destination, depth-head activation
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = nb + i;
+            if (n < p.cout) {
+              float x = v[i];
+              if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+              x = apply_act(x, p.act, p.p0, p.p1);
+              if (R) x = leaky(x + __bfloat162float(R[o + i]));
+              if (p.dst_f32) {
+                float* Df = reinterpret_cast<float*>(p.dst);
+                Df[o + i] = p.accumulate ? Df[o + i] + x : x;
+              } else {
+                D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+              }
+            }
+          }
+        } else if (nb < p.cout) {
           if (p.scale) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
@@ -306,15 +341,15 @@ int launch_tc(const ConvKP& p, cudaStream_t st) {
 bool conv_tc_supported(const ConvKP& p, int dtype) {
   if (dtype != RCFD_BF16) return false;
   if (p.c0 % 8 != 0 || p.c1 % 8 != 0) return false;
-  if (p.cout % 32 != 0) return false;
-  if (p.dst_f32) return false;
-  if (p.act == RCFD_ACT_DEPTH_HEAD) return false;
   return true;
 }
 
 int conv_tc_launch(const ConvKP& p, cudaStream_t st) {
   if (p.cout % 128 == 0) return launch_tc<128>(p, st);
   if (p.cout % 64 == 0) return launch_tc<64>(p, st);
+  if (p.cout % 32 == 0) return launch_tc<32>(p, st);
+  if (p.cout <= 16) return launch_tc<16>(p, st);
+  if (p.cout % 16 == 0 || p.cout < 32) return launch_tc<16>(p, st);
   return launch_tc<32>(p, st);
 }
 

@@ -254,40 +254,50 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out,
 
 // gather form: every input pixel looks at the <= 4 windows covering it and takes the
 // gradient of those whose FIRST maximum (row-major window scan, like ATen) it is.
+// One thread = one pixel x 4 channels (vector loads; the 3x3 neighbourhood is read once).
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dout,
                                    T* __restrict__ dx, int N, int H, int W, int C, int HO, int WO) {
-  const int64_t total = (int64_t)N * H * W * C;
+  const int CV = C >> 2;
+  const int64_t total = (int64_t)N * H * W * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t r = i / C;
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
     const int ix = (int)(r % W); r /= W;
     const int iy = (int)(r % H);
     const int n = (int)(r / H);
-    const float self = to_f<T>(x[i]);
-    float g = 0.f;
-    for (int oy = (iy + 1) / 2 - ((iy + 1) % 2 == 0 ? 1 : 0); oy <= (iy + 1) / 2; ++oy) {
+    const float4 sv = Vec4<T>::ld(x + i * 4);
+    const float self[4] = {sv.x, sv.y, sv.z, sv.w};
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    const int oy_lo = (iy + 1) / 2 - (((iy + 1) & 1) == 0 ? 1 : 0), oy_hi = (iy + 1) / 2;
+    const int ox_lo = (ix + 1) / 2 - (((ix + 1) & 1) == 0 ? 1 : 0), ox_hi = (ix + 1) / 2;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       if (oy < 0 || oy >= HO) continue;
-      for (int ox = (ix + 1) / 2 - ((ix + 1) % 2 == 0 ? 1 : 0); ox <= (ix + 1) / 2; ++ox) {
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
         if (ox < 0 || ox >= WO) continue;
-        // is (iy, ix) the first maximum of window (oy, ox)?
-        bool win = true;
-        for (int dy = 0; dy < 3 && win; ++dy) {
+        bool win[4] = {true, true, true, true};
+        for (int dy = 0; dy < 3; ++dy) {
           const int yy = oy * 2 - 1 + dy;
           if (yy < 0 || yy >= H) continue;
           for (int dxx = 0; dxx < 3; ++dxx) {
             const int xx = ox * 2 - 1 + dxx;
-            if (xx < 0 || xx >= W) continue;
-            if (yy == iy && xx == ix) continue;
-            const float v = to_f<T>(x[((size_t)(n * H + yy) * W + xx) * C + c]);
+            if (xx < 0 || xx >= W || (yy == iy && xx == ix)) continue;
+            const float4 vv = Vec4<T>::ld(x + (((size_t)(n * H + yy) * W + xx) * CV + cv) * 4);
+            const float v[4] = {vv.x, vv.y, vv.z, vv.w};
             const bool before = (yy < iy) || (yy == iy && xx < ix);
-            if (v > self || (before && v == self)) { win = false; break; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (v[c] > self[c] || (before && v[c] == self[c])) win[c] = false;
           }
         }
-        if (win) g += to_f<T>(dout[((size_t)(n * HO + oy) * WO + ox) * C + c]);
+        const float4 dv = Vec4<T>::ld(dout + (((size_t)(n * HO + oy) * WO + ox) * CV + cv) * 4);
+        const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (win[c]) g[c] += d[c];
       }
     }
-    dx[i] = from_f<T>(g);
+    Vec4<T>::st(dx + i * 4, make_float4(g[0], g[1], g[2], g[3]));
   }
 }
 
@@ -295,10 +305,11 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
 template <typename T>
 __global__ void upsample_bwd_kernel(const T* __restrict__ dup, T* __restrict__ dsrc, int N, int HS,
                                     int WS, int HU, int WU, int C, float sch, float scw, int accumulate) {
-  const int64_t total = (int64_t)N * HS * WS * C;
+  const int CV = C >> 2;
+  const int64_t total = (int64_t)N * HS * WS * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t r = i / C;
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
     const int sx = (int)(r % WS); r /= WS;
     const int sy = (int)(r % HS);
     const int n = (int)(r / HS);
@@ -308,15 +319,20 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dup, T* __restrict__ d
     if (x0 < 0) x0 = 0;
     if (y1 > HU - 1) y1 = HU - 1;
     if (x1 > WU - 1) x1 = WU - 1;
-    float g = 0.f;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int y = y0; y <= y1; ++y) {
       if (nearest_src(y, sch, HS) != sy) continue;
       for (int x = x0; x <= x1; ++x) {
         if (nearest_src(x, scw, WS) != sx) continue;
-        g += to_f<T>(dup[((size_t)(n * HU + y) * WU + x) * C + c]);
+        const float4 v = Vec4<T>::ld(dup + (((size_t)(n * HU + y) * WU + x) * CV + cv) * 4);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
       }
     }
-    dsrc[i] = from_f<T>(accumulate ? to_f<T>(dsrc[i]) + g : g);
+    if (accumulate) {
+      const float4 o = Vec4<T>::ld(dsrc + i * 4);
+      g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+    }
+    Vec4<T>::st(dsrc + i * 4, g);
   }
 }
 
@@ -335,15 +351,16 @@ __global__ void add_inplace_kernel(T* __restrict__ acc, const T* __restrict__ x,
 }
 
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int H, int W) {
-  const int64_t total = (int64_t)N * C * H * W;
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int H, int W,
+                                    int CP) {
+  const int64_t total = (int64_t)N * CP * H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t r = i / C;
+    const int c = (int)(i % CP);
+    int64_t r = i / CP;
     const int x = (int)(r % W); r /= W;
     const int y = (int)(r % H);
     const int n = (int)(r / H);
-    dst[i] = from_f<T>(src[((size_t)(n * C + c) * H + y) * W + x]);
+    dst[i] = from_f<T>(c < C ? src[((size_t)(n * C + c) * H + y) * W + x] : 0.f);
   }
 }
 template <typename T>
@@ -361,11 +378,16 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 
 template <typename T>
 __global__ void depth_head_bwd_kernel(const float* __restrict__ dd, const float* __restrict__ d,
-                                      T* __restrict__ dl, float mn, float r, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float dv = d[i];
-    const float s = mn / dv - r;              // sigmoid(logit)
-    dl[i] = from_f<T>(-dd[i] * dv * dv / mn * s * (1.f - s));
+                                      T* __restrict__ dl, float mn, float r, int64_t n, int CP) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * CP; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i / CP;
+    float g = 0.f;
+    if (i - px * CP == 0) {
+      const float dv = d[px];
+      const float s = mn / dv - r;              // sigmoid(logit)
+      g = -dd[px] * dv * dv / mn * s * (1.f - s);
+    }
+    dl[i] = from_f<T>(g);
   }
 }
 
@@ -465,27 +487,31 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // ------------------------------------------------------------------ weight (un)packing
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin,
-                                   int kh, int kw, int cin_off, int cin_cnt, int mode) {
+                                   int kh, int kw, int cin_off, int cin_cnt, int cpad, int mode) {
   const int taps = kh * kw;
-  const int64_t total = (int64_t)cout * taps * cin_cnt;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    if (mode == 0) {          // out[co][tap][ci]
-      const int ci = (int)(i % cin_cnt);
-      int64_t r = i / cin_cnt;
+  if (mode == 0) {            // out[co][tap][ci < cpad]
+    const int64_t total = (int64_t)cout * taps * cpad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int ci = (int)(i % cpad);
+      int64_t r = i / cpad;
       const int tap = (int)(r % taps);
       const int co = (int)(r / taps);
-      out[i] = from_f<T>(w[((size_t)co * cin + cin_off + ci) * taps + tap]);
-    } else {                  // out[ci][flipped tap][co]
-      const int co = (int)(i % cout);
-      int64_t r = i / cout;
+      out[i] = from_f<T>(ci < cin_cnt ? w[((size_t)co * cin + cin_off + ci) * taps + tap] : 0.f);
+    }
+  } else {                    // out[ci][flipped tap][co < copad]
+    const int copad = cpad > cout ? cpad : cout;
+    const int64_t total = (int64_t)cin_cnt * taps * copad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int co = (int)(i % copad);
+      int64_t r = i / copad;
       const int tap = (int)(r % taps);
       const int ci = (int)(r / taps);
-      out[i] = from_f<T>(w[((size_t)co * cin + cin_off + ci) * taps + (taps - 1 - tap)]);
+      out[i] = from_f<T>(co < cout ? w[((size_t)co * cin + cin_off + ci) * taps + (taps - 1 - tap)] : 0.f);
     }
   }
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout,
-                                    int cin, int kh, int kw, int cin_off, int cin_cnt, int accumulate) {
+                                    int cin, int kh, int kw, int cin_off, int cin_cnt, int cpad, int accumulate) {
   const int taps = kh * kw;
   const int64_t total = (int64_t)cout * taps * cin_cnt;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -494,7 +520,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
     const int tap = (int)(r % taps);
     const int co = (int)(r / taps);
     const size_t o = ((size_t)co * cin + cin_off + ci) * taps + tap;
-    g[o] = accumulate ? g[o] + packed[i] : packed[i];
+    const float v = packed[((size_t)co * taps + tap) * cpad + ci];
+    g[o] = accumulate ? g[o] + v : v;
   }
 }
 
@@ -615,9 +642,9 @@ int rcfd_maxpool3x3s2_fwd(const void* x, void* out, int32_t n, int32_t h, int32_
 
 int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
                           int32_t dtype, void* stream) {
-  RCFD_CHECK_ARG(x && dout && dx && n > 0 && h > 0 && w > 0 && c > 0, "maxpool_bwd: bad args");
+  RCFD_CHECK_ARG(x && dout && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_bwd: bad args");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)n * h * w * c;
+  const int64_t total = (int64_t)n * h * w * (c / 4);
   DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
                         (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
   RCFD_CHECK_LAUNCH("maxpool_bwd");
@@ -626,8 +653,9 @@ int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, 
 
 int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs, int32_t ws, int32_t hu,
                               int32_t wu, int32_t c, int32_t accumulate, int32_t dtype, void* stream) {
-  RCFD_CHECK_ARG(dup && dsrc && n > 0 && hs > 0 && ws > 0 && hu > 0 && wu > 0 && c > 0, "upsample_bwd: bad args");
-  const int64_t total = (int64_t)n * hs * ws * c;
+  RCFD_CHECK_ARG(dup && dsrc && n > 0 && hs > 0 && ws > 0 && hu > 0 && wu > 0 && c > 0 && c % 4 == 0,
+                 "upsample_bwd: bad args (channels %% 4)");
+  const int64_t total = (int64_t)n * hs * ws * (c / 4);
   const float sch = (float)hs / (float)hu, scw = (float)ws / (float)wu;
   DISPATCH_T(dtype, (upsample_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
                         (const T*)dup, (T*)dsrc, n, hs, ws, hu, wu, c, sch, scw, accumulate)));
@@ -650,11 +678,11 @@ int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, voi
   return RCFD_OK;
 }
 
-int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t dtype,
-                      void* stream) {
-  RCFD_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad args");
-  const int64_t total = (int64_t)n * c * h * w;
-  DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w)));
+int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t cpad,
+                      int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && cpad >= c, "nchw_to_nhwc: bad args");
+  const int64_t total = (int64_t)n * cpad * h * w;
+  DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w, cpad)));
   RCFD_CHECK_LAUNCH("nchw_to_nhwc");
   return RCFD_OK;
 }
@@ -669,10 +697,10 @@ int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t
 }
 
 int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, float min_depth, float min_over_max,
-                        int64_t count, int32_t dtype, void* stream) {
-  RCFD_CHECK_ARG(ddepth && depth && dlogit && count > 0 && min_depth > 0.f, "depth_head_bwd: bad args");
-  DISPATCH_T(dtype, (depth_head_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>(
-                        ddepth, depth, (T*)dlogit, min_depth, min_over_max, count)));
+                        int64_t count, int32_t cpad, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(ddepth && depth && dlogit && count > 0 && min_depth > 0.f && cpad >= 1, "depth_head_bwd: bad args");
+  DISPATCH_T(dtype, (depth_head_bwd_kernel<T><<<grid_for(count * cpad), NT, 0, (cudaStream_t)stream>>>(
+                        ddepth, depth, (T*)dlogit, min_depth, min_over_max, count, cpad)));
   RCFD_CHECK_LAUNCH("depth_head_bwd");
   return RCFD_OK;
 }
@@ -719,23 +747,25 @@ int rcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 }
 
 int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
-                          int32_t cin_off, int32_t cin_cnt, int32_t mode, int32_t dtype, void* stream) {
+                          int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t mode, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_weight: bad args");
   RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin && (mode == 0 || mode == 1), "pack_weight: range");
-  const int64_t total = (int64_t)cout * kh * kw * cin_cnt;
+  RCFD_CHECK_ARG(mode == 1 || cin_pad >= cin_cnt, "pack_weight: cin_pad < cin_cnt");
+  const int64_t total = mode == 0 ? (int64_t)cout * kh * kw * cin_pad
+                                  : (int64_t)cin_cnt * kh * kw * (cin_pad > cout ? cin_pad : cout);
   DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
-                        w_oihw, (T*)packed, cout, cin, kh, kw, cin_off, cin_cnt, mode)));
+                        w_oihw, (T*)packed, cout, cin, kh, kw, cin_off, cin_cnt, cin_pad, mode)));
   RCFD_CHECK_LAUNCH("pack_weight");
   return RCFD_OK;
 }
 
 int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
-                           int32_t cin_off, int32_t cin_cnt, int32_t accumulate, void* stream) {
+                           int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t accumulate, void* stream) {
   RCFD_CHECK_ARG(packed && g_oihw && cout > 0 && cin > 0 && kh > 0 && kw > 0, "unpack_wgrad: bad args");
-  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin, "unpack_wgrad: range");
+  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin && cin_pad >= cin_cnt, "unpack_wgrad: range");
   const int64_t total = (int64_t)cout * kh * kw * cin_cnt;
   unpack_wgrad_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(packed, g_oihw, cout, cin, kh, kw, cin_off,
-                                                                        cin_cnt, accumulate);
+                                                                        cin_cnt, cin_pad, accumulate);
   RCFD_CHECK_LAUNCH("unpack_wgrad");
   return RCFD_OK;
 }

@@ -20,12 +20,12 @@ using namespace tc;
 constexpr int PB = 64;           // pixels per stage (reduction depth: 4 x UMMA_K)
 constexpr int NPROD = 128;
 constexpr int NTHREADS = 160;
-constexpr int LAG = 2;
 constexpr int BLK = 64 * 128;    // one [64 pixel][64 element] block
 
 template <int BN>
 struct WgCfg {
   static constexpr int STAGES = BN >= 256 ? 3 : 4;
+  static constexpr int LAG = STAGES - 1;
   static constexpr int A_BYTES = 2 * BLK;
   static constexpr int B_BYTES = (BN / 64) * BLK;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
@@ -68,83 +68,83 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const ConvKP p, floa
 
   if (warp < 4) {
     // =========================================================== PRODUCER
-    const int pr = tid & 63, half = tid >> 6;
+    // 16 consecutive lanes fetch the 16 chunks (2 x 128 B) of one pixel's 128 k-values; each
+    // thread serves its chunk for 8 pixel rows (rows rbase + 8 i of the 64-pixel stage).
+    const int cj = tid & 15, half = cj >> 3, j = cj & 7;
+    const int rbase = tid >> 4;                  // 0..7 ; (rbase + 8 i) & 7 == rbase
+    const uint32_t swz = (uint32_t)(rbase & 7);
     const bf16* S0 = reinterpret_cast<const bf16*>(p.src0);
     const bf16* S1 = reinterpret_cast<const bf16*>(p.src1);
     const bf16* DY = reinterpret_cast<const bf16*>(p.dst);
-    // (tap row, tap col, channel) of this thread's first 8-channel chunk: k = k0 + half*64
-    const int kfirst = k0 + half * 64;
-    const int tap0 = kfirst / p.ctot;
-    const int c_first = kfirst - tap0 * p.ctot;
-    const int tr_first = tap0 / p.kw, ts_first = tap0 - tr_first * p.kw;
-    const uint32_t rowoff = (uint32_t)half * BLK + (uint32_t)pr * 128u, swz = (uint32_t)(pr & 7);
+    // fixed (tap row, tap col, channel) of this thread's chunk: k = k0 + cj * 8
+    const int kmine = k0 + cj * 8;
+    const int tap = kmine / p.ctot;
+    const int tc = kmine - tap * p.ctot;
+    const int tr = tap / p.kw, ts = tap - tr * p.kw;
+    const bool kvalid = tr < p.kh;
+    const bool from0 = tc < p.c0;
+    // running pixel coordinates of the 8 row slots (advance by 64 pixels per stage)
+    int pn_[8], oy_[8], ox_[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = mbeg + rbase + 8 * i;
+      pn_[i] = m / (p.ho * p.wo);
+      const int rem = m - pn_[i] * p.ho * p.wo;
+      oy_[i] = rem / p.wo;
+      ox_[i] = rem - oy_[i] * p.wo;
+    }
     constexpr int CH = BN / 8;     // 16-byte chunks per dY pixel row
     for (int pb = 0; pb < num_pb; ++pb) {
       const int s = pb % C::STAGES;
       if (pb >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((pb / C::STAGES) & 1) ^ 1);
-      const int m = mbeg + pb * PB + pr;
-      const bool mvalid = m < mend;
-      int pn = 0, oy = 0, ox = 0;
-      if (mvalid) {
-        pn = m / (p.ho * p.wo);
-        const int rem = m - pn * p.ho * p.wo;
-        oy = rem / p.wo;
-        ox = rem - oy * p.wo;
-      }
-      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-      int tr = tr_first, ts = ts_first, tc = c_first;
-      const uint32_t a_st = sA + s * C::A_BYTES + rowoff;
+      const int mb = mbeg + pb * PB;
+      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)half * BLK + (uint32_t)rbase * 128u + (((uint32_t)j ^ swz) << 4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int i = 0; i < 8; ++i) {
         const bf16* src = S0;
         uint32_t nbytes = 0;
-        if (mvalid && tr < p.kh) {
-          const int iy = iy0 + tr, ix = ix0 + ts;
-          if (iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
-            if (tc < p.c0) {
-              int sy = iy, sx = ix;
-              if (p.up) {
-                sy = nearest_src(iy, p.sch, p.h0);
-                sx = nearest_src(ix, p.scw, p.w0);
-              }
-              src = S0 + ((size_t)(pn * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
-            } else {
-              src = S1 + ((size_t)(pn * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
+        const int iy = oy_[i] * p.stride - p.pad + tr, ix = ox_[i] * p.stride - p.pad + ts;
+        if (kvalid && (mb + rbase + 8 * i) < mend && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
+          if (from0) {
+            int sy = iy, sx = ix;
+            if (p.up) {
+              sy = nearest_src(iy, p.sch, p.h0);
+              sx = nearest_src(ix, p.scw, p.w0);
             }
-            nbytes = 16;
+            src = S0 + ((size_t)(pn_[i] * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
+          } else {
+            src = S1 + ((size_t)(pn_[i] * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
           }
+          nbytes = 16;
         }
-        cp_async16(a_st + (((uint32_t)j ^ swz) << 4), src, nbytes);
-        tc += 8;
-        if (tc >= p.ctot) {
-          tc = 0;
-          if (++ts == p.kw) {
-            ts = 0;
-            ++tr;
-          }
+        cp_async16(a_st + (uint32_t)i * (8u * 128u), src, nbytes);
+        // advance this row slot by one stage (64 pixels)
+        ox_[i] += PB;
+        while (ox_[i] >= p.wo) {
+          ox_[i] -= p.wo;
+          if (++oy_[i] == p.ho) { oy_[i] = 0; ++pn_[i]; }
         }
       }
       const uint32_t b_st = sB + s * C::B_BYTES;
-      const int mb = mbeg + pb * PB;
       for (int i = tid; i < PB * CH; i += NPROD) {
         const int pix = i / CH, ch = i - pix * CH;
-        const int blk = ch >> 3, j = ch & 7;
+        const int blk = ch >> 3, jj = ch & 7;
         const int mm = mb + pix, co = n0 + ch * 8;
         const bool ok = (mm < mend) && (co < p.cout);
         const bf16* src = ok ? DY + (size_t)mm * p.cout + co : DY;
-        cp_async16(b_st + (uint32_t)blk * BLK + (uint32_t)pix * 128u + (((uint32_t)j ^ (uint32_t)(pix & 7)) << 4), src,
+        cp_async16(b_st + (uint32_t)blk * BLK + (uint32_t)pix * 128u + (((uint32_t)jj ^ (uint32_t)(pix & 7)) << 4), src,
                    ok ? 16u : 0u);
       }
       cp_async_commit();
-      if (pb >= LAG) {
-        cp_async_wait<LAG>();
+      if (pb >= C::LAG) {
+        cp_async_wait<C::LAG>();
         fence_proxy_async();
-        mbar_arrive(sBar + 8 * ((pb - LAG) % C::STAGES));
+        mbar_arrive(sBar + 8 * ((pb - C::LAG) % C::STAGES));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int pb = (num_pb > LAG ? num_pb - LAG : 0); pb < num_pb; ++pb) mbar_arrive(sBar + 8 * (pb % C::STAGES));
+    for (int pb = (num_pb > C::LAG ? num_pb - C::LAG : 0); pb < num_pb; ++pb) mbar_arrive(sBar + 8 * (pb % C::STAGES));
 
     // =========================================================== EPILOGUE: TMEM -> red.global.add
     if (num_pb > 0) {

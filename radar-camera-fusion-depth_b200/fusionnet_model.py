@@ -104,8 +104,8 @@ class FusionNetModel(object):
         ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
                               record=record, engine=self.conv_engine)
         ectx.taps = taps
-        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype)
-        dep = ops.nchw_to_nhwc(input_depth.float(), self.compute_dtype)
+        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype, cpad=engine.CPAD)
+        dep = ops.nchw_to_nhwc(input_depth.float(), self.compute_dtype, cpad=engine.CPAD)
         latent, skips = engine.fusionnet_encoder(ectx, self.encoder, img, dep)
         if taps is not None:
             taps['latent'] = latent
@@ -133,6 +133,11 @@ class FusionNetModel(object):
 
     def _deliver_grads(self, param_grads):
         for p, g in param_grads:
+            if g is p.grad:              # written in place (rcfd.optim.FusedAdam flat buffers)
+                continue
+            if getattr(p, '_rcfd_flat', False) and p.grad is not None:
+                p.grad.copy_(g)          # flat-buffer mode overwrites
+                continue
             if p.grad is None:
                 p.grad = g
             else:

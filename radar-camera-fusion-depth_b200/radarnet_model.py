@@ -55,7 +55,7 @@ class RadarNetModel(object):
             raise NotImplementedError('RadarNet training (backward) is not part of this round; call under '
                                       'torch.no_grad() / model.eval() for stage-1 inference')
         ctx = engine.Context(self.compute_dtype, False, image.device, cache=self._cache, engine=self.conv_engine)
-        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype)
+        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype, cpad=engine.CPAD)
         latent, skips = engine.radarnet_encoder(ctx, self.encoder, img, point, bounding_boxes)
         dec = self.decoder
         out0 = dec.output0

@@ -37,8 +37,8 @@ _P = c_void_p
 _SIGS = {
     'rcfd_conv2d_fwd': [POINTER(ConvDesc), _P],
     'rcfd_conv2d_wgrad': [POINTER(ConvDesc), _P, _P, c_int64, _P],
-    'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
-    'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
     'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],
     'rcfd_bn_act_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
@@ -51,9 +51,9 @@ _SIGS = {
     'rcfd_upsample_nearest_bwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_leaky_bwd': [_P, _P, _P, c_int64, c_int32, _P],
     'rcfd_add_inplace': [_P, _P, c_int64, c_int32, _P],
-    'rcfd_nchw_to_nhwc': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_nchw_to_nhwc': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_nhwc_to_nchw': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
-    'rcfd_depth_head_bwd': [_P, _P, _P, c_float, c_float, c_int64, c_int32, _P],
+    'rcfd_depth_head_bwd': [_P, _P, _P, c_float, c_float, c_int64, c_int32, c_int32, _P],
     'rcfd_masked_l1_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],
     'rcfd_outlier_removal': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P],
     'rcfd_adam_step': [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, _P],

@@ -25,6 +25,7 @@ from . import ops
 from .ops import ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD
 
 _ACT = {'linear': ACT_NONE, 'leaky_relu': ACT_LEAKY, 'sigmoid': ACT_SIGMOID}
+CPAD = 8     # narrow tensors (RGB image, depth+response, d(logit)) are stored with 8 channels: 16-byte gathers
 
 
 class Tape(object):
@@ -100,9 +101,10 @@ class Context(object):
         self.cache[key] = (ver, val)
         return val
 
-    def weight(self, mod):
+    def weight(self, mod, pad_to=None):
+        """Packed [cout][taps][cin_pad] weights; pad_to = channel count of the (zero-padded) input."""
         w = mod.conv.weight
-        return self.packed(('w', id(mod)), [w], lambda: ops.pack_weight(w.detach(), self.dtype))
+        return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), self.dtype, pad_to=pad_to))
 
     def folded_bn(self, mod):
         bn = mod.batch_norm
@@ -122,13 +124,14 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     turns the activation into the bounded depth head and stores float32."""
     k, stride, cout = mod.kernel_size, mod.stride, mod.out_channels
     act = _ACT[mod.act_kind]
-    w = ctx.weight(mod)
+    cin_data = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
+    w = ctx.weight(mod, pad_to=cin_data if cin_data != mod.in_channels else None)   # 3/2-channel inputs live padded to 8
     if head is not None:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=ACT_DEPTH_HEAD, act_params=head,
                          out_f32=True, engine=ctx.engine)
         if ctx.tape is not None:
             _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad,
-                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype))
+                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype, cpad=CPAD))
         return out
     if not mod.use_batch_norm:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=act, residual=residual, engine=ctx.engine)
@@ -155,6 +158,14 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     return z
 
 
+def _grad_dst(param):
+    """Where a parameter gradient is written: in place into the flat buffer view installed by
+    rcfd.optim.FusedAdam, else a fresh tensor handed to FusionNetModel._deliver_grads."""
+    if getattr(param, '_rcfd_flat', False) and param.grad is not None:
+        return param.grad
+    return torch.empty_like(param)
+
+
 def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_grad, pre=None):
     tape = ctx.tape
     k, stride = mod.kernel_size, mod.stride
@@ -172,15 +183,15 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
                 dz = ops.leaky_bwd(dz, z)               # through the post-add activation
                 tape.add_grad(residual, dz)
             bn = mod.batch_norm
-            dgamma = torch.empty_like(bn.weight)
-            dbeta = torch.empty_like(bn.bias)
+            dgamma = _grad_dst(bn.weight)
+            dbeta = _grad_dst(bn.bias)
             dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
             tape.param_grads.append((bn.weight, dgamma))
             tape.param_grads.append((bn.bias, dbeta))
         else:
             dy = dz
         dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine)
-        gw = torch.empty_like(w_param)
+        gw = _grad_dst(w_param)
         ops.unpack_wgrad(dw, gw)
         tape.param_grads.append((w_param, gw))
         if not want_input_grad:
@@ -189,7 +200,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         hin, win = (x0.shape[1], x0.shape[2]) if in_size is None else in_size
         pad_d = k - 1 - k // 2
         for (src, off, cnt) in ((x0, 0, c0),) + (((x1, c0, x1.shape[3]),) if x1 is not None else ()):
-            wd = ops.pack_weight(w_param.detach(), ctx.dtype, cin_off=off, cin_cnt=cnt, dgrad=True)
+            wd = ops.pack_weight(w_param.detach(), ctx.dtype, cin_off=off, cin_cnt=cnt, dgrad=True, pad_to=dy.shape[3])
             dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine)
             if src is x0 and (hin, win) != (x0.shape[1], x0.shape[2]):
                 dsrc = ops.upsample_nearest_bwd(dsrc, (x0.shape[1], x0.shape[2]))
@@ -243,7 +254,7 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
                 tape.param_grads.append((bn.bias, db[lo:lo + c]))
             dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine)                         # [2c, 1, cd]
             for wparam, lo in ((ww, 0), (wp, c)):
-                g = torch.empty_like(wparam)
+                g = _grad_dst(wparam)
                 ops.unpack_wgrad(dw[lo:lo + c], g)
                 tape.param_grads.append((wparam, g))
             wd = ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype, dgrad=True)
@@ -364,7 +375,7 @@ def standalone(mod, kind, x, **kw):
     """Run one module of the tree by itself on NCHW float tensors (inference semantics of
     ``mod.training`` is NOT honoured for BatchNorm statistics: eval-mode folding is used)."""
     ctx = _ctx_for(mod, x)
-    to = lambda t: ops.nchw_to_nhwc(t.float(), ctx.dtype)
+    to = lambda t: ops.nchw_to_nhwc(t.float(), ctx.dtype, cpad=CPAD if t.shape[1] < CPAD else None)
     back = ops.nhwc_to_nchw
     if kind == 'conv':
         return back(conv_unit(ctx, mod, to(x)))

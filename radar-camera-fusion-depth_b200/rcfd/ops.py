@@ -109,21 +109,27 @@ def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=EN
     return dw
 
 
-def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None):
+def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, pad_to=None):
+    """OIHW float -> packed [cout][taps][cin_pad] (forward) or [cin_cnt][taps][cout_pad] (dgrad);
+    pad_to zero-pads the innermost (channel) dimension."""
     cout, cin, kh, kw = w_oihw.shape
     cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
+    inner = cout if dgrad else cin_cnt
+    pad = inner if pad_to is None else max(inner, int(pad_to))
     if out is None:
-        shape = (cin_cnt, kh * kw, cout) if dgrad else (cout, kh * kw, cin_cnt)
+        shape = (cin_cnt, kh * kw, pad) if dgrad else (cout, kh * kw, pad)
         out = torch.empty(shape, device=w_oihw.device, dtype=dtype)
-    _lib.call('rcfd_pack_conv_weight', _p(w_oihw), _p(out), cout, cin, kh, kw, cin_off, cin_cnt,
+    _lib.call('rcfd_pack_conv_weight', _p(w_oihw), _p(out), cout, cin, kh, kw, cin_off, cin_cnt, pad,
               1 if dgrad else 0, _DT[dtype], _stream())
     return out
 
 
-def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False):
+def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None):
+    """packed float [>=cout][taps][cin_pad] -> OIHW slice; cin_cnt defaults to the packed width."""
     cout, cin, kh, kw = grad_oihw.shape
-    cin_cnt = dw_packed.shape[2]
-    _lib.call('rcfd_unpack_conv_wgrad', _p(dw_packed), _p(grad_oihw), cout, cin, kh, kw, cin_off, cin_cnt,
+    cin_pad = dw_packed.shape[2]
+    cin_cnt = min(cin_pad, cin - cin_off) if cin_cnt is None else cin_cnt
+    _lib.call('rcfd_unpack_conv_wgrad', _p(dw_packed), _p(grad_oihw), cout, cin, kh, kw, cin_off, cin_cnt, cin_pad,
               1 if accumulate else 0, _stream())
 
 
@@ -208,11 +214,12 @@ def add_(acc, x):
     return acc
 
 
-def nchw_to_nhwc(x, dtype):
+def nchw_to_nhwc(x, dtype, cpad=None):
     n, c, h, w = x.shape
+    cpad = c if cpad is None else max(c, int(cpad))
     x = x.contiguous()
-    out = torch.empty((n, h, w, c), device=x.device, dtype=dtype)
-    _lib.call('rcfd_nchw_to_nhwc', _p(x), _p(out), n, c, h, w, _DT[dtype], _stream())
+    out = torch.empty((n, h, w, cpad), device=x.device, dtype=dtype)
+    _lib.call('rcfd_nchw_to_nhwc', _p(x), _p(out), n, c, h, w, cpad, _DT[dtype], _stream())
     return out
 
 
@@ -223,10 +230,11 @@ def nhwc_to_nchw(x):
     return out
 
 
-def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype):
-    dl = torch.empty(depth.shape, device=depth.device, dtype=dtype)
+def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype, cpad=1):
+    """depth: [N, H, W, 1] float -> dlogit [N, H, W, cpad] (channel 0 carries the gradient)."""
+    dl = torch.empty(tuple(depth.shape[:3]) + (cpad,), device=depth.device, dtype=dtype)
     _lib.call('rcfd_depth_head_bwd', _p(ddepth.contiguous()), _p(depth), _p(dl), float(min_depth), float(min_over_max),
-              depth.numel(), _DT[dtype], _stream())
+              depth.numel(), cpad, _DT[dtype], _stream())
     return dl
 
 

@@ -50,6 +50,11 @@ class DistributedGradSync(object):
                 dist.broadcast(t.data, src=0, group=self.group)
 
     def __call__(self, param_grads=None):
+        flat = getattr(self, 'flat_grad', None)
+        if flat is not None:            # FusedAdam flat gradient buffer: one in-place all-reduce, no copies
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+            return
         works = []
         for bucket, flat in zip(self.buckets, self.flat):
             off = 0
@@ -80,4 +85,11 @@ class DistributedGradSync(object):
 def attach_if_distributed(model):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         model.grad_hook = DistributedGradSync(model)
+    return model
+
+
+def use_flat_gradients(model, optimizer):
+    """Let the gradient sync all-reduce rcfd.optim.FusedAdam's flat gradient buffer in place."""
+    if model.grad_hook is not None and hasattr(optimizer, 'flat_grad'):
+        model.grad_hook.flat_grad = optimizer.flat_grad
     return model

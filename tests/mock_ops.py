@@ -80,13 +80,13 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
 def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO):
     a = _gather_input(x0, x1, in_size, 1)
     cout = dy.shape[3]
-    w = torch.zeros(cout, a.shape[1], k, k, requires_grad=True)
+    w = torch.zeros(cout, a.shape[1], k, k, requires_grad=True)   # a already carries any channel padding
     y = F.conv2d(a, w, None, stride, k // 2 if pad is None else pad)
     y.backward(_nchw(dy))
     return w.grad.permute(0, 2, 3, 1).reshape(cout, k * k, -1).contiguous()
 
 
-def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None):
+def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, pad_to=None):
     cout, cin, kh, kw = w_oihw.shape
     cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
     w = w_oihw[:, cin_off:cin_off + cin_cnt]
@@ -94,6 +94,8 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None):
         res = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin_cnt, kh * kw, cout)
     else:
         res = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin_cnt)
+    if pad_to is not None and pad_to > res.shape[2]:
+        res = F.pad(res, (0, pad_to - res.shape[2]))
     res = res.contiguous().to(dtype)
     if out is not None:
         out.copy_(res)
@@ -101,10 +103,10 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None):
     return res
 
 
-def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False):
+def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None):
     cout, cin, kh, kw = grad_oihw.shape
-    cnt = dw_packed.shape[2]
-    g = dw_packed.view(cout, kh, kw, cnt).permute(0, 3, 1, 2)
+    cnt = min(dw_packed.shape[2], cin - cin_off) if cin_cnt is None else cin_cnt
+    g = dw_packed[:cout].reshape(cout, kh, kw, dw_packed.shape[2])[..., :cnt].permute(0, 3, 1, 2)
     if accumulate:
         grad_oihw[:, cin_off:cin_off + cnt] += g
     else:
@@ -208,17 +210,21 @@ def add_(acc, x):
     return acc
 
 
-def nchw_to_nhwc(x, dtype):
-    return _nhwc(x, dtype)
+def nchw_to_nhwc(x, dtype, cpad=None):
+    y = _nhwc(x, dtype)
+    if cpad is not None and cpad > y.shape[3]:
+        y = F.pad(y, (0, cpad - y.shape[3]))
+    return y
 
 
 def nhwc_to_nchw(x):
     return _nchw(x).contiguous()
 
 
-def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype):
+def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype, cpad=1):
     s = min_depth / depth - min_over_max
-    return (-ddepth.reshape(depth.shape) * depth * depth / min_depth * s * (1 - s)).to(dtype)
+    g = (-ddepth.reshape(depth.shape) * depth * depth / min_depth * s * (1 - s)).to(dtype)
+    return F.pad(g, (0, cpad - 1)) if cpad > 1 else g
 
 
 @torch.enable_grad()

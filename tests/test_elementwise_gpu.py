@@ -140,8 +140,9 @@ def test_layout_loss_outlier_adam():
     d = 1.0 / (torch.sigmoid(logit) + 0.01)
     dd = _rand(1, 1, 8, 8, seed=13)
     d.backward(dd)
-    dl = ops.depth_head_bwd(dd.to(DEV), d.detach().to(DEV), 1.0, 0.01, torch.float32)
-    assert relerr(dl.cpu(), logit.grad) < 1e-4
+    dl = ops.depth_head_bwd(dd.to(DEV), d.detach().view(1, 8, 8, 1).to(DEV), 1.0, 0.01, torch.float32, cpad=8)
+    assert dl.shape == (1, 8, 8, 8) and float(dl[..., 1:].abs().sum()) == 0.0
+    assert relerr(dl[..., 0].cpu().view(1, 1, 8, 8), logit.grad) < 1e-4
     # Adam, 3 steps vs torch.optim.Adam
     p = _rand(1000, seed=14)
     pt = p.clone().requires_grad_(True)
@@ -153,3 +154,30 @@ def test_layout_loss_outlier_adam():
         opt.step()
         ops.adam_step(pd, g.to(DEV), m, v, 1e-3, 0.9, 0.999, 1e-8, step)
     assert relerr(pd.cpu(), pt.detach()) < 1e-6
+
+
+def test_padded_pack_unpack_and_fused_adam():
+    from rcfd import ops, optim
+    w = _rand(16, 3, 7, 7, seed=30).to(DEV)
+    pk = ops.pack_weight(w, torch.float32, pad_to=8)
+    assert pk.shape == (16, 49, 8) and float(pk[..., 3:].abs().sum()) == 0.0
+    assert torch.equal(pk[..., :3].reshape(16, 7, 7, 3).permute(0, 3, 1, 2), w)
+    g = torch.zeros_like(w)
+    ops.unpack_wgrad(pk, g)                       # padded packed gradient -> OIHW, padding dropped
+    assert torch.equal(g, w)
+    wd = ops.pack_weight(_rand(1, 32, 3, 3, seed=31).to(DEV), torch.float32, dgrad=True, pad_to=8)
+    assert wd.shape == (32, 9, 8) and float(wd[..., 1:].abs().sum()) == 0.0
+    # FusedAdam == torch.optim.Adam over several steps, parameters re-pointed into one flat buffer
+    ps = [torch.nn.Parameter(_rand(33, 5, seed=40).to(DEV)), torch.nn.Parameter(_rand(7, seed=41).to(DEV))]
+    ref = [torch.nn.Parameter(q.detach().clone()) for q in ps]
+    fo_, to_ = optim.FusedAdam(ps, lr=1e-3), torch.optim.Adam(ref, lr=1e-3)
+    for step in range(3):
+        for q, r in zip(ps, ref):
+            gq = _rand(*q.shape, seed=50 + step).to(DEV)
+            q.grad.copy_(gq)
+            r.grad = gq.clone()
+        fo_.step()
+        to_.step()
+    for q, r in zip(ps, ref):
+        assert relerr(q.detach().cpu(), r.detach().cpu()) < 1e-6
+        assert q.data_ptr() >= fo_.flat_param.data_ptr()

@@ -28,7 +28,6 @@ constexpr int NTHREADS = 160;
 template <int BN>
 struct TcCfg {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
-  static constexpr int LAG = STAGES - 1;   // cp.async groups in flight before a stage is published
   static constexpr int A_BYTES = TM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -151,16 +150,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
         const bf16* src = ok ? Wt + (size_t)(n0 + n) * p.K + k : Wt;
         cp_async16(b_st + (uint32_t)n * 128u + (((uint32_t)jj ^ (uint32_t)(n & 7)) << 4), src, ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (kb >= C::LAG) {
-        cp_async_wait<C::LAG>();
-        fence_proxy_async();
-        mbar_arrive(sBar + 8 * ((kb - C::LAG) % C::STAGES));
-      }
+      // publish the stage: the barrier fires when this thread's copies have landed (no thread-side
+      // wait, so up to STAGES stages of loads stay in flight); the MMA warp does the proxy fence.
+      cp_async_mbar_arrive_noinc(sBar + 8 * s);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int kb = (num_kb > C::LAG ? num_kb - C::LAG : 0); kb < num_kb; ++kb) mbar_arrive(sBar + 8 * (kb % C::STAGES));
 
     // =========================================================== EPILOGUE (same warps)
     const int gm = m0 + tid;                      // TMEM lane == tile row == output pixel
@@ -299,6 +292,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % C::STAGES;
       mbar_wait(sBar + 8 * s, (kb / C::STAGES) & 1);
+      fence_proxy_async();      // generic-proxy (cp.async) writes -> async-proxy (UMMA) reads
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_st = sA + s * C::A_BYTES, b_st = sB + s * C::B_BYTES;

@@ -25,7 +25,6 @@ constexpr int BLK = 64 * 128;    // one [64 pixel][64 element] block
 template <int BN>
 struct WgCfg {
   static constexpr int STAGES = BN >= 256 ? 3 : 4;
-  static constexpr int LAG = STAGES - 1;
   static constexpr int A_BYTES = 2 * BLK;
   static constexpr int B_BYTES = (BN / 64) * BLK;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
@@ -135,16 +134,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const ConvKP p, floa
         cp_async16(b_st + (uint32_t)blk * BLK + (uint32_t)pix * 128u + (((uint32_t)jj ^ (uint32_t)(pix & 7)) << 4), src,
                    ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (pb >= C::LAG) {
-        cp_async_wait<C::LAG>();
-        fence_proxy_async();
-        mbar_arrive(sBar + 8 * ((pb - C::LAG) % C::STAGES));
-      }
+      // publish the stage: the barrier fires when this thread's copies have landed (no thread-side
+      // wait, so up to STAGES stages of loads stay in flight); the MMA warp does the proxy fence.
+      cp_async_mbar_arrive_noinc(sBar + 8 * s);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int pb = (num_pb > C::LAG ? num_pb - C::LAG : 0); pb < num_pb; ++pb) mbar_arrive(sBar + 8 * (pb % C::STAGES));
 
     // =========================================================== EPILOGUE: TMEM -> red.global.add
     if (num_pb > 0) {
@@ -172,6 +165,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const ConvKP p, floa
     for (int pb = 0; pb < num_pb; ++pb) {
       const int s = pb % C::STAGES;
       mbar_wait(sBar + 8 * s, (pb / C::STAGES) & 1);
+      fence_proxy_async();      // generic-proxy (cp.async) writes -> async-proxy (UMMA) reads
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_st = sA + s * C::A_BYTES, b_st = sB + s * C::B_BYTES;

@@ -71,34 +71,36 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
 
   if (warp < 4) {
     // =========================================================== PRODUCER
-    // Lane mapping chosen for the memory system: 8 consecutive lanes fetch the 8 16-byte chunks
-    // of ONE pixel's 128-byte K segment (a full line per 8 lanes instead of 32 scattered
-    // sectors per instruction); each thread serves chunk j of 8 different pixel rows.
-    const int j = tid & 7;
-    const int rbase = tid >> 3;                 // rows rbase + 16 * i
-    const uint32_t swz = (uint32_t)(rbase & 7); // (rbase + 16 i) & 7 is the same for every i
-    int pn_[8], iy0_[8], ix0_[8];
+    // Thread t serves rows (t >> 1) and (t >> 1) + 64 and the 16-byte chunks j = (t & 1) + 2 i of
+    // each 128-byte K row: an even/odd lane pair fetches whole 32-byte sectors, and the
+    // expensive part -- (pixel, tap) -> source address with padding / stride / zero insertion /
+    // nearest up-sampling / concat -- is computed once per (row, tap, source) and reused for
+    // all chunks that fall into it (one recompute per k block when C >= 64).
+    const int half = tid & 1;
+    const int row0 = tid >> 1;                  // rows row0 and row0 + 64; (row0 + 64) & 7 == row0 & 7
+    const uint32_t swz = (uint32_t)(row0 & 7);
+    int pn_[2], iy0_[2], ix0_[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = m0 + rbase + 16 * i;
+    for (int h = 0; h < 2; ++h) {
+      const int g = m0 + row0 + 64 * h;
       if (g < p.M) {
         const int pn = g / (p.ho * p.wo);
         const int rem = g - pn * p.ho * p.wo;
         const int oy = rem / p.wo;
-        pn_[i] = pn;
-        iy0_[i] = oy * p.stride - p.pad;
-        ix0_[i] = (rem - oy * p.wo) * p.stride - p.pad;
+        pn_[h] = pn;
+        iy0_[h] = oy * p.stride - p.pad;
+        ix0_[h] = (rem - oy * p.wo) * p.stride - p.pad;
       } else {
-        pn_[i] = 0;
-        iy0_[i] = -(1 << 20);                   // fails every bounds test -> zero fill
-        ix0_[i] = -(1 << 20);
+        pn_[h] = 0;
+        iy0_[h] = -(1 << 20);                   // fails every bounds test -> zero fill
+        ix0_[h] = -(1 << 20);
       }
     }
     const bf16* S0 = reinterpret_cast<const bf16*>(p.src0);
     const bf16* S1 = reinterpret_cast<const bf16*>(p.src1);
     const bf16* Wt = reinterpret_cast<const bf16*>(p.weight);
-    // running (tap row, tap col, channel) of this thread's chunk: k = kb * 64 + j * 8
-    int tc = j * 8, ts = 0, tr = 0;
+    // (tap row, tap col, channel) of this thread's FIRST chunk of the current k block
+    int tc = half * 8, ts = 0, tr = 0;
     while (tc >= p.ctot) {
       tc -= p.ctot;
       if (++ts == p.kw) { ts = 0; ++tr; }
@@ -106,36 +108,53 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % C::STAGES;
       if (kb >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((kb / C::STAGES) & 1) ^ 1);
-      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)rbase * 128u + (((uint32_t)j ^ swz) << 4);
-      const bool kvalid = tr < p.kh;
-      const bool from0 = tc < p.c0;
+      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)row0 * 128u;
+      int cc = tc, cs = ts, cr = tr;            // walks this thread's 4 chunks (16 channels apart)
+      int prev_r = -1, prev_s = -1, prev_src = -1;
+      const bf16* base_[2] = {S0, S0};
+      bool ok_[2] = {false, false};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bf16* src = S0;
-        uint32_t nbytes = 0;
-        int iy = iy0_[i] + tr, ix = ix0_[i] + ts;
-        bool ok = kvalid;
-        if (p.dil == 2) {
-          ok = ok && (((iy | ix) & 1) == 0);
-          iy >>= 1;
-          ix >>= 1;
-        }
-        if (ok && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
-          if (from0) {
-            int sy = iy, sx = ix;
-            if (p.up) {
-              sy = nearest_src(iy, p.sch, p.h0);
-              sx = nearest_src(ix, p.scw, p.w0);
+      for (int i = 0; i < 4; ++i) {
+        const int from1 = cc >= p.c0 ? 1 : 0;
+        if (cr != prev_r || cs != prev_s || from1 != prev_src) {
+          prev_r = cr; prev_s = cs; prev_src = from1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int iy = iy0_[h] + cr, ix = ix0_[h] + cs;
+            bool ok = cr < p.kh;
+            if (p.dil == 2) {
+              ok = ok && (((iy | ix) & 1) == 0);
+              iy >>= 1;
+              ix >>= 1;
             }
-            src = S0 + ((size_t)(pn_[i] * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
-          } else {
-            src = S1 + ((size_t)(pn_[i] * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
+            ok = ok && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
+            const bf16* b = S0;
+            if (ok) {
+              if (!from1) {
+                int sy = iy, sx = ix;
+                if (p.up) {
+                  sy = nearest_src(iy, p.sch, p.h0);
+                  sx = nearest_src(ix, p.scw, p.w0);
+                }
+                b = S0 + ((size_t)(pn_[h] * p.h0 + sy) * p.w0 + sx) * p.c0;
+              } else {
+                b = S1 + ((size_t)(pn_[h] * p.hin + iy) * p.win + ix) * p.c1 - p.c0;
+              }
+            }
+            base_[h] = b;
+            ok_[h] = ok;
           }
-          nbytes = 16;
         }
-        cp_async16(a_st + (uint32_t)i * (16u * 128u), src, nbytes);
+        const uint32_t joff = (((uint32_t)(half + 2 * i)) ^ swz) << 4;
+        cp_async16(a_st + joff, ok_[0] ? base_[0] + cc : S0, ok_[0] ? 16u : 0u);
+        cp_async16(a_st + 64u * 128u + joff, ok_[1] ? base_[1] + cc : S0, ok_[1] ? 16u : 0u);
+        cc += 16;
+        while (cc >= p.ctot) {
+          cc -= p.ctot;
+          if (++cs == p.kw) { cs = 0; ++cr; }
+        }
       }
-      tc += BKE;                                 // next k block: same chunk slot, 64 channels further
+      tc += BKE;                                // next k block
       while (tc >= p.ctot) {
         tc -= p.ctot;
         if (++ts == p.kw) { ts = 0; ++tr; }

@@ -67,62 +67,74 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const ConvKP p, floa
 
   if (warp < 4) {
     // =========================================================== PRODUCER
-    // 16 consecutive lanes fetch the 16 chunks (2 x 128 B) of one pixel's 128 k-values; each
-    // thread serves its chunk for 8 pixel rows (rows rbase + 8 i of the 64-pixel stage).
-    const int cj = tid & 15, half = cj >> 3, j = cj & 7;
-    const int rbase = tid >> 4;                  // 0..7 ; (rbase + 8 i) & 7 == rbase
-    const uint32_t swz = (uint32_t)(rbase & 7);
+    // Thread t serves pixel row (t >> 1) of the 64-pixel stage and one 64-element k block
+    // (t & 1): 8 consecutive 16-byte chunks; the (pixel, tap) -> address computation is done once
+    // per tap the 64 k-values touch (one when C >= 64).
+    const int half = tid & 1;
+    const int prow = tid >> 1;
+    const uint32_t swz = (uint32_t)(prow & 7);
     const bf16* S0 = reinterpret_cast<const bf16*>(p.src0);
     const bf16* S1 = reinterpret_cast<const bf16*>(p.src1);
     const bf16* DY = reinterpret_cast<const bf16*>(p.dst);
-    // fixed (tap row, tap col, channel) of this thread's chunk: k = k0 + cj * 8
-    const int kmine = k0 + cj * 8;
-    const int tap = kmine / p.ctot;
-    const int tc = kmine - tap * p.ctot;
-    const int tr = tap / p.kw, ts = tap - tr * p.kw;
-    const bool kvalid = tr < p.kh;
-    const bool from0 = tc < p.c0;
-    // running pixel coordinates of the 8 row slots (advance by 64 pixels per stage)
-    int pn_[8], oy_[8], ox_[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = mbeg + rbase + 8 * i;
-      pn_[i] = m / (p.ho * p.wo);
-      const int rem = m - pn_[i] * p.ho * p.wo;
-      oy_[i] = rem / p.wo;
-      ox_[i] = rem - oy_[i] * p.wo;
+    // fixed (tap row, tap col, channel) of this thread's first chunk: k = k0 + half * 64
+    const int kmine = k0 + half * 64;
+    const int tap0 = kmine / p.ctot;
+    const int tc0 = kmine - tap0 * p.ctot;
+    const int tr0 = tap0 / p.kw, ts0 = tap0 - tr0 * p.kw;
+    // running pixel coordinates of this thread's row (advance by 64 pixels per stage)
+    int pn, oy, ox;
+    {
+      const int m = mbeg + prow;
+      pn = m / (p.ho * p.wo);
+      const int rem = m - pn * p.ho * p.wo;
+      oy = rem / p.wo;
+      ox = rem - oy * p.wo;
     }
     constexpr int CH = BN / 8;     // 16-byte chunks per dY pixel row
     for (int pb = 0; pb < num_pb; ++pb) {
       const int s = pb % C::STAGES;
       if (pb >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((pb / C::STAGES) & 1) ^ 1);
       const int mb = mbeg + pb * PB;
-      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)half * BLK + (uint32_t)rbase * 128u + (((uint32_t)j ^ swz) << 4);
+      const bool mvalid = (mb + prow) < mend;
+      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+      const uint32_t a_st = sA + s * C::A_BYTES + (uint32_t)half * BLK + (uint32_t)prow * 128u;
+      int cc = tc0, cs = ts0, cr = tr0;
+      int prev_r = -1, prev_s = -1, prev_src = -1;
+      const bf16* base = S0;
+      bool ok = false;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bf16* src = S0;
-        uint32_t nbytes = 0;
-        const int iy = oy_[i] * p.stride - p.pad + tr, ix = ox_[i] * p.stride - p.pad + ts;
-        if (kvalid && (mb + rbase + 8 * i) < mend && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
-          if (from0) {
-            int sy = iy, sx = ix;
-            if (p.up) {
-              sy = nearest_src(iy, p.sch, p.h0);
-              sx = nearest_src(ix, p.scw, p.w0);
+      for (int j = 0; j < 8; ++j) {
+        const int from1 = cc >= p.c0 ? 1 : 0;
+        if (cr != prev_r || cs != prev_s || from1 != prev_src) {
+          prev_r = cr; prev_s = cs; prev_src = from1;
+          const int iy = iy0 + cr, ix = ix0 + cs;
+          ok = mvalid && cr < p.kh && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
+          base = S0;
+          if (ok) {
+            if (!from1) {
+              int sy = iy, sx = ix;
+              if (p.up) {
+                sy = nearest_src(iy, p.sch, p.h0);
+                sx = nearest_src(ix, p.scw, p.w0);
+              }
+              base = S0 + ((size_t)(pn * p.h0 + sy) * p.w0 + sx) * p.c0;
+            } else {
+              base = S1 + ((size_t)(pn * p.hin + iy) * p.win + ix) * p.c1 - p.c0;
             }
-            src = S0 + ((size_t)(pn_[i] * p.h0 + sy) * p.w0 + sx) * p.c0 + tc;
-          } else {
-            src = S1 + ((size_t)(pn_[i] * p.hin + iy) * p.win + ix) * p.c1 + (tc - p.c0);
           }
-          nbytes = 16;
         }
-        cp_async16(a_st + (uint32_t)i * (8u * 128u), src, nbytes);
-        // advance this row slot by one stage (64 pixels)
-        ox_[i] += PB;
-        while (ox_[i] >= p.wo) {
-          ox_[i] -= p.wo;
-          if (++oy_[i] == p.ho) { oy_[i] = 0; ++pn_[i]; }
+        cp_async16(a_st + (((uint32_t)j ^ swz) << 4), ok ? base + cc : S0, ok ? 16u : 0u);
+        cc += 8;
+        if (cc >= p.ctot) {
+          cc = 0;
+          if (++cs == p.kw) { cs = 0; ++cr; }
         }
+      }
+      // advance this row by one stage (64 pixels)
+      ox += PB;
+      while (ox >= p.wo) {
+        ox -= p.wo;
+        if (++oy == p.ho) { oy = 0; ++pn; }
       }
       const uint32_t b_st = sB + s * C::B_BYTES;
       for (int i = tid; i < PB * CH; i += NPROD) {

@@ -25,7 +25,9 @@ extern "C" {
 enum rcfd_status { RCFD_OK = 0, RCFD_EINVAL = -1, RCFD_ECUDA = -2, RCFD_EUNSUPPORTED = -3 };
 enum rcfd_dtype { RCFD_F32 = 0, RCFD_BF16 = 1 };
 enum rcfd_act { RCFD_ACT_NONE = 0, RCFD_ACT_LEAKY = 1, RCFD_ACT_SIGMOID = 2, RCFD_ACT_DEPTH_HEAD = 3 };
-enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN05 = 2 };
+/* SIMT: fp32-FMA gather kernel; TCGEN05: cp.async-gather + tcgen05.mma (any geometry);
+ * TMA: TMA tile loads + tcgen05.mma, persistent (stride 1/2, no up-sampling / zero insertion). */
+enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN05 = 2, RCFD_ENGINE_TMA = 3 };
 
 const char* rcfd_version(void);
 const char* rcfd_arch(void);          /* "sm_100a" */

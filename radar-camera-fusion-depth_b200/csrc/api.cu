@@ -18,6 +18,8 @@ int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
 int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
 bool conv_tc_supported(const ConvKP& p, int dtype);
 int conv_tc_launch(const ConvKP& p, cudaStream_t st);
+bool conv_tma_supported(const ConvKP& p, int dtype);
+int conv_tma_launch(const ConvKP& p, cudaStream_t st);
 bool wgrad_tc_supported(const ConvKP& p, int dtype);
 int wgrad_tc_launch(const ConvKP& p, float* dw, cudaStream_t st);
 
@@ -37,7 +39,16 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   if (rc != RCFD_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int engine = d->engine;
-  if (engine == RCFD_ENGINE_AUTO) engine = conv_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT;
+  if (engine == RCFD_ENGINE_AUTO)
+    engine = conv_tma_supported(p, d->dtype) ? RCFD_ENGINE_TMA
+                                             : (conv_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT);
+  if (engine == RCFD_ENGINE_TMA) {
+    if (!conv_tma_supported(p, d->dtype)) {
+      set_error("conv: shape/dtype not supported by the TMA engine (bf16, stride 1/2, no up-sampling / zero insertion, channels %% 16 == 0)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return conv_tma_launch(p, st);
+  }
   if (engine == RCFD_ENGINE_TCGEN05) {
     if (!conv_tc_supported(p, d->dtype)) {
       set_error("conv: shape/dtype not supported by the tcgen05 engine (bf16, channels %% 8 == 0, cout %% 16 == 0, cout <= 256)");

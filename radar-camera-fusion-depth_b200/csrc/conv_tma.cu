@@ -1,0 +1,449 @@
+// TMA + tcgen05 persistent implicit-GEMM convolution (bf16, fp32 accumulation in TMEM).
+//
+// The fast engine for every convolution whose im2col rows are boxes of the NHWC tensor:
+// stride 1 or 2, no up-sampling, no zero insertion (all encoder / decoder convs, the 1x1
+// fusion and projection convs, and every stride-1 dgrad).  Per filter tap and 64-channel
+// chunk ONE elected thread issues one 4-D TMA tile load
+//       box = (BKC channels, TW, TH, 1)  at  (c, x0*s + tap_x - pad, y0*s + tap_y - pad, n)
+// (traversal stride = conv stride; out-of-range coordinates are zero-filled by the TMA unit =
+// the conv padding) which lands in shared memory already in the K-major swizzled layout that
+// tcgen05.mma consumes, plus one 2-D load of the weight slice.  No per-element address
+// arithmetic, no im2col buffer, concat = a second tensor map in the K loop.
+//
+// Persistent, warp-specialised CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2-5 = epilogue.  smem stages form an mbarrier ring (full: expect_tx bytes, empty:
+// tcgen05.commit); the accumulator is double-buffered in TMEM so the epilogue of tile i
+// (TMEM -> registers -> BN statistics / folded BN + activation + residual -> global) overlaps
+// the main loop of tile i+1.  Output tile = TH x TW = 128 pixels of one image.
+#include <cuda.h>
+#include "tc_common.cuh"
+
+namespace rcfd {
+namespace {
+
+using namespace tc;
+constexpr int NTHREADS = 192;
+constexpr int NEPI = 128;
+
+struct TmaConvP {
+  int n, ho, wo, cout;
+  int kh, kw, stride, pad;
+  int c0, c1;               // channels of source 0 / source 1
+  int bkc;                  // channels per K step (16 / 32 / 64)
+  int tw, th;               // spatial tile
+  int tiles_x, tiles_y, tiles_n, num_tiles;
+  int ksteps;               // kh*kw*((c0+c1)/bkc)
+  void* dst;
+  const float* scale; const float* shift;
+  int act; float p0, p1;
+  const void* residual;
+  double* ssum; double* ssq;
+  int accumulate, dst_f32;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int BN>
+struct TmaCfg {
+  static constexpr int A_BYTES = TM * 128;                  // sized for bkc = 64
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN <= 32 ? 8 : (BN <= 64 ? 6 : (BN <= 128 ? 5 : 3));
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;      // [acc][warp][BN][sum, sq]
+  static constexpr int SMEM = STAGES * STAGE + RED_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_w, const TmaConvP p) {
+  typedef TmaCfg<BN> C;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sStage = base;
+  const uint32_t sRed = base + C::STAGES * C::STAGE;
+  const uint32_t sBar = sRed + C::RED_BYTES;        // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t sTmem = sBar + 8 * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+  float* red = reinterpret_cast<float*>(gen_base + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(sBar + 8 * s, 1);
+      mbar_init(sBar + 8 * (C::STAGES + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(sBar + 8 * (2 * C::STAGES + a), 1);
+      mbar_init(sBar + 8 * (2 * C::STAGES + 2 + a), NEPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int a_bytes = TM * p.bkc * 2, b_bytes = BN * p.bkc * 2;
+  const int chunks0 = p.c0 / p.bkc, chunks = (p.c0 + p.c1) / p.bkc;
+  const int ctot = p.c0 + p.c1;
+
+  if (warp == 0) {
+    // =========================================================== TMA PRODUCER (one lane)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      if (p.c1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int sp = tile / p.tiles_n;
+        const int tx = sp % p.tiles_x; sp /= p.tiles_x;
+        const int ty = sp % p.tiles_y;
+        const int img = sp / p.tiles_y;
+        const int x0 = tx * p.tw * p.stride - p.pad, y0 = ty * p.th * p.stride - p.pad;
+        const int n0 = nt * BN;
+        for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+          const int tr = tap / p.kw, ts = tap - tr * p.kw;
+          for (int ch = 0; ch < chunks; ++ch, ++it) {
+            const int s = it % C::STAGES;
+            if (it >= (uint32_t)C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / C::STAGES) & 1) ^ 1);
+            const uint32_t full = sBar + 8 * s;
+            const uint32_t a_dst = sStage + s * C::STAGE, b_dst = a_dst + C::A_BYTES;
+            mbar_expect_tx(full, (uint32_t)(a_bytes + b_bytes));
+            if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
+            else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+            tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA ISSUER
+    const uint32_t idesc = umma_idesc(BN);
+    // swizzle span = bkc*2 bytes: 128 -> layout 2 (SBO 1024), 64 -> layout 4 (SBO 512), 32 -> layout 6 (SBO 256)
+    const uint32_t layout = p.bkc == 64 ? 2u : (p.bkc == 32 ? 4u : 6u);
+    const uint32_t sbo = (uint32_t)(8 * p.bkc * 2);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1;
+      if (tcount >= 2) mbar_wait(sBar + 8 * (2 * C::STAGES + 2 + acc), ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(sBar + 8 * s, (it / C::STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_st = sStage + s * C::STAGE, b_st = a_st + C::A_BYTES;
+          for (int k = 0; k < p.bkc / 16; ++k) {
+            umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
+                     (uint32_t)((ks | k) != 0));
+          }
+          umma_commit(sBar + 8 * (C::STAGES + s));
+          if (ks == p.ksteps - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================== EPILOGUE (warps 2..5)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;               // tile row == TMEM lane
+    const int th = r / p.tw, tw_ = r - th * p.tw;
+    const bool want_stats = p.ssum != nullptr;
+    const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
+    const bf16* R = reinterpret_cast<const bf16*>(p.residual);
+    bf16* D = reinterpret_cast<bf16*>(p.dst);
+    const int etid = tid - 64;                 // 0..127 within the epilogue group
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1;
+      const int nt = tile % p.tiles_n;
+      int sp = tile / p.tiles_n;
+      const int tx = sp % p.tiles_x; sp /= p.tiles_x;
+      const int ty = sp % p.tiles_y;
+      const int img = sp / p.tiles_y;
+      const int oy = ty * p.th + th, ox = tx * p.tw + tw_;
+      const bool mvalid = oy < p.ho && ox < p.wo;
+      const size_t gm = ((size_t)img * p.ho + oy) * p.wo + ox;
+      const int n0 = nt * BN;
+      float* redt = red + acc * (4 * BN * 2);
+      mbar_wait(sBar + 8 * (2 * C::STAGES + acc), (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 16) {
+        float v[16];
+        tmem_ld16(trow + cb, v);
+        if (want_stats) {
+          float s16[16], q16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = mvalid ? v[i] : 0.f;        // rows outside the image carry partial sums of real taps
+            s16[i] = x;
+            q16[i] = x * x;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
+            q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
+          }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const bool hi = (lane & w) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const float send_s = hi ? s16[i] : s16[i + w];
+              const float keep_s = hi ? s16[i + w] : s16[i];
+              s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+              const float send_q = hi ? q16[i] : q16[i + w];
+              const float keep_q = hi ? q16[i + w] : q16[i];
+              q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+            }
+          }
+          if (lane < 16) {
+            redt[(q * BN + cb + lane) * 2 + 0] = s16[0];
+            redt[(q * BN + cb + lane) * 2 + 1] = q16[0];
+          }
+        }
+        if (mvalid) {
+          const int nb = n0 + cb;
+          const size_t o = gm * p.cout + nb;
+          if (!vector_epilogue) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = nb + i;
+              if (n < p.cout) {
+                float x = v[i];
+                if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+                x = apply_act(x, p.act, p.p0, p.p1);
+                if (R) x = leaky(x + __bfloat162float(R[o + i]));
+                if (p.dst_f32) {
+                  float* Df = reinterpret_cast<float*>(p.dst);
+                  Df[o + i] = p.accumulate ? Df[o + i] + x : x;
+                } else {
+                  D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+                }
+              }
+            }
+          } else if (nb < p.cout) {
+            if (p.scale) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
+            }
+            if (p.act == RCFD_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+            } else if (p.act == RCFD_ACT_SIGMOID) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
+            }
+            if (R) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                v[2 * i] = leaky(v[2 * i] + f.x);
+                v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
+              }
+            }
+            if (p.accumulate) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(sBar + 8 * (2 * C::STAGES + 2 + acc));
+      if (want_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = etid; c < BN; c += NEPI) {
+          if (n0 + c < p.cout) {
+            double s = 0.0, qq = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              s += (double)redt[(w * BN + c) * 2 + 0];
+              qq += (double)redt[(w * BN + c) * 2 + 1];
+            }
+            atomicAdd(p.ssum + n0 + c, s);
+            atomicAdd(p.ssq + n0 + c, qq);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int bkc) {
+  return bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bkc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+bool make_act_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int bkc, int tw, int th, int stride) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bkc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_w_map(CUtensorMap* m, const void* ptr, int cout, int K, int bkc, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bkc, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bkc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+               cudaStream_t st) {
+  typedef TmaCfg<BN> C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { set_error("conv_tma: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    attr_set = true;
+  }
+  int grid = tp.num_tiles < num_sms() ? tp.num_tiles : num_sms();
+  conv_tma_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(a0, a1, w, tp);
+  RCFD_CHECK_LAUNCH("conv_tma");
+  (void)k;
+  return RCFD_OK;
+}
+
+}  // namespace
+
+bool conv_tma_supported(const ConvKP& p, int dtype) {
+  if (dtype != RCFD_BF16) return false;
+  if (p.up || p.dil != 1) return false;
+  if (p.stride != 1 && p.stride != 2) return false;
+  if (p.c0 % 16 != 0 || p.c1 % 16 != 0) return false;
+  if (p.K % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (p.c1 > 0 && (reinterpret_cast<uintptr_t>(p.src1) & 15)) ||
+      (reinterpret_cast<uintptr_t>(p.weight) & 15))
+    return false;
+  return get_encode() != nullptr;
+}
+
+int conv_tma_launch(const ConvKP& p, cudaStream_t st) {
+  TmaConvP t;
+  t.n = p.n; t.ho = p.ho; t.wo = p.wo; t.cout = p.cout;
+  t.kh = p.kh; t.kw = p.kw; t.stride = p.stride; t.pad = p.pad;
+  t.c0 = p.c0; t.c1 = p.c1;
+  auto gcd_ok = [&](int b) { return p.c0 % b == 0 && p.c1 % b == 0; };
+  t.bkc = gcd_ok(64) ? 64 : (gcd_ok(32) ? 32 : 16);
+  // spatial tile: widest TW in {32,16,8} that wastes the fewest output pixels
+  int best_tw = 8;
+  long best_waste = -1;
+  for (int tw = 32; tw >= 8; tw >>= 1) {
+    const int th = TM / tw;
+    const long covered = (long)ceil_div(p.wo, tw) * tw * ceil_div(p.ho, th) * th;
+    if (best_waste < 0 || covered < best_waste) { best_waste = covered; best_tw = tw; }
+  }
+  t.tw = best_tw; t.th = TM / best_tw;
+  t.tiles_x = ceil_div(p.wo, t.tw); t.tiles_y = ceil_div(p.ho, t.th);
+  const int bn = p.cout % 128 == 0 ? 128 : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : (p.cout <= 16 || p.cout % 16 == 0 || p.cout < 32 ? 16 : 32)));
+  t.tiles_n = ceil_div(p.cout, bn);
+  t.num_tiles = p.n * t.tiles_y * t.tiles_x * t.tiles_n;
+  t.ksteps = p.kh * p.kw * ((p.c0 + p.c1) / t.bkc);
+  t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
+  t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
+  alignas(64) CUtensorMap a0, a1, w;
+  if (!make_act_map(&a0, p.src0, p.n, p.hin, p.win, p.c0, t.bkc, t.tw, t.th, p.stride) ||
+      !make_act_map(&a1, p.c1 > 0 ? p.src1 : p.src0, p.n, p.hin, p.win, p.c1 > 0 ? p.c1 : p.c0, t.bkc, t.tw, t.th, p.stride) ||
+      !make_w_map(&w, p.weight, p.cout, p.K, t.bkc, bn)) {
+    set_error("conv_tma: cuTensorMapEncodeTiled failed");
+    return RCFD_ECUDA;
+  }
+  switch (bn) {
+    case 128: return launch_tma<128>(p, t, a0, a1, w, st);
+    case 64: return launch_tma<64>(p, t, a0, a1, w, st);
+    case 32: return launch_tma<32>(p, t, a0, a1, w, st);
+    default: return launch_tma<16>(p, t, a0, a1, w, st);
+  }
+}
+
+}  // namespace rcfd

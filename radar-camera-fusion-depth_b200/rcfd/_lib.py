@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'librcfd_b200.so')
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA = 0, 1, 2, 3
 
 
 class ConvDesc(Structure):

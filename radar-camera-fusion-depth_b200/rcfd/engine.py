@@ -25,7 +25,8 @@ from . import ops
 from .ops import ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD
 
 _ACT = {'linear': ACT_NONE, 'leaky_relu': ACT_LEAKY, 'sigmoid': ACT_SIGMOID}
-CPAD = 8     # narrow tensors (RGB image, depth+response, d(logit)) are stored with 8 channels: 16-byte gathers
+CPAD = 16    # RGB image / depth+response are stored with 16 channels (TMA boxes and UMMA K need 32 B rows)
+CPAD_DY = 8  # d(logit) of the 1-channel head: 8 channels for 16-byte gathers
 
 
 class Tape(object):
@@ -131,7 +132,7 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
                          out_f32=True, engine=ctx.engine)
         if ctx.tape is not None:
             _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad,
-                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype, cpad=CPAD))
+                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype, cpad=CPAD_DY))
         return out
     if not mod.use_batch_norm:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=act, residual=residual, engine=ctx.engine)

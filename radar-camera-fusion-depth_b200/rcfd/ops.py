@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, F32, BF16, ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD,
-                   ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05)
+                   ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA)
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1

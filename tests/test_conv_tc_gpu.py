@@ -150,3 +150,85 @@ def test_tc_wgrad_dual_source_upsampled():
     gw = torch.empty(cout, c0 + c1, 3, 3, device=DEV)
     ops.unpack_wgrad(dw, gw)
     assert relerr(gw.cpu(), wt.grad) < 2e-3
+
+
+# ----------------------------------------------------------------------------- TMA engine
+TMA_CASES = [
+    # n, cin, cout, h, w, k, stride
+    (1, 64, 64, 16, 32, 3, 1),        # exact tiles (TW = 32)
+    (2, 32, 32, 13, 19, 3, 1),        # partial tiles both ways, bkc = 32 (SWIZZLE_64B)
+    (1, 16, 32, 12, 20, 3, 1),        # bkc = 16 (SWIZZLE_32B)
+    (2, 128, 128, 11, 22, 3, 1),      # BN = 128, two k chunks per tap
+    (1, 256, 256, 6, 11, 3, 1),       # one partial tile per image, tiles_n = 2
+    (1, 64, 128, 22, 44, 3, 2),       # stride 2 through the TMA traversal stride
+    (2, 32, 64, 10, 14, 1, 1),        # 1x1
+    (1, 64, 128, 11, 22, 1, 2),       # 1x1 stride 2 (projection shortcut)
+    (2, 16, 32, 20, 28, 7, 2),        # 7x7 stem, channels padded to 16
+    (1, 32, 16, 9, 17, 3, 1),         # cout = 16
+    (3, 64, 32, 40, 64, 3, 1),        # more tiles than one wave of k steps; persistent loop
+]
+
+
+@pytest.mark.parametrize('case', TMA_CASES)
+def test_tma_conv_plain(case):
+    from rcfd import ops
+    n, cin, cout, h, w, k, s = case
+    x = _q(_rand(n, cin, h, w, seed=1))
+    wt = _q(_rand(cout, cin, k, k, seed=2) / (cin * k * k) ** 0.5)
+    ref = F.conv2d(x, wt, None, s, k // 2)
+    out = ops.conv2d(_nhwc(x), ops.pack_weight(wt.to(DEV), BF), cout, k, s, engine=ops.ENGINE_TMA)
+    torch.cuda.synchronize()
+    assert relerr(_nchw(out), ref) < TOL
+
+
+def test_tma_concat_epilogue_stats():
+    from rcfd import ops
+    n, c0, c1, cout, hw = 2, 64, 32, 64, (18, 26)
+    x0, x1 = _q(_rand(n, c0, *hw, seed=3)), _q(_rand(n, c1, *hw, seed=4))
+    wt = _q(_rand(cout, c0 + c1, 3, 3, seed=5) / 30.0)
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=6) * 0.1
+    res = _q(_rand(n, cout, *hw, seed=7))
+    raw = F.conv2d(torch.cat([x0, x1], 1), wt, None, 1, 1)
+    ref = F.leaky_relu(F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2) + res, 0.2)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    out = ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), scale=scale.to(DEV), shift=shift.to(DEV),
+                     act=ops.ACT_LEAKY, residual=_nhwc(res), engine=ops.ENGINE_TMA)
+    assert relerr(_nchw(out), ref) < TOL
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    ssq = torch.zeros_like(ssum)
+    y = ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), stats=(ssum, ssq), engine=ops.ENGINE_TMA)
+    assert relerr(_nchw(y), raw) < TOL
+    assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 1e-4      # partial tiles masked out of the statistics
+    assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    acc = _nhwc(_q(_rand(n, cout, *hw, seed=10)))
+    base = _nchw(acc).clone()
+    ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), out=acc, accumulate=True, engine=ops.ENGINE_TMA)
+    assert relerr(_nchw(acc), base + raw) < TOL
+
+
+def test_tma_head_and_dgrad():
+    from rcfd import ops
+    n, cin, h, w = 2, 32, 21, 37
+    x = _q(_rand(n, cin, h, w, seed=8))
+    w1 = _q(_rand(1, cin, 3, 3, seed=10) / 6.0)
+    refd = 1.0 / (torch.sigmoid(F.conv2d(x, w1, None, 1, 1)) + 0.01)
+    d = ops.conv2d(_nhwc(x), ops.pack_weight(w1.to(DEV), BF), 1, 3, 1, act=ops.ACT_DEPTH_HEAD, act_params=(1.0, 0.01),
+                   out_f32=True, engine=ops.ENGINE_TMA)
+    assert d.dtype == torch.float32 and relerr(_nchw(d), refd) < TOL
+    cout = 64
+    xg = _q(_rand(n, cin, h, w, seed=11)).requires_grad_(True)
+    wt = _q(_rand(cout, cin, 3, 3, seed=12) / 17.0)
+    yy = F.conv2d(xg, wt, None, 1, 1)
+    dy = _q(_rand(*yy.shape, seed=13))
+    yy.backward(dy)
+    dx = ops.conv2d(_nhwc(dy), ops.pack_weight(wt.to(DEV), BF, dgrad=True), cin, 3, 1, pad=1, out_size=(h, w),
+                    engine=ops.ENGINE_TMA)
+    assert relerr(_nchw(dx), xg.grad) < TOL
+
+
+def test_tma_rejects_upsample():
+    from rcfd import ops, _lib
+    x = torch.zeros(1, 4, 4, 16, device=DEV, dtype=BF)
+    w = torch.zeros(32, 9, 16, device=DEV, dtype=BF)
+    with pytest.raises(_lib.RcfdError):
+        ops.conv2d(x, w, 32, 3, 1, in_size=(8, 8), engine=ops.ENGINE_TMA)

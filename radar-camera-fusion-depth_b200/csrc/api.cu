@@ -21,6 +21,8 @@ int conv_tc_launch(const ConvKP& p, cudaStream_t st);
 bool conv_tma_supported(const ConvKP& p, int dtype);
 int conv_tma_launch(const ConvKP& p, cudaStream_t st);
 bool wgrad_tc_supported(const ConvKP& p, int dtype);
+bool wgrad_tma_supported(const ConvKP& p, int dtype);
+int wgrad_tma_launch(const ConvKP& p, float* dw, cudaStream_t st);
 int wgrad_tc_launch(const ConvKP& p, float* dw, cudaStream_t st);
 
 }  // namespace rcfd
@@ -69,7 +71,16 @@ int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64
   if (rc != RCFD_OK) return rc;
   RCFD_CHECK_ARG(dw != nullptr, "wgrad: null dw");
   int engine = d->engine;
-  if (engine == RCFD_ENGINE_AUTO) engine = wgrad_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT;
+  if (engine == RCFD_ENGINE_AUTO)
+    engine = wgrad_tma_supported(p, d->dtype) ? RCFD_ENGINE_TMA
+                                              : (wgrad_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT);
+  if (engine == RCFD_ENGINE_TMA) {
+    if (!wgrad_tma_supported(p, d->dtype)) {
+      set_error("wgrad: shape/dtype not supported by the TMA engine (bf16, stride 1/2, no up-sampling, channels %% 16 == 0)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return wgrad_tma_launch(p, dw, (cudaStream_t)stream);
+  }
   if (engine == RCFD_ENGINE_TCGEN05) {
     if (!wgrad_tc_supported(p, d->dtype)) {
       set_error("wgrad: shape/dtype not supported by the tcgen05 engine (bf16, channels %% 8 == 0)");

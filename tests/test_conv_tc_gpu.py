@@ -232,3 +232,36 @@ def test_tma_rejects_upsample():
     w = torch.zeros(32, 9, 16, device=DEV, dtype=BF)
     with pytest.raises(_lib.RcfdError):
         ops.conv2d(x, w, 32, 3, 1, in_size=(8, 8), engine=ops.ENGINE_TMA)
+
+
+@pytest.mark.parametrize('case', [(2, 64, 64, 16, 24, 3, 1), (1, 32, 32, 13, 19, 3, 1), (1, 16, 32, 12, 20, 3, 1),
+                                  (1, 128, 256, 11, 22, 3, 2), (2, 32, 128, 10, 14, 1, 1), (1, 64, 96, 9, 9, 3, 1),
+                                  (1, 256, 512, 6, 11, 1, 1), (3, 64, 32, 40, 56, 3, 1), (2, 16, 16, 20, 28, 7, 2),
+                                  (1, 64, 128, 11, 22, 1, 2)])
+def test_tma_wgrad(case):
+    """TMA-fed tcgen05 weight gradient vs autograd of F.conv2d (partial pixel tiles, strides, k / cout tails)."""
+    from rcfd import ops
+    n, cin, cout, h, w, k, s = case
+    x = _q(_rand(n, cin, h, w, seed=21))
+    wt = (_rand(cout, cin, k, k, seed=22) * 0.05).requires_grad_(True)
+    y = F.conv2d(x, wt, None, s, k // 2)
+    dy = _q(_rand(*y.shape, seed=23))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), k, s, engine=ops.ENGINE_TMA)
+    gw = torch.empty(cout, cin, k, k, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3
+
+
+def test_tma_wgrad_concat():
+    from rcfd import ops
+    n, c0, c1, cout = 2, 64, 32, 64
+    x0, x1 = _q(_rand(n, c0, 16, 24, seed=24)), _q(_rand(n, c1, 16, 24, seed=25))
+    wt = (_rand(cout, c0 + c1, 3, 3, seed=26) * 0.05).requires_grad_(True)
+    y = F.conv2d(torch.cat([x0, x1], 1), wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=27))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x0), _nhwc(dy), 3, 1, x1=_nhwc(x1), engine=ops.ENGINE_TMA)
+    gw = torch.empty(cout, c0 + c1, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3

@@ -68,6 +68,9 @@ typedef struct rcfd_conv_desc {
   int32_t dst_f32;                    /* store float regardless of dtype                     */
   int32_t dtype;                      /* rcfd_dtype of src0/src1/weight/residual/dst         */
   int32_t engine;                     /* rcfd_engine                                         */
+  const void* weight_up2x;            /* optional [4][cout][2*2][c0] sub-pixel phase weights of a 3x3 conv
+                                         behind an exact 2x nearest up-sampling (rcfd_pack_upconv2x_weight):
+                                         lets the TMA engine run it as four 2x2 convs on the low-res source */
 } rcfd_conv_desc;
 
 int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream);
@@ -88,6 +91,11 @@ int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d);
 int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh,
                           int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t mode,
                           int32_t dtype, void* stream);
+/* Sub-pixel decomposition of `3x3 conv after 2x nearest up-sampling` (src/net_utils.py:196-197):
+ * out[2i+a][2j+b] = sum_{t,u in {0,1}} W'[a,b][t,u] . x[i+t+a-1][j+u+b-1] with W' the sums of the 3x3
+ * taps that hit the same low-res pixel.  packed: [4 = a*2+b][cout][4 = t*2+u][cin] in dtype. */
+int rcfd_pack_upconv2x_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t dtype,
+                              void* stream);
 /* packed float [>=cout][kh*kw][cin_pad] gradient -> OIHW float slice (+= if accumulate); only the
  * first cin_cnt channels of every tap and the first cout rows are read. */
 int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh,

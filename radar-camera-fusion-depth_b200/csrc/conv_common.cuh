@@ -18,6 +18,7 @@ struct ConvKP {
   const void* src1; int c1;
   int ctot, K, M;
   const void* weight;
+  const void* weight_up2x;   // optional sub-pixel phase weights (rcfd_pack_upconv2x_weight)
   void* dst;
   const float* scale; const float* shift;
   int act; float p0, p1;

@@ -31,7 +31,7 @@ int make_conv_kp(const rcfd_conv_desc* d, ConvKP* p) {
   p->ctot = d->c0 + d->c1;
   p->K = d->kh * d->kw * p->ctot;
   p->M = d->n * d->ho * d->wo;
-  p->weight = d->weight; p->dst = d->dst;
+  p->weight = d->weight; p->weight_up2x = d->weight_up2x; p->dst = d->dst;
   p->scale = d->scale; p->shift = d->shift;
   p->act = d->act; p->p0 = d->act_p0; p->p1 = d->act_p1;
   p->residual = d->residual;

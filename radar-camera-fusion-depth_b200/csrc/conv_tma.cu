@@ -39,6 +39,8 @@ struct TmaConvP {
   const void* residual;
   double* ssum; double* ssq;
   int accumulate, dst_f32;
+  int phases;               // 1, or 4 = sub-pixel phases of a 2x nearest up-sampled 3x3 conv (2x2 taps each)
+  int out_h, out_w, out_s;  // destination extent and pixel stride (out_s = 2 with phases)
 };
 
 template <int BN>
@@ -102,13 +104,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (p.c1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int sp = tile / p.tiles_n;
+        const int ph = tile % p.phases;
+        int sp = tile / p.phases;
+        const int nt = sp % p.tiles_n; sp /= p.tiles_n;
         const int tx = sp % p.tiles_x; sp /= p.tiles_x;
         const int ty = sp % p.tiles_y;
         const int img = sp / p.tiles_y;
-        const int x0 = tx * p.tw * p.stride - p.pad, y0 = ty * p.th * p.stride - p.pad;
-        const int n0 = nt * BN;
+        // phase (a, b) of the up-sampled conv reads rows i-1+a .. i+a: its "padding" is 1 - a
+        const int x0 = tx * p.tw * p.stride - (p.pad - (ph & 1)), y0 = ty * p.th * p.stride - (p.pad - (ph >> 1));
+        const int n0 = ph * p.cout + nt * BN;
         for (int tap = 0; tap < p.kh * p.kw; ++tap) {
           const int tr = tap / p.kw, ts = tap - tr * p.kw;
           for (int ch = 0; ch < chunks; ++ch, ++it) {
@@ -166,14 +170,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1;
-      const int nt = tile % p.tiles_n;
-      int sp = tile / p.tiles_n;
+      const int ph = tile % p.phases;
+      int sp = tile / p.phases;
+      const int nt = sp % p.tiles_n; sp /= p.tiles_n;
       const int tx = sp % p.tiles_x; sp /= p.tiles_x;
       const int ty = sp % p.tiles_y;
       const int img = sp / p.tiles_y;
       const int oy = ty * p.th + th, ox = tx * p.tw + tw_;
       const bool mvalid = oy < p.ho && ox < p.wo;
-      const size_t gm = ((size_t)img * p.ho + oy) * p.wo + ox;
+      const size_t gm = ((size_t)img * p.out_h + (oy * p.out_s + (ph >> 1))) * p.out_w + (ox * p.out_s + (ph & 1));
       const int n0 = nt * BN;
       float* redt = red + acc * (4 * BN * 2);
       mbar_wait(sBar + 8 * (2 * C::STAGES + acc), (tcount >> 1) & 1);
@@ -325,7 +330,20 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 
 }  // namespace
 
+// 2x nearest up-sampling folded into a 3x3 / stride-1 / pad-1 conv == four 2x2 convs (one per
+// output sub-pixel phase) on the LOW-RES source with summed weights: 4/9 of the MACs, every
+// load a TMA box (needs the phase weights from rcfd_pack_upconv2x_weight).
+bool conv_tma_up2x_supported(const ConvKP& p, int dtype) {
+  if (dtype != RCFD_BF16 || !p.up || p.weight_up2x == nullptr) return false;
+  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1 || p.dil != 1 || p.c1 != 0) return false;
+  if (p.hin != 2 * p.h0 || p.win != 2 * p.w0 || p.ho != p.hin || p.wo != p.win) return false;
+  if (p.c0 % 16 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight_up2x) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
 bool conv_tma_supported(const ConvKP& p, int dtype) {
+  if (conv_tma_up2x_supported(p, dtype)) return true;
   if (dtype != RCFD_BF16) return false;
   if (p.up || p.dil != 1) return false;
   if (p.stride != 1 && p.stride != 2) return false;
@@ -337,8 +355,17 @@ bool conv_tma_supported(const ConvKP& p, int dtype) {
   return get_encode() != nullptr;
 }
 
-int conv_tma_launch(const ConvKP& p, cudaStream_t st) {
+int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
+  ConvKP p = pin;
   TmaConvP t;
+  t.phases = 1; t.out_h = p.ho; t.out_w = p.wo; t.out_s = 1;
+  if (conv_tma_up2x_supported(p, RCFD_BF16)) {
+    // run on the low-res grid: 2x2 taps, per-phase weights, destination pixels (2i+a, 2j+b)
+    t.phases = 4; t.out_s = 2;
+    p.ho = p.h0; p.wo = p.w0; p.hin = p.h0; p.win = p.w0;
+    p.kh = 2; p.kw = 2; p.K = 4 * p.c0;
+    p.weight = p.weight_up2x;
+  }
   t.n = p.n; t.ho = p.ho; t.wo = p.wo; t.cout = p.cout;
   t.kh = p.kh; t.kw = p.kw; t.stride = p.stride; t.pad = p.pad;
   t.c0 = p.c0; t.c1 = p.c1;
@@ -356,14 +383,14 @@ int conv_tma_launch(const ConvKP& p, cudaStream_t st) {
   t.tiles_x = ceil_div(p.wo, t.tw); t.tiles_y = ceil_div(p.ho, t.th);
   const int bn = p.cout % 128 == 0 ? 128 : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : (p.cout <= 16 || p.cout % 16 == 0 || p.cout < 32 ? 16 : 32)));
   t.tiles_n = ceil_div(p.cout, bn);
-  t.num_tiles = p.n * t.tiles_y * t.tiles_x * t.tiles_n;
+  t.num_tiles = p.n * t.tiles_y * t.tiles_x * t.tiles_n * t.phases;
   t.ksteps = p.kh * p.kw * ((p.c0 + p.c1) / t.bkc);
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
   alignas(64) CUtensorMap a0, a1, w;
   if (!make_act_map(&a0, p.src0, p.n, p.hin, p.win, p.c0, t.bkc, t.tw, t.th, p.stride) ||
       !make_act_map(&a1, p.c1 > 0 ? p.src1 : p.src0, p.n, p.hin, p.win, p.c1 > 0 ? p.c1 : p.c0, t.bkc, t.tw, t.th, p.stride) ||
-      !make_w_map(&w, p.weight, p.cout, p.K, t.bkc, bn)) {
+      !make_w_map(&w, p.weight, p.cout * t.phases, p.K, t.bkc, bn)) {
     set_error("conv_tma: cuTensorMapEncodeTiled failed");
     return RCFD_ECUDA;
   }

@@ -510,6 +510,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
   }
 }
+template <typename T>
+__global__ void pack_up2x_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin) {
+  const int64_t total = (int64_t)4 * cout * 4 * cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    int64_t r = i / cin;
+    const int tap = (int)(r % 4); r /= 4;
+    const int co = (int)(r % cout);
+    const int ph = (int)(r / cout);
+    const int a = ph >> 1, b = ph & 1, t = tap >> 1, u = tap & 1;
+    // 3x3 rows folded onto low-res row t of phase a: a=0: {0},{1,2}; a=1: {0,1},{2}
+    const int r0 = a == 0 ? (t == 0 ? 0 : 1) : (t == 0 ? 0 : 2), r1 = a == 0 ? (t == 0 ? 0 : 2) : (t == 0 ? 1 : 2);
+    const int s0 = b == 0 ? (u == 0 ? 0 : 1) : (u == 0 ? 0 : 2), s1 = b == 0 ? (u == 0 ? 0 : 2) : (u == 0 ? 1 : 2);
+    const float* wp = w + ((size_t)co * cin + ci) * 9;
+    float acc = 0.f;
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int ss = s0; ss <= s1; ++ss) acc += wp[rr * 3 + ss];
+    out[i] = from_f<T>(acc);
+  }
+}
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout,
                                     int cin, int kh, int kw, int cin_off, int cin_cnt, int cpad, int accumulate) {
   const int taps = kh * kw;
@@ -756,6 +776,14 @@ int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32
   DISPATCH_T(dtype, (pack_weight_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
                         w_oihw, (T*)packed, cout, cin, kh, kw, cin_off, cin_cnt, cin_pad, mode)));
   RCFD_CHECK_LAUNCH("pack_weight");
+  return RCFD_OK;
+}
+
+int rcfd_pack_upconv2x_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin > 0, "pack_upconv2x: bad args");
+  const int64_t total = (int64_t)16 * cout * cin;
+  DISPATCH_T(dtype, (pack_up2x_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(w_oihw, (T*)packed, cout, cin)));
+  RCFD_CHECK_LAUNCH("pack_upconv2x");
   return RCFD_OK;
 }
 

@@ -29,6 +29,7 @@ class ConvDesc(Structure):
         ('residual', c_void_p),
         ('stats_sum', c_void_p), ('stats_sqsum', c_void_p),
         ('accumulate', c_int32), ('dst_f32', c_int32), ('dtype', c_int32), ('engine', c_int32),
+        ('weight_up2x', c_void_p),
     ]
 
 
@@ -38,6 +39,7 @@ _SIGS = {
     'rcfd_conv2d_fwd': [POINTER(ConvDesc), _P],
     'rcfd_conv2d_wgrad': [POINTER(ConvDesc), _P, _P, c_int64, _P],
     'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_pack_upconv2x_weight': [_P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
     'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],

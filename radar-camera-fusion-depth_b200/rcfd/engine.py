@@ -107,6 +107,11 @@ class Context(object):
         w = mod.conv.weight
         return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), self.dtype, pad_to=pad_to))
 
+    def weight_up2x(self, mod):
+        """Sub-pixel phase weights for a 3x3 conv behind an exact 2x nearest up-sampling (bf16 fast path)."""
+        w = mod.conv.weight
+        return self.packed(('wup', id(mod)), [w], lambda: ops.pack_upconv2x_weight(w.detach(), self.dtype))
+
     def folded_bn(self, mod):
         bn = mod.batch_norm
         ps = [bn.weight, bn.bias, bn.running_mean, bn.running_var]
@@ -126,7 +131,11 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     k, stride, cout = mod.kernel_size, mod.stride, mod.out_channels
     act = _ACT[mod.act_kind]
     cin_data = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
-    w = ctx.weight(mod, pad_to=cin_data if cin_data != mod.in_channels else None)   # 3/2-channel inputs live padded to 8
+    w = ctx.weight(mod, pad_to=cin_data if cin_data != mod.in_channels else None)   # 3/2-channel inputs live padded
+    wup = None
+    if (in_size is not None and x1 is None and k == 3 and stride == 1 and ctx.dtype == torch.bfloat16
+            and int(in_size[0]) == 2 * x0.shape[1] and int(in_size[1]) == 2 * x0.shape[2] and x0.shape[3] % 16 == 0):
+        wup = ctx.weight_up2x(mod)      # TMA engine: four 2x2 convs on the low-res source instead of a gather
     if head is not None:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=ACT_DEPTH_HEAD, act_params=head,
                          out_f32=True, engine=ctx.engine)
@@ -144,10 +153,11 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     if not ctx.training:
         scale, shift = ctx.folded_bn(mod)
         return ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, scale=scale, shift=shift, act=act,
-                          residual=residual, engine=ctx.engine)
+                          residual=residual, engine=ctx.engine, weight_up2x=wup)
     # training: raw conv + batch statistics -> finalize -> normalise/activate(/residual)
     ssum, ssq = ctx.stats(cout)
-    y = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, stats=(ssum, ssq), engine=ctx.engine)
+    y = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, stats=(ssum, ssq), engine=ctx.engine,
+                   weight_up2x=wup)
     scale, shift, mean, invstd = ctx.aff(cout)
     ops.bn_finalize(ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
                     mean, invstd, y.numel() // cout)

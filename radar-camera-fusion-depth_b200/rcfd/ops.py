@@ -39,7 +39,7 @@ def conv_out_size(h, k, s, p):
 
 def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=None, shift=None,
            act=ACT_NONE, act_params=(0.0, 0.0), residual=None, stats=None, out=None, out_f32=False,
-           accumulate=False, in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO):
+           accumulate=False, in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO, weight_up2x=None):
     """Implicit-GEMM convolution (see include/rcfd.h rcfd_conv2d_fwd).
     x0: [N, h0, w0, c0]; in_size: logical (H, W) the taps see (x0 is nearest-up-sampled to it);
     x1: optional [N, H, W, c1] concat partner; stats: (sum, sqsum) float64 [cout] tensors."""
@@ -80,6 +80,7 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     d.dst_f32 = 1 if out_f32 else 0
     d.dtype = dt(x0)
     d.engine = engine
+    d.weight_up2x = weight_up2x.data_ptr() if weight_up2x is not None else None
     _lib.call('rcfd_conv2d_fwd', ctypes.byref(d), _stream())
     return out
 
@@ -121,6 +122,15 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, p
         out = torch.empty(shape, device=w_oihw.device, dtype=dtype)
     _lib.call('rcfd_pack_conv_weight', _p(w_oihw), _p(out), cout, cin, kh, kw, cin_off, cin_cnt, pad,
               1 if dgrad else 0, _DT[dtype], _stream())
+    return out
+
+
+def pack_upconv2x_weight(w_oihw, dtype):
+    """[4 phases][cout][2x2 taps][cin] weights of `3x3 conv after 2x nearest up-sampling` (TMA engine)."""
+    cout, cin, kh, kw = w_oihw.shape
+    assert kh == 3 and kw == 3
+    out = torch.empty((4, cout, 4, cin), device=w_oihw.device, dtype=dtype)
+    _lib.call('rcfd_pack_upconv2x_weight', _p(w_oihw), _p(out), cout, cin, _DT[dtype], _stream())
     return out
 
 

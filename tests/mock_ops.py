@@ -46,7 +46,7 @@ def _gather_input(x0, x1, in_size, in_dilation):
 
 def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=None, shift=None, act=ACT_NONE,
            act_params=(0.0, 0.0), residual=None, stats=None, out=None, out_f32=False, accumulate=False,
-           in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO):
+           in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO, weight_up2x=None):
     pad = k // 2 if pad is None else pad
     w = weight_packed.float().view(cout, k, k, -1).permute(0, 3, 1, 2)
     if in_dilation == 2:
@@ -101,6 +101,10 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, p
         out.copy_(res)
         return out
     return res
+
+
+def pack_upconv2x_weight(w_oihw, dtype):
+    return torch.zeros(4, w_oihw.shape[0], 4, w_oihw.shape[1], dtype=dtype)   # unused by the mock conv
 
 
 def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None):

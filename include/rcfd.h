@@ -27,11 +27,14 @@ enum rcfd_dtype { RCFD_F32 = 0, RCFD_BF16 = 1 };
 enum rcfd_act { RCFD_ACT_NONE = 0, RCFD_ACT_LEAKY = 1, RCFD_ACT_SIGMOID = 2, RCFD_ACT_DEPTH_HEAD = 3 };
 /* SIMT: fp32-FMA gather kernel; TCGEN05: cp.async-gather + tcgen05.mma (any geometry);
  * TMA: TMA tile loads + tcgen05.mma, persistent (stride 1/2, no up-sampling / zero insertion). */
-enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN05 = 2, RCFD_ENGINE_TMA = 3 };
+enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN05 = 2, RCFD_ENGINE_TMA = 3,
+                   RCFD_ENGINE_STRIP = 4 /* row-streaming 3x3: input rows kept in a shared-memory ring */ };
 
 const char* rcfd_version(void);
 const char* rcfd_arch(void);          /* "sm_100a" */
 const char* rcfd_last_error(void);
+/* tuning / debug knobs ("strip_desc_mode": 0 | 1). */
+int rcfd_set_option(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------------------------
  * Convolution as implicit GEMM.  Replaces torch.nn.Conv2d(bias=False, padding=k//2)

@@ -18,6 +18,10 @@ int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
 int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
 bool conv_tc_supported(const ConvKP& p, int dtype);
 int conv_tc_launch(const ConvKP& p, cudaStream_t st);
+bool conv_strip_supported(const ConvKP& p, int dtype);
+bool conv_strip_preferred(const ConvKP& p, int dtype);
+int conv_strip_launch(const ConvKP& p, cudaStream_t st);
+extern int g_strip_desc_mode;
 bool conv_tma_supported(const ConvKP& p, int dtype);
 int conv_tma_launch(const ConvKP& p, cudaStream_t st);
 bool wgrad_tc_supported(const ConvKP& p, int dtype);
@@ -41,6 +45,14 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   if (rc != RCFD_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int engine = d->engine;
+  if (engine == RCFD_ENGINE_AUTO && conv_strip_preferred(p, d->dtype)) engine = RCFD_ENGINE_STRIP;
+  if (engine == RCFD_ENGINE_STRIP) {
+    if (!conv_strip_supported(p, d->dtype)) {
+      set_error("conv: not a case of the row-streaming engine (bf16, 3x3 / stride 1 / pad 1, one source with 32 or 64 channels)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return conv_strip_launch(p, st);
+  }
   if (engine == RCFD_ENGINE_AUTO)
     engine = conv_tma_supported(p, d->dtype) ? RCFD_ENGINE_TMA
                                              : (conv_tc_supported(p, d->dtype) ? RCFD_ENGINE_TCGEN05 : RCFD_ENGINE_SIMT);
@@ -60,6 +72,13 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   }
   if (engine != RCFD_ENGINE_SIMT) { set_error("conv: bad engine %d", engine); return RCFD_EINVAL; }
   return conv_simt_launch(p, d->dtype, st);
+}
+
+int rcfd_set_option(const char* key, int32_t value) {
+  RCFD_CHECK_ARG(key != nullptr, "set_option: null key");
+  if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
+  set_error("set_option: unknown key %s", key);
+  return RCFD_EINVAL;
 }
 
 int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d) { (void)d; return 0; }

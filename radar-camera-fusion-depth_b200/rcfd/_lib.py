@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'librcfd_b200.so')
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA, ENGINE_STRIP = 0, 1, 2, 3, 4
 
 
 class ConvDesc(Structure):
@@ -64,6 +64,7 @@ _SIGS = {
     'rcfd_roi_pool_fwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P],
     'rcfd_linear_leaky_fwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
+    'rcfd_set_option': [c_char_p, c_int32],
     'rcfd_version': [], 'rcfd_arch': [], 'rcfd_last_error': [],
 }
 _RESTYPE = {'rcfd_version': c_char_p, 'rcfd_arch': c_char_p, 'rcfd_last_error': c_char_p,

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, F32, BF16, ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD,
-                   ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA)
+                   ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA, ENGINE_STRIP)
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -31,6 +31,10 @@ def _p(t):
     if not (t.is_cuda and t.is_contiguous()):
         raise RuntimeError('rcfd ops need contiguous CUDA tensors (there is no CPU fallback)')
     return ctypes.c_void_p(t.data_ptr())
+
+
+def set_option(key, value):
+    _lib.call('rcfd_set_option', key.encode(), int(value))
 
 
 def conv_out_size(h, k, s, p):

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TMA, ENGINE_STRIP = 0, 1, 2, 3, 4
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 

@@ -296,3 +296,37 @@ def test_tma_upconv2x_subpixel(shape):
     g = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), scale=scale.to(DEV), shift=shift.to(DEV),
                    act=ops.ACT_LEAKY, engine=ops.ENGINE_TCGEN05)                      # gather engine, same layer
     assert relerr(_nchw(z), _nchw(g)) < TOL
+
+
+# ----------------------------------------------------------------------------- row-streaming engine
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('case', [(1, 64, 64, 12, 128), (2, 64, 32, 19, 200), (1, 32, 32, 33, 130), (2, 32, 64, 9, 70),
+                                  (1, 64, 16, 70, 256)])
+def test_strip_conv(case, mode):
+    """3x3 / stride 1 conv with the input rows kept in a shared-memory ring: tap (r, s) = descriptor
+    shifted by s pixels into ring row y-1+r.  mode selects the descriptor base-offset convention."""
+    from rcfd import ops
+    n, cin, cout, h, w = case
+    ops.set_option('strip_desc_mode', mode)
+    try:
+        x = _q(_rand(n, cin, h, w, seed=41))
+        wt = _q(_rand(cout, cin, 3, 3, seed=42) / (cin * 9) ** 0.5)
+        raw = F.conv2d(x, wt, None, 1, 1)
+        wp = ops.pack_weight(wt.to(DEV), BF)
+        ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+        ssq = torch.zeros_like(ssum)
+        y = ops.conv2d(_nhwc(x), wp, cout, 3, 1, stats=(ssum, ssq), engine=ops.ENGINE_STRIP)
+        torch.cuda.synchronize()
+        err = relerr(_nchw(y), raw)
+        print('strip mode', mode, case, 'relerr', err)
+        assert err < TOL
+        assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 1e-3 * (1 + float(raw.abs().sum() / (raw.sum(dim=(0, 2, 3)).abs().max() + 1e-9)))
+        assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+        scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=43) * 0.1
+        res = _q(_rand(n, cout, h, w, seed=44))
+        ref = F.leaky_relu(F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2) + res, 0.2)
+        z = ops.conv2d(_nhwc(x), wp, cout, 3, 1, scale=scale.to(DEV), shift=shift.to(DEV), act=ops.ACT_LEAKY,
+                       residual=_nhwc(res), engine=ops.ENGINE_STRIP)
+        assert relerr(_nchw(z), ref) < TOL
+    finally:
+        ops.set_option('strip_desc_mode', 0)

@@ -299,12 +299,13 @@ def test_tma_upconv2x_subpixel(shape):
 
 
 # ----------------------------------------------------------------------------- row-streaming engine
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [0])
 @pytest.mark.parametrize('case', [(1, 64, 64, 12, 128), (2, 64, 32, 19, 200), (1, 32, 32, 33, 130), (2, 32, 64, 9, 70),
                                   (1, 64, 16, 70, 256)])
 def test_strip_conv(case, mode):
     """3x3 / stride 1 conv with the input rows kept in a shared-memory ring: tap (r, s) = descriptor
-    shifted by s pixels into ring row y-1+r.  mode selects the descriptor base-offset convention."""
+    shifted by s pixels into ring row y-1+r (descriptor base offset 0: the swizzle is a function of the
+    absolute shared-memory address -- measured on B200: the other convention gives garbage)."""
     from rcfd import ops
     n, cin, cout, h, w = case
     ops.set_option('strip_desc_mode', mode)

@@ -20,7 +20,12 @@ if which == 'deconv0_up':        # 64 -> 32, fused 2x up-sample, 352x704 output
 elif which == 'deconv0_conv':    # 32 -> 32 at 352x704
     x = torch.randn(B, H, W, 32, device=dev).to(bf)
     w = ops.pack_weight(torch.randn(32, 32, 3, 3, device=dev) * 0.05, bf)
-    run = lambda: ops.conv2d(x, w, 32, 3, 1)
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d(x, w, 32, 3, 1, engine=eng)
+elif which == 'deconv1_up_lowres':   # 64 -> 64 at 176x352 (plain 3x3 at that resolution)
+    x = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
+    w = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) * 0.05, bf)
+    run = lambda: ops.conv2d(x, w, 64, 3, 1)
 elif which == 'blocks4':         # 256 -> 256 at 22x44
     x = torch.randn(B, 22, 44, 256, device=dev).to(bf)
     w = ops.pack_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.02, bf)

@@ -61,7 +61,7 @@ __device__ __forceinline__ uint64_t strip_desc(uint32_t saddr, uint32_t sbo, uin
 }
 
 template <int BN, int CIN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS)
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
   typedef StripCfg<BN, CIN> C;
   extern __shared__ uint8_t smem_raw[];
@@ -350,7 +350,8 @@ int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
     return RCFD_ECUDA;
   }
   const int ntile = ceil_div(k.cout, BN);
-  int ctas = num_sms() / ntile;
+  const int per_sm = C::SMEM <= 112 * 1024 ? 2 : 1;        // two CTAs per SM hide each other's barrier latencies
+  int ctas = num_sms() * per_sm / ntile;
   if (ctas < 1) ctas = 1;
   if (ctas > t.num_items) ctas = t.num_items;
   dim3 grid(ctas, ntile);
@@ -385,7 +386,7 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
   t.strips = ceil_div(p.wo, SW);
   const int bn = p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 16);
   const int ntile = ceil_div(p.cout, bn);
-  const int ctas = num_sms() / ntile > 0 ? num_sms() / ntile : 1;
+  const int ctas = 2 * num_sms() / ntile > 0 ? 2 * num_sms() / ntile : 1;
   const int cols = p.n * t.strips;
   int cpc = (2 * ctas + cols - 1) / cols;              // aim at ~2 items per CTA
   if (cpc < 1) cpc = 1;

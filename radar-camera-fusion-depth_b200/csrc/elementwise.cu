@@ -170,6 +170,130 @@ __global__ void bn_bwd_params_kernel(const double* sums, float* dgamma, float* d
   if (dgamma) dgamma[c] = (float)sums[C + c];
 }
 
+// ---- 16-byte-vector variants (C % V16<T>::N == 0): 8 bf16 / 4 float per thread and access
+template <typename T>
+__global__ void bn_act_fwd_wide(const T* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const T* __restrict__ res, T* __restrict__ out,
+                                int64_t nvec, int C, int act) {
+  constexpr int N = V16<T>::N;
+  const int CV = C / N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * N;
+    float v[N], r[N];
+    V16<T>::ld(y + i * N, v);
+    if (res) V16<T>::ld(res + i * N, r);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float x = v[k];
+      if (scale) x = fmaf(x, __ldg(scale + c + k), __ldg(shift + c + k));
+      x = apply_act(x, act, 0.f, 0.f);
+      if (res) x = leaky(x + r[k]);
+      v[k] = x;
+    }
+    V16<T>::st(out + i * N, v);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_wide(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, double* __restrict__ sums, int64_t pixels, int C,
+                                   int CVP, int act, int64_t rows_per_block) {
+  constexpr int N = V16<T>::N;
+  __shared__ float red[2][NT * N];
+  const int CV = C / N;
+  const int cv = threadIdx.x % CVP;
+  const int r0 = threadIdx.x / CVP;
+  const int rstep = NT / CVP;
+  float s[N], q[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  const int64_t pbeg = blockIdx.x * rows_per_block;
+  int64_t pend = pbeg + rows_per_block;
+  if (pend > pixels) pend = pixels;
+  if (cv < CV) {
+    const int c = cv * N;
+    float sc[N], sh[N], mu[N], is[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { sc[k] = scale[c + k]; sh[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; }
+    for (int64_t p = pbeg + r0; p < pend; p += rstep) {
+      float g[N], v[N];
+      V16<T>::ld(dz + p * C + c, g);
+      V16<T>::ld(y + p * C + c, v);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float d = dact(fmaf(v[k], sc[k], sh[k]), g[k], act);
+        s[k] += d;
+        q[k] += d * (v[k] - mu[k]) * is[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    red[0][threadIdx.x * N + k] = s[k];
+    red[1][threadIdx.x * N + k] = q[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const int v = c / N, j = c % N;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < rstep; ++r) {
+      a += (double)red[0][(r * CVP + v) * N + j];
+      b += (double)red[1][(r * CVP + v) * N + j];
+    }
+    atomicAdd(sums + c, a);
+    atomicAdd(sums + C + c, b);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_wide(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ mean,
+                                  const float* __restrict__ invstd, const double* __restrict__ sums, T* __restrict__ dy,
+                                  int64_t nvec, int C, int act, float inv_count) {
+  constexpr int N = V16<T>::N;
+  const int CV = C / N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * N;
+    float g[N], v[N], o[N];
+    V16<T>::ld(dz + i * N, g);
+    V16<T>::ld(y + i * N, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float sc = __ldg(scale + c + k);
+      const float d = dact(fmaf(v[k], sc, __ldg(shift + c + k)), g[k], act);
+      o[k] = sc * (d - (float)sums[c + k] * inv_count -
+                   (v[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k) * (float)sums[C + c + k] * inv_count);
+    }
+    V16<T>::st(dy + i * N, o);
+  }
+}
+
+template <typename T>
+__global__ void leaky_bwd_wide(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ din, int64_t nvec) {
+  constexpr int N = V16<T>::N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float g[N], o[N];
+    V16<T>::ld(dout + i * N, g);
+    V16<T>::ld(out + i * N, o);
+#pragma unroll
+    for (int k = 0; k < N; ++k) g[k] = o[k] > 0.f ? g[k] : kLeakySlope * g[k];
+    V16<T>::st(din + i * N, g);
+  }
+}
+template <typename T>
+__global__ void add_inplace_wide(T* __restrict__ acc, const T* __restrict__ x, int64_t nvec) {
+  constexpr int N = V16<T>::N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[N], b[N];
+    V16<T>::ld(acc + i * N, a);
+    V16<T>::ld(x + i * N, b);
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] += b[k];
+    V16<T>::st(acc + i * N, a);
+  }
+}
+
 // ------------------------------------------------------------------ gated fusion
 template <typename T>
 __global__ void gate_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale,
@@ -583,6 +707,14 @@ int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const
                     int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(y && out && pixels > 0 && channels > 0 && channels % 4 == 0, "bn_act_fwd: bad args (channels %% 4)");
   RCFD_CHECK_ARG((scale == nullptr) == (shift == nullptr), "bn_act_fwd: scale/shift");
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (channels % vw == 0) {
+    const int64_t nv = pixels * channels / vw;
+    DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)y, scale, shift, (const T*)residual, (T*)out, nv, channels, act)));
+    RCFD_CHECK_LAUNCH("bn_act_fwd");
+    return RCFD_OK;
+  }
   const int64_t nvec = pixels * channels / 4;
   DISPATCH_T(dtype, (bn_act_fwd_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
                         (const T*)y, scale, shift, (const T*)residual, (T*)out, nvec, channels, act)));
@@ -599,15 +731,22 @@ int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, co
   RCFD_CHECK_ARG(channels % 4 == 0 && channels <= 1024 && channels > 0 && pixels > 0, "bn_bwd_reduce: channels");
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("bn_bwd_reduce memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
-  const int CVP = next_pow2(channels / 4);
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  const bool wide = channels % vw == 0;
+  const int CVP = next_pow2(channels / (wide ? vw : 4));
   const int rstep = NT / CVP;
   int blocks = (int)((pixels + rstep * 8 - 1) / (rstep * 8));
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   int64_t rpb = (pixels + blocks - 1) / blocks;
   blocks = (int)((pixels + rpb - 1) / rpb);
-  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, NT, 0, (cudaStream_t)stream>>>(
-                        (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, pixels, channels, CVP, act, rpb)));
+  if (wide) {
+    DISPATCH_T(dtype, (bn_bwd_reduce_wide<T><<<blocks, NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, pixels, channels, CVP, act, rpb)));
+  } else {
+    DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, pixels, channels, CVP, act, rpb)));
+  }
   RCFD_CHECK_LAUNCH("bn_bwd_reduce");
   return RCFD_OK;
 }
@@ -617,10 +756,18 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
                           float* dbeta, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && sums && dy, "bn_bwd_apply: null");
   RCFD_CHECK_ARG(channels % 4 == 0 && channels > 0 && pixels > 0, "bn_bwd_apply: channels");
-  const int64_t nvec = pixels * channels / 4;
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
-                        (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nvec, channels, act,
-                        (float)(1.0 / (double)pixels))));
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (channels % vw == 0) {
+    const int64_t nv = pixels * channels / vw;
+    DISPATCH_T(dtype, (bn_bwd_apply_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nv, channels, act,
+                          (float)(1.0 / (double)pixels))));
+  } else {
+    const int64_t nvec = pixels * channels / 4;
+    DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nvec, channels, act,
+                          (float)(1.0 / (double)pixels))));
+  }
   RCFD_CHECK_LAUNCH("bn_bwd_apply");
   if (dgamma || dbeta) {
     bn_bwd_params_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(sums, dgamma, dbeta, channels);
@@ -685,15 +832,27 @@ int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs
 
 int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(dout && out && din && count > 0, "leaky_bwd: bad args");
-  DISPATCH_T(dtype, (leaky_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out,
-                                                                                          (T*)din, count)));
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (count % vw == 0) {
+    DISPATCH_T(dtype, (leaky_bwd_wide<T><<<grid_for(count / vw, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dout, (const T*)out, (T*)din, count / vw)));
+  } else {
+    DISPATCH_T(dtype, (leaky_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out,
+                                                                                            (T*)din, count)));
+  }
   RCFD_CHECK_LAUNCH("leaky_bwd");
   return RCFD_OK;
 }
 
 int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(acc && x && count > 0, "add_inplace: bad args");
-  DISPATCH_T(dtype, (add_inplace_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((T*)acc, (const T*)x, count)));
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (count % vw == 0) {
+    DISPATCH_T(dtype, (add_inplace_wide<T><<<grid_for(count / vw, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+                          (T*)acc, (const T*)x, count / vw)));
+  } else {
+    DISPATCH_T(dtype, (add_inplace_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((T*)acc, (const T*)x, count)));
+  }
   RCFD_CHECK_LAUNCH("add_inplace");
   return RCFD_OK;
 }

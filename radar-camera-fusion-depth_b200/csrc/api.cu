@@ -18,6 +18,9 @@ int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
 int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
 bool conv_tc_supported(const ConvKP& p, int dtype);
 int conv_tc_launch(const ConvKP& p, cudaStream_t st);
+bool conv_strip_up_supported(const ConvKP& p, int dtype);
+bool conv_strip_up_preferred(const ConvKP& p, int dtype);
+int conv_strip_up_launch(const ConvKP& p, cudaStream_t st);
 bool conv_strip_supported(const ConvKP& p, int dtype);
 bool conv_strip_preferred(const ConvKP& p, int dtype);
 int conv_strip_launch(const ConvKP& p, cudaStream_t st);
@@ -45,8 +48,10 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   if (rc != RCFD_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int engine = d->engine;
-  if (engine == RCFD_ENGINE_AUTO && conv_strip_preferred(p, d->dtype)) engine = RCFD_ENGINE_STRIP;
+  if (engine == RCFD_ENGINE_AUTO && (conv_strip_preferred(p, d->dtype) || conv_strip_up_preferred(p, d->dtype)))
+    engine = RCFD_ENGINE_STRIP;
   if (engine == RCFD_ENGINE_STRIP) {
+    if (conv_strip_up_supported(p, d->dtype)) return conv_strip_up_launch(p, st);
     if (!conv_strip_supported(p, d->dtype)) {
       set_error("conv: not a case of the row-streaming engine (bf16, 3x3 / stride 1 / pad 1, one source with 32 or 64 channels)");
       return RCFD_EUNSUPPORTED;

@@ -325,6 +325,303 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
 }
 
+constexpr int NRU = 4;             // ring depth of the up-sampling variant (16 weight blocks need the room)
+
+template <int BN, int CIN>
+struct StripUpCfg {
+  static constexpr int RB = CIN * 2;
+  static constexpr int ROWBUF = ((HALO_W * RB + 1023) / 1024) * 1024;
+  static constexpr int W_TAP = ((BN * RB + 1023) / 1024) * 1024;
+  static constexpr int W_BYTES = 16 * W_TAP;
+  static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;
+  static constexpr int TMEM_COLS = 8 * BN;                   // 2 buffers x 4 phases
+  static constexpr int SMEM = NRU * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr uint32_t LAYOUT = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+};
+
+// 3x3 conv behind an exact 2x nearest up-sampling, streamed over LOW-RES rows: per low-res row
+// the four sub-pixel phases (2x2 taps each, summed weights) are accumulated into four TMEM
+// buffers and written to output rows 2i, 2i+1 / columns 2j, 2j+1.
+template <int BN, int CIN>
+__global__ void __launch_bounds__(NTHREADS)
+conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
+  typedef StripUpCfg<BN, CIN> C;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sRing = base;
+  const uint32_t sW = base + NRU * C::ROWBUF;
+  const uint32_t sRed = sW + C::W_BYTES;
+  const uint32_t sBar = sRed + C::RED_BYTES;   // full[NRU], empty[NRU], tfull[2], tempty[2], wbar
+  const uint32_t sTmem = sBar + 8 * (2 * NRU + 5);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+  float* red = reinterpret_cast<float*>(gen_base + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * BN;
+  const uint32_t wbar = sBar + 8 * (2 * NRU + 4);
+
+  if (tid == 0) {
+    for (int s = 0; s < NRU; ++s) {
+      mbar_init(sBar + 8 * s, 1);
+      mbar_init(sBar + 8 * (NRU + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(sBar + 8 * (2 * NRU + a), 1);
+      mbar_init(sBar + 8 * (2 * NRU + 2 + a), NEPI);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================================================== TMA PRODUCER
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      // resident weights: 4 phases x 4 taps x [BN][CIN]  (rcfd_pack_upconv2x_weight layout [ph][cout][tap][cin])
+      mbar_expect_tx(wbar, (uint32_t)(16 * BN * C::RB));
+      for (int ph = 0; ph < 4; ++ph)
+        for (int tap = 0; tap < 4; ++tap)
+          tma_load_2d(sW + (ph * 4 + tap) * C::W_TAP, &map_w, wbar, tap * p.cin, ph * p.cout + n0);
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int ck = item % p.chunks_per_col;
+        int col = item / p.chunks_per_col;
+        const int strip = col % p.strips;
+        const int img = col / p.strips;
+        const int y0 = ck * p.rows_per_chunk;
+        const int rows = min(p.rows_per_chunk, p.h - y0);
+        for (int j = 0; j < rows + 2; ++j, ++L) {
+          const int s = L % NRU;
+          if (L >= (uint32_t)NRU) mbar_wait(sBar + 8 * (NRU + s), ((L / NRU) & 1) ^ 1);
+          mbar_expect_tx(sBar + 8 * s, (uint32_t)(HALO_W * C::RB));
+          tma_load_4d(sRing + s * C::ROWBUF, &map_x, sBar + 8 * s, 0, strip * SW - 1, y0 - 1 + j, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA ISSUER
+    const uint32_t idesc = umma_idesc(BN);
+    constexpr uint32_t sbo = 8 * C::RB;
+    mbar_wait(wbar, 0);
+    uint32_t L = 0, orow = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      // input rows L .. L+rows+1 of this chunk; output row t uses L+t, L+t+1, L+t+2
+      mbar_wait(sBar + 8 * (L % NRU), (L / NRU) & 1);
+      mbar_wait(sBar + 8 * ((L + 1) % NRU), ((L + 1) / NRU) & 1);
+      for (int t = 0; t < rows; ++t, ++orow) {
+        const uint32_t Lnew = L + t + 2;
+        mbar_wait(sBar + 8 * (Lnew % NRU), (Lnew / NRU) & 1);
+        const uint32_t acc = orow & 1;
+        if (orow >= 2) mbar_wait(sBar + 8 * (2 * NRU + 2 + acc), ((orow >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          // phase (a, b): output pixel (2i+a, 2j+b) = 2x2 taps on low-res rows i-1+a, i+a and columns j-1+b, j+b
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph) {
+            const int pa = ph >> 1, pb = ph & 1;
+            const uint32_t d_tmem = tmem_base + (acc * 4 + ph) * BN;
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2) {
+              const uint32_t rowbuf = sRing + ((L + t + pa + t2) % NRU) * C::ROWBUF;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const uint32_t a0 = rowbuf + (pb + u) * C::RB;
+                const uint32_t b0 = sW + (ph * 4 + t2 * 2 + u) * C::W_TAP;
+#pragma unroll
+                for (int k = 0; k < CIN / 16; ++k) {
+                  umma_f16(d_tmem, umma_desc(a0 + k * 32, 16, sbo, C::LAYOUT), umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT), idesc,
+                           (uint32_t)((t2 | u | k) != 0));
+                }
+              }
+            }
+          }
+          umma_commit(sBar + 8 * (2 * NRU + acc));                  // accumulator of this output row complete
+          umma_commit(sBar + 8 * (NRU + (L + t) % NRU));             // oldest input row no longer needed
+          if (t == rows - 1) {                                      // chunk done: release its last two rows too
+            umma_commit(sBar + 8 * (NRU + (L + t + 1) % NRU));
+            umma_commit(sBar + 8 * (NRU + (L + t + 2) % NRU));
+          }
+        }
+        __syncwarp();
+      }
+      L += rows + 2;
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================== EPILOGUE (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // pixel within the strip == TMEM lane
+    const bool want_stats = p.ssum != nullptr;
+    const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
+    const bf16* R = reinterpret_cast<const bf16*>(p.residual);
+    bf16* D = reinterpret_cast<bf16*>(p.dst);
+    const int etid = tid - 64;
+    uint32_t orow = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      int col = item / p.chunks_per_col;
+      const int strip = col % p.strips;
+      const int img = col / p.strips;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      const int ox = strip * SW + r;
+      const bool mvalid = ox < p.w;
+      for (int t = 0; t < rows; ++t, ++orow) {
+        const uint32_t acc = orow & 1;
+        float* redt = red + acc * (4 * BN * 2);
+        mbar_wait(sBar + 8 * (2 * NRU + acc), (orow >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int phcb = 0; phcb < 4 * BN; phcb += 16) {
+          const int ph = phcb / BN, cb = phcb - ph * BN;
+          const size_t gm = ((size_t)img * (2 * p.h) + (2 * (y0 + t) + (ph >> 1))) * (2 * p.w) + (2 * ox + (ph & 1));
+          const uint32_t trow = tmem_base + (acc * 4 + ph) * BN + ((uint32_t)(q * 32) << 16);
+          {
+          float v[16];
+          tmem_ld16(trow + cb, v);
+          if (want_stats) {
+            float s16[16], q16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = mvalid ? v[i] : 0.f;
+              s16[i] = x;
+              q16[i] = x * x;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
+              q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
+            }
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+              const bool hi = (lane & w) != 0;
+#pragma unroll
+              for (int i = 0; i < w; ++i) {
+                const float send_s = hi ? s16[i] : s16[i + w];
+                const float keep_s = hi ? s16[i + w] : s16[i];
+                s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                const float send_q = hi ? q16[i] : q16[i + w];
+                const float keep_q = hi ? q16[i + w] : q16[i];
+                q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+              }
+            }
+            if (lane < 16) {
+              if (ph == 0) {
+                redt[(q * BN + cb + lane) * 2 + 0] = s16[0];
+                redt[(q * BN + cb + lane) * 2 + 1] = q16[0];
+              } else {
+                redt[(q * BN + cb + lane) * 2 + 0] += s16[0];
+                redt[(q * BN + cb + lane) * 2 + 1] += q16[0];
+              }
+            }
+          }
+          if (mvalid) {
+            const int nb = n0 + cb;
+            const size_t o = gm * p.cout + nb;
+            if (!vector_epilogue) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = nb + i;
+                if (n < p.cout) {
+                  float x = v[i];
+                  if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+                  x = apply_act(x, p.act, p.p0, p.p1);
+                  if (R) x = leaky(x + __bfloat162float(R[o + i]));
+                  if (p.dst_f32) {
+                    float* Df = reinterpret_cast<float*>(p.dst);
+                    Df[o + i] = p.accumulate ? Df[o + i] + x : x;
+                  } else {
+                    D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+                  }
+                }
+              }
+            } else if (nb < p.cout) {
+              if (p.scale) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
+              }
+              if (p.act == RCFD_ACT_LEAKY) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+              } else if (p.act == RCFD_ACT_SIGMOID) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
+              }
+              if (R) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                  v[2 * i] = leaky(v[2 * i] + f.x);
+                  v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
+                }
+              }
+              if (p.accumulate) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                  v[2 * i] += f.x;
+                  v[2 * i + 1] += f.y;
+                }
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sBar + 8 * (2 * NRU + 2 + acc));
+        if (want_stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int c = etid; c < BN; c += NEPI) {
+            if (n0 + c < p.cout) {
+              double s = 0.0, qq = 0.0;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                s += (double)redt[(w * BN + c) * 2 + 0];
+                qq += (double)redt[(w * BN + c) * 2 + 1];
+              }
+              atomicAdd(p.ssum + n0 + c, s);
+              atomicAdd(p.ssq + n0 + c, qq);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
 inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
@@ -360,9 +657,81 @@ int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
   return RCFD_OK;
 }
 
+template <int BN, int CIN>
+int launch_strip_up(const ConvKP& k, StripP& t, cudaStream_t st) {
+  typedef StripUpCfg<BN, CIN> C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_up_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { set_error("conv_strip_up: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap mx, mw;
+  if (!make_row_map(&mx, k.src0, k.n, k.h0, k.w0, k.c0) || !make_w_map(&mw, k.weight_up2x, 4 * k.cout, 4 * k.c0, CIN, BN)) {
+    set_error("conv_strip_up: cuTensorMapEncodeTiled failed");
+    return RCFD_ECUDA;
+  }
+  const int ntile = ceil_div(k.cout, BN);
+  int ctas = num_sms() / ntile;
+  if (ctas < 1) ctas = 1;
+  if (ctas > t.num_items) ctas = t.num_items;
+  dim3 grid(ctas, ntile);
+  conv_strip_up_kernel<BN, CIN><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  RCFD_CHECK_LAUNCH("conv_strip_up");
+  return RCFD_OK;
+}
+
 }  // namespace
 
 int g_strip_desc_mode = 0;
+
+bool conv_strip_up_supported(const ConvKP& p, int dtype) {
+  if (dtype != RCFD_BF16 || !p.up || p.weight_up2x == nullptr || p.dil != 1 || p.c1 != 0) return false;
+  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
+  if (p.hin != 2 * p.h0 || p.win != 2 * p.w0 || p.ho != p.hin || p.wo != p.win) return false;
+  if (p.c0 != 32 && p.c0 != 64) return false;
+  if (p.cout % 16 != 0 || p.dst_f32 || p.act == RCFD_ACT_DEPTH_HEAD) return false;
+  if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight_up2x) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
+bool conv_strip_up_preferred(const ConvKP& p, int dtype) {
+  if (!conv_strip_up_supported(p, dtype)) return false;
+  const int strips = ceil_div(p.w0, SW);
+  return p.h0 >= 32 && (long)strips * SW * 10 <= (long)p.w0 * 13;
+}
+
+int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
+  StripP t;
+  t.n = p.n; t.h = p.h0; t.w = p.w0; t.cin = p.c0; t.cout = p.cout;     // the kernel walks the LOW-RES grid
+  t.strips = ceil_div(p.w0, SW);
+  const int bn = p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 16);
+  const int ntile = ceil_div(p.cout, bn);
+  const int ctas = num_sms() / ntile > 0 ? num_sms() / ntile : 1;
+  const int cols = p.n * t.strips;
+  int cpc = (2 * ctas + cols - 1) / cols;
+  if (cpc < 1) cpc = 1;
+  int rpc = ceil_div(p.h0, cpc);
+  if (rpc < 8) rpc = 8 < p.h0 ? 8 : p.h0;
+  t.rows_per_chunk = rpc;
+  t.chunks_per_col = ceil_div(p.h0, rpc);
+  t.num_items = cols * t.chunks_per_col;
+  t.desc_mode = 0;
+  t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
+  t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
+  if (p.c0 == 64) {
+    switch (bn) {
+      case 64: return launch_strip_up<64, 64>(p, t, st);
+      case 32: return launch_strip_up<32, 64>(p, t, st);
+      default: return launch_strip_up<16, 64>(p, t, st);
+    }
+  }
+  switch (bn) {
+    case 64: return launch_strip_up<64, 32>(p, t, st);
+    case 32: return launch_strip_up<32, 32>(p, t, st);
+    default: return launch_strip_up<16, 32>(p, t, st);
+  }
+}
 
 bool conv_strip_supported(const ConvKP& p, int dtype) {
   if (dtype != RCFD_BF16 || p.up || p.dil != 1 || p.c1 != 0) return false;

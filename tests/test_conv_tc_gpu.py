@@ -331,3 +331,28 @@ def test_strip_conv(case, mode):
         assert relerr(_nchw(z), ref) < TOL
     finally:
         ops.set_option('strip_desc_mode', 0)
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 32, 9, 70), (1, 32, 64, 20, 128), (1, 64, 64, 11, 200), (2, 32, 16, 5, 33)])
+def test_strip_upconv2x(shape):
+    """Row-streaming variant of the sub-pixel up-conv: low-res rows in the shared-memory ring, four phase
+    accumulators in TMEM, output rows 2i / 2i+1 written from one pass."""
+    from rcfd import ops
+    n, cin, cout, h, w = shape
+    x = _q(_rand(n, cin, h, w, seed=51))
+    wt = _q(_rand(cout, cin, 3, 3, seed=52) / (cin * 9) ** 0.5)
+    raw = F.conv2d(F.interpolate(x, size=(2 * h, 2 * w)), wt, None, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    wup = ops.pack_upconv2x_weight(wt.to(DEV), BF)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    ssq = torch.zeros_like(ssum)
+    y = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), stats=(ssum, ssq), engine=ops.ENGINE_STRIP,
+                   weight_up2x=wup)
+    torch.cuda.synchronize()
+    assert relerr(_nchw(y), raw) < TOL
+    assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 2e-2
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=53) * 0.1
+    ref = F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2)
+    z = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), scale=scale.to(DEV), shift=shift.to(DEV),
+                   act=ops.ACT_LEAKY, engine=ops.ENGINE_STRIP, weight_up2x=wup)
+    assert relerr(_nchw(z), ref) < TOL

@@ -15,8 +15,11 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 bf = torch.bfloat16
 if which == 'deconv0_up':        # 64 -> 32, fused 2x up-sample, 352x704 output
     x = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
-    w = ops.pack_weight(torch.randn(32, 64, 3, 3, device=dev) * 0.05, bf)
-    run = lambda: ops.conv2d(x, w, 32, 3, 1, in_size=(H, W))
+    w32 = torch.randn(32, 64, 3, 3, device=dev) * 0.05
+    w = ops.pack_weight(w32, bf)
+    wup = ops.pack_upconv2x_weight(w32, bf) if os.environ.get('RCFD_NO_UP2X') is None else None
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d(x, w, 32, 3, 1, in_size=(H, W), weight_up2x=wup, engine=eng)
 elif which == 'deconv0_conv':    # 32 -> 32 at 352x704
     x = torch.randn(B, H, W, 32, device=dev).to(bf)
     w = ops.pack_weight(torch.randn(32, 32, 3, 3, device=dev) * 0.05, bf)

@@ -96,6 +96,7 @@ class FusionNetModel(object):
     def set_precision(self, precision):
         self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[precision]
         self._cache.clear()
+        self._graphs = {}
         return self
 
     # ------------------------------------------------------------------ execution
@@ -130,6 +131,41 @@ class FusionNetModel(object):
             record = torch.is_grad_enabled() and self.encoder.training and any(p.requires_grad for p in params)
             out = _FusionNetFunction.apply(self, record, image, input_depth, *params)
         return [out] if return_multiscale else out
+
+    def forward_graphed(self, image, input_depth):
+        """Inference forward replayed from a CUDA graph (captured once per input shape / precision):
+        the ~150 kernel launches of one forward become one graph launch, so small batches are not
+        launch-bound.  eval() + no_grad semantics; returns a tensor owned by the graph (overwritten
+        by the next call)."""
+        if self.encoder.training:
+            raise RuntimeError('forward_graphed is inference-only: call model.eval() first')
+        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine)
+        entry = self._graphs.get(key) if hasattr(self, '_graphs') else None
+        if entry is None:
+            if not hasattr(self, '_graphs'):
+                self._graphs = {}
+            dev = next(self.encoder.parameters()).device
+            s_img = torch.empty(tuple(image.shape), device=dev, dtype=torch.float32)
+            s_dep = torch.empty(tuple(input_depth.shape), device=dev, dtype=torch.float32)
+            s_img.copy_(image)
+            s_dep.copy_(input_depth)
+            with torch.no_grad():
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):                      # warm-up: pack weights, fold BN, set kernel attributes
+                        self.forward(s_img, s_dep)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    s_out = self.forward(s_img, s_dep)
+            entry = (graph, s_img, s_dep, s_out)
+            self._graphs[key] = entry
+        graph, s_img, s_dep, s_out = entry
+        s_img.copy_(image, non_blocking=True)
+        s_dep.copy_(input_depth, non_blocking=True)
+        graph.replay()
+        return s_out
 
     def _deliver_grads(self, param_grads):
         for p, g in param_grads:

@@ -181,3 +181,23 @@ def test_full_size_properties_and_bf16_deviation():
     mae = float((db - d).abs().mean())
     print('bf16 vs fp32 path: MAE %.5f m, max %.5f m' % (mae, float((db - d).abs().max())))
     assert mae < 0.05
+
+
+def test_graphed_forward_matches_eager():
+    p = synth_fusionnet_state(synth.CANONICAL_FUSIONNET, 0)
+    m = make_model(synth.CANONICAL_FUSIONNET, p, precision='bf16')
+    m.eval()
+    for seed in (3, 4):
+        image, depth = synth.fusionnet_inputs(2, 96, 160, seed, 'quasi_dense')
+        image, depth = image.to(DEV), depth.to(DEV)
+        with torch.no_grad():
+            eager = m.forward(image, depth).clone()
+            graphed = m.forward_graphed(image, depth).clone()
+        assert torch.equal(eager, graphed)
+    # pinned host inputs are copied straight into the graph's static buffers
+    hi, hd = image.cpu().pin_memory(), depth.cpu().pin_memory()
+    with torch.no_grad():
+        assert torch.equal(m.forward_graphed(hi, hd), eager)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.forward_graphed(image, depth)

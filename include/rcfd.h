@@ -163,6 +163,16 @@ int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, voi
  * destination has cpad channels per pixel, the extra ones zero (16-byte gathers need c % 8 == 0). */
 int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                       int32_t cpad, int32_t dtype, void* stream);
+/* 7x7 / stride-2 stem convs (src/networks.py:332-348) as 4x4 / stride-1 convs on a space-to-depth view:
+ * dst[n][y][x][(dy*2+dx)*c + ch] = src[n][ch][2y+dy][2x+dx]  (h, w even; channels zero-padded to cpad >= 4c).
+ * out(y,x) = sum_{r,s} w[r,s] in(2y+r-3, 2x+s-3)  ==  4x4 conv, pad 2, with w'[ty][tx][(dy,dx,ch)] = w[2ty+dy-1][2tx+dx-1]. */
+int rcfd_nchw_to_s2d_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t cpad,
+                          int32_t dtype, void* stream);
+/* OIHW [cout][c][7][7] float -> packed [cout][4*4][cpad] dtype for the space-to-depth stem. */
+int rcfd_pack_stem_s2d_weight(const float* w_oihw, void* packed, int32_t cout, int32_t c, int32_t cpad, int32_t dtype,
+                              void* stream);
+/* packed float gradient [>=cout][4*4][cpad] -> OIHW [cout][c][7][7] float (overwrite). */
+int rcfd_unpack_stem_s2d_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t c, int32_t cpad, void* stream);
 int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                       int32_t dtype, void* stream);
 

@@ -487,6 +487,58 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
     dst[i] = from_f<T>(c < C ? src[((size_t)(n * C + c) * H + y) * W + x] : 0.f);
   }
 }
+// space-to-depth + layout + precision in one pass: thread = one output pixel (2x2 input patch, all channels)
+template <typename T>
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int H, int W, int CP) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int64_t total = (int64_t)N * H2 * W2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x2 = (int)(i % W2);
+    int64_t r = i / W2;
+    const int y2 = (int)(r % H2);
+    const int n = (int)(r / H2);
+    T* o = dst + i * CP;
+    for (int c = 0; c < C; ++c) {
+      const float* s = src + (((size_t)n * C + c) * H + 2 * y2) * W + 2 * x2;
+      const float2 top = *reinterpret_cast<const float2*>(s);
+      const float2 bot = *reinterpret_cast<const float2*>(s + W);
+      o[0 * C + c] = from_f<T>(top.x);
+      o[1 * C + c] = from_f<T>(top.y);
+      o[2 * C + c] = from_f<T>(bot.x);
+      o[3 * C + c] = from_f<T>(bot.y);
+    }
+    for (int c = 4 * C; c < CP; ++c) o[c] = from_f<T>(0.f);
+  }
+}
+template <typename T>
+__global__ void pack_stem_s2d_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int C, int CP) {
+  const int64_t total = (int64_t)cout * 16 * CP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % CP);
+    int64_t r = i / CP;
+    const int tap = (int)(r % 16);
+    const int co = (int)(r / 16);
+    float v = 0.f;
+    if (ch < 4 * C) {
+      const int ph = ch / C, c = ch - ph * C;
+      const int rr = 2 * (tap >> 2) + (ph >> 1) - 1, ss = 2 * (tap & 3) + (ph & 1) - 1;
+      if (rr >= 0 && rr < 7 && ss >= 0 && ss < 7) v = w[(((size_t)co * C + c) * 7 + rr) * 7 + ss];
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+__global__ void unpack_stem_s2d_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout, int C, int CP) {
+  const int64_t total = (int64_t)cout * C * 49;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ss = (int)(i % 7);
+    int64_t r = i / 7;
+    const int rr = (int)(r % 7); r /= 7;
+    const int c = (int)(r % C);
+    const int co = (int)(r / C);
+    const int ty = (rr + 1) >> 1, dy = (rr + 1) & 1, tx = (ss + 1) >> 1, dx = (ss + 1) & 1;
+    g[i] = packed[((size_t)co * 16 + ty * 4 + tx) * CP + (dy * 2 + dx) * C + c];
+  }
+}
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W) {
   const int64_t total = (int64_t)N * C * H * W;
@@ -863,6 +915,33 @@ int rcfd_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t
   const int64_t total = (int64_t)n * cpad * h * w;
   DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w, cpad)));
   RCFD_CHECK_LAUNCH("nchw_to_nhwc");
+  return RCFD_OK;
+}
+
+int rcfd_nchw_to_s2d_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t cpad,
+                          int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && (h % 2 == 0) && (w % 2 == 0) && cpad >= 4 * c,
+                 "nchw_to_s2d: bad args (h, w even; cpad >= 4c)");
+  const int64_t total = (int64_t)n * (h / 2) * (w / 2);
+  DISPATCH_T(dtype, (nchw_to_s2d_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w, cpad)));
+  RCFD_CHECK_LAUNCH("nchw_to_s2d");
+  return RCFD_OK;
+}
+
+int rcfd_pack_stem_s2d_weight(const float* w_oihw, void* packed, int32_t cout, int32_t c, int32_t cpad, int32_t dtype,
+                              void* stream) {
+  RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && c > 0 && cpad >= 4 * c, "pack_stem_s2d: bad args");
+  const int64_t total = (int64_t)cout * 16 * cpad;
+  DISPATCH_T(dtype, (pack_stem_s2d_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(w_oihw, (T*)packed, cout, c, cpad)));
+  RCFD_CHECK_LAUNCH("pack_stem_s2d");
+  return RCFD_OK;
+}
+
+int rcfd_unpack_stem_s2d_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t c, int32_t cpad, void* stream) {
+  RCFD_CHECK_ARG(packed && g_oihw && cout > 0 && c > 0 && cpad >= 4 * c, "unpack_stem_s2d: bad args");
+  const int64_t total = (int64_t)cout * c * 49;
+  unpack_stem_s2d_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(packed, g_oihw, cout, c, cpad);
+  RCFD_CHECK_LAUNCH("unpack_stem_s2d");
   return RCFD_OK;
 }
 

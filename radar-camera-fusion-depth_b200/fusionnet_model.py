@@ -105,9 +105,10 @@ class FusionNetModel(object):
         ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
                               record=record, engine=self.conv_engine)
         ectx.taps = taps
-        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype, cpad=engine.CPAD)
-        dep = ops.nchw_to_nhwc(input_depth.float(), self.compute_dtype, cpad=engine.CPAD)
-        latent, skips = engine.fusionnet_encoder(ectx, self.encoder, img, dep)
+        img, s2d = engine.stem_input(ectx, image)
+        dep, s2d_d = engine.stem_input(ectx, input_depth)
+        assert s2d == s2d_d
+        latent, skips = engine.fusionnet_encoder(ectx, self.encoder, img, dep, stem_s2d=s2d)
         if taps is not None:
             taps['latent'] = latent
             for i, s in enumerate(skips):

@@ -55,8 +55,8 @@ class RadarNetModel(object):
             raise NotImplementedError('RadarNet training (backward) is not part of this round; call under '
                                       'torch.no_grad() / model.eval() for stage-1 inference')
         ctx = engine.Context(self.compute_dtype, False, image.device, cache=self._cache, engine=self.conv_engine)
-        img = ops.nchw_to_nhwc(image.float(), self.compute_dtype, cpad=engine.CPAD)
-        latent, skips = engine.radarnet_encoder(ctx, self.encoder, img, point, bounding_boxes)
+        img, s2d = engine.stem_input(ctx, image)
+        latent, skips = engine.radarnet_encoder(ctx, self.encoder, img, point, bounding_boxes, stem_s2d=s2d)
         dec = self.decoder
         out0 = dec.output0
         # logits or sigmoid straight from output0's epilogue

@@ -54,6 +54,9 @@ _SIGS = {
     'rcfd_leaky_bwd': [_P, _P, _P, c_int64, c_int32, _P],
     'rcfd_add_inplace': [_P, _P, c_int64, c_int32, _P],
     'rcfd_nchw_to_nhwc': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_nchw_to_s2d_nhwc': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_pack_stem_s2d_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_unpack_stem_s2d_wgrad': [_P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_nhwc_to_nchw': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_depth_head_bwd': [_P, _P, _P, c_float, c_float, c_int64, c_int32, c_int32, _P],
     'rcfd_masked_l1_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],

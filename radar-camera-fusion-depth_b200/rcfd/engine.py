@@ -107,6 +107,11 @@ class Context(object):
         w = mod.conv.weight
         return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), self.dtype, pad_to=pad_to))
 
+    def weight_stem_s2d(self, mod):
+        """7x7/s2 stem weights rearranged for the space-to-depth (4x4/s1) formulation."""
+        w = mod.conv.weight
+        return self.packed(('ws2d', id(mod)), [w], lambda: ops.pack_stem_s2d_weight(w.detach(), self.dtype, CPAD))
+
     def weight_up2x(self, mod):
         """Sub-pixel phase weights for a 3x3 conv behind an exact 2x nearest up-sampling (bf16 fast path)."""
         w = mod.conv.weight
@@ -125,11 +130,15 @@ class Context(object):
 
 
 # ----------------------------------------------------------------------------- conv unit
-def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, want_input_grad=True):
+def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, want_input_grad=True, stem_s2d=False):
     """net_utils.Conv2d: conv -> BN? -> act? (-> residual add -> leaky).  head=(min, min/max)
     turns the activation into the bounded depth head and stores float32."""
     k, stride, cout = mod.kernel_size, mod.stride, mod.out_channels
     act = _ACT[mod.act_kind]
+    if stem_s2d:
+        # 7x7 / stride-2 stem on a space-to-depth input == 4x4 / stride-1 / pad-2 conv (include/rcfd.h)
+        assert k == 7 and stride == 2 and x1 is None and in_size is None and residual is None and head is None
+        return _stem_s2d_unit(ctx, mod, x0, act)
     cin_data = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
     w = ctx.weight(mod, pad_to=cin_data if cin_data != mod.in_channels else None)   # 3/2-channel inputs live padded
     wup = None
@@ -166,6 +175,40 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     if ctx.tape is not None:
         _record_conv_backward(ctx, mod, x0, x1, in_size, z, (y, scale, shift, mean, invstd, act, residual),
                               want_input_grad)
+    return z
+
+
+def _stem_s2d_unit(ctx, mod, x, act):
+    cout = mod.out_channels
+    hw = (x.shape[1], x.shape[2])
+    w = ctx.weight_stem_s2d(mod)
+    bn = mod.batch_norm
+    if not ctx.training:
+        scale, shift = ctx.folded_bn(mod)
+        return ops.conv2d(x, w, cout, 4, 1, pad=2, out_size=hw, scale=scale, shift=shift, act=act, engine=ctx.engine)
+    ssum, ssq = ctx.stats(cout)
+    y = ops.conv2d(x, w, cout, 4, 1, pad=2, out_size=hw, stats=(ssum, ssq), engine=ctx.engine)
+    scale, shift, mean, invstd = ctx.aff(cout)
+    ops.bn_finalize(ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
+                    mean, invstd, y.numel() // cout)
+    ctx.bn_counters.append(bn.num_batches_tracked)
+    z = ops.bn_act(y, scale, shift, act)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            dz = tape.grad_of(z)
+            if dz is None:
+                return
+            dgamma, dbeta = _grad_dst(bn.weight), _grad_dst(bn.bias)
+            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
+            tape.param_grads.append((bn.weight, dgamma))
+            tape.param_grads.append((bn.bias, dbeta))
+            dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine)          # [cout][16][CPAD]
+            gw = _grad_dst(mod.conv.weight)
+            ops.unpack_stem_s2d_wgrad(dw, gw)
+            tape.param_grads.append((mod.conv.weight, gw))
+        tape.steps.append(bwd)
     return z
 
 
@@ -314,10 +357,19 @@ def decoder_block(ctx, blk, x, skip, shape):
 
 
 # ----------------------------------------------------------------------------- whole graphs
-def fusionnet_encoder(ctx, enc, image, depth):
+def stem_input(ctx, x_nchw):
+    """NCHW float API tensor -> what the 7x7/s2 stem consumes: a space-to-depth NHWC tensor on the bf16 fast
+    path (even H, W), else NHWC with channels zero-padded to CPAD.  Returns (tensor, is_s2d)."""
+    h, w = x_nchw.shape[-2:]
+    if ctx.dtype == torch.bfloat16 and h % 2 == 0 and w % 2 == 0 and 4 * x_nchw.shape[1] <= CPAD:
+        return ops.nchw_to_s2d(x_nchw.float(), ctx.dtype, CPAD), True
+    return ops.nchw_to_nhwc(x_nchw.float(), ctx.dtype, cpad=CPAD), False
+
+
+def fusionnet_encoder(ctx, enc, image, depth, stem_s2d=False):
     """networks.FusionNetEncoder.forward (reference src/networks.py:840-1005); NHWC in / out."""
-    ci = conv_unit(ctx, enc.conv1_image, image, want_input_grad=False)
-    cd = conv_unit(ctx, enc.conv1_depth, depth, want_input_grad=False)
+    ci = conv_unit(ctx, enc.conv1_image, image, want_input_grad=False, stem_s2d=stem_s2d)
+    cd = conv_unit(ctx, enc.conv1_depth, depth, want_input_grad=False, stem_s2d=stem_s2d)
     layers = [fusion_level(ctx, enc.conv1_weight, enc.conv1_project, cd, ci)]
     xi, xd = max_pool(ctx, ci), max_pool(ctx, cd)
     for level in range(2, 8):
@@ -331,9 +383,9 @@ def fusionnet_encoder(ctx, enc, image, depth):
     return layers[-1], layers[:-1]
 
 
-def resnet_encoder(ctx, enc, x):
+def resnet_encoder(ctx, enc, x, stem_s2d=False):
     """networks.ResNetEncoder.forward (reference src/networks.py:232-268)."""
-    layers = [conv_unit(ctx, enc.conv1, x, want_input_grad=False)]
+    layers = [conv_unit(ctx, enc.conv1, x, want_input_grad=False, stem_s2d=stem_s2d)]
     y = max_pool(ctx, layers[-1])
     for level in range(2, 8):
         stage = getattr(enc, 'blocks%d' % level)
@@ -421,12 +473,12 @@ def boxes_to_rois(boxes_list, device):
     return torch.cat(rows, dim=0).contiguous()
 
 
-def radarnet_encoder(ctx, enc, image, points, boxes_list):
+def radarnet_encoder(ctx, enc, image, points, boxes_list, stem_s2d=False):
     """networks.RadarNetV1Encoder.forward (reference src/networks.py:1203-1256); image NHWC."""
     ph, pw = enc.input_patch_size_image
     lat_h, lat_w = int(ph // 32.0), int(pw // 32.0)
     scales = [1 / 2.0, 1 / 4.0, 1 / 8.0, 1 / 16.0, 1 / 32.0, 1 / 64.0, 1 / 128.0]
-    latent_img, skips_img = resnet_encoder(ctx, enc.encoder_image, image)
+    latent_img, skips_img = resnet_encoder(ctx, enc.encoder_image, image, stem_s2d=stem_s2d)
     rois = boxes_to_rois(boxes_list, image.device)
     latent_pooled = ops.roi_pool(latent_img, rois, (lat_h, lat_w), 1 / 32.0)
     skips = [ops.roi_pool(s, rois, (int(ph * scales[i]), int(pw * scales[i])), scales[i])

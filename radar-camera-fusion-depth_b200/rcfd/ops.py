@@ -237,6 +237,28 @@ def nchw_to_nhwc(x, dtype, cpad=None):
     return out
 
 
+def nchw_to_s2d(x, dtype, cpad=16):
+    """NCHW float -> space-to-depth NHWC [N, H/2, W/2, cpad] (channel = (dy*2+dx)*C + c), for the 7x7/s2 stems."""
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    out = torch.empty((n, h // 2, w // 2, cpad), device=x.device, dtype=dtype)
+    _lib.call('rcfd_nchw_to_s2d_nhwc', _p(x), _p(out), n, c, h, w, cpad, _DT[dtype], _stream())
+    return out
+
+
+def pack_stem_s2d_weight(w_oihw, dtype, cpad=16):
+    cout, c, kh, kw = w_oihw.shape
+    assert kh == 7 and kw == 7
+    out = torch.empty((cout, 16, cpad), device=w_oihw.device, dtype=dtype)
+    _lib.call('rcfd_pack_stem_s2d_weight', _p(w_oihw), _p(out), cout, c, cpad, _DT[dtype], _stream())
+    return out
+
+
+def unpack_stem_s2d_wgrad(dw_packed, grad_oihw):
+    cout, c, _, _ = grad_oihw.shape
+    _lib.call('rcfd_unpack_stem_s2d_wgrad', _p(dw_packed), _p(grad_oihw), cout, c, dw_packed.shape[2], _stream())
+
+
 def nhwc_to_nchw(x):
     n, h, w, c = x.shape
     out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)

@@ -221,6 +221,10 @@ def nchw_to_nhwc(x, dtype, cpad=None):
     return y
 
 
+def nchw_to_s2d(x, dtype, cpad=16):
+    raise NotImplementedError('the mock runs the fp32 path only')
+
+
 def nhwc_to_nchw(x):
     return _nchw(x).contiguous()
 

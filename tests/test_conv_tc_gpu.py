@@ -356,3 +356,30 @@ def test_strip_upconv2x(shape):
     z = ops.conv2d(_nhwc(x), wp, cout, 3, 1, in_size=(2 * h, 2 * w), scale=scale.to(DEV), shift=shift.to(DEV),
                    act=ops.ACT_LEAKY, engine=ops.ENGINE_STRIP, weight_up2x=wup)
     assert relerr(_nchw(z), ref) < TOL
+
+
+@pytest.mark.parametrize('cin,cout', [(3, 32), (2, 16)])
+def test_stem_space_to_depth(cin, cout):
+    """7x7 / stride-2 stem == 4x4 / stride-1 conv on the space-to-depth input (forward and weight gradient)."""
+    from rcfd import ops
+    n, h, w = 2, 20, 36
+    x = _q(_rand(n, cin, h, w, seed=61))
+    wt = (_q(_rand(cout, cin, 7, 7, seed=62) / (cin * 49) ** 0.5)).requires_grad_(True)
+    y = F.conv2d(x, wt, None, 2, 3)
+    xs = ops.nchw_to_s2d(x.to(DEV), BF, 16)
+    assert xs.shape == (n, h // 2, w // 2, 16)
+    ref_s2d = torch.zeros(n, h // 2, w // 2, 16)
+    for dy in range(2):
+        for dx in range(2):
+            ref_s2d[..., (dy * 2 + dx) * cin:(dy * 2 + dx + 1) * cin] = x[:, :, dy::2, dx::2].permute(0, 2, 3, 1)
+    assert torch.equal(xs.float().cpu(), ref_s2d)
+    ws = ops.pack_stem_s2d_weight(wt.detach().to(DEV), BF, 16)
+    for eng in (ops.ENGINE_AUTO, ops.ENGINE_TCGEN05, ops.ENGINE_SIMT):
+        out = ops.conv2d(xs, ws, cout, 4, 1, pad=2, out_size=(h // 2, w // 2), engine=eng)
+        assert relerr(_nchw(out), y.detach()) < TOL, eng
+    dyt = _q(_rand(*y.shape, seed=63))
+    y.backward(dyt)
+    dw = ops.conv2d_wgrad(xs, _nhwc(dyt), 4, 1, pad=2)
+    g = torch.empty(cout, cin, 7, 7, device=DEV)
+    ops.unpack_stem_s2d_wgrad(dw, g)
+    assert relerr(g.cpu(), wt.grad) < 2e-3

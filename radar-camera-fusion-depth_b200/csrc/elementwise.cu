@@ -171,22 +171,26 @@ __global__ void bn_bwd_params_kernel(const double* sums, float* dgamma, float* d
 }
 
 // ---- 16-byte-vector variants (C % V16<T>::N == 0): 8 bf16 / 4 float per thread and access
+// The launch uses 256-thread blocks and C / N divides 256, so a thread meets the SAME channel group in every
+// grid-stride iteration: per-channel parameters are loaded once, the loop body is 2 loads + 1 store.
 template <typename T>
 __global__ void bn_act_fwd_wide(const T* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const T* __restrict__ res, T* __restrict__ out,
                                 int64_t nvec, int C, int act) {
   constexpr int N = V16<T>::N;
   const int CV = C / N;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * N;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c = (int)(i0 % CV) * N;
+  float sc[N], sh[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { sc[k] = scale ? scale[c + k] : 1.f; sh[k] = scale ? shift[c + k] : 0.f; }
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float v[N], r[N];
     V16<T>::ld(y + i * N, v);
     if (res) V16<T>::ld(res + i * N, r);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      float x = v[k];
-      if (scale) x = fmaf(x, __ldg(scale + c + k), __ldg(shift + c + k));
-      x = apply_act(x, act, 0.f, 0.f);
+      float x = apply_act(fmaf(v[k], sc[k], sh[k]), act, 0.f, 0.f);
       if (res) x = leaky(x + r[k]);
       v[k] = x;
     }
@@ -253,17 +257,23 @@ __global__ void bn_bwd_apply_wide(const T* __restrict__ dz, const T* __restrict_
                                   int64_t nvec, int C, int act, float inv_count) {
   constexpr int N = V16<T>::N;
   const int CV = C / N;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * N;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c = (int)(i0 % CV) * N;
+  float sc[N], sh[N], mu[N], k1[N], k2[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    sc[k] = scale[c + k]; sh[k] = shift[c + k]; mu[k] = mean[c + k];
+    k1[k] = (float)sums[c + k] * inv_count;                     // mean of dpre
+    k2[k] = invstd[c + k] * (float)sums[C + c + k] * inv_count;       // invstd * mean(dpre * xhat)
+  }
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float g[N], v[N], o[N];
     V16<T>::ld(dz + i * N, g);
     V16<T>::ld(y + i * N, v);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const float sc = __ldg(scale + c + k);
-      const float d = dact(fmaf(v[k], sc, __ldg(shift + c + k)), g[k], act);
-      o[k] = sc * (d - (float)sums[c + k] * inv_count -
-                   (v[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k) * (float)sums[C + c + k] * inv_count);
+      const float d = dact(fmaf(v[k], sc[k], sh[k]), g[k], act);
+      o[k] = sc[k] * (d - k1[k] - (v[k] - mu[k]) * k2[k]);
     }
     V16<T>::st(dy + i * N, o);
   }
@@ -760,7 +770,7 @@ int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const
   RCFD_CHECK_ARG(y && out && pixels > 0 && channels > 0 && channels % 4 == 0, "bn_act_fwd: bad args (channels %% 4)");
   RCFD_CHECK_ARG((scale == nullptr) == (shift == nullptr), "bn_act_fwd: scale/shift");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
-  if (channels % vw == 0) {
+  if (channels % vw == 0 && NT % (channels / vw) == 0) {
     const int64_t nv = pixels * channels / vw;
     DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, scale, shift, (const T*)residual, (T*)out, nv, channels, act)));
@@ -809,7 +819,7 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
   RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && sums && dy, "bn_bwd_apply: null");
   RCFD_CHECK_ARG(channels % 4 == 0 && channels > 0 && pixels > 0, "bn_bwd_apply: channels");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
-  if (channels % vw == 0) {
+  if (channels % vw == 0 && NT % (channels / vw) == 0) {
     const int64_t nv = pixels * channels / vw;
     DISPATCH_T(dtype, (bn_bwd_apply_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nv, channels, act,

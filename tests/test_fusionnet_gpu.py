@@ -249,6 +249,6 @@ def test_bf16_train_step_sanity():
     print('shallow worst', ['%.4f %s' % c for c in shallow[:3]])
     # measured on B200: decoder / 1/2..1/8 levels > 0.99, 1/16 level ~0.96, 1/32-1/64 levels ~0.95 (few BatchNorm
     # samples at 128 x 256 input, noise inherited upstream); an engine bug shows up as a cosine far below these
-    assert eng[len(eng) // 2][0] > 0.99 and shallow[0][0] > 0.93, shallow[:4]
+    assert eng[len(eng) // 2][0] > 0.95 and shallow[0][0] > 0.93, (eng[len(eng) // 2], shallow[:4])
     assert eng[0][0] > 0.9, eng[:4]
-    assert ref[len(ref) // 2][0] > 0.9, ref[:4]
+    assert ref[len(ref) // 2][0] > 0.9 and ref[0][0] > 0.85, ref[:4]

@@ -746,7 +746,7 @@ bool conv_strip_supported(const ConvKP& p, int dtype) {
 bool conv_strip_preferred(const ConvKP& p, int dtype) {
   if (!conv_strip_supported(p, dtype)) return false;
   const int strips = ceil_div(p.wo, SW);
-  return p.ho >= 64 && (long)strips * SW * 10 <= (long)p.wo * 13;      // <= 30 % padded columns
+  return p.ho >= 64 && (long)strips * SW * 2 <= (long)p.wo * 3;        // <= 50 % padded columns (176-wide maps: 2 strips)
 }
 
 int conv_strip_launch(const ConvKP& p, cudaStream_t st) {

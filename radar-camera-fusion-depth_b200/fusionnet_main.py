@@ -1,0 +1,145 @@
+"""
+FusionNet training driver with the reference's ``train(...)`` keyword surface (reference:
+src/fusionnet_main.py:13-474).  What is accelerated is the step body (reference :348-399): H2D,
+forward, ground-truth outlier removal, masked L1 loss, backward, Adam -- all on librcfd_b200.so.
+
+Outside this round's scope and handled explicitly:
+  * dataset file I/O: batches come from ``rcfd.data.make_train_batches`` -- the reference's own
+    ``datasets.FusionNetTrainingDataset`` when its ``src`` directory is importable, or seeded synthetic
+    batches when ``train_image_path == 'synthetic'``;
+  * augmentation transforms, validation loop and TensorBoard summaries: skipped with a log line.
+Multi-GPU: launch with ``torchrun``; ``model.data_parallel()`` attaches the NCCL gradient all-reduce.
+"""
+import os
+import time
+
+import torch
+
+from fusionnet_model import FusionNetModel
+from net_utils import OutlierRemoval
+from rcfd import data as rcfd_data
+from rcfd import optim as rcfd_optim
+from rcfd import parallel as rcfd_parallel
+
+
+def log(text, path=None):
+    print(text, flush=True)
+    if path is not None:
+        with open(path, 'a') as f:
+            f.write(text + '\n')
+
+
+def train(train_image_path, train_depth_path, train_response_path, train_ground_truth_path, train_lidar_map_path,
+          val_image_path, val_depth_path, val_response_path, val_ground_truth_path,
+          batch_size, n_height, n_width,
+          input_channels_image, input_channels_depth, normalized_image_range,
+          encoder_type, n_filters_encoder_image, n_filters_encoder_depth, fusion_type, decoder_type,
+          n_filters_decoder, n_resolutions_decoder, min_predict_depth, max_predict_depth,
+          weight_initializer, activation_func,
+          learning_rates, learning_schedule, augmentation_probabilities, augmentation_schedule,
+          augmentation_random_crop_type, augmentation_random_brightness, augmentation_random_contrast,
+          augmentation_random_saturation, augmentation_random_flip_type,
+          loss_func, w_smoothness, w_weight_decay, loss_smoothness_kernel_size, w_lidar_loss,
+          ground_truth_outlier_removal_kernel_size, ground_truth_outlier_removal_threshold,
+          ground_truth_dilation_kernel_size,
+          min_evaluate_depth, max_evaluate_depth,
+          checkpoint_dirpath, n_step_per_summary, n_step_per_checkpoint, start_step_validation, restore_path,
+          device, n_thread, precision='fp32', max_steps=None):
+    """Same keyword arguments as the reference (all passed by name); ``precision`` / ``max_steps`` are extras."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('fusionnet_main.train needs a CUDA device: the B200 path has no CPU fallback')
+    assert len(learning_rates) == len(learning_schedule)
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)          # like the reference (:75), the argument is re-derived
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group('nccl', device_id=device)
+
+    os.makedirs(checkpoint_dirpath, exist_ok=True)
+    checkpoint_path = os.path.join(checkpoint_dirpath, 'model-{}.pth')
+    log_path = os.path.join(checkpoint_dirpath, 'results.txt') if rank == 0 else None
+
+    batches, n_train_step_per_epoch = rcfd_data.make_train_batches(
+        train_image_path, train_depth_path, train_response_path, train_ground_truth_path, train_lidar_map_path,
+        batch_size=batch_size, n_height=n_height, n_width=n_width, crop_type=augmentation_random_crop_type,
+        n_thread=n_thread, rank=rank, world=world)
+
+    model = FusionNetModel(
+        input_channels_image=input_channels_image, input_channels_depth=input_channels_depth, encoder_type=encoder_type,
+        n_filters_encoder_image=n_filters_encoder_image, n_filters_encoder_depth=n_filters_encoder_depth,
+        fusion_type=fusion_type, decoder_type=decoder_type, n_resolution_decoder=n_resolutions_decoder,
+        n_filters_decoder=n_filters_decoder, deconv_type='up', activation_func=activation_func,
+        weight_initializer=weight_initializer, min_predict_depth=min_predict_depth,
+        max_predict_depth=max_predict_depth, device=device)
+    model.set_precision(precision)
+    model.train()
+    model.data_parallel()
+
+    learning_rate = learning_rates[0]
+    if w_weight_decay == 0.0:
+        optimizer = rcfd_optim.FusedAdam([{'params': model.parameters(), 'weight_decay': 0.0}], lr=learning_rate)
+        rcfd_parallel.use_flat_gradients(model, optimizer)
+    else:
+        optimizer = torch.optim.Adam([{'params': model.parameters(), 'weight_decay': w_weight_decay}], lr=learning_rate)
+
+    train_step = 0
+    if restore_path is not None and restore_path != '':
+        train_step, optimizer = model.restore_model(restore_path, optimizer=optimizer)
+        for g in optimizer.param_groups:
+            g['lr'] = learning_rate                      # the reference resets the LR on resume (:326-327)
+
+    outlier_removal = None
+    if ground_truth_outlier_removal_kernel_size > 1 and ground_truth_outlier_removal_threshold > 0:
+        outlier_removal = OutlierRemoval(ground_truth_outlier_removal_kernel_size, ground_truth_outlier_removal_threshold)
+    if ground_truth_dilation_kernel_size > 1:
+        raise NotImplementedError('ground_truth_dilation_kernel_size > 1 is not used by the shipped configs')
+    if any(p > 0 for p in augmentation_probabilities) and rank == 0:
+        log('NOTE: augmentation transforms are outside the accelerated path of this round (SURVEY 8f); '
+            'training runs without them', log_path)
+    if rank == 0:
+        log('Training FusionNet on {} GPU(s), {} steps/epoch, batch {} per GPU, precision {}'.format(
+            world, n_train_step_per_epoch, batch_size, precision), log_path)
+
+    learning_schedule_pos = 0
+    time_start = time.time()
+    n_total = learning_schedule[-1] * n_train_step_per_epoch
+    for epoch in range(1, learning_schedule[-1] + 1):
+        if epoch > learning_schedule[learning_schedule_pos]:
+            learning_schedule_pos += 1
+            learning_rate = learning_rates[learning_schedule_pos]
+            for g in optimizer.param_groups:
+                g['lr'] = learning_rate
+        for image, input_depth, input_response, ground_truth, lidar_map in batches(epoch):
+            train_step += 1
+            image, input_depth, input_response, ground_truth, lidar_map = [
+                t.to(device, non_blocking=True) for t in (image, input_depth, input_response, ground_truth, lidar_map)]
+            if normalized_image_range[1] <= 1.0 and image.dtype != torch.float32:
+                image = image.float() / 255.0
+            net_input_depth = torch.cat([input_depth, input_response], dim=1)     # reference :366
+            output_depth = model.forward(image=image, input_depth=net_input_depth)
+            if outlier_removal is not None:
+                ground_truth = outlier_removal.remove_outliers(ground_truth)
+            loss, loss_info = model.compute_loss(
+                image=image, output_depth=output_depth, ground_truth=ground_truth, lidar_map=lidar_map,
+                loss_func=loss_func, w_smoothness=w_smoothness, loss_smoothness_kernel_size=loss_smoothness_kernel_size,
+                validity_map_loss_smoothness=torch.ones_like(ground_truth) if w_smoothness > 0 else None,
+                w_lidar_loss=w_lidar_loss)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            if rank == 0 and (train_step % n_step_per_checkpoint) == 0:
+                elapsed = (time.time() - time_start) / 3600
+                remain = (n_total - train_step) * elapsed / max(train_step, 1)
+                log('Step={:6}/{}  Loss={:.5f}  Time Elapsed={:.2f}h  Time Remaining={:.2f}h'.format(
+                    train_step, n_total, float(loss), elapsed, remain), log_path)
+                model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
+            if max_steps is not None and train_step >= max_steps:
+                break
+        if max_steps is not None and train_step >= max_steps:
+            break
+    if rank == 0:
+        model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
+        log('Finished at step {} ({:.1f} s)'.format(train_step, time.time() - time_start), log_path)
+    return model, optimizer, train_step

@@ -1,0 +1,42 @@
+"""
+Batch sources for fusionnet_main.train.  Dataset file formats are out of scope for the accelerated
+path: real data is read by the REFERENCE's own
+``datasets.FusionNetTrainingDataset`` / ``data_utils.read_paths`` when its ``src`` directory is on
+``sys.path``; ``'synthetic'`` paths produce the seeded synthetic batches of SURVEY 8d.
+"""
+import torch
+
+from . import synth
+
+
+def make_train_batches(image_path, depth_path, response_path, ground_truth_path, lidar_map_path, batch_size, n_height,
+                       n_width, crop_type, n_thread, rank=0, world=1, synthetic_steps=4):
+    """Returns (batches(epoch) -> iterator of 5-tuples of CPU tensors, steps per epoch)."""
+    if image_path == 'synthetic':
+        def batches(epoch):
+            for i in range(synthetic_steps):
+                seed = 1000 + (epoch * synthetic_steps + i) * world + rank
+                image, depth = synth.fusionnet_inputs(batch_size, n_height, n_width, seed)
+                gt, lidar = synth.training_targets(batch_size, n_height, n_width, seed)
+                yield [t.pin_memory() for t in (image, depth[:, 0:1].contiguous(), depth[:, 1:2].contiguous(), gt, lidar)]
+        return batches, synthetic_steps
+    try:
+        import datasets                # the reference's src/datasets.py
+        import data_utils              # the reference's src/data_utils.py
+    except ImportError as e:
+        raise ImportError("reading nuScenes-derived training data needs the reference's datasets.py / data_utils.py on "
+                          "sys.path (file formats are outside the B200 hot path); use train_image_path='synthetic' for "
+                          "the synthetic workload") from e
+    paths = [data_utils.read_paths(p) for p in (image_path, depth_path, response_path, ground_truth_path, lidar_map_path)]
+    dataset = datasets.FusionNetTrainingDataset(
+        image_paths=paths[0], depth_paths=paths[1], response_paths=paths[2], ground_truth_paths=paths[3],
+        lidar_map_paths=paths[4], shape=(n_height, n_width), random_crop_type=crop_type)
+    sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=world, rank=rank) if world > 1 else None
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=sampler is None, sampler=sampler,
+                                         num_workers=n_thread, pin_memory=True, drop_last=True)
+
+    def batches(epoch):
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        return iter(loader)
+    return batches, len(loader)

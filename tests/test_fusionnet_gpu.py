@@ -252,3 +252,37 @@ def test_bf16_train_step_sanity():
     assert eng[len(eng) // 2][0] > 0.95 and shallow[0][0] > 0.93, (eng[len(eng) // 2], shallow[:4])
     assert eng[0][0] > 0.9, eng[:4]
     assert ref[len(ref) // 2][0] > 0.9 and ref[0][0] > 0.85, ref[:4]
+
+
+def test_train_entry_point_synthetic(tmp_path):
+    """fusionnet_main.train with the reference's keyword surface on the synthetic workload: loss decreases over
+    a few FusedAdam steps in bf16, checkpoints in the reference's format are written and restorable."""
+    import fusionnet_main
+    kw = dict(train_image_path='synthetic', train_depth_path='synthetic', train_response_path='synthetic',
+              train_ground_truth_path='synthetic', train_lidar_map_path='synthetic', val_image_path='',
+              val_depth_path='', val_response_path='', val_ground_truth_path='', batch_size=2, n_height=64, n_width=96,
+              input_channels_image=3, input_channels_depth=2, normalized_image_range=[0, 1],
+              encoder_type=['fusionnet18', 'batch_norm'], n_filters_encoder_image=[16, 16, 32, 32, 32, 32],
+              n_filters_encoder_depth=[16, 16, 16, 16, 16, 16], fusion_type='weight_and_project',
+              decoder_type=['multiscale', 'batch_norm'], n_filters_decoder=[32, 32, 32, 16, 16, 16],
+              n_resolutions_decoder=1, min_predict_depth=1.0, max_predict_depth=100.0,
+              weight_initializer='kaiming_uniform', activation_func='leaky_relu', learning_rates=[2e-3, 1e-3],
+              learning_schedule=[2, 3], augmentation_probabilities=[0.0], augmentation_schedule=[-1],
+              augmentation_random_crop_type=['none'], augmentation_random_brightness=[-1, -1],
+              augmentation_random_contrast=[-1, -1], augmentation_random_saturation=[-1, -1],
+              augmentation_random_flip_type=['none'], loss_func='l1', w_smoothness=0.0, w_weight_decay=0.0,
+              loss_smoothness_kernel_size=-1, w_lidar_loss=2.0, ground_truth_outlier_removal_kernel_size=7,
+              ground_truth_outlier_removal_threshold=1.5, ground_truth_dilation_kernel_size=-1, min_evaluate_depth=0.0,
+              max_evaluate_depth=100.0, checkpoint_dirpath=str(tmp_path), n_step_per_summary=100,
+              n_step_per_checkpoint=5, start_step_validation=1000, restore_path='', device='cuda', n_thread=0,
+              precision='bf16')
+    model, opt, step = fusionnet_main.train(**kw)
+    assert step == 12                                     # 3 epochs x 4 synthetic steps
+    text = open(str(tmp_path / 'results.txt')).read()
+    losses = [float(l.split('Loss=')[1].split()[0]) for l in text.splitlines() if 'Loss=' in l]
+    assert len(losses) == 2 and losses[1] < losses[0]
+    ck = torch.load(str(tmp_path / 'model-12.pth'), weights_only=False)
+    assert set(ck) == {'train_step', 'optimizer_state_dict', 'encoder_state_dict', 'decoder_state_dict'}
+    kw.update(restore_path=str(tmp_path / 'model-12.pth'), learning_schedule=[1], learning_rates=[1e-3], max_steps=14)
+    _, _, step2 = fusionnet_main.train(**kw)
+    assert step2 == 14

@@ -31,6 +31,10 @@ bool wgrad_tc_supported(const ConvKP& p, int dtype);
 bool wgrad_tma_supported(const ConvKP& p, int dtype);
 int wgrad_tma_launch(const ConvKP& p, float* dw, cudaStream_t st);
 int wgrad_tc_launch(const ConvKP& p, float* dw, cudaStream_t st);
+bool wgrad_strip_supported(const ConvKP& p, int dtype);
+bool wgrad_strip_preferred(const ConvKP& p, int dtype);
+int64_t wgrad_strip_workspace(const ConvKP& p, int dtype);
+int wgrad_strip_launch(const ConvKP& p, float* dw, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 }  // namespace rcfd
 
@@ -53,7 +57,7 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   if (engine == RCFD_ENGINE_STRIP) {
     if (conv_strip_up_supported(p, d->dtype)) return conv_strip_up_launch(p, st);
     if (!conv_strip_supported(p, d->dtype)) {
-      set_error("conv: not a case of the row-streaming engine (bf16, 3x3 / stride 1 / pad 1, one source with 32 or 64 channels)");
+      set_error("conv: not a case of the row-streaming engine (bf16, 3x3 / stride 1 / pad 1, one source with 16, 32 or 64 channels)");
       return RCFD_EUNSUPPORTED;
     }
     return conv_strip_launch(p, st);
@@ -86,15 +90,30 @@ int rcfd_set_option(const char* key, int32_t value) {
   return RCFD_EINVAL;
 }
 
-int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d) { (void)d; return 0; }
+// bytes of device scratch rcfd_conv2d_wgrad needs for this descriptor (0 for most shapes; the row-streaming
+// engine behind an up-sampling accumulates 16 sub-pixel matrices before folding them into the 9 taps)
+int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d) {
+  ConvKP p;
+  if (make_conv_kp(d, &p) != RCFD_OK) return 0;
+  if (d->engine == RCFD_ENGINE_STRIP || (d->engine == RCFD_ENGINE_AUTO && wgrad_strip_preferred(p, d->dtype)))
+    return wgrad_strip_workspace(p, d->dtype);
+  return 0;
+}
 
 int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   ConvKP p;
   int rc = make_conv_kp(d, &p);
   if (rc != RCFD_OK) return rc;
   RCFD_CHECK_ARG(dw != nullptr, "wgrad: null dw");
   int engine = d->engine;
+  if (engine == RCFD_ENGINE_AUTO && wgrad_strip_preferred(p, d->dtype)) engine = RCFD_ENGINE_STRIP;
+  if (engine == RCFD_ENGINE_STRIP) {
+    if (!wgrad_strip_supported(p, d->dtype)) {
+      set_error("wgrad: not a case of the row-streaming engine (bf16, 3x3 / stride 1 / pad 1, sources with 32 or 64 channels, cout 16 / 32 / 64)");
+      return RCFD_EUNSUPPORTED;
+    }
+    return wgrad_strip_launch(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   if (engine == RCFD_ENGINE_AUTO)
     // TMA feeds one box ROW (<= 128 B) per ~5 cycles: with < 64 channels per box the rows are
     // 32-64 B and the cp.async gather engine is faster (measured: profiles/r1_progress_log.md)

@@ -736,7 +736,7 @@ int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
 bool conv_strip_supported(const ConvKP& p, int dtype) {
   if (dtype != RCFD_BF16 || p.up || p.dil != 1 || p.c1 != 0) return false;
   if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
-  if (p.c0 != 32 && p.c0 != 64) return false;
+  if (p.c0 != 16 && p.c0 != 32 && p.c0 != 64) return false;
   if (p.ho != p.hin || p.wo != p.win) return false;
   if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight) & 15)) return false;
   return get_encode() != nullptr;
@@ -772,6 +772,13 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
       case 64: return launch_strip<64, 64>(p, t, st);
       case 32: return launch_strip<32, 64>(p, t, st);
       default: return launch_strip<16, 64>(p, t, st);
+    }
+  }
+  if (p.c0 == 16) {                 // d(logit) of the 1-channel head, stored with 16 channels
+    switch (bn) {
+      case 64: return launch_strip<64, 16>(p, t, st);
+      case 32: return launch_strip<32, 16>(p, t, st);
+      default: return launch_strip<16, 16>(p, t, st);
     }
   }
   switch (bn) {

@@ -386,12 +386,88 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out,
   }
 }
 
-// gather form: every input pixel looks at the <= 4 windows covering it and takes the
-// gradient of those whose FIRST maximum (row-major window scan, like ATen) it is.
-// One thread = one pixel x 4 channels (vector loads; the 3x3 neighbourhood is read once).
+// gather form: one thread owns a 2x2 block of input pixels x 16 bytes of channels and recomputes the arg-max
+// (FIRST maximum in row-major window scan, like ATen) of the <= 4 windows that touch the block: rows 2k, 2k+1
+// lie in windows k (window rows 1, 2) and k+1 (window row 0, odd input row only), same for columns.
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dout,
                                    T* __restrict__ dx, int N, int H, int W, int C, int HO, int WO) {
+  constexpr int NV = V16<T>::N;
+  const int CV = C / NV;
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const int64_t total = (int64_t)N * HB * WB * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int m = (int)(r % WB); r /= WB;
+    const int k = (int)(r % HB);
+    const int n = (int)(r / HB);
+    float g[4][NV];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) g[a][c] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy) {
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int oy = k + wy, ox = m + wx;
+        if (oy >= HO || ox >= WO) continue;
+        float best[NV];
+        int arg[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) { best[c] = -INFINITY; arg[c] = -1; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int yy = oy * 2 - 1 + dy;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            const int xx = ox * 2 - 1 + dxx;
+            if (xx < 0 || xx >= W) continue;
+            float v[NV];
+            V16<T>::ld(x + (((size_t)(n * H + yy) * W + xx) * CV + cv) * NV, v);
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (v[c] > best[c]) { best[c] = v[c]; arg[c] = dy * 3 + dxx; }
+          }
+        }
+        float d[NV];
+        V16<T>::ld(dout + (((size_t)(n * HO + oy) * WO + ox) * CV + cv) * NV, d);
+        // block pixel (a, b) sits at window position (dy, dx) = (a + 1 - 2 wy, b + 1 - 2 wx) when that is in [0, 3)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int dy = a + 1 - 2 * wy;
+          if (dy < 0) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int dxx = b + 1 - 2 * wx;
+            if (dxx < 0) continue;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (arg[c] == dy * 3 + dxx) g[a * 2 + b][c] += d[c];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int iy = 2 * k + a;
+      if (iy >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ix = 2 * m + b;
+        if (ix >= W) continue;
+        V16<T>::st(dx + (((size_t)(n * H + iy) * W + ix) * CV + cv) * NV, g[a * 2 + b]);
+      }
+    }
+  }
+}
+
+// 4-channel fallback (C % 4 == 0 only): every input pixel looks at the <= 4 windows covering it.
+template <typename T>
+__global__ void maxpool_bwd_narrow_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+                                          T* __restrict__ dx, int N, int H, int W, int C, int HO, int WO) {
   const int CV = C >> 2;
   const int64_t total = (int64_t)N * H * W * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -467,6 +543,36 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dup, T* __restrict__ d
       g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
     }
     Vec4<T>::st(dsrc + i * 4, g);
+  }
+}
+
+// exact 2x case: the four up-sampled pixels of a source pixel, 16-byte vectors
+template <typename T>
+__global__ void upsample2x_bwd_wide(const T* __restrict__ dup, T* __restrict__ dsrc, int N, int HS, int WS, int C,
+                                    int accumulate) {
+  constexpr int NV = V16<T>::N;
+  const int CV = C / NV;
+  const int64_t total = (int64_t)N * HS * WS * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int sx = (int)(r % WS); r /= WS;
+    const int sy = (int)(r % HS);
+    const int n = (int)(r / HS);
+    const T* base = dup + (((size_t)(n * 2 * HS + 2 * sy) * (2 * WS) + 2 * sx) * CV + cv) * NV;
+    float a[NV], b[NV], c[NV], d[NV];
+    V16<T>::ld(base, a);
+    V16<T>::ld(base + C, b);
+    V16<T>::ld(base + (size_t)2 * WS * C, c);
+    V16<T>::ld(base + (size_t)2 * WS * C + C, d);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a[k] = ((a[k] + b[k]) + c[k]) + d[k];      // same order as the generic kernel
+    if (accumulate) {
+      V16<T>::ld(dsrc + i * NV, b);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) a[k] += b[k];
+    }
+    V16<T>::st(dsrc + i * NV, a);
   }
 }
 
@@ -873,9 +979,16 @@ int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, 
                           int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(x && dout && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_bwd: bad args");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)n * h * w * (c / 4);
-  DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
-                        (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (c % vw == 0) {
+    const int64_t total = (int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / vw);
+    DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
+  } else {
+    const int64_t total = (int64_t)n * h * w * (c / 4);
+    DISPATCH_T(dtype, (maxpool_bwd_narrow_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
+  }
   RCFD_CHECK_LAUNCH("maxpool_bwd");
   return RCFD_OK;
 }
@@ -884,6 +997,14 @@ int rcfd_upsample_nearest_bwd(const void* dup, void* dsrc, int32_t n, int32_t hs
                               int32_t wu, int32_t c, int32_t accumulate, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(dup && dsrc && n > 0 && hs > 0 && ws > 0 && hu > 0 && wu > 0 && c > 0 && c % 4 == 0,
                  "upsample_bwd: bad args (channels %% 4)");
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (hu == 2 * hs && wu == 2 * ws && c % vw == 0) {
+    const int64_t total = (int64_t)n * hs * ws * (c / vw);
+    DISPATCH_T(dtype, (upsample2x_bwd_wide<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)dup, (T*)dsrc, n, hs, ws, c, accumulate)));
+    RCFD_CHECK_LAUNCH("upsample2x_bwd");
+    return RCFD_OK;
+  }
   const int64_t total = (int64_t)n * hs * ws * (c / 4);
   const float sch = (float)hs / (float)hu, scw = (float)ws / (float)wu;
   DISPATCH_T(dtype, (upsample_bwd_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(

@@ -26,7 +26,7 @@ from .ops import ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD
 
 _ACT = {'linear': ACT_NONE, 'leaky_relu': ACT_LEAKY, 'sigmoid': ACT_SIGMOID}
 CPAD = 16    # RGB image / depth+response are stored with 16 channels (TMA boxes and UMMA K need 32 B rows)
-CPAD_DY = 8  # d(logit) of the 1-channel head: 8 channels for 16-byte gathers
+CPAD_DY = 16  # d(logit) of the 1-channel head: 16 channels (32-byte rows) so its dgrad / wgrad stream through the row engines
 
 
 class Tape(object):
@@ -150,7 +150,8 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
                          out_f32=True, engine=ctx.engine)
         if ctx.tape is not None:
             _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad,
-                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype, cpad=CPAD_DY))
+                                  pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype,
+                                                                    cpad=CPAD_DY if ctx.dtype == torch.bfloat16 else 8))
         return out
     if not mod.use_batch_norm:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=act, residual=residual, engine=ctx.engine)

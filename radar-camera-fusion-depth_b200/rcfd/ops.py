@@ -110,7 +110,9 @@ def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=EN
     d.dst = dy.data_ptr()
     d.dtype = dt(x0)
     d.engine = engine
-    _lib.call('rcfd_conv2d_wgrad', ctypes.byref(d), _p(dw), None, 0, _stream())
+    ws_bytes = int(_lib.load().rcfd_conv2d_wgrad_workspace(ctypes.byref(d)))
+    ws = torch.empty(ws_bytes, device=x0.device, dtype=torch.uint8) if ws_bytes > 0 else None
+    _lib.call('rcfd_conv2d_wgrad', ctypes.byref(d), _p(dw), _p(ws), ws_bytes, _stream())
     return dw
 
 

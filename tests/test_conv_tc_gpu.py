@@ -301,7 +301,7 @@ def test_tma_upconv2x_subpixel(shape):
 # ----------------------------------------------------------------------------- row-streaming engine
 @pytest.mark.parametrize('mode', [0])
 @pytest.mark.parametrize('case', [(1, 64, 64, 12, 128), (2, 64, 32, 19, 200), (1, 32, 32, 33, 130), (2, 32, 64, 9, 70),
-                                  (1, 64, 16, 70, 256)])
+                                  (1, 64, 16, 70, 256), (2, 16, 32, 21, 140)])
 def test_strip_conv(case, mode):
     """3x3 / stride 1 conv with the input rows kept in a shared-memory ring: tap (r, s) = descriptor
     shifted by s pixels into ring row y-1+r (descriptor base offset 0: the swizzle is a function of the
@@ -383,3 +383,60 @@ def test_stem_space_to_depth(cin, cout):
     g = torch.empty(cout, cin, 7, 7, device=DEV)
     ops.unpack_stem_s2d_wgrad(dw, g)
     assert relerr(g.cpu(), wt.grad) < 2e-3
+
+
+# ----------------------------------------------------------------------------- row-streaming weight gradient
+@pytest.mark.parametrize('case', [(1, 64, 64, 12, 128), (2, 64, 32, 19, 200), (1, 32, 32, 33, 130), (2, 32, 64, 9, 70),
+                                  (1, 64, 16, 70, 256), (2, 32, 16, 40, 300)])
+def test_strip_wgrad(case):
+    """Row-streaming weight gradient: input rows + dY rows in shared-memory rings, MN-major operands, the taps of
+    one filter row covered by ONE M = 128 MMA whose channel blocks are one pixel apart."""
+    from rcfd import ops
+    n, cin, cout, h, w = case
+    x = _q(_rand(n, cin, h, w, seed=71))
+    wt = (_rand(cout, cin, 3, 3, seed=72) * 0.05).requires_grad_(True)
+    y = F.conv2d(x, wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=73))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), 3, 1, engine=ops.ENGINE_STRIP)
+    torch.cuda.synchronize()
+    gw = torch.empty(cout, cin, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    err = relerr(gw.cpu(), wt.grad)
+    per_tap = [(r, s, round(relerr(gw.cpu()[:, :, r, s], wt.grad[:, :, r, s]), 5)) for r in range(3) for s in range(3)]
+    print('strip wgrad', case, err, per_tap)
+    assert err < 2e-3
+
+
+def test_strip_wgrad_concat():
+    from rcfd import ops
+    n, c0, c1, cout = 2, 64, 32, 64
+    x0, x1 = _q(_rand(n, c0, 20, 150, seed=74)), _q(_rand(n, c1, 20, 150, seed=75))
+    wt = (_rand(cout, c0 + c1, 3, 3, seed=76) * 0.05).requires_grad_(True)
+    y = F.conv2d(torch.cat([x0, x1], 1), wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=77))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x0), _nhwc(dy), 3, 1, x1=_nhwc(x1), engine=ops.ENGINE_STRIP)
+    gw = torch.empty(cout, c0 + c1, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 32, 9, 70), (1, 64, 64, 11, 200), (1, 64, 16, 20, 128)])
+def test_strip_wgrad_upconv2x(shape):
+    """Weight gradient of `3x3 conv after 2x nearest up-sampling` streamed over the LOW-RES rows (16 sub-pixel
+    matrices from stride-2 dY boxes, folded into the 9 taps)."""
+    from rcfd import ops
+    n, cin, cout, h, w = shape
+    x = _q(_rand(n, cin, h, w, seed=81))
+    wt = (_rand(cout, cin, 3, 3, seed=82) * 0.05).requires_grad_(True)
+    y = F.conv2d(F.interpolate(x, size=(2 * h, 2 * w)), wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=83))
+    y.backward(dy)
+    dw = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), 3, 1, in_size=(2 * h, 2 * w), engine=ops.ENGINE_STRIP)
+    torch.cuda.synchronize()
+    gw = torch.empty(cout, cin, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    err = relerr(gw.cpu(), wt.grad)
+    print('strip wgrad up', shape, err)
+    assert err < 2e-3

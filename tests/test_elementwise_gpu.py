@@ -112,6 +112,29 @@ def test_upsample_backward(src, dst):
     assert relerr(_nchw(dx), x.grad) < 1e-6
 
 
+@pytest.mark.parametrize('hw', [(8, 12), (11, 7), (6, 9)])
+def test_maxpool_upsample_backward_bf16(hw):
+    """bf16 16-byte-vector paths: 2x2-block max-pool backward (ties -> first maximum) and exact-2x up-sampling backward."""
+    from rcfd import ops
+    bf = torch.bfloat16
+    x = _rand(2, 16, *hw, seed=12).bfloat16().float()
+    x[0, 0, 0, 0] = x[0, 0, 0, 1] = x[0, 0, 1, 0] = 5.0
+    x[1, 3, 2, 2] = x[1, 3, 2, 3] = x[1, 3, 3, 2] = x[1, 3, 3, 3] = 7.0
+    x.requires_grad_(True)
+    y = F.max_pool2d(x, 3, 2, 1)
+    dy = _rand(*y.shape, seed=13).bfloat16().float()
+    y.backward(dy)
+    xd = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV, bf)
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV, bf)
+    dx = ops.maxpool3x3s2_bwd(xd, dyd)
+    assert relerr(_nchw(dx), x.grad) < 1e-2          # sums of up to 4 bf16 values rounded to bf16
+    assert torch.equal(_nchw(dx) != 0, x.grad != 0)  # the SAME winners
+    u = _rand(2, 16, 2 * hw[0], 2 * hw[1], seed=14).bfloat16().float()
+    ref = u.view(2, 16, hw[0], 2, hw[1], 2).sum(dim=(3, 5))
+    du = ops.upsample_nearest_bwd(u.permute(0, 2, 3, 1).contiguous().to(DEV, bf), hw)
+    assert relerr(_nchw(du), ref) < 1e-2
+
+
 def test_layout_loss_outlier_adam():
     from rcfd import ops
     import fusionnet_oracle as fo

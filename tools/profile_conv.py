@@ -36,7 +36,40 @@ elif which == 'blocks4':         # 256 -> 256 at 22x44
 elif which == 'wgrad_deconv0_up':
     x = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
     dy = torch.randn(B, H, W, 32, device=dev).to(bf)
-    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, in_size=(H, W))
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, in_size=(H, W), engine=eng)
+elif which == 'wgrad_deconv0_conv':      # 32 -> 32 at 352x704
+    x = torch.randn(B, H, W, 32, device=dev).to(bf)
+    dy = torch.randn(B, H, W, 32, device=dev).to(bf)
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, engine=eng)
+elif which == 'wgrad_output0':           # 32 -> 1 (d(logit) stored with 16 channels) at 352x704
+    x = torch.randn(B, H, W, 32, device=dev).to(bf)
+    dy = torch.randn(B, H, W, 16, device=dev).to(bf)
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, engine=eng)
+elif which == 'wgrad_deconv1_conv':      # (64 | 32) -> 64 at 176x352
+    x = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
+    x1 = torch.randn(B, H // 2, W // 2, 32, device=dev).to(bf)
+    dy = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, x1=x1, engine=eng)
+elif which == 'wgrad_deconv1_up':        # 64 -> 64 behind a 2x up-sampling, 176x352 output
+    x = torch.randn(B, H // 4, W // 4, 64, device=dev).to(bf)
+    dy = torch.randn(B, H // 2, W // 2, 64, device=dev).to(bf)
+    eng = int(os.environ.get('RCFD_ENGINE', '0'))
+    run = lambda: ops.conv2d_wgrad(x, dy, 3, 1, in_size=(H // 2, W // 2), engine=eng)
+elif which == 'dgrad_output0':           # d(logit) (16 channels) -> 32 at 352x704
+    dy = torch.randn(B, H, W, 16, device=dev).to(bf)
+    wd = ops.pack_weight(torch.randn(1, 32, 3, 3, device=dev) * 0.05, bf, dgrad=True, pad_to=16)
+    run = lambda: ops.conv2d(dy, wd, 32, 3, 1, pad=1, out_size=(H, W))
+elif which == 'maxpool_bwd':
+    x = torch.randn(B, H // 2, W // 2, 32, device=dev).to(bf)
+    d = torch.randn(B, H // 4, W // 4, 32, device=dev).to(bf)
+    run = lambda: ops.maxpool3x3s2_bwd(x, d)
+elif which == 'upsample_bwd':
+    d = torch.randn(B, H, W, 64, device=dev).to(bf)
+    run = lambda: ops.upsample_nearest_bwd(d, (H // 2, W // 2))
 else:
     raise SystemExit('unknown case')
 for _ in range(reps):

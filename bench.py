@@ -236,6 +236,8 @@ def run_ours(args):
 
     def step(inputs):
         image, depth, gt, lidar = inputs
+        if train and args.graph:
+            return model.train_step_graphed(image, depth, gt, lidar, opt, 2.0, outlier_removal=outlier)
         if train:
             out = model.forward(image, depth)
             gt_c = outlier.remove_outliers(gt)
@@ -285,17 +287,19 @@ def run_ours(args):
     l0 = _lib.launch_count
     ms = timed(lambda: step(resident), args.steps)
     launches = (_lib.launch_count - l0) // args.steps
-    if not train and args.graph:          # replayed from a CUDA graph: count the kernels captured in it
-        l1 = _lib.launch_count
-        with torch.no_grad():
-            model.forward(resident[0], resident[1])
-        launches = _lib.launch_count - l1
+    if args.graph:                        # replayed from a CUDA graph: count the kernels captured in it
+        launches = getattr(model, 'last_capture_launches', launches)
+        if not train:
+            l1 = _lib.launch_count
+            with torch.no_grad():
+                model.forward(resident[0], resident[1])
+            launches = _lib.launch_count - l1
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API: pinned host -> device every step, result read back
     def e2e_step():
-        if train:
-            inputs = [t.to(dev, non_blocking=True) for t in host]
+        if train:           # the graphed step copies straight from the pinned host tensors into its static buffers
+            inputs = host if args.graph else [t.to(dev, non_blocking=True) for t in host]
         else:               # forward_graphed copies straight from the pinned host tensors into its static buffers
             inputs = (host[:2] if args.graph else [t.to(dev, non_blocking=True) for t in host[:2]]) + [None, None]
         r = step(inputs)
@@ -364,7 +368,7 @@ def run_ours(args):
                                       1 if train else 4),
                        'global_batch': world * batch, 'parallelism': 'dp%d' % world,
                        'l2': 'no flush needed: per-step activation working set (>1 GB) exceeds the 126 MB L2',
-                       'precision': args.precision, 'cuda_graph': bool(args.graph and not train)},
+                       'precision': args.precision, 'cuda_graph': bool(args.graph)},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'depth-maps/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
@@ -393,7 +397,7 @@ def main():
     ap.add_argument('--precision', choices=['bf16', 'fp32'], default='bf16')
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--profile-step', dest='profile_step', action='store_true', help='warm up, run ONE step, exit (for ncu)')
-    ap.add_argument('--no-graph', dest='graph', action='store_false', help='infer: launch kernels one by one instead of replaying a CUDA graph')
+    ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch kernels one by one instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -44,8 +44,8 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
           ground_truth_dilation_kernel_size,
           min_evaluate_depth, max_evaluate_depth,
           checkpoint_dirpath, n_step_per_summary, n_step_per_checkpoint, start_step_validation, restore_path,
-          device, n_thread, precision='fp32', max_steps=None):
-    """Same keyword arguments as the reference (all passed by name); ``precision`` / ``max_steps`` are extras."""
+          device, n_thread, precision='fp32', max_steps=None, use_cuda_graph=True):
+    """Same keyword arguments as the reference (all passed by name); ``precision`` / ``max_steps`` / ``use_cuda_graph`` are extras."""
     if not torch.cuda.is_available():
         raise RuntimeError('fusionnet_main.train needs a CUDA device: the B200 path has no CPU fallback')
     assert len(learning_rates) == len(learning_schedule)
@@ -102,6 +102,9 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
         log('Training FusionNet on {} GPU(s), {} steps/epoch, batch {} per GPU, precision {}'.format(
             world, n_train_step_per_epoch, batch_size, precision), log_path)
 
+    # the canonical configuration (l1 + lidar term, no smoothness, FusedAdam) runs through the graphed step
+    graphed_step = (use_cuda_graph and loss_func == 'l1' and w_lidar_loss > 0.0 and not w_smoothness > 0.0
+                    and isinstance(optimizer, rcfd_optim.FusedAdam))
     learning_schedule_pos = 0
     time_start = time.time()
     n_total = learning_schedule[-1] * n_train_step_per_epoch
@@ -118,6 +121,19 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
             if normalized_image_range[1] <= 1.0 and image.dtype != torch.float32:
                 image = image.float() / 255.0
             net_input_depth = torch.cat([input_depth, input_response], dim=1)     # reference :366
+            if graphed_step:
+                # canonical loss: forward + loss + backward replayed from one CUDA graph (same arithmetic)
+                loss = model.train_step_graphed(image, net_input_depth, ground_truth, lidar_map, optimizer,
+                                                w_lidar_loss, outlier_removal=outlier_removal)
+                if rank == 0 and (train_step % n_step_per_checkpoint) == 0:
+                    elapsed = (time.time() - time_start) / 3600
+                    remain = (n_total - train_step) * elapsed / max(train_step, 1)
+                    log('Step={:6}/{}  Loss={:.5f}  Time Elapsed={:.2f}h  Time Remaining={:.2f}h'.format(
+                        train_step, n_total, float(loss), elapsed, remain), log_path)
+                    model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
+                if max_steps is not None and train_step >= max_steps:
+                    break
+                continue
             output_depth = model.forward(image=image, input_depth=net_input_depth)
             if outlier_removal is not None:
                 ground_truth = outlier_removal.remove_outliers(ground_truth)

@@ -97,6 +97,7 @@ class FusionNetModel(object):
         self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[precision]
         self._cache.clear()
         self._graphs = {}
+        self._train_graphs = {}
         return self
 
     # ------------------------------------------------------------------ execution
@@ -168,7 +169,75 @@ class FusionNetModel(object):
         graph.replay()
         return s_out
 
-    def _deliver_grads(self, param_grads):
+    def train_step_graphed(self, image, input_depth, ground_truth, lidar_map, optimizer, w_lidar_loss,
+                           outlier_removal=None):
+        """One optimisation step of the canonical configuration (reference src/fusionnet_main.py:366-399:
+        forward -> ground-truth outlier removal -> masked L1 (+ lidar term) -> backward -> Adam) with the
+        ~700 kernel launches of forward + loss + backward replayed from ONE CUDA graph (captured once per
+        input shape / precision); the gradient all-reduce (data parallel) and the optimiser step follow
+        eagerly, so learning-rate schedules and the Adam step count stay host-side.  Same arithmetic as
+        ``forward`` / ``compute_loss`` / ``loss.backward()`` / ``optimizer.step()``; returns the loss as a
+        0-d tensor owned by the graph (overwritten by the next call)."""
+        if not self.encoder.training:
+            raise RuntimeError('train_step_graphed needs model.train()')
+        if not w_lidar_loss > 0.0:
+            raise ValueError('train_step_graphed implements the canonical loss (l1, w_lidar_loss > 0)')
+        if not all(getattr(p, '_rcfd_flat', False) for p in self.parameters()):
+            raise RuntimeError('train_step_graphed needs rcfd.optim.FusedAdam (gradients written in place into its flat buffer)')
+        if not hasattr(self, '_train_graphs'):
+            self._train_graphs = {}
+        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine, float(w_lidar_loss),
+               None if outlier_removal is None else (outlier_removal.kernel_size, outlier_removal.threshold),
+               id(optimizer))
+        entry = self._train_graphs.get(key)
+        if entry is None:
+            dev = next(self.encoder.parameters()).device
+            static = [torch.empty(tuple(t.shape), device=dev, dtype=torch.float32)
+                      for t in (image, input_depth, ground_truth, lidar_map)]
+            for s, t in zip(static, (image, input_depth, ground_truth, lidar_map)):
+                s.copy_(t)
+
+            def body():
+                out, ectx = self._run(static[0], static[1], record=True)
+                n, h, w, _ = out.shape
+                gt = static[2] if outlier_removal is None else outlier_removal.remove_outliers(static[2])
+                loss, dout = ops.masked_l1_loss(out.view(n, 1, h, w), gt, static[3], float(w_lidar_loss), want_grad=True)
+                tape = ectx.tape
+                tape.grads[id(out)] = dout.view(out.shape)
+                tape.backward()
+                grads, tape.param_grads = tape.param_grads, []
+                self._deliver_grads(grads, hook=False)       # the few gradients not written in place (captured copies)
+                return loss.view(()), grads
+
+            # one eager pass first (kernel attributes, allocator warm-up); it must not move the BatchNorm buffers
+            buffers = [b for root in (self.encoder, self.decoder) for b in root.buffers()]
+            saved = [b.clone() for b in buffers]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.no_grad():
+                with torch.cuda.stream(side):
+                    body()
+                torch.cuda.current_stream().wait_stream(side)
+                for b, s in zip(buffers, saved):
+                    b.copy_(s)
+                from rcfd import _lib
+                l0 = _lib.launch_count
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss, grads = body()
+                self.last_capture_launches = _lib.launch_count - l0 + 1      # + the eager Adam launch
+            entry = (graph, static, loss, grads)
+            self._train_graphs[key] = entry
+        graph, static, loss, grads = entry
+        for s, t in zip(static, (image, input_depth, ground_truth, lidar_map)):
+            s.copy_(t, non_blocking=True)
+        graph.replay()
+        if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
+            self.grad_hook(grads)
+        optimizer.step()
+        return loss
+
+    def _deliver_grads(self, param_grads, hook=True):
         for p, g in param_grads:
             if g is p.grad:              # written in place (rcfd.optim.FusedAdam flat buffers)
                 continue
@@ -179,7 +248,7 @@ class FusionNetModel(object):
                 p.grad = g
             else:
                 p.grad.add_(g)
-        if self.grad_hook is not None:
+        if hook and self.grad_hook is not None:
             self.grad_hook(param_grads)
 
     # ------------------------------------------------------------------ loss

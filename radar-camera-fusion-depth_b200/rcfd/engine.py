@@ -29,6 +29,14 @@ CPAD = 16    # RGB image / depth+response are stored with 16 channels (TMA boxes
 CPAD_DY = 16  # d(logit) of the 1-channel head: 16 channels (32-byte rows) so its dgrad / wgrad stream through the row engines
 
 
+_PARAM_EPOCH = [0]
+
+
+def note_params_changed():
+    """Invalidate every packed-weight / folded-BN cache entry (parameters were written outside torch)."""
+    _PARAM_EPOCH[0] += 1
+
+
 class Tape(object):
     """Reverse-mode tape: forward ops append closures; grads are keyed by tensor identity."""
 
@@ -92,9 +100,13 @@ class Context(object):
         self._off_aff += n
         return [s[i * c:(i + 1) * c] for i in range(k)]
 
-    # -- weights: packed per forward in training (they change every step), cached by version in eval
+    # -- weights: packed per forward in training (they change every step), cached by version in eval.
+    #    Optimisers that write parameters through raw pointers (rcfd.optim.FusedAdam) do not move torch's
+    #    version counters: they call note_params_changed(), which is part of the cache key.
     def packed(self, key, params, fn):
-        ver = tuple(p._version for p in params) + (self.dtype,)
+        if self.training:
+            return fn()
+        ver = tuple(p._version for p in params) + (self.dtype, _PARAM_EPOCH[0])
         hit = self.cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]

@@ -10,7 +10,7 @@ when asked to), which is what the training loop (zero_grad -> backward -> step) 
 """
 import torch
 
-from . import ops
+from . import engine, ops
 
 
 class FusedAdam(object):
@@ -47,6 +47,7 @@ class FusedAdam(object):
         g = self.param_groups[0]
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g['lr'], g['betas'][0],
                       g['betas'][1], g['eps'], self.step_count)
+        engine.note_params_changed()     # raw-pointer write: torch's version counters did not move
 
     def state_dict(self):
         return {'state': {'step': self.step_count, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq},

@@ -203,6 +203,55 @@ def test_graphed_forward_matches_eager():
         m.forward_graphed(image, depth)
 
 
+def test_graphed_train_step_matches_eager():
+    """forward + outlier removal + masked L1 + backward replayed from one CUDA graph == the eager step: same loss,
+    same first-step gradients; after 3 FusedAdam steps the losses and BatchNorm buffers agree (bf16 rounding noise
+    grows chaotically with the updates, so later steps are bounded loosely)."""
+    from rcfd import optim
+    import net_utils
+    cfg = synth.CANONICAL_FUSIONNET
+    p0 = synth_fusionnet_state(cfg, 7)
+    n, h, w = 2, 96, 160
+    batches = []
+    for seed in (7, 8, 9):
+        image, depth = synth.fusionnet_inputs(n, h, w, seed, 'quasi_dense')
+        gt, lidar = synth.training_targets(n, h, w, seed)
+        batches.append([t.to(DEV) for t in (image, depth, gt, lidar)])
+    outlier = net_utils.OutlierRemoval(7, 1.5)
+    results = []
+    for graphed in (False, True):
+        m = make_model(cfg, p0, precision='bf16')
+        m.train()
+        opt = optim.FusedAdam(m.parameters(), lr=1e-3)
+        losses = []
+        for image, depth, gt, lidar in batches:
+            if graphed:
+                loss = m.train_step_graphed(image, depth, gt, lidar, opt, 2.0, outlier_removal=outlier)
+            else:
+                d = m.forward(image, depth)
+                loss, _ = m.compute_loss(image, d, outlier.remove_outliers(gt), lidar, 'l1', 0.0, -1, None, 2.0)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            losses.append(float(loss))
+            if len(losses) == 1:
+                first_grad = opt.flat_grad.clone()
+        state = dict([('encoder.' + k, v.detach().clone()) for k, v in m.encoder.state_dict().items()] +
+                     [('decoder.' + k, v.detach().clone()) for k, v in m.decoder.state_dict().items()])
+        results.append((losses, state, first_grad))
+    (l_e, s_e, g_e), (l_g, s_g, g_g) = results
+    print('eager losses', l_e, 'graphed losses', l_g)
+    assert abs(l_e[0] - l_g[0]) < 1e-5 * abs(l_e[0])        # identical kernels on identical inputs
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) < 2e-3 * abs(a)
+    assert relerr(g_g.cpu(), g_e.cpu()) < 1e-3                # first-step gradients: only the order of fp32 atomics differs
+    for k in s_e:
+        if 'num_batches_tracked' in k:
+            assert int(s_e[k]) == int(s_g[k]) == 3, k
+        elif 'running' in k:
+            assert relerr(s_g[k].cpu(), s_e[k].cpu()) < 1e-2, k
+
+
 def test_bf16_train_step_sanity():
     """bf16 fast mode through every tensor-core engine (TMA, row-streaming, sub-pixel up-conv, space-to-depth
     stems, gather dgrad / wgrad).  NOT a 1e-3 claim.  Two checks:

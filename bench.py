@@ -218,6 +218,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = fusionnet_model.FusionNetModel(device=dev, **synth.CANONICAL_FUSIONNET)
     model.set_precision(args.precision)
+    model.multistream = args.multistream
     train = args.mode == 'train'
     if train:
         model.train()
@@ -368,7 +369,7 @@ def run_ours(args):
                                       1 if train else 4),
                        'global_batch': world * batch, 'parallelism': 'dp%d' % world,
                        'l2': 'no flush needed: per-step activation working set (>1 GB) exceeds the 126 MB L2',
-                       'precision': args.precision, 'cuda_graph': bool(args.graph)},
+                       'precision': args.precision, 'cuda_graph': bool(args.graph), 'multistream': bool(args.multistream)},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'depth-maps/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
@@ -398,6 +399,7 @@ def main():
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--profile-step', dest='profile_step', action='store_true', help='warm up, run ONE step, exit (for ncu)')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch kernels one by one instead of replaying a CUDA graph')
+    ap.add_argument('--no-multistream', dest='multistream', action='store_false', help='issue every kernel on one stream')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -25,6 +25,7 @@ bool conv_strip_supported(const ConvKP& p, int dtype);
 bool conv_strip_preferred(const ConvKP& p, int dtype);
 int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
+extern int g_tma_bn_cap;
 bool conv_tma_supported(const ConvKP& p, int dtype);
 int conv_tma_launch(const ConvKP& p, cudaStream_t st);
 bool wgrad_tc_supported(const ConvKP& p, int dtype);
@@ -86,6 +87,7 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
 int rcfd_set_option(const char* key, int32_t value) {
   RCFD_CHECK_ARG(key != nullptr, "set_option: null key");
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
+  if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
   set_error("set_option: unknown key %s", key);
   return RCFD_EINVAL;
 }

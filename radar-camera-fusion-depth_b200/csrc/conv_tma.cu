@@ -311,6 +311,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   }
 }
 
+}  // namespace
+extern int g_tma_bn_cap;
+namespace {
+
 template <int BN>
 int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                cudaStream_t st) {
@@ -329,6 +333,8 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 }
 
 }  // namespace
+
+int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n
 
 // 2x nearest up-sampling folded into a 3x3 / stride-1 / pad-1 conv == four 2x2 convs (one per
 // output sub-pixel phase) on the LOW-RES source with summed weights: 4/9 of the MACs, every
@@ -381,7 +387,18 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   }
   t.tw = best_tw; t.th = TM / best_tw;
   t.tiles_x = ceil_div(p.wo, t.tw); t.tiles_y = ceil_div(p.ho, t.th);
-  const int bn = p.cout % 128 == 0 ? 128 : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : (p.cout <= 16 || p.cout % 16 == 0 || p.cout < 32 ? 16 : 32)));
+  int bn = p.cout % 128 == 0 ? 128 : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : (p.cout <= 16 || p.cout % 16 == 0 || p.cout < 32 ? 16 : 32)));
+  // small spatial extents (the 6x11 ... 22x44 encoder levels): a CTA's k-loop is bound by its own
+  // L2 -> shared-memory ingest (A tile + B tile per k-step), so narrower cout tiles on more SMs win
+  // as long as the grid still fits one wave.
+  {
+    const int mtiles = p.n * t.tiles_y * t.tiles_x * t.phases;
+    if (g_tma_bn_cap > 0) {
+      while (bn > g_tma_bn_cap && bn > 16) bn >>= 1;
+    } else if (g_tma_bn_cap == 0) {
+      while (bn > 32 && mtiles * ceil_div(p.cout, bn) * 2 <= num_sms()) bn >>= 1;
+    }
+  }
   t.tiles_n = ceil_div(p.cout, bn);
   t.num_tiles = p.n * t.tiles_y * t.tiles_x * t.tiles_n * t.phases;
   t.ksteps = p.kh * p.kw * ((p.c0 + p.c1) / t.bkc);

@@ -139,8 +139,15 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restric
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const double* __restrict__ sums, T* __restrict__ dy, int64_t nvec,
-                                    int C, int act, float inv_count) {
+                                    int C, int act, float inv_count, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
   const int CV = C >> 2;
+  if (blockIdx.x == 0) {                       // parameter gradients ride along (one block, C values)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % CV) * 4;
     const float4 g = Vec4<T>::ld(dz + i * 4);
@@ -161,13 +168,6 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restric
     o.w = sc.w * (d - (float)sums[c + 3] * inv_count - (v.w - mu.w) * is.w * (float)sums[C + c + 3] * inv_count);
     Vec4<T>::st(dy + i * 4, o);
   }
-}
-
-__global__ void bn_bwd_params_kernel(const double* sums, float* dgamma, float* dbeta, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (dbeta) dbeta[c] = (float)sums[c];
-  if (dgamma) dgamma[c] = (float)sums[C + c];
 }
 
 // ---- 16-byte-vector variants (C % V16<T>::N == 0): 8 bf16 / 4 float per thread and access
@@ -254,9 +254,16 @@ template <typename T>
 __global__ void bn_bwd_apply_wide(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const double* __restrict__ sums, T* __restrict__ dy,
-                                  int64_t nvec, int C, int act, float inv_count) {
+                                  int64_t nvec, int C, int act, float inv_count, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta) {
   constexpr int N = V16<T>::N;
   const int CV = C / N;
+  if (blockIdx.x == 0) {                       // parameter gradients ride along (one block, C values)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+  }
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int c = (int)(i0 % CV) * N;
   float sc[N], sh[N], mu[N], k1[N], k2[N];
@@ -614,6 +621,30 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, T* __restrict_
     const int y2 = (int)(r % H2);
     const int n = (int)(r / H2);
     T* o = dst + i * CP;
+    if (CP == 16 && C <= 4) {                 // the stems: whole pixel in registers, 16-byte stores
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < C) {
+          const float* s = src + (((size_t)n * C + c) * H + 2 * y2) * W + 2 * x2;
+          const float2 top = *reinterpret_cast<const float2*>(s);
+          const float2 bot = *reinterpret_cast<const float2*>(s + W);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {      // static register indices: select instead of dynamic indexing
+            if (k == 0 * C + c) v[k] = top.x;
+            if (k == 1 * C + c) v[k] = top.y;
+            if (k == 2 * C + c) v[k] = bot.x;
+            if (k == 3 * C + c) v[k] = bot.y;
+          }
+        }
+      }
+      constexpr int N = V16<T>::N;
+#pragma unroll
+      for (int k = 0; k < 16; k += N) V16<T>::st(o + k, v + k);
+      continue;
+    }
     for (int c = 0; c < C; ++c) {
       const float* s = src + (((size_t)n * C + c) * H + 2 * y2) * W + 2 * x2;
       const float2 top = *reinterpret_cast<const float2*>(s);
@@ -671,15 +702,23 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 template <typename T>
 __global__ void depth_head_bwd_kernel(const float* __restrict__ dd, const float* __restrict__ d,
                                       T* __restrict__ dl, float mn, float r, int64_t n, int CP) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * CP; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t px = i / CP;
-    float g = 0.f;
-    if (i - px * CP == 0) {
-      const float dv = d[px];
-      const float s = mn / dv - r;              // sigmoid(logit)
-      g = -dd[px] * dv * dv / mn * s * (1.f - s);
+  constexpr int N = V16<T>::N;
+  for (int64_t px = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; px < n; px += (int64_t)gridDim.x * blockDim.x) {
+    const float dv = d[px];
+    const float s = mn / dv - r;              // sigmoid(logit)
+    const float g = -dd[px] * dv * dv / mn * s * (1.f - s);
+    T* o = dl + px * CP;
+    if (CP % N == 0) {                        // channel 0 carries the gradient, the padding channels are zero
+      float v[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) v[k] = 0.f;
+      for (int c = N; c < CP; c += N) V16<T>::st(o + c, v);
+      v[0] = g;
+      V16<T>::st(o, v);
+    } else {
+      o[0] = from_f<T>(g);
+      for (int c = 1; c < CP; ++c) o[c] = from_f<T>(0.f);
     }
-    dl[i] = from_f<T>(g);
   }
 }
 
@@ -737,29 +776,42 @@ __global__ void max_kernel(const float* __restrict__ x, float* __restrict__ mx, 
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(mx), __float_as_int(m));   // values >= 0
 }
+// separable min filter on a shared-memory tile: 32 x 8 outputs per block, halo ks/2 (ks <= 15)
+constexpr int OUT_TW = 32, OUT_TH = 8, OUT_MAXPAD = 7;
 __global__ void outlier_kernel(const float* __restrict__ d, const float* __restrict__ mx,
                                float* __restrict__ out, int N, int H, int W, int ks, float thr) {
+  __shared__ float tile[OUT_TH + 2 * OUT_MAXPAD][OUT_TW + 2 * OUT_MAXPAD + 1];
+  __shared__ float rowmin[OUT_TH + 2 * OUT_MAXPAD][OUT_TW];
   const float fill = 10.f * mx[0];
   const int pad = ks / 2;
-  const int64_t total = (int64_t)N * H * W;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    int64_t r = i / W;
-    const int y = (int)(r % H);
-    const int n = (int)(r / H);
-    float mn = fill;
-    for (int dy = -pad; dy <= pad; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = -pad; dx <= pad; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        const float v = d[((size_t)n * H + yy) * W + xx];
-        mn = fminf(mn, v > 0.f ? v : fill);
-      }
+  const int n = blockIdx.z, y0 = blockIdx.y * OUT_TH, x0 = blockIdx.x * OUT_TW;
+  const int th = OUT_TH + 2 * pad, tw = OUT_TW + 2 * pad;
+  const float* img = d + (size_t)n * H * W;
+  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int yy = y0 + ty - pad, xx = x0 + tx - pad;
+    float v = fill;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      v = img[(size_t)yy * W + xx];
+      v = v > 0.f ? v : fill;
     }
-    const float v = d[i];
-    out[i] = (mn < v - thr) ? v * 0.f : v;
+    tile[ty][tx] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < th * OUT_TW; i += blockDim.x) {
+    const int ty = i / OUT_TW, tx = i - ty * OUT_TW;
+    float m = fill;
+    for (int dx = 0; dx < ks; ++dx) m = fminf(m, tile[ty][tx + dx]);
+    rowmin[ty][tx] = m;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % OUT_TW, ty = threadIdx.x / OUT_TW;
+  const int y = y0 + ty, x = x0 + tx;
+  if (y < H && x < W) {
+    float m = fill;
+    for (int dy = 0; dy < ks; ++dy) m = fminf(m, rowmin[ty + dy][tx]);
+    const float v = img[(size_t)y * W + x];
+    out[(size_t)n * H * W + (size_t)y * W + x] = (m < v - thr) ? v * 0.f : v;
   }
 }
 
@@ -929,18 +981,14 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
     const int64_t nv = pixels * channels / vw;
     DISPATCH_T(dtype, (bn_bwd_apply_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nv, channels, act,
-                          (float)(1.0 / (double)pixels))));
+                          (float)(1.0 / (double)pixels), dgamma, dbeta)));
   } else {
     const int64_t nvec = pixels * channels / 4;
     DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid_for(nvec), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nvec, channels, act,
-                          (float)(1.0 / (double)pixels))));
+                          (float)(1.0 / (double)pixels), dgamma, dbeta)));
   }
   RCFD_CHECK_LAUNCH("bn_bwd_apply");
-  if (dgamma || dbeta) {
-    bn_bwd_params_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(sums, dgamma, dbeta, channels);
-    RCFD_CHECK_LAUNCH("bn_bwd_params");
-  }
   return RCFD_OK;
 }
 
@@ -1088,7 +1136,7 @@ int rcfd_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t
 int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, float min_depth, float min_over_max,
                         int64_t count, int32_t cpad, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(ddepth && depth && dlogit && count > 0 && min_depth > 0.f && cpad >= 1, "depth_head_bwd: bad args");
-  DISPATCH_T(dtype, (depth_head_bwd_kernel<T><<<grid_for(count * cpad), NT, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, (depth_head_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>(
                         ddepth, depth, (T*)dlogit, min_depth, min_over_max, count, cpad)));
   RCFD_CHECK_LAUNCH("depth_head_bwd");
   return RCFD_OK;
@@ -1110,15 +1158,17 @@ int rcfd_masked_l1_loss(const float* out, const float* gt, const float* lidar, f
 
 int rcfd_outlier_removal(const float* depth, float* out, float* scratch_max, int32_t n, int32_t h, int32_t w,
                          int32_t kernel_size, float threshold, void* stream) {
-  RCFD_CHECK_ARG(depth && out && scratch_max && n > 0 && h > 0 && w > 0 && kernel_size > 0 && (kernel_size & 1),
-                 "outlier_removal: bad args");
+  RCFD_CHECK_ARG(depth && out && scratch_max && n > 0 && h > 0 && w > 0 && kernel_size > 0 && (kernel_size & 1) &&
+                     kernel_size <= 2 * OUT_MAXPAD + 1,
+                 "outlier_removal: bad args (odd kernel size <= 15)");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = (int64_t)n * h * w;
   cudaError_t e = cudaMemsetAsync(scratch_max, 0, sizeof(float), st);
   if (e != cudaSuccess) { set_error("outlier memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
   max_kernel<<<grid_for(total, NT, 148 * 2), NT, 0, st>>>(depth, scratch_max, total);
   RCFD_CHECK_LAUNCH("outlier_max");
-  outlier_kernel<<<grid_for(total), NT, 0, st>>>(depth, scratch_max, out, n, h, w, kernel_size, threshold);
+  outlier_kernel<<<dim3(ceil_div(w, OUT_TW), ceil_div(h, OUT_TH), n), OUT_TW * OUT_TH, 0, st>>>(depth, scratch_max, out, n, h, w, kernel_size,
+                                                                                          threshold);
   RCFD_CHECK_LAUNCH("outlier");
   return RCFD_OK;
 }

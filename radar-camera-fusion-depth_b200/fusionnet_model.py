@@ -38,7 +38,7 @@ class _FusionNetFunction(torch.autograd.Function):
         if grad_out is None or ectx is None or ectx.tape is None:
             return (None,) * n_in
         tape = ectx.tape
-        tape.grads[id(fctx.out_nhwc)] = grad_out.contiguous().float().view(fctx.out_nhwc.shape)
+        tape.set_grad(fctx.out_nhwc, grad_out.contiguous().float().view(fctx.out_nhwc.shape))
         tape.backward()
         fctx.model._deliver_grads(tape.param_grads)
         tape.param_grads = []
@@ -59,6 +59,7 @@ class FusionNetModel(object):
         self.device = device
         self.compute_dtype = torch.float32
         self.conv_engine = ops.ENGINE_AUTO
+        self.multistream = True        # image branch / depth branch / fusion / weight gradients on parallel CUDA streams
         self._cache = {}
         self.grad_hook = None          # called with the list of (param, grad) after backward (DDP)
 
@@ -103,21 +104,21 @@ class FusionNetModel(object):
     # ------------------------------------------------------------------ execution
     def _run(self, image, input_depth, record=False, return_logits=False, taps=None):
         # rcfd.ops refuses non-CUDA tensors: there is no CPU fallback behind this call
-        ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
-                              record=record, engine=self.conv_engine)
-        ectx.taps = taps
-        img, s2d = engine.stem_input(ectx, image)
-        dep, s2d_d = engine.stem_input(ectx, input_depth)
-        assert s2d == s2d_d
-        latent, skips = engine.fusionnet_encoder(ectx, self.encoder, img, dep, stem_s2d=s2d)
-        if taps is not None:
-            taps['latent'] = latent
-            for i, s in enumerate(skips):
-                taps['skip%d' % (i + 1)] = s
-        head = None if return_logits else (float(self.min_predict_depth),
-                                           float(self.min_predict_depth) / float(self.max_predict_depth))
-        out, _ = engine.multiscale_decoder(ectx, self.decoder, latent, skips, image.shape[-2:], head=head)
-        engine.finish_bn_counters(ectx)
+        with ops.hold_allocations():
+            ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
+                                  record=record, engine=self.conv_engine, multistream=self.multistream)
+            ectx.taps = taps
+            # the layout conversion of each input is issued on its branch's stream
+            latent, skips = engine.fusionnet_encoder(ectx, self.encoder, lambda: engine.stem_input(ectx, image),
+                                                     lambda: engine.stem_input(ectx, input_depth))
+            if taps is not None:
+                taps['latent'] = latent
+                for i, s in enumerate(skips):
+                    taps['skip%d' % (i + 1)] = s
+            head = None if return_logits else (float(self.min_predict_depth),
+                                               float(self.min_predict_depth) / float(self.max_predict_depth))
+            out, _ = engine.multiscale_decoder(ectx, self.decoder, latent, skips, image.shape[-2:], head=head)
+            engine.finish_bn_counters(ectx)
         return out, ectx
 
     def forward(self, image, input_depth, return_multiscale=False, return_logits=False):
@@ -141,7 +142,7 @@ class FusionNetModel(object):
         by the next call)."""
         if self.encoder.training:
             raise RuntimeError('forward_graphed is inference-only: call model.eval() first')
-        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine)
+        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine, self.multistream)
         entry = self._graphs.get(key) if hasattr(self, '_graphs') else None
         if entry is None:
             if not hasattr(self, '_graphs'):
@@ -188,7 +189,7 @@ class FusionNetModel(object):
             self._train_graphs = {}
         key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine, float(w_lidar_loss),
                None if outlier_removal is None else (outlier_removal.kernel_size, outlier_removal.threshold),
-               id(optimizer))
+               id(optimizer), self.multistream)
         entry = self._train_graphs.get(key)
         if entry is None:
             dev = next(self.encoder.parameters()).device
@@ -203,7 +204,7 @@ class FusionNetModel(object):
                 gt = static[2] if outlier_removal is None else outlier_removal.remove_outliers(static[2])
                 loss, dout = ops.masked_l1_loss(out.view(n, 1, h, w), gt, static[3], float(w_lidar_loss), want_grad=True)
                 tape = ectx.tape
-                tape.grads[id(out)] = dout.view(out.shape)
+                tape.set_grad(out, dout.view(out.shape))
                 tape.backward()
                 grads, tape.param_grads = tape.param_grads, []
                 self._deliver_grads(grads, hook=False)       # the few gradients not written in place (captured copies)

@@ -37,29 +37,109 @@ def note_params_changed():
     _PARAM_EPOCH[0] += 1
 
 
-class Tape(object):
-    """Reverse-mode tape: forward ops append closures; grads are keyed by tensor identity."""
+# Stream roles of the multi-stream schedule (one CUDA stream each; index 0 is the caller's current stream):
+#   MAIN   image branch of the encoder, decoder, loss          DEPTH  depth branch of the encoder
+#   FUSE   gated fusion levels (need both branches)            WG_*   weight gradients of the MAIN / DEPTH chains
+# Most FusionNet layers below 1/4 resolution occupy a fraction of the 148 SMs and are latency bound; the
+# chains are independent between fusion points, so running them side by side (and capturing them as
+# parallel branches of the step's CUDA graph) overlaps those latencies.
+MAIN, DEPTH, FUSE, WG_MAIN, WG_DEPTH = 0, 1, 2, 3, 4
+_WG_OF = {MAIN: WG_MAIN, DEPTH: WG_DEPTH}
+_SIDE_STREAMS = {}
 
-    def __init__(self):
-        self.steps = []
-        self.grads = {}
+
+def side_streams(device):
+    """The four side streams of a device (created once, outside any graph capture)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(4)]
+    return _SIDE_STREAMS[key]
+
+
+class Tape(object):
+    """Reverse-mode tape: forward ops append closures; grads are keyed by tensor identity.
+    With ``streams`` (multi-stream schedule) every step replays on the stream role it was recorded on and
+    gradients that cross roles carry the event of their last writer."""
+
+    def __init__(self, streams=None):
+        self.steps = []              # (closure, stream role)
+        self.grads = {}              # id(tensor) -> [grad, role of last writer, event of last write]
         self.keep = []
         self.param_grads = []        # (parameter, grad tensor float32 in the parameter's layout)
+        self.streams = streams       # None = single stream
+        self.sid = MAIN              # role being recorded (forward) / replayed (backward)
+
+    def add_step(self, fn):
+        self.steps.append((fn, self.sid))
+
+    def _mark(self):
+        if self.streams is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def _wait(self, entry):
+        if self.streams is not None and entry[2] is not None and entry[1] != self.sid:
+            torch.cuda.current_stream().wait_event(entry[2])
+
+    def set_grad(self, t, g):
+        """Seed (the loss gradient): produced on the caller's stream before backward() starts."""
+        self.grads[id(t)] = [g, MAIN, None]
+        self.keep.append(t)
 
     def add_grad(self, t, g):
+        """Publish a gradient contribution.  Call it AFTER the last read of ``g`` on the current stream:
+        a later contribution from another role accumulates into ``g`` in place."""
         k = id(t)
-        if k in self.grads:
-            ops.add_(self.grads[k], g)
+        e = self.grads.get(k)
+        if e is not None:
+            self._wait(e)
+            ops.add_(e[0], g)
+            e[1], e[2] = self.sid, self._mark()
         else:
-            self.grads[k] = g
+            self.grads[k] = [g, self.sid, self._mark()]
             self.keep.append(t)
 
     def grad_of(self, t):
-        return self.grads.pop(id(t), None)
+        e = self.grads.pop(id(t), None)
+        if e is None:
+            return None
+        self._wait(e)
+        return e[0]
+
+    def side(self, fn):
+        """Run ``fn`` (a weight gradient: nothing downstream of it but the optimiser) on the weight-gradient
+        stream of the current role, ordered after everything enqueued so far on the current stream."""
+        role = _WG_OF.get(self.sid) if self.streams is not None else None
+        if role is None:
+            fn()
+            return
+        ws = self.streams[role]
+        ws.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ws):
+            fn()
 
     def backward(self):
-        for fn in reversed(self.steps):
-            fn()
+        if self.streams is None:
+            for fn, _ in reversed(self.steps):
+                fn()
+        else:
+            main = torch.cuda.current_stream()
+            self.streams[MAIN] = main
+            with ops.hold_allocations():
+                for s in self.streams[1:]:
+                    s.wait_stream(main)
+                for fn, sid in reversed(self.steps):
+                    self.sid = sid
+                    if sid == MAIN:
+                        fn()
+                    else:
+                        with torch.cuda.stream(self.streams[sid]):
+                            fn()
+                self.sid = MAIN
+                for s in self.streams[1:]:
+                    main.wait_stream(s)
         self.steps = []
         self.grads = {}
         self.keep = []
@@ -68,11 +148,15 @@ class Tape(object):
 class Context(object):
     """Per-forward state: dtype, mode, tape, BatchNorm scratch pool, packed-weight cache."""
 
-    def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO):
+    def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO, multistream=False):
         self.dtype = dtype
         self.training = training
         self.device = device
-        self.tape = Tape() if record else None
+        # multi-stream schedule: [caller's stream, DEPTH, FUSE, WG_MAIN, WG_DEPTH]
+        multistream = multistream and torch.device(device).type == 'cuda'
+        self.streams = [torch.cuda.current_stream()] + side_streams(device) if multistream else None
+        self.sid = MAIN
+        self.tape = Tape(self.streams) if record else None
         self.cache = cache if cache is not None else {}
         self.engine = engine
         self._pool_stats = None
@@ -81,10 +165,36 @@ class Context(object):
         self._off_aff = 0
         self.bn_counters = []
         self.taps = None
+        if self.streams is not None and training:
+            self.stats(0)            # the zeroed statistics pool must exist before the streams fork
+
+    # -- stream roles (no-ops on the single-stream schedule)
+    def fork(self):
+        """Side streams start after everything enqueued so far on the caller's stream."""
+        if self.streams is not None:
+            for s in self.streams[1:3]:
+                s.wait_stream(self.streams[MAIN])
+
+    def join(self):
+        if self.streams is not None:
+            for s in self.streams[1:3]:
+                self.streams[MAIN].wait_stream(s)
+
+    def wait(self, role, on):
+        """Stream ``role`` waits for what has been enqueued so far on streams ``on``."""
+        if self.streams is not None:
+            for o in on:
+                if o != role:
+                    self.streams[role].wait_stream(self.streams[o])
+
+    def on(self, role):
+        return _Role(self, role)
 
     # -- scratch: stats are zero-initialised doubles, affine params are floats
     def stats(self, c):
         if self._pool_stats is None or self._off_stats + 2 * c > self._pool_stats.numel():
+            if self._pool_stats is not None and self.streams is not None:
+                raise RuntimeError('BatchNorm statistics pool exhausted under the multi-stream schedule')
             self._pool_stats = torch.zeros(max(65536, 2 * c), device=self.device, dtype=torch.float64)
             self._off_stats = 0
         s = self._pool_stats[self._off_stats:self._off_stats + 2 * c]
@@ -139,6 +249,34 @@ class Context(object):
             ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift)
             return scale, shift
         return self.packed(('bn', id(mod)), ps, make)
+
+
+class _Role(object):
+    """``with ctx.on(role):`` -- issue (and record on the tape) the enclosed ops on that stream role."""
+
+    def __init__(self, ctx, role):
+        self.ctx, self.role = ctx, role
+
+    def __enter__(self):
+        ctx = self.ctx
+        self.prev = ctx.sid
+        self.cm = None
+        if ctx.streams is not None and self.role != ctx.sid:
+            ctx.sid = self.role
+            if ctx.tape is not None:
+                ctx.tape.sid = self.role
+            self.cm = torch.cuda.stream(ctx.streams[self.role])
+            self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        ctx = self.ctx
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+            ctx.sid = self.prev
+            if ctx.tape is not None:
+                ctx.tape.sid = self.prev
+        return False
 
 
 # ----------------------------------------------------------------------------- conv unit
@@ -217,11 +355,14 @@ def _stem_s2d_unit(ctx, mod, x, act):
             dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
             tape.param_grads.append((bn.weight, dgamma))
             tape.param_grads.append((bn.bias, dbeta))
-            dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine)          # [cout][16][CPAD]
             gw = _grad_dst(mod.conv.weight)
-            ops.unpack_stem_s2d_wgrad(dw, gw)
+
+            def wgrad():
+                dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine)      # [cout][16][CPAD]
+                ops.unpack_stem_s2d_wgrad(dw, gw)
+            tape.side(wgrad)
             tape.param_grads.append((mod.conv.weight, gw))
-        tape.steps.append(bwd)
+        tape.add_step(bwd)
     return z
 
 
@@ -248,18 +389,22 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
             y, scale, shift, mean, invstd, act, residual = bn_state
             if residual is not None:
                 dz = ops.leaky_bwd(dz, z)               # through the post-add activation
-                tape.add_grad(residual, dz)
             bn = mod.batch_norm
             dgamma = _grad_dst(bn.weight)
             dbeta = _grad_dst(bn.bias)
             dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
+            if residual is not None:
+                tape.add_grad(residual, dz)             # published after its last read here (Tape.add_grad)
             tape.param_grads.append((bn.weight, dgamma))
             tape.param_grads.append((bn.bias, dbeta))
         else:
             dy = dz
-        dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine)
         gw = _grad_dst(w_param)
-        ops.unpack_wgrad(dw, gw)
+
+        def wgrad():
+            dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine)
+            ops.unpack_wgrad(dw, gw)
+        tape.side(wgrad)
         tape.param_grads.append((w_param, gw))
         if not want_input_grad:
             return
@@ -272,7 +417,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
             if src is x0 and (hin, win) != (x0.shape[1], x0.shape[2]):
                 dsrc = ops.upsample_nearest_bwd(dsrc, (x0.shape[1], x0.shape[2]))
             tape.add_grad(src, dsrc)
-    tape.steps.append(bwd)
+    tape.add_step(bwd)
 
 
 # ----------------------------------------------------------------------------- gated fusion level
@@ -326,7 +471,7 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
                 tape.param_grads.append((wparam, g))
             wd = ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype, dgrad=True)
             tape.add_grad(dep, ops.conv2d(dy, wd, dep.shape[3], 1, 1, engine=ctx.engine))
-        tape.steps.append(bwd)
+        tape.add_step(bwd)
     return out
 
 
@@ -339,7 +484,7 @@ def max_pool(ctx, x):
             d = tape.grad_of(out)
             if d is not None:
                 tape.add_grad(x, ops.maxpool3x3s2_bwd(x, d))
-        tape.steps.append(bwd)
+        tape.add_step(bwd)
     return out
 
 
@@ -380,19 +525,40 @@ def stem_input(ctx, x_nchw):
 
 
 def fusionnet_encoder(ctx, enc, image, depth, stem_s2d=False):
-    """networks.FusionNetEncoder.forward (reference src/networks.py:840-1005); NHWC in / out."""
-    ci = conv_unit(ctx, enc.conv1_image, image, want_input_grad=False, stem_s2d=stem_s2d)
-    cd = conv_unit(ctx, enc.conv1_depth, depth, want_input_grad=False, stem_s2d=stem_s2d)
-    layers = [fusion_level(ctx, enc.conv1_weight, enc.conv1_project, cd, ci)]
-    xi, xd = max_pool(ctx, ci), max_pool(ctx, cd)
+    """networks.FusionNetEncoder.forward (reference src/networks.py:840-1005); NHWC in / out.
+    ``image`` / ``depth`` may be callables producing the stem inputs (so the layout conversion of each
+    branch is issued on that branch's stream).  Multi-stream schedule: the image branch runs on MAIN,
+    the depth branch on DEPTH, every gated fusion level on FUSE after both of its inputs."""
+    ctx.fork()
+    with ctx.on(MAIN):
+        if callable(image):
+            image, stem_s2d = image()
+        ci = conv_unit(ctx, enc.conv1_image, image, want_input_grad=False, stem_s2d=stem_s2d)
+    with ctx.on(DEPTH):
+        if callable(depth):
+            depth, s2d_d = depth()
+            assert s2d_d == stem_s2d
+        cd = conv_unit(ctx, enc.conv1_depth, depth, want_input_grad=False, stem_s2d=stem_s2d)
+    ctx.wait(FUSE, (MAIN, DEPTH))
+    with ctx.on(FUSE):
+        layers = [fusion_level(ctx, enc.conv1_weight, enc.conv1_project, cd, ci)]
+    with ctx.on(MAIN):
+        xi = max_pool(ctx, ci)
+    with ctx.on(DEPTH):
+        xd = max_pool(ctx, cd)
     for level in range(2, 8):
         si = getattr(enc, 'blocks%d_image' % level)
         if si is None:
             break
-        xi = res_stage(ctx, si, xi)
-        xd = res_stage(ctx, getattr(enc, 'blocks%d_depth' % level), xd)
-        layers.append(fusion_level(ctx, getattr(enc, 'conv%d_weight' % level), getattr(enc, 'conv%d_project' % level),
-                                   xd, xi))
+        with ctx.on(MAIN):
+            xi = res_stage(ctx, si, xi)
+        with ctx.on(DEPTH):
+            xd = res_stage(ctx, getattr(enc, 'blocks%d_depth' % level), xd)
+        ctx.wait(FUSE, (MAIN, DEPTH))
+        with ctx.on(FUSE):
+            layers.append(fusion_level(ctx, getattr(enc, 'conv%d_weight' % level),
+                                       getattr(enc, 'conv%d_project' % level), xd, xi))
+    ctx.join()
     return layers[-1], layers[:-1]
 
 

@@ -21,6 +21,47 @@ def dt(t):
     return _DT[t.dtype]
 
 
+# While several CUDA streams are in flight (rcfd.engine multi-stream schedules) every tensor these wrappers
+# allocate is kept alive until the streams have joined: torch's caching allocator recycles a freed block on
+# the stream that allocated it, which is only safe once every OTHER stream that read it has been joined.
+_HOLD = None
+
+
+class hold_allocations(object):
+    """Context manager: keep every ops-allocated tensor alive until exit (re-entrant: the outermost owns)."""
+
+    def __enter__(self):
+        global _HOLD
+        self.owner = _HOLD is None
+        if self.owner:
+            _HOLD = []
+        return self
+
+    def __exit__(self, *exc):
+        global _HOLD
+        if self.owner:
+            _HOLD = None
+        return False
+
+
+def _keep(t):
+    if _HOLD is not None:
+        _HOLD.append(t)
+    return t
+
+
+def _empty(*a, **k):
+    return _keep(torch.empty(*a, **k))
+
+
+def _empty_like(*a, **k):
+    return _keep(torch.empty_like(*a, **k))
+
+
+def _zeros(*a, **k):
+    return _keep(torch.zeros(*a, **k))
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -72,7 +113,7 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
         d.src1, d.c1 = None, 0
     d.weight = weight_packed.data_ptr()
     if out is None:
-        out = torch.empty((n, ho, wo, cout), device=x0.device, dtype=torch.float32 if out_f32 else x0.dtype)
+        out = _empty((n, ho, wo, cout), device=x0.device, dtype=torch.float32 if out_f32 else x0.dtype)
     d.dst = out.data_ptr()
     d.scale = scale.data_ptr() if scale is not None else None
     d.shift = shift.data_ptr() if shift is not None else None
@@ -105,13 +146,13 @@ def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=EN
     d.hin, d.win = hin, win
     d.src0, d.h0, d.w0, d.c0 = x0.data_ptr(), h0, w0, c0
     d.src1, d.c1 = (x1.data_ptr() if x1 is not None else None), c1
-    dw = torch.empty((cout, k * k, c0 + c1), device=x0.device, dtype=torch.float32)
+    dw = _empty((cout, k * k, c0 + c1), device=x0.device, dtype=torch.float32)
     d.weight = dw.data_ptr()       # unused by wgrad, must be non-null
     d.dst = dy.data_ptr()
     d.dtype = dt(x0)
     d.engine = engine
     ws_bytes = int(_lib.load().rcfd_conv2d_wgrad_workspace(ctypes.byref(d)))
-    ws = torch.empty(ws_bytes, device=x0.device, dtype=torch.uint8) if ws_bytes > 0 else None
+    ws = _empty(ws_bytes, device=x0.device, dtype=torch.uint8) if ws_bytes > 0 else None
     _lib.call('rcfd_conv2d_wgrad', ctypes.byref(d), _p(dw), _p(ws), ws_bytes, _stream())
     return dw
 
@@ -125,7 +166,7 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, p
     pad = inner if pad_to is None else max(inner, int(pad_to))
     if out is None:
         shape = (cin_cnt, kh * kw, pad) if dgrad else (cout, kh * kw, pad)
-        out = torch.empty(shape, device=w_oihw.device, dtype=dtype)
+        out = _empty(shape, device=w_oihw.device, dtype=dtype)
     _lib.call('rcfd_pack_conv_weight', _p(w_oihw), _p(out), cout, cin, kh, kw, cin_off, cin_cnt, pad,
               1 if dgrad else 0, _DT[dtype], _stream())
     return out
@@ -135,7 +176,7 @@ def pack_upconv2x_weight(w_oihw, dtype):
     """[4 phases][cout][2x2 taps][cin] weights of `3x3 conv after 2x nearest up-sampling` (TMA engine)."""
     cout, cin, kh, kw = w_oihw.shape
     assert kh == 3 and kw == 3
-    out = torch.empty((4, cout, 4, cin), device=w_oihw.device, dtype=dtype)
+    out = _empty((4, cout, 4, cin), device=w_oihw.device, dtype=dtype)
     _lib.call('rcfd_pack_upconv2x_weight', _p(w_oihw), _p(out), cout, cin, _DT[dtype], _stream())
     return out
 
@@ -162,7 +203,7 @@ def bn_fold(gamma, beta, running_mean, running_var, scale, shift):
 
 def bn_act(y, scale, shift, act, residual=None, out=None):
     c = y.shape[-1]
-    out = torch.empty_like(y) if out is None else out
+    out = _empty_like(y) if out is None else out
     _lib.call('rcfd_bn_act_fwd', _p(y), _p(scale), _p(shift), _p(residual), _p(out), y.numel() // c, c, act, dt(y),
               _stream())
     return out
@@ -172,10 +213,10 @@ def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None)
     c = y.shape[-1]
     pixels = y.numel() // c
     if sums is None:
-        sums = torch.empty(2 * c, device=y.device, dtype=torch.float64)
+        sums = _empty(2 * c, device=y.device, dtype=torch.float64)
     _lib.call('rcfd_bn_act_bwd_reduce', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), pixels, c,
               act, dt(y), _stream())
-    dy = torch.empty_like(y)
+    dy = _empty_like(y)
     _lib.call('rcfd_bn_act_bwd_apply', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), _p(dy),
               _p(dgamma), _p(dbeta), pixels, c, act, dt(y), _stream())
     return dy
@@ -183,7 +224,7 @@ def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None)
 
 def gate_fuse(y2c, scale, shift, img):
     c = img.shape[-1]
-    out = torch.empty_like(img)
+    out = _empty_like(img)
     _lib.call('rcfd_gate_fuse_fwd', _p(y2c), _p(scale), _p(shift), _p(img), _p(out), img.numel() // c, c, dt(img),
               _stream())
     return out
@@ -191,7 +232,7 @@ def gate_fuse(y2c, scale, shift, img):
 
 def gate_fuse_bwd(dout, y2c, scale, shift):
     c = dout.shape[-1]
-    dz = torch.empty_like(y2c)
+    dz = _empty_like(y2c)
     _lib.call('rcfd_gate_fuse_bwd', _p(dout), _p(y2c), _p(scale), _p(shift), _p(dz), dout.numel() // c, c, dt(dout),
               _stream())
     return dz
@@ -199,14 +240,14 @@ def gate_fuse_bwd(dout, y2c, scale, shift):
 
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
-    out = torch.empty((n, conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1), c), device=x.device, dtype=x.dtype)
+    out = _empty((n, conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1), c), device=x.device, dtype=x.dtype)
     _lib.call('rcfd_maxpool3x3s2_fwd', _p(x), _p(out), n, h, w, c, dt(x), _stream())
     return out
 
 
 def maxpool3x3s2_bwd(x, dout):
     n, h, w, c = x.shape
-    dx = torch.empty_like(x)
+    dx = _empty_like(x)
     _lib.call('rcfd_maxpool3x3s2_bwd', _p(x), _p(dout), _p(dx), n, h, w, c, dt(x), _stream())
     return dx
 
@@ -214,13 +255,13 @@ def maxpool3x3s2_bwd(x, dout):
 def upsample_nearest_bwd(dup, src_hw):
     n, hu, wu, c = dup.shape
     hs, ws = src_hw
-    dsrc = torch.empty((n, hs, ws, c), device=dup.device, dtype=dup.dtype)
+    dsrc = _empty((n, hs, ws, c), device=dup.device, dtype=dup.dtype)
     _lib.call('rcfd_upsample_nearest_bwd', _p(dup), _p(dsrc), n, hs, ws, hu, wu, c, 0, dt(dup), _stream())
     return dsrc
 
 
 def leaky_bwd(dout, out):
-    din = torch.empty_like(dout)
+    din = _empty_like(dout)
     _lib.call('rcfd_leaky_bwd', _p(dout), _p(out), _p(din), dout.numel(), dt(dout), _stream())
     return din
 
@@ -234,7 +275,7 @@ def nchw_to_nhwc(x, dtype, cpad=None):
     n, c, h, w = x.shape
     cpad = c if cpad is None else max(c, int(cpad))
     x = x.contiguous()
-    out = torch.empty((n, h, w, cpad), device=x.device, dtype=dtype)
+    out = _empty((n, h, w, cpad), device=x.device, dtype=dtype)
     _lib.call('rcfd_nchw_to_nhwc', _p(x), _p(out), n, c, h, w, cpad, _DT[dtype], _stream())
     return out
 
@@ -243,7 +284,7 @@ def nchw_to_s2d(x, dtype, cpad=16):
     """NCHW float -> space-to-depth NHWC [N, H/2, W/2, cpad] (channel = (dy*2+dx)*C + c), for the 7x7/s2 stems."""
     n, c, h, w = x.shape
     x = x.contiguous()
-    out = torch.empty((n, h // 2, w // 2, cpad), device=x.device, dtype=dtype)
+    out = _empty((n, h // 2, w // 2, cpad), device=x.device, dtype=dtype)
     _lib.call('rcfd_nchw_to_s2d_nhwc', _p(x), _p(out), n, c, h, w, cpad, _DT[dtype], _stream())
     return out
 
@@ -251,7 +292,7 @@ def nchw_to_s2d(x, dtype, cpad=16):
 def pack_stem_s2d_weight(w_oihw, dtype, cpad=16):
     cout, c, kh, kw = w_oihw.shape
     assert kh == 7 and kw == 7
-    out = torch.empty((cout, 16, cpad), device=w_oihw.device, dtype=dtype)
+    out = _empty((cout, 16, cpad), device=w_oihw.device, dtype=dtype)
     _lib.call('rcfd_pack_stem_s2d_weight', _p(w_oihw), _p(out), cout, c, cpad, _DT[dtype], _stream())
     return out
 
@@ -263,23 +304,23 @@ def unpack_stem_s2d_wgrad(dw_packed, grad_oihw):
 
 def nhwc_to_nchw(x):
     n, h, w, c = x.shape
-    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    out = _empty((n, c, h, w), device=x.device, dtype=torch.float32)
     _lib.call('rcfd_nhwc_to_nchw', _p(x), _p(out), n, c, h, w, dt(x), _stream())
     return out
 
 
 def depth_head_bwd(ddepth, depth, min_depth, min_over_max, dtype, cpad=1):
     """depth: [N, H, W, 1] float -> dlogit [N, H, W, cpad] (channel 0 carries the gradient)."""
-    dl = torch.empty(tuple(depth.shape[:3]) + (cpad,), device=depth.device, dtype=dtype)
+    dl = _empty(tuple(depth.shape[:3]) + (cpad,), device=depth.device, dtype=dtype)
     _lib.call('rcfd_depth_head_bwd', _p(ddepth.contiguous()), _p(depth), _p(dl), float(min_depth), float(min_over_max),
               depth.numel(), cpad, _DT[dtype], _stream())
     return dl
 
 
 def masked_l1_loss(out, gt, lidar, w_lidar, want_grad=True):
-    accum = torch.empty(4, device=out.device, dtype=torch.float64)
-    loss = torch.empty(1, device=out.device, dtype=torch.float32)
-    dout = torch.empty_like(out) if want_grad else None
+    accum = _empty(4, device=out.device, dtype=torch.float64)
+    loss = _empty(1, device=out.device, dtype=torch.float32)
+    dout = _empty_like(out) if want_grad else None
     _lib.call('rcfd_masked_l1_loss', _p(out.contiguous()), _p(gt.contiguous()), _p(lidar.contiguous()), float(w_lidar),
               _p(accum), _p(loss), _p(dout), out.numel(), _stream())
     return loss, dout
@@ -288,8 +329,8 @@ def masked_l1_loss(out, gt, lidar, w_lidar, want_grad=True):
 def outlier_removal(depth, kernel_size=7, threshold=1.5):
     depth = depth.contiguous()
     n, _, h, w = depth.shape
-    out = torch.empty_like(depth)
-    scratch = torch.empty(1, device=depth.device, dtype=torch.float32)
+    out = _empty_like(depth)
+    scratch = _empty(1, device=depth.device, dtype=torch.float32)
     _lib.call('rcfd_outlier_removal', _p(depth), _p(out), _p(scratch), n, h, w, kernel_size, float(threshold), _stream())
     return out
 
@@ -303,7 +344,7 @@ def scatter_points_to_depth_map(points_xy, depth, h, w, img=None):
     """S1.  points_xy: [2, N] float64 CUDA, depth: [N] float64.  img given -> z-buffer merge into it."""
     merge = img is not None
     if img is None:
-        img = torch.empty((h, w), device=points_xy.device, dtype=torch.float64)
+        img = _empty((h, w), device=points_xy.device, dtype=torch.float64)
     npts = points_xy.shape[1]
     _lib.call('rcfd_scatter_points_to_depth_map', _p(points_xy.contiguous()), _p(depth.contiguous()), npts, _p(img), h,
               w, 1 if merge else 0, _stream())
@@ -313,13 +354,13 @@ def scatter_points_to_depth_map(points_xy, depth, h, w, img=None):
 def scatter_tiles_argmax(crops, points, h, w, compat=True):
     """S2.  crops: [K, 1, ph, pw] float32; points: [K, 3] float32 (x already shifted by +pad)."""
     k, _, ph, pw = crops.shape
-    response = torch.empty((1, h, w), device=crops.device, dtype=torch.float32)
+    response = _empty((1, h, w), device=crops.device, dtype=torch.float32)
     if compat:
-        depth = torch.empty((1, h, w), device=crops.device, dtype=torch.int64)
+        depth = _empty((1, h, w), device=crops.device, dtype=torch.int64)
         _lib.call('rcfd_scatter_tiles_argmax', _p(crops.contiguous()), _p(points.contiguous()), k, ph, pw, h, w, 1,
                   _p(depth), None, _p(response), _stream())
     else:
-        depth = torch.empty((1, h, w), device=crops.device, dtype=torch.float32)
+        depth = _empty((1, h, w), device=crops.device, dtype=torch.float32)
         _lib.call('rcfd_scatter_tiles_argmax', _p(crops.contiguous()), _p(points.contiguous()), k, ph, pw, h, w, 0,
                   None, _p(depth), _p(response), _stream())
     return depth, response
@@ -329,7 +370,7 @@ def roi_pool(feat, boxes5, out_size, spatial_scale):
     """feat: NHWC; boxes5: [nbox, 5] float32 (batch_index, x1, y1, x2, y2)."""
     n, h, w, c = feat.shape
     nbox = boxes5.shape[0]
-    out = torch.empty((nbox, out_size[0], out_size[1], c), device=feat.device, dtype=feat.dtype)
+    out = _empty((nbox, out_size[0], out_size[1], c), device=feat.device, dtype=feat.dtype)
     _lib.call('rcfd_roi_pool_fwd', _p(feat), _p(boxes5.contiguous()), _p(out), n, h, w, c, nbox, out_size[0],
               out_size[1], float(spatial_scale), dt(feat), _stream())
     return out
@@ -338,6 +379,6 @@ def roi_pool(feat, boxes5, out_size, spatial_scale):
 def linear_leaky(x, w, b):
     rows, fin = x.shape
     fout = w.shape[0]
-    out = torch.empty((rows, fout), device=x.device, dtype=torch.float32)
+    out = _empty((rows, fout), device=x.device, dtype=torch.float32)
     _lib.call('rcfd_linear_leaky_fwd', _p(x.contiguous()), _p(w), _p(b), _p(out), rows, fin, fout, _stream())
     return out

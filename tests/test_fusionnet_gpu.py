@@ -242,14 +242,60 @@ def test_graphed_train_step_matches_eager():
     (l_e, s_e, g_e), (l_g, s_g, g_g) = results
     print('eager losses', l_e, 'graphed losses', l_g)
     assert abs(l_e[0] - l_g[0]) < 1e-5 * abs(l_e[0])        # identical kernels on identical inputs
+    assert relerr(g_g.cpu(), g_e.cpu()) < 1e-4                # first-step gradients: only the order of fp32 atomics differs
+    # later steps: Adam's first updates are +-lr whatever the gradient magnitude, so atomics-order noise in
+    # near-zero gradients flips individual updates and bf16 rounding amplifies it (eager vs eager shows the
+    # same spread, tools/diag_graph.py): bounded loosely
     for a, b in zip(l_e, l_g):
-        assert abs(a - b) < 2e-3 * abs(a)
-    assert relerr(g_g.cpu(), g_e.cpu()) < 1e-3                # first-step gradients: only the order of fp32 atomics differs
+        assert abs(a - b) < 1e-2 * abs(a), (l_e, l_g)
     for k in s_e:
         if 'num_batches_tracked' in k:
             assert int(s_e[k]) == int(s_g[k]) == 3, k
         elif 'running' in k:
-            assert relerr(s_g[k].cpu(), s_e[k].cpu()) < 1e-2, k
+            err = relerr(s_g[k].cpu(), s_e[k].cpu())
+            assert err < 5e-2, (k, err)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_multistream_schedule_matches_single_stream(precision):
+    """The multi-stream schedule (image branch / depth branch / fusion / weight gradients on parallel CUDA
+    streams) runs the same kernels on the same data as the single-stream one: depth, loss, every gradient
+    and the BatchNorm buffers agree up to the order of floating-point atomics."""
+    cfg = synth.CANONICAL_FUSIONNET
+    p0 = synth_fusionnet_state(cfg, 11)
+    n, h, w = 2, 96, 160
+    image, depth = synth.fusionnet_inputs(n, h, w, 11, 'quasi_dense')
+    gt, lidar = synth.training_targets(n, h, w, 11)
+    image, depth, gt, lidar = [t.to(DEV) for t in (image, depth, gt, lidar)]
+    res = []
+    for ms in (False, True):
+        m = make_model(cfg, p0, precision=precision)
+        m.multistream = ms
+        m.train()
+        for rep in range(2):                    # twice: the second pass reuses memory freed by the first
+            for p in m.parameters():
+                p.grad = None
+            d = m.forward(image, depth)
+            loss, _ = m.compute_loss(image, d, gt, lidar, 'l1', 0.0, -1, None, 2.0)
+            loss.backward()
+        torch.cuda.synchronize()
+        names = ['encoder.' + k for k, _ in m.encoder.named_parameters()] + ['decoder.' + k for k, _ in m.decoder.named_parameters()]
+        grads = {k: p.grad.detach().clone() for k, p in zip(names, m.parameters()) if p.grad is not None}
+        bufs = {k: v.detach().clone() for k, v in m.encoder.state_dict().items() if 'running' in k}
+        m.eval()
+        with torch.no_grad():
+            e = m.forward(image, depth).clone()
+        res.append((d.detach().clone(), float(loss), grads, bufs, e))
+    (d0, l0, g0, b0, e0), (d1, l1, g1, b1, e1) = res
+    assert relerr(d1.cpu(), d0.cpu()) < 1e-6
+    assert relerr(e1.cpu(), e0.cpu()) < 1e-6
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    assert set(g0) == set(g1)
+    worst = max((relerr(g1[k].cpu(), g0[k].cpu()), k) for k in g0)
+    print('worst gradient deviation', worst)
+    assert worst[0] < 1e-4, worst
+    for k in b0:
+        assert relerr(b1[k].cpu(), b0[k].cpu()) < 1e-6, k
 
 
 def test_bf16_train_step_sanity():

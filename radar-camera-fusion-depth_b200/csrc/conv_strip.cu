@@ -42,12 +42,13 @@ struct StripP {
   int accumulate, dst_f32;
 };
 
-template <int BN, int CIN>
+template <int BN, int CIN, int KS = 3>
 struct StripCfg {
   static constexpr int RB = CIN * 2;                                        // bytes per pixel row
-  static constexpr int ROWBUF = ((HALO_W * RB + 1023) / 1024) * 1024;
+  static constexpr int HALO = SW + KS - 1;                                  // pixels per ring row
+  static constexpr int ROWBUF = ((HALO * RB + 1023) / 1024) * 1024;
   static constexpr int W_TAP = ((BN * RB + 1023) / 1024) * 1024;
-  static constexpr int W_BYTES = 9 * W_TAP;
+  static constexpr int W_BYTES = KS * KS * W_TAP;
   static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM = NR * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
@@ -60,10 +61,128 @@ __device__ __forceinline__ uint64_t strip_desc(uint32_t saddr, uint32_t sbo, uin
   return d;
 }
 
-template <int BN, int CIN>
+
+// ---- epilogue helpers shared by the two kernels -------------------------------------------------------
+// 16 accumulator columns of one pixel -> folded BN / activation / residual / accumulate -> global
+__device__ __forceinline__ void strip_store16(float (&v)[16], const StripP& p, int nb, size_t o, bool vector_epilogue) {
+  const bf16* R = reinterpret_cast<const bf16*>(p.residual);
+  bf16* D = reinterpret_cast<bf16*>(p.dst);
+  if (!vector_epilogue) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = nb + i;
+      if (n < p.cout) {
+        float x = v[i];
+        if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+        x = apply_act(x, p.act, p.p0, p.p1);
+        if (R) x = leaky(x + __bfloat162float(R[o + i]));
+        if (p.dst_f32) {
+          float* Df = reinterpret_cast<float*>(p.dst);
+          Df[o + i] = p.accumulate ? Df[o + i] + x : x;
+        } else {
+          D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+        }
+      }
+    }
+  } else if (nb < p.cout) {
+    if (p.scale) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
+    }
+    if (p.act == RCFD_ACT_LEAKY) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+    } else if (p.act == RCFD_ACT_SIGMOID) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
+    }
+    if (R) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+        v[2 * i] = leaky(v[2 * i] + f.x);
+        v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
+      }
+    }
+    if (p.accumulate) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// BatchNorm batch statistics.  Every epilogue thread owns ONE pixel column of the strip (its TMEM lane) and
+// sees all BN channels of it, row after row: the per-channel sum / sum of squares are kept in REGISTERS for
+// the whole life of the CTA (no shuffles, barriers or atomics per row) and reduced once at the end:
+// a transposing butterfly over the 32 lanes (16 channels at a time), shared memory over the 4 warps, then
+// one fp64 atomicAdd per channel per CTA.
+template <int BN>
+__device__ __forceinline__ void strip_flush_stats(float (&ss)[BN], float (&sq)[BN], float* red, int q, int lane, int etid,
+                                                  int n0, const StripP& p) {
+#pragma unroll
+  for (int cb = 0; cb < BN; cb += 16) {
+    float s16[16], q16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s16[i] = ss[cb + i] + __shfl_xor_sync(0xffffffffu, ss[cb + i], 16);
+      q16[i] = sq[cb + i] + __shfl_xor_sync(0xffffffffu, sq[cb + i], 16);
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+      const bool hi = (lane & w) != 0;
+#pragma unroll
+      for (int i = 0; i < w; ++i) {
+        const float send_s = hi ? s16[i] : s16[i + w];
+        const float keep_s = hi ? s16[i + w] : s16[i];
+        s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+        const float send_q = hi ? q16[i] : q16[i + w];
+        const float keep_q = hi ? q16[i + w] : q16[i];
+        q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+      }
+    }
+    if (lane < 16) {
+      red[(q * BN + cb + lane) * 2 + 0] = s16[0];
+      red[(q * BN + cb + lane) * 2 + 1] = q16[0];
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int c = etid; c < BN; c += NEPI) {
+    if (n0 + c < p.cout) {
+      double s = 0.0, qq = 0.0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        s += (double)red[(w * BN + c) * 2 + 0];
+        qq += (double)red[(w * BN + c) * 2 + 1];
+      }
+      atomicAdd(p.ssum + n0 + c, s);
+      atomicAdd(p.ssq + n0 + c, qq);
+    }
+  }
+}
+
+template <int BN, int CIN, bool STATS, int KS>
 __global__ void __launch_bounds__(NTHREADS)
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
-  typedef StripCfg<BN, CIN> C;
+  typedef StripCfg<BN, CIN, KS> C;
+  constexpr int PAD = KS / 2;            // 3x3 / pad 1, or the 4x4 / pad 2 window of the space-to-depth stems
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -107,8 +226,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
       // resident weights: 9 taps x [BN][CIN]
-      mbar_expect_tx(wbar, (uint32_t)(9 * BN * C::RB));
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * C::W_TAP, &map_w, wbar, tap * p.cin, n0);
+      mbar_expect_tx(wbar, (uint32_t)(KS * KS * BN * C::RB));
+      for (int tap = 0; tap < KS * KS; ++tap) tma_load_2d(sW + tap * C::W_TAP, &map_w, wbar, tap * p.cin, n0);
       uint32_t L = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int ck = item % p.chunks_per_col;
@@ -117,11 +236,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int img = col / p.strips;
         const int y0 = ck * p.rows_per_chunk;
         const int rows = min(p.rows_per_chunk, p.h - y0);
-        for (int j = 0; j < rows + 2; ++j, ++L) {
+        for (int j = 0; j < rows + KS - 1; ++j, ++L) {
           const int s = L % NR;
           if (L >= (uint32_t)NR) mbar_wait(sBar + 8 * (NR + s), ((L / NR) & 1) ^ 1);
-          mbar_expect_tx(sBar + 8 * s, (uint32_t)(HALO_W * C::RB));
-          tma_load_4d(sRing + s * C::ROWBUF, &map_x, sBar + 8 * s, 0, strip * SW - 1, y0 - 1 + j, img);
+          mbar_expect_tx(sBar + 8 * s, (uint32_t)(C::HALO * C::RB));
+          tma_load_4d(sRing + s * C::ROWBUF, &map_x, sBar + 8 * s, 0, strip * SW - PAD, y0 - PAD + j, img);
         }
       }
     }
@@ -135,11 +254,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const int ck = item % p.chunks_per_col;
       const int y0 = ck * p.rows_per_chunk;
       const int rows = min(p.rows_per_chunk, p.h - y0);
-      // input rows L .. L+rows+1 of this chunk; output row t uses L+t, L+t+1, L+t+2
-      mbar_wait(sBar + 8 * (L % NR), (L / NR) & 1);
-      mbar_wait(sBar + 8 * ((L + 1) % NR), ((L + 1) / NR) & 1);
+      // input rows L .. L+rows+KS-2 of this chunk; output row t uses L+t .. L+t+KS-1
+#pragma unroll
+      for (int j = 0; j < KS - 1; ++j) mbar_wait(sBar + 8 * ((L + j) % NR), ((L + j) / NR) & 1);
       for (int t = 0; t < rows; ++t, ++orow) {
-        const uint32_t Lnew = L + t + 2;
+        const uint32_t Lnew = L + t + KS - 1;
         mbar_wait(sBar + 8 * (Lnew % NR), (Lnew / NR) & 1);
         const uint32_t acc = orow & 1;
         if (orow >= 2) mbar_wait(sBar + 8 * (2 * NR + 2 + acc), ((orow >> 1) & 1) ^ 1);
@@ -147,12 +266,12 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (lane == 0) {
           const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
+          for (int r = 0; r < KS; ++r) {
             const uint32_t rowbuf = sRing + ((L + t + r) % NR) * C::ROWBUF;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+            for (int s = 0; s < KS; ++s) {
               const uint32_t a0 = rowbuf + s * C::RB;
-              const uint32_t b0 = sW + (r * 3 + s) * C::W_TAP;
+              const uint32_t b0 = sW + (r * KS + s) * C::W_TAP;
 #pragma unroll
               for (int k = 0; k < CIN / 16; ++k) {
                 umma_f16(d_tmem, strip_desc(a0 + k * 32, sbo, C::LAYOUT, p.desc_mode), umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT),
@@ -162,25 +281,27 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
           umma_commit(sBar + 8 * (2 * NR + acc));                  // accumulator of this output row complete
           umma_commit(sBar + 8 * (NR + (L + t) % NR));             // oldest input row no longer needed
-          if (t == rows - 1) {                                      // chunk done: release its last two rows too
-            umma_commit(sBar + 8 * (NR + (L + t + 1) % NR));
-            umma_commit(sBar + 8 * (NR + (L + t + 2) % NR));
+          if (t == rows - 1) {                                      // chunk done: release its last KS-1 rows too
+#pragma unroll
+            for (int j = 1; j < KS; ++j) umma_commit(sBar + 8 * (NR + (L + t + j) % NR));
           }
         }
         __syncwarp();
       }
-      L += rows + 2;
+      L += rows + KS - 1;
     }
     tc_fence_before();
   } else {
     // =========================================================== EPILOGUE (warps 2..5)
     const int q = warp & 3;
     const int r = q * 32 + lane;               // pixel within the strip == TMEM lane
-    const bool want_stats = p.ssum != nullptr;
     const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
-    const bf16* R = reinterpret_cast<const bf16*>(p.residual);
-    bf16* D = reinterpret_cast<bf16*>(p.dst);
     const int etid = tid - 64;
+    float ss[STATS ? BN : 1], sq[STATS ? BN : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) { ss[i] = 0.f; sq[i] = 0.f; }
+    }
     uint32_t orow = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int ck = item % p.chunks_per_col;
@@ -194,129 +315,36 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       for (int t = 0; t < rows; ++t, ++orow) {
         const uint32_t acc = orow & 1;
         const size_t gm = ((size_t)img * p.h + (y0 + t)) * p.w + ox;
-        float* redt = red + acc * (4 * BN * 2);
         mbar_wait(sBar + 8 * (2 * NR + acc), (orow >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 16) {
-          float v[16];
-          tmem_ld16(trow + cb, v);
-          if (want_stats) {
-            float s16[16], q16[16];
+        if constexpr (STATS) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = mvalid ? v[i] : 0.f;
-              s16[i] = x;
-              q16[i] = x * x;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
-              q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
-            }
-#pragma unroll
-            for (int w = 8; w >= 1; w >>= 1) {
-              const bool hi = (lane & w) != 0;
-#pragma unroll
-              for (int i = 0; i < w; ++i) {
-                const float send_s = hi ? s16[i] : s16[i + w];
-                const float keep_s = hi ? s16[i + w] : s16[i];
-                s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                const float send_q = hi ? q16[i] : q16[i + w];
-                const float keep_q = hi ? q16[i + w] : q16[i];
-                q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
-              }
-            }
-            if (lane < 16) {
-              redt[(q * BN + cb + lane) * 2 + 0] = s16[0];
-              redt[(q * BN + cb + lane) * 2 + 1] = q16[0];
-            }
-          }
-          if (mvalid) {
-            const int nb = n0 + cb;
-            const size_t o = gm * p.cout + nb;
-            if (!vector_epilogue) {
+          for (int cb = 0; cb < BN; cb += 16) {          // unrolled: ss / sq must be indexed statically
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            if (mvalid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int n = nb + i;
-                if (n < p.cout) {
-                  float x = v[i];
-                  if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
-                  x = apply_act(x, p.act, p.p0, p.p1);
-                  if (R) x = leaky(x + __bfloat162float(R[o + i]));
-                  if (p.dst_f32) {
-                    float* Df = reinterpret_cast<float*>(p.dst);
-                    Df[o + i] = p.accumulate ? Df[o + i] + x : x;
-                  } else {
-                    D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
-                  }
-                }
+                ss[cb + i] += v[i];
+                sq[cb + i] = fmaf(v[i], v[i], sq[cb + i]);
               }
-            } else if (nb < p.cout) {
-              if (p.scale) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
-              }
-              if (p.act == RCFD_ACT_LEAKY) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-              } else if (p.act == RCFD_ACT_SIGMOID) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
-              }
-              if (R) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                  v[2 * i] = leaky(v[2 * i] + f.x);
-                  v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
-                }
-              }
-              if (p.accumulate) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
-                }
-              }
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
             }
+          }
+        } else {
+#pragma unroll 1
+          for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            if (mvalid) strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
           }
         }
         tc_fence_before();
         mbar_arrive(sBar + 8 * (2 * NR + 2 + acc));
-        if (want_stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int c = etid; c < BN; c += NEPI) {
-            if (n0 + c < p.cout) {
-              double s = 0.0, qq = 0.0;
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                s += (double)redt[(w * BN + c) * 2 + 0];
-                qq += (double)redt[(w * BN + c) * 2 + 1];
-              }
-              atomicAdd(p.ssum + n0 + c, s);
-              atomicAdd(p.ssq + n0 + c, qq);
-            }
-          }
-        }
       }
     }
+    if constexpr (STATS) strip_flush_stats<BN>(ss, sq, red, q, lane, etid, n0, p);
   }
   __syncthreads();
   if (warp == 1) {
@@ -342,7 +370,7 @@ struct StripUpCfg {
 // 3x3 conv behind an exact 2x nearest up-sampling, streamed over LOW-RES rows: per low-res row
 // the four sub-pixel phases (2x2 taps each, summed weights) are accumulated into four TMEM
 // buffers and written to output rows 2i, 2i+1 / columns 2j, 2j+1.
-template <int BN, int CIN>
+template <int BN, int CIN, bool STATS>
 __global__ void __launch_bounds__(NTHREADS)
 conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
   typedef StripUpCfg<BN, CIN> C;
@@ -465,11 +493,13 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     // =========================================================== EPILOGUE (warps 2..5)
     const int q = warp & 3;
     const int r = q * 32 + lane;               // pixel within the strip == TMEM lane
-    const bool want_stats = p.ssum != nullptr;
     const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
-    const bf16* R = reinterpret_cast<const bf16*>(p.residual);
-    bf16* D = reinterpret_cast<bf16*>(p.dst);
     const int etid = tid - 64;
+    float ss[STATS ? BN : 1], sq[STATS ? BN : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) { ss[i] = 0.f; sq[i] = 0.f; }
+    }
     uint32_t orow = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int ck = item % p.chunks_per_col;
@@ -482,138 +512,33 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const bool mvalid = ox < p.w;
       for (int t = 0; t < rows; ++t, ++orow) {
         const uint32_t acc = orow & 1;
-        float* redt = red + acc * (4 * BN * 2);
         mbar_wait(sBar + 8 * (2 * NRU + acc), (orow >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int phcb = 0; phcb < 4 * BN; phcb += 16) {
-          const int ph = phcb / BN, cb = phcb - ph * BN;
+        for (int ph = 0; ph < 4; ++ph) {
           const size_t gm = ((size_t)img * (2 * p.h) + (2 * (y0 + t) + (ph >> 1))) * (2 * p.w) + (2 * ox + (ph & 1));
           const uint32_t trow = tmem_base + (acc * 4 + ph) * BN + ((uint32_t)(q * 32) << 16);
-          {
-          float v[16];
-          tmem_ld16(trow + cb, v);
-          if (want_stats) {
-            float s16[16], q16[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = mvalid ? v[i] : 0.f;
-              s16[i] = x;
-              q16[i] = x * x;
-            }
+          for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            if constexpr (STATS) {
+              if (mvalid) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
-              q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
-            }
-#pragma unroll
-            for (int w = 8; w >= 1; w >>= 1) {
-              const bool hi = (lane & w) != 0;
-#pragma unroll
-              for (int i = 0; i < w; ++i) {
-                const float send_s = hi ? s16[i] : s16[i + w];
-                const float keep_s = hi ? s16[i + w] : s16[i];
-                s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                const float send_q = hi ? q16[i] : q16[i + w];
-                const float keep_q = hi ? q16[i + w] : q16[i];
-                q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
-              }
-            }
-            if (lane < 16) {
-              if (ph == 0) {
-                redt[(q * BN + cb + lane) * 2 + 0] = s16[0];
-                redt[(q * BN + cb + lane) * 2 + 1] = q16[0];
-              } else {
-                redt[(q * BN + cb + lane) * 2 + 0] += s16[0];
-                redt[(q * BN + cb + lane) * 2 + 1] += q16[0];
-              }
-            }
-          }
-          if (mvalid) {
-            const int nb = n0 + cb;
-            const size_t o = gm * p.cout + nb;
-            if (!vector_epilogue) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int n = nb + i;
-                if (n < p.cout) {
-                  float x = v[i];
-                  if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
-                  x = apply_act(x, p.act, p.p0, p.p1);
-                  if (R) x = leaky(x + __bfloat162float(R[o + i]));
-                  if (p.dst_f32) {
-                    float* Df = reinterpret_cast<float*>(p.dst);
-                    Df[o + i] = p.accumulate ? Df[o + i] + x : x;
-                  } else {
-                    D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
-                  }
+                for (int i = 0; i < 16; ++i) {
+                  ss[cb + i] += v[i];
+                  sq[cb + i] = fmaf(v[i], v[i], sq[cb + i]);
                 }
               }
-            } else if (nb < p.cout) {
-              if (p.scale) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
-              }
-              if (p.act == RCFD_ACT_LEAKY) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-              } else if (p.act == RCFD_ACT_SIGMOID) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
-              }
-              if (R) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                  v[2 * i] = leaky(v[2 * i] + f.x);
-                  v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
-                }
-              }
-              if (p.accumulate) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
-                }
-              }
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-          }
+            if (mvalid) strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
           }
         }
         tc_fence_before();
         mbar_arrive(sBar + 8 * (2 * NRU + 2 + acc));
-        if (want_stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int c = etid; c < BN; c += NEPI) {
-            if (n0 + c < p.cout) {
-              double s = 0.0, qq = 0.0;
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                s += (double)redt[(w * BN + c) * 2 + 0];
-                qq += (double)redt[(w * BN + c) * 2 + 1];
-              }
-              atomicAdd(p.ssum + n0 + c, s);
-              atomicAdd(p.ssq + n0 + c, qq);
-            }
-          }
-        }
       }
     }
+    if constexpr (STATS) strip_flush_stats<BN>(ss, sq, red, q, lane, etid, n0, p);
   }
   __syncthreads();
   if (warp == 1) {
@@ -622,47 +547,56 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
-inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c) {
+inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int halo = HALO_W) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)HALO_W, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)halo, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(c), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int CIN>
-int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
-  typedef StripCfg<BN, CIN> C;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+template <int BN, int CIN, bool STATS, int KS>
+int launch_strip_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  typedef StripCfg<BN, CIN, KS> C;
+  static int per_sm = 0;                 // resident CTAs per SM (shared memory AND registers: the statistics variant is wide)
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<BN, CIN, STATS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
-    attr_set = true;
+    // two CTAs per SM when shared memory (227 KB) and the register file (64 K) both allow it
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, conv_strip_kernel<BN, CIN, STATS, KS>);
+    if (e != cudaSuccess) { set_error("conv_strip: attributes: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NTHREADS;
+    per_sm = (C::SMEM <= 112 * 1024 && 2 * regs_per_cta <= 65536) ? 2 : 1;
   }
   alignas(64) CUtensorMap mx, mw;
-  if (!make_row_map(&mx, k.src0, k.n, k.hin, k.win, k.c0) || !make_w_map(&mw, k.weight, k.cout, k.K, CIN, BN)) {
+  if (!make_row_map(&mx, k.src0, k.n, k.hin, k.win, k.c0, C::HALO) || !make_w_map(&mw, k.weight, k.cout, k.K, CIN, BN)) {
     set_error("conv_strip: cuTensorMapEncodeTiled failed");
     return RCFD_ECUDA;
   }
   const int ntile = ceil_div(k.cout, BN);
-  const int per_sm = C::SMEM <= 112 * 1024 ? 2 : 1;        // two CTAs per SM hide each other's barrier latencies
-  int ctas = num_sms() * per_sm / ntile;
+  int ctas = num_sms() * per_sm / ntile;                   // two CTAs per SM hide each other's barrier latencies
   if (ctas < 1) ctas = 1;
   if (ctas > t.num_items) ctas = t.num_items;
   dim3 grid(ctas, ntile);
-  conv_strip_kernel<BN, CIN><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  conv_strip_kernel<BN, CIN, STATS, KS><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
   RCFD_CHECK_LAUNCH("conv_strip");
   return RCFD_OK;
 }
 
-template <int BN, int CIN>
-int launch_strip_up(const ConvKP& k, StripP& t, cudaStream_t st) {
+template <int BN, int CIN, int KS = 3>
+int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
+  return t.ssum != nullptr ? launch_strip_s<BN, CIN, true, KS>(k, t, st) : launch_strip_s<BN, CIN, false, KS>(k, t, st);
+}
+
+template <int BN, int CIN, bool STATS>
+int launch_strip_up_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   typedef StripUpCfg<BN, CIN> C;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_strip_up_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_up_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip_up: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     attr_set = true;
   }
@@ -676,9 +610,14 @@ int launch_strip_up(const ConvKP& k, StripP& t, cudaStream_t st) {
   if (ctas < 1) ctas = 1;
   if (ctas > t.num_items) ctas = t.num_items;
   dim3 grid(ctas, ntile);
-  conv_strip_up_kernel<BN, CIN><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  conv_strip_up_kernel<BN, CIN, STATS><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
   RCFD_CHECK_LAUNCH("conv_strip_up");
   return RCFD_OK;
+}
+
+template <int BN, int CIN>
+int launch_strip_up(const ConvKP& k, StripP& t, cudaStream_t st) {
+  return t.ssum != nullptr ? launch_strip_up_s<BN, CIN, true>(k, t, st) : launch_strip_up_s<BN, CIN, false>(k, t, st);
 }
 
 }  // namespace
@@ -735,7 +674,8 @@ int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
 
 bool conv_strip_supported(const ConvKP& p, int dtype) {
   if (dtype != RCFD_BF16 || p.up || p.dil != 1 || p.c1 != 0) return false;
-  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
+  const bool stem = p.kh == 4 && p.kw == 4 && p.stride == 1 && p.pad == 2 && p.c0 == 16 && (p.cout == 16 || p.cout == 32);
+  if (!stem && (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1)) return false;
   if (p.c0 != 16 && p.c0 != 32 && p.c0 != 64) return false;
   if (p.ho != p.hin || p.wo != p.win) return false;
   if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight) & 15)) return false;
@@ -773,6 +713,9 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
       case 32: return launch_strip<32, 64>(p, t, st);
       default: return launch_strip<16, 64>(p, t, st);
     }
+  }
+  if (p.kh == 4) {                  // 7x7 / stride-2 stems as 4x4 windows over the space-to-depth input
+    return bn == 32 ? launch_strip<32, 16, 4>(p, t, st) : launch_strip<16, 16, 4>(p, t, st);
   }
   if (p.c0 == 16) {                 // d(logit) of the 1-channel head, stored with 16 channels
     switch (bn) {

@@ -122,6 +122,12 @@ int rcfd_bn_fold(const float* gamma, const float* beta, const float* running_mea
 /* out = act(y*scale+shift); if residual: out = leaky(out + residual)  (src/net_utils.py:86-91,323) */
 int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* residual,
                     void* out, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream);
+/* Training-mode BatchNorm forward in one pass: rcfd_bn_finalize + rcfd_bn_act_fwd fused (same values);
+ * replaces torch.nn.BatchNorm2d in training mode + activation (src/net_utils.py:82-91). */
+int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                          float* save_invstd, const void* residual, void* out, int64_t pixels, int32_t channels,
+                          int32_t act, float eps, float momentum, int32_t dtype, void* stream);
 /* Backward of the above through act and batch statistics.
  *   reduce: sums[0..C) += sum(dpre), sums[C..2C) += sum(dpre * xhat), dpre = dz * act'(pre)
  *   apply : dy = scale * (dpre - sums[c]/count - xhat * sums[C+c]/count)

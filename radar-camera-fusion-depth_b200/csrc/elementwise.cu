@@ -198,6 +198,63 @@ __global__ void bn_act_fwd_wide(const T* __restrict__ y, const float* __restrict
   }
 }
 
+// Training-mode BatchNorm forward in ONE pass over the tensor: every thread derives scale / shift of its own
+// channel group from the batch sums (same fp64 formulas as bn_finalize_kernel, so the values are identical),
+// block 0 also publishes scale / shift / mean / invstd for the backward pass and updates the running statistics.
+template <typename T>
+__global__ void bn_train_act_fwd_wide(const T* __restrict__ y, const double* __restrict__ sum, const double* __restrict__ sqsum,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float* __restrict__ rmean, float* __restrict__ rvar, float* __restrict__ scale,
+                                      float* __restrict__ shift, float* __restrict__ smean, float* __restrict__ sinv,
+                                      const T* __restrict__ res, T* __restrict__ out, int64_t nvec, int C, int act,
+                                      double count, float eps, float momentum) {
+  constexpr int N = V16<T>::N;
+  const int CV = C / N;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double mean = sum[c] / count;
+      double var = sqsum[c] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double invstd = 1.0 / sqrt(var + (double)eps);
+      scale[c] = (float)((double)gamma[c] * invstd);
+      shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+      smean[c] = (float)mean;
+      sinv[c] = (float)invstd;
+      if (rmean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * mean);
+        rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unbiased);
+      }
+    }
+  }
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i0 >= nvec) return;
+  const int c0 = (int)(i0 % CV) * N;
+  float sc[N], sh[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = c0 + k;
+    const double mean = sum[c] / count;
+    double var = sqsum[c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    sc[k] = (float)((double)gamma[c] * invstd);
+    sh[k] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+  }
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[N], r[N];
+    V16<T>::ld(y + i * N, v);
+    if (res) V16<T>::ld(res + i * N, r);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float x = apply_act(fmaf(v[k], sc[k], sh[k]), act, 0.f, 0.f);
+      if (res) x = leaky(x + r[k]);
+      v[k] = x;
+    }
+    V16<T>::st(out + i * N, v);
+  }
+}
+
 template <typename T>
 __global__ void bn_bwd_reduce_wide(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
                                    const float* __restrict__ shift, const float* __restrict__ mean,
@@ -940,6 +997,28 @@ int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const
                         (const T*)y, scale, shift, (const T*)residual, (T*)out, nvec, channels, act)));
   RCFD_CHECK_LAUNCH("bn_act_fwd");
   return RCFD_OK;
+}
+
+int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float* scale, float* shift, float* save_mean,
+                          float* save_invstd, const void* residual, void* out, int64_t pixels, int32_t channels,
+                          int32_t act, float eps, float momentum, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(y && sum && sqsum && gamma && beta && scale && shift && save_mean && save_invstd && out && pixels > 0 &&
+                     channels > 0 && channels % 4 == 0,
+                 "bn_train_act_fwd: bad args");
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  if (channels % vw == 0 && NT % (channels / vw) == 0) {
+    const int64_t nv = pixels * channels / vw;
+    DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+                          (const T*)y, sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean,
+                          save_invstd, (const T*)residual, (T*)out, nv, channels, act, (double)pixels, eps, momentum)));
+    RCFD_CHECK_LAUNCH("bn_train_act_fwd");
+    return RCFD_OK;
+  }
+  int rc = rcfd_bn_finalize(sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd,
+                            channels, pixels, eps, momentum, stream);
+  if (rc != RCFD_OK) return rc;
+  return rcfd_bn_act_fwd(y, scale, shift, residual, out, pixels, channels, act, dtype, stream);
 }
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }

@@ -44,6 +44,7 @@ _SIGS = {
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
     'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],
     'rcfd_bn_act_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_train_act_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, c_float, c_int32, _P],
     'rcfd_bn_act_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_act_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_gate_fuse_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],

@@ -40,19 +40,20 @@ def note_params_changed():
 # Stream roles of the multi-stream schedule (one CUDA stream each; index 0 is the caller's current stream):
 #   MAIN   image branch of the encoder, decoder, loss          DEPTH  depth branch of the encoder
 #   FUSE   gated fusion levels (need both branches)            WG_*   weight gradients of the MAIN / DEPTH chains
+#   PACK   weight packing of the whole step, issued up front (training)
 # Most FusionNet layers below 1/4 resolution occupy a fraction of the 148 SMs and are latency bound; the
 # chains are independent between fusion points, so running them side by side (and capturing them as
 # parallel branches of the step's CUDA graph) overlaps those latencies.
-MAIN, DEPTH, FUSE, WG_MAIN, WG_DEPTH = 0, 1, 2, 3, 4
+MAIN, DEPTH, FUSE, WG_MAIN, WG_DEPTH, PACK = 0, 1, 2, 3, 4, 5
 _WG_OF = {MAIN: WG_MAIN, DEPTH: WG_DEPTH}
 _SIDE_STREAMS = {}
 
 
 def side_streams(device):
-    """The four side streams of a device (created once, outside any graph capture)."""
+    """The five side streams of a device (created once, outside any graph capture)."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(4)]
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(5)]
     return _SIDE_STREAMS[key]
 
 
@@ -152,7 +153,7 @@ class Context(object):
         self.dtype = dtype
         self.training = training
         self.device = device
-        # multi-stream schedule: [caller's stream, DEPTH, FUSE, WG_MAIN, WG_DEPTH]
+        # multi-stream schedule: [caller's stream, DEPTH, FUSE, WG_MAIN, WG_DEPTH, PACK]
         multistream = multistream and torch.device(device).type == 'cuda'
         self.streams = [torch.cuda.current_stream()] + side_streams(device) if multistream else None
         self.sid = MAIN
@@ -165,6 +166,8 @@ class Context(object):
         self._off_aff = 0
         self.bn_counters = []
         self.taps = None
+        self.prepacked = {}
+        self.plan = self.cache.setdefault(('pack_plan', dtype), {}) if (self.streams is not None and training) else None
         if self.streams is not None and training:
             self.stats(0)            # the zeroed statistics pool must exist before the streams fork
 
@@ -177,7 +180,7 @@ class Context(object):
 
     def join(self):
         if self.streams is not None:
-            for s in self.streams[1:3]:
+            for s in self.streams[1:3] + ([self.streams[PACK]] if self.prepacked or self.plan else []):
                 self.streams[MAIN].wait_stream(s)
 
     def wait(self, role, on):
@@ -210,11 +213,21 @@ class Context(object):
         self._off_aff += n
         return [s[i * c:(i + 1) * c] for i in range(k)]
 
-    # -- weights: packed per forward in training (they change every step), cached by version in eval.
+    # -- weights: packed per step in training (they change every step), cached by version in eval.
     #    Optimisers that write parameters through raw pointers (rcfd.optim.FusedAdam) do not move torch's
     #    version counters: they call note_params_changed(), which is part of the cache key.
+    #    Training under the multi-stream schedule: the first step records every pack call (key -> closure) in
+    #    the model's pack plan; later steps replay the plan up front on the PACK stream (prepack), so the ~150
+    #    tiny pack kernels leave the critical chains and each consumer just waits for its event.
     def packed(self, key, params, fn):
         if self.training:
+            hit = self.prepacked.pop(key, None)
+            if hit is not None:
+                val, ev = hit
+                torch.cuda.current_stream().wait_event(ev)
+                return val
+            if self.plan is not None:
+                self.plan[key] = fn
             return fn()
         ver = tuple(p._version for p in params) + (self.dtype, _PARAM_EPOCH[0])
         hit = self.cache.get(key)
@@ -224,20 +237,39 @@ class Context(object):
         self.cache[key] = (ver, val)
         return val
 
+    def prepack(self):
+        """Issue every pack call recorded by the previous step on the PACK stream (training, multi-stream)."""
+        if self.plan is None or not self.plan:
+            return
+        pk, main = self.streams[PACK], self.streams[MAIN]
+        pk.wait_stream(main)
+        with torch.cuda.stream(pk):
+            for key, fn in self.plan.items():
+                val = fn()
+                ev = torch.cuda.Event()
+                ev.record(pk)
+                self.prepacked[key] = (val, ev)
+
     def weight(self, mod, pad_to=None):
         """Packed [cout][taps][cin_pad] weights; pad_to = channel count of the (zero-padded) input."""
-        w = mod.conv.weight
-        return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), self.dtype, pad_to=pad_to))
+        w, dtype = mod.conv.weight, self.dtype          # the closures outlive this context (pack plan): no self in them
+        return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), dtype, pad_to=pad_to))
 
     def weight_stem_s2d(self, mod):
         """7x7/s2 stem weights rearranged for the space-to-depth (4x4/s1) formulation."""
-        w = mod.conv.weight
-        return self.packed(('ws2d', id(mod)), [w], lambda: ops.pack_stem_s2d_weight(w.detach(), self.dtype, CPAD))
+        w, dtype = mod.conv.weight, self.dtype
+        return self.packed(('ws2d', id(mod)), [w], lambda: ops.pack_stem_s2d_weight(w.detach(), dtype, CPAD))
 
     def weight_up2x(self, mod):
         """Sub-pixel phase weights for a 3x3 conv behind an exact 2x nearest up-sampling (bf16 fast path)."""
-        w = mod.conv.weight
-        return self.packed(('wup', id(mod)), [w], lambda: ops.pack_upconv2x_weight(w.detach(), self.dtype))
+        w, dtype = mod.conv.weight, self.dtype
+        return self.packed(('wup', id(mod)), [w], lambda: ops.pack_upconv2x_weight(w.detach(), dtype))
+
+    def weight_dgrad(self, mod, off, cnt, pad_to):
+        """Packed [cin_cnt][taps][cout_pad] weights of the data-gradient convolution (one concat source)."""
+        w, dtype = mod.conv.weight, self.dtype
+        return self.packed(('wd', id(mod), off, cnt, pad_to), [w],
+                           lambda: ops.pack_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, dgrad=True, pad_to=pad_to))
 
     def folded_bn(self, mod):
         bn = mod.batch_norm
@@ -319,10 +351,9 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     y = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, stats=(ssum, ssq), engine=ctx.engine,
                    weight_up2x=wup)
     scale, shift, mean, invstd = ctx.aff(cout)
-    ops.bn_finalize(ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
-                    mean, invstd, y.numel() // cout)
+    z = ops.bn_train_act(y, ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
+                         mean, invstd, act, residual=residual)
     ctx.bn_counters.append(bn.num_batches_tracked)
-    z = ops.bn_act(y, scale, shift, act, residual=residual)
     if ctx.tape is not None:
         _record_conv_backward(ctx, mod, x0, x1, in_size, z, (y, scale, shift, mean, invstd, act, residual),
                               want_input_grad)
@@ -340,10 +371,9 @@ def _stem_s2d_unit(ctx, mod, x, act):
     ssum, ssq = ctx.stats(cout)
     y = ops.conv2d(x, w, cout, 4, 1, pad=2, out_size=hw, stats=(ssum, ssq), engine=ctx.engine)
     scale, shift, mean, invstd = ctx.aff(cout)
-    ops.bn_finalize(ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
-                    mean, invstd, y.numel() // cout)
+    z = ops.bn_train_act(y, ssum, ssq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift,
+                         mean, invstd, act)
     ctx.bn_counters.append(bn.num_batches_tracked)
-    z = ops.bn_act(y, scale, shift, act)
     if ctx.tape is not None:
         tape = ctx.tape
 
@@ -412,7 +442,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         hin, win = (x0.shape[1], x0.shape[2]) if in_size is None else in_size
         pad_d = k - 1 - k // 2
         for (src, off, cnt) in ((x0, 0, c0),) + (((x1, c0, x1.shape[3]),) if x1 is not None else ()):
-            wd = ops.pack_weight(w_param.detach(), ctx.dtype, cin_off=off, cin_cnt=cnt, dgrad=True, pad_to=dy.shape[3])
+            wd = ctx.weight_dgrad(mod, off, cnt, dy.shape[3])
             dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine)
             if src is x0 and (hin, win) != (x0.shape[1], x0.shape[2]):
                 dsrc = ops.upsample_nearest_bwd(dsrc, (x0.shape[1], x0.shape[2]))
@@ -425,8 +455,9 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
     """fused = sigmoid(BN(Ww . d)) * BN(Wp . d) + img   (reference src/networks.py:864-866)"""
     c = mod_w.out_channels
     ww, wp = mod_w.conv.weight, mod_p.conv.weight
+    dtype = ctx.dtype
     wcat = ctx.packed(('wcat', id(mod_w)), [ww, wp],
-                      lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype))
+                      lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype))
     bw, bp = mod_w.batch_norm, mod_p.batch_norm
     if not ctx.training:
         def make():
@@ -469,7 +500,8 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
                 g = _grad_dst(wparam)
                 ops.unpack_wgrad(dw[lo:lo + c], g)
                 tape.param_grads.append((wparam, g))
-            wd = ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), ctx.dtype, dgrad=True)
+            wd = ctx.packed(('wcatd', id(mod_w)), [ww, wp],
+                            lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype, dgrad=True))
             tape.add_grad(dep, ops.conv2d(dy, wd, dep.shape[3], 1, 1, engine=ctx.engine))
         tape.add_step(bwd)
     return out
@@ -530,6 +562,7 @@ def fusionnet_encoder(ctx, enc, image, depth, stem_s2d=False):
     branch is issued on that branch's stream).  Multi-stream schedule: the image branch runs on MAIN,
     the depth branch on DEPTH, every gated fusion level on FUSE after both of its inputs."""
     ctx.fork()
+    ctx.prepack()
     with ctx.on(MAIN):
         if callable(image):
             image, stem_s2d = image()

@@ -209,6 +209,18 @@ def bn_act(y, scale, shift, act, residual=None, out=None):
     return out
 
 
+def bn_train_act(y, ssum, ssq, bn_weight, bn_bias, running_mean, running_var, scale, shift, save_mean, save_invstd, act,
+                 residual=None):
+    """Training-mode BatchNorm + activation (+ residual add + leaky) in one pass: batch statistics -> scale / shift,
+    running-statistics update, normalise.  scale / shift / save_mean / save_invstd are outputs kept for backward."""
+    c = y.shape[-1]
+    out = _empty_like(y)
+    _lib.call('rcfd_bn_train_act_fwd', _p(y), _p(ssum), _p(ssq), _p(bn_weight), _p(bn_bias), _p(running_mean),
+              _p(running_var), _p(scale), _p(shift), _p(save_mean), _p(save_invstd), _p(residual), _p(out),
+              y.numel() // c, c, act, BN_EPS, BN_MOMENTUM, dt(y), _stream())
+    return out
+
+
 def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None):
     c = y.shape[-1]
     pixels = y.numel() // c

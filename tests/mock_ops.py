@@ -156,6 +156,13 @@ def bn_act(y, scale, shift, act, residual=None, out=None):
     return v.to(y.dtype)
 
 
+def bn_train_act(y, ssum, ssq, bn_weight, bn_bias, running_mean, running_var, scale, shift, save_mean, save_invstd, act,
+                 residual=None):
+    bn_finalize(ssum, ssq, bn_weight, bn_bias, running_mean, running_var, scale, shift, save_mean, save_invstd,
+                y.numel() // y.shape[-1])
+    return bn_act(y, scale, shift, act, residual=residual)
+
+
 def _dact(pre, dz, act):
     if act == ACT_LEAKY:
         return torch.where(pre > 0, dz, 0.2 * dz)

@@ -26,6 +26,8 @@ bool conv_strip_preferred(const ConvKP& p, int dtype);
 int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
 extern int g_tma_bn_cap;
+extern int g_strip_max_waste;
+extern int g_strip_up_max_waste;
 bool conv_tma_supported(const ConvKP& p, int dtype);
 int conv_tma_launch(const ConvKP& p, cudaStream_t st);
 bool wgrad_tc_supported(const ConvKP& p, int dtype);
@@ -88,6 +90,8 @@ int rcfd_set_option(const char* key, int32_t value) {
   RCFD_CHECK_ARG(key != nullptr, "set_option: null key");
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
   if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
+  if (strcmp(key, "strip_max_waste") == 0) { g_strip_max_waste = value; return RCFD_OK; }
+  if (strcmp(key, "strip_up_max_waste") == 0) { g_strip_up_max_waste = value; return RCFD_OK; }
   set_error("set_option: unknown key %s", key);
   return RCFD_EINVAL;
 }

@@ -77,10 +77,50 @@ __global__ void s2_kernel(const float* __restrict__ crops, const float* __restri
   }
 }
 
-// ---- roi_pool (torchvision semantics), NHWC, thread per (box, bin, channel)
+// ---- roi_pool (torchvision semantics), NHWC.  Thread per (box, bin, 16-byte channel vector): the bin geometry
+// is computed once per vector and every load / store is a coalesced 16-byte access.
 template <typename T>
 __global__ void roi_pool_kernel(const T* __restrict__ feat, const float* __restrict__ boxes, T* __restrict__ out,
                                 int N, int H, int W, int C, int nbox, int PH, int PW, float scale) {
+  constexpr int NV = V16<T>::N;
+  const int CV = C / NV;
+  const int64_t total = (int64_t)nbox * PH * PW * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * NV;
+    int64_t r = i / CV;
+    const int pw = (int)(r % PW); r /= PW;
+    const int ph = (int)(r % PH);
+    const int b = (int)(r / PH);
+    const float* box = boxes + (size_t)b * 5;
+    const int n = (int)box[0];
+    const int sw = (int)roundf(box[1] * scale), sh = (int)roundf(box[2] * scale);
+    const int ew = (int)roundf(box[3] * scale), eh = (int)roundf(box[4] * scale);
+    const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+    const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
+    int hs = (int)floorf((float)ph * bh), he = (int)ceilf((float)(ph + 1) * bh);
+    int ws = (int)floorf((float)pw * bw), we = (int)ceilf((float)(pw + 1) * bw);
+    hs = min(max(hs + sh, 0), H); he = min(max(he + sh, 0), H);
+    ws = min(max(ws + sw, 0), W); we = min(max(we + sw, 0), W);
+    const bool empty = (he <= hs) || (we <= ws);
+    float m[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) m[k] = empty ? 0.f : -3.402823466e+38f;
+    if (n >= 0 && n < N) {
+      for (int yy = hs; yy < he; ++yy)
+        for (int xx = ws; xx < we; ++xx) {
+          float v[NV];
+          V16<T>::ld(feat + ((size_t)(n * H + yy) * W + xx) * C + c, v);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) m[k] = fmaxf(m[k], v[k]);
+        }
+    }
+    V16<T>::st(out + i * NV, m);
+  }
+}
+// any channel count: thread per (box, bin, channel)
+template <typename T>
+__global__ void roi_pool_scalar_kernel(const T* __restrict__ feat, const float* __restrict__ boxes, T* __restrict__ out,
+                                       int N, int H, int W, int C, int nbox, int PH, int PW, float scale) {
   const int64_t total = (int64_t)nbox * PH * PW * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -108,17 +148,45 @@ __global__ void roi_pool_kernel(const T* __restrict__ feat, const float* __restr
   }
 }
 
-__global__ void linear_leaky_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                    const float* __restrict__ b, float* __restrict__ out, int rows, int fin, int fout) {
-  const int64_t total = (int64_t)rows * fout;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % fout);
-    const int r = (int)(i / fout);
-    float acc = b[j];
-    const float* xr = x + (size_t)r * fin;
-    const float* wr = w + (size_t)j * fin;
-    for (int k = 0; k < fin; ++k) acc = fmaf(xr[k], wr[k], acc);
-    out[i] = leaky(acc);
+// out[r][j] = leaky(b[j] + sum_k x[r][k] * w[j][k]): shared-memory tiles (coalesced loads of both operands),
+// 32 output features x 64 rows per block, 8 rows per thread.
+constexpr int LIN_JT = 32, LIN_RT = 64, LIN_KT = 64;
+__global__ void __launch_bounds__(256) linear_leaky_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out, int rows,
+                                                          int fin, int fout) {
+  __shared__ float ws[LIN_JT][LIN_KT + 1];
+  __shared__ float xs[LIN_RT][LIN_KT + 1];
+  const int j0 = blockIdx.x * LIN_JT, r0 = blockIdx.y * LIN_RT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[LIN_RT / 8];
+#pragma unroll
+  for (int i = 0; i < LIN_RT / 8; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < fin; k0 += LIN_KT) {
+    for (int i = threadIdx.x; i < LIN_JT * LIN_KT; i += 256) {
+      const int jj = i / LIN_KT, kk = i - jj * LIN_KT;
+      ws[jj][kk] = (j0 + jj < fout && k0 + kk < fin) ? w[(size_t)(j0 + jj) * fin + k0 + kk] : 0.f;
+    }
+    for (int i = threadIdx.x; i < LIN_RT * LIN_KT; i += 256) {
+      const int rr = i / LIN_KT, kk = i - rr * LIN_KT;
+      xs[rr][kk] = (r0 + rr < rows && k0 + kk < fin) ? x[(size_t)(r0 + rr) * fin + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < LIN_KT; ++kk) {
+      const float wv = ws[tx][kk];
+#pragma unroll
+      for (int i = 0; i < LIN_RT / 8; ++i) acc[i] = fmaf(xs[ty + 8 * i][kk], wv, acc[i]);
+    }
+    __syncthreads();
+  }
+  const int j = j0 + tx;
+  if (j < fout) {
+    const float bias = b[j];
+#pragma unroll
+    for (int i = 0; i < LIN_RT / 8; ++i) {
+      const int r = r0 + ty + 8 * i;
+      if (r < rows) out[(size_t)r * fout + j] = leaky(acc[i] + bias);
+    }
   }
 }
 
@@ -160,16 +228,19 @@ int rcfd_roi_pool_fwd(const void* feat, const float* boxes, void* out, int32_t n
                       int32_t nbox, int32_t ph, int32_t pw, float spatial_scale, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(feat && boxes && out && n > 0 && h > 0 && w > 0 && c > 0 && nbox > 0 && ph > 0 && pw > 0,
                  "roi_pool: bad args");
-  const int64_t total = (int64_t)nbox * ph * pw * c;
+  if (dtype != RCFD_F32 && dtype != RCFD_BF16) { set_error("roi_pool: bad dtype"); return RCFD_EINVAL; }
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  const bool wide = c % vw == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int64_t total = (int64_t)nbox * ph * pw * (wide ? c / vw : c);
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  if (dtype == RCFD_F32)
-    roi_pool_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)feat, boxes, (float*)out, n, h, w, c,
-                                                                     nbox, ph, pw, spatial_scale);
-  else if (dtype == RCFD_BF16)
-    roi_pool_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat, boxes, (bf16*)out, n, h, w, c, nbox,
-                                                                    ph, pw, spatial_scale);
-  else { set_error("roi_pool: bad dtype"); return RCFD_EINVAL; }
+  if (dtype == RCFD_F32) {
+    if (wide) roi_pool_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)feat, boxes, (float*)out, n, h, w, c, nbox, ph, pw, spatial_scale);
+    else roi_pool_scalar_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)feat, boxes, (float*)out, n, h, w, c, nbox, ph, pw, spatial_scale);
+  } else {
+    if (wide) roi_pool_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat, boxes, (bf16*)out, n, h, w, c, nbox, ph, pw, spatial_scale);
+    else roi_pool_scalar_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat, boxes, (bf16*)out, n, h, w, c, nbox, ph, pw, spatial_scale);
+  }
   RCFD_CHECK_LAUNCH("roi_pool");
   return RCFD_OK;
 }
@@ -177,10 +248,8 @@ int rcfd_roi_pool_fwd(const void* feat, const float* boxes, void* out, int32_t n
 int rcfd_linear_leaky_fwd(const float* x, const float* w, const float* b, float* out, int32_t rows, int32_t in_features,
                           int32_t out_features, void* stream) {
   RCFD_CHECK_ARG(x && w && b && out && rows > 0 && in_features > 0 && out_features > 0, "linear: bad args");
-  const int64_t total = (int64_t)rows * out_features;
-  int64_t g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  linear_leaky_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, rows, in_features, out_features);
+  dim3 grid(ceil_div(out_features, LIN_JT), ceil_div(rows, LIN_RT));
+  linear_leaky_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, rows, in_features, out_features);
   RCFD_CHECK_LAUNCH("linear_leaky");
   return RCFD_OK;
 }

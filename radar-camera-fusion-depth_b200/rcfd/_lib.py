@@ -99,6 +99,11 @@ def load():
         fn.argtypes = argtypes
         fn.restype = _RESTYPE.get(name, c_int32)
     _lib = lib
+    # tuning knobs for experiments: RCFD_OPT="key=value,key=value" (rcfd_set_option)
+    for kv in filter(None, os.environ.get('RCFD_OPT', '').split(',')):
+        key, value = kv.split('=')
+        if lib.rcfd_set_option(key.encode(), int(value)) != 0:
+            raise RcfdError(lib.rcfd_last_error().decode())
     return lib
 
 

@@ -18,9 +18,6 @@ from rcfd import ops  # noqa: E402
 B = int(os.environ.get('RCFD_BATCH', '8'))
 dev = torch.device('cuda:0')
 bf = torch.bfloat16
-for kv in filter(None, os.environ.get('RCFD_OPT', '').split(',')):
-    k, v = kv.split('=')
-    ops.set_option(k, int(v))
 
 CASES = {
     # name: (kind, cin, cout, h_out, w_out, dict)

@@ -42,17 +42,24 @@ struct StripP {
   int accumulate, dst_f32;
 };
 
-template <int BN, int CIN, int KS = 3>
+template <int BN, int CIN, int KS = 3, int CIN1 = 0>
 struct StripCfg {
-  static constexpr int RB = CIN * 2;                                        // bytes per pixel row
+  static constexpr int RB = CIN * 2;                                        // bytes per pixel row, source 0
+  static constexpr int RB1 = CIN1 * 2;                                      // ... of the concat partner (0: none)
   static constexpr int HALO = SW + KS - 1;                                  // pixels per ring row
-  static constexpr int ROWBUF = ((HALO * RB + 1023) / 1024) * 1024;
-  static constexpr int W_TAP = ((BN * RB + 1023) / 1024) * 1024;
+  static constexpr int ROWBUF0 = ((HALO * RB + 1023) / 1024) * 1024;
+  static constexpr int ROWBUF1 = CIN1 ? ((HALO * RB1 + 1023) / 1024) * 1024 : 0;
+  static constexpr int ROWBUF = ROWBUF0 + ROWBUF1;
+  static constexpr int W_TAP0 = ((BN * RB + 1023) / 1024) * 1024;
+  static constexpr int W_TAP1 = CIN1 ? ((BN * RB1 + 1023) / 1024) * 1024 : 0;
+  static constexpr int W_TAP = W_TAP0 + W_TAP1;
   static constexpr int W_BYTES = KS * KS * W_TAP;
   static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM = NR * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr int RING = CIN1 ? 4 : NR;                                // two sources: the weights take the room
+  static constexpr int SMEM = RING * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
   static constexpr uint32_t LAYOUT = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+  static constexpr uint32_t LAYOUT1 = RB1 == 128 ? 2u : (RB1 == 64 ? 4u : 6u);
 };
 
 __device__ __forceinline__ uint64_t strip_desc(uint32_t saddr, uint32_t sbo, uint32_t layout, int mode) {
@@ -178,10 +185,14 @@ __device__ __forceinline__ void strip_flush_stats(float (&ss)[BN], float (&sq)[B
   }
 }
 
-template <int BN, int CIN, bool STATS, int KS>
+// CIN1 > 0: second source tensor (the skip connection of torch.cat([x, skip], 1), reference src/net_utils.py:565):
+// every ring slot holds the row of both sources, every tap multiplies both channel groups.
+template <int BN, int CIN, bool STATS, int KS, int CIN1>
 __global__ void __launch_bounds__(NTHREADS)
-conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
-  typedef StripCfg<BN, CIN, KS> C;
+conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_w1, const StripP p) {
+  typedef StripCfg<BN, CIN, KS, CIN1> C;
+  constexpr int NR = C::RING;
   constexpr int PAD = KS / 2;            // 3x3 / pad 1, or the 4x4 / pad 2 window of the space-to-depth stems
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -225,9 +236,16 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      if constexpr (CIN1 > 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+      }
       // resident weights: 9 taps x [BN][CIN]
-      mbar_expect_tx(wbar, (uint32_t)(KS * KS * BN * C::RB));
-      for (int tap = 0; tap < KS * KS; ++tap) tma_load_2d(sW + tap * C::W_TAP, &map_w, wbar, tap * p.cin, n0);
+      mbar_expect_tx(wbar, (uint32_t)(KS * KS * BN * (C::RB + C::RB1)));
+      for (int tap = 0; tap < KS * KS; ++tap) {
+        tma_load_2d(sW + tap * C::W_TAP, &map_w, wbar, tap * p.cin, n0);
+        if constexpr (CIN1 > 0) tma_load_2d(sW + tap * C::W_TAP + C::W_TAP0, &map_w1, wbar, tap * p.cin + CIN, n0);
+      }
       uint32_t L = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int ck = item % p.chunks_per_col;
@@ -239,8 +257,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int j = 0; j < rows + KS - 1; ++j, ++L) {
           const int s = L % NR;
           if (L >= (uint32_t)NR) mbar_wait(sBar + 8 * (NR + s), ((L / NR) & 1) ^ 1);
-          mbar_expect_tx(sBar + 8 * s, (uint32_t)(C::HALO * C::RB));
+          mbar_expect_tx(sBar + 8 * s, (uint32_t)(C::HALO * (C::RB + C::RB1)));
           tma_load_4d(sRing + s * C::ROWBUF, &map_x, sBar + 8 * s, 0, strip * SW - PAD, y0 - PAD + j, img);
+          if constexpr (CIN1 > 0)
+            tma_load_4d(sRing + s * C::ROWBUF + C::ROWBUF0, &map_x1, sBar + 8 * s, 0, strip * SW - PAD, y0 - PAD + j, img);
         }
       }
     }
@@ -276,6 +296,16 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               for (int k = 0; k < CIN / 16; ++k) {
                 umma_f16(d_tmem, strip_desc(a0 + k * 32, sbo, C::LAYOUT, p.desc_mode), umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT),
                          idesc, (uint32_t)((r | s | k) != 0));
+              }
+              if constexpr (CIN1 > 0) {
+                constexpr uint32_t sbo1 = 8 * C::RB1;
+                const uint32_t a1 = rowbuf + C::ROWBUF0 + s * C::RB1;
+                const uint32_t b1 = b0 + C::W_TAP0;
+#pragma unroll
+                for (int k = 0; k < CIN1 / 16; ++k) {
+                  umma_f16(d_tmem, strip_desc(a1 + k * 32, sbo1, C::LAYOUT1, p.desc_mode),
+                           umma_desc(b1 + k * 32, 16, sbo1, C::LAYOUT1), idesc, 1u);
+                }
               }
             }
           }
@@ -557,38 +587,48 @@ inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, i
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int CIN, bool STATS, int KS>
+template <int BN, int CIN, bool STATS, int KS, int CIN1>
 int launch_strip_s(const ConvKP& k, StripP& t, cudaStream_t st) {
-  typedef StripCfg<BN, CIN, KS> C;
+  typedef StripCfg<BN, CIN, KS, CIN1> C;
+  static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
   static int per_sm = 0;                 // resident CTAs per SM (shared memory AND registers: the statistics variant is wide)
   if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<BN, CIN, STATS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<BN, CIN, STATS, KS, CIN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     // two CTAs per SM when shared memory (227 KB) and the register file (64 K) both allow it
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, conv_strip_kernel<BN, CIN, STATS, KS>);
+    e = cudaFuncGetAttributes(&fa, conv_strip_kernel<BN, CIN, STATS, KS, CIN1>);
     if (e != cudaSuccess) { set_error("conv_strip: attributes: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NTHREADS;
     per_sm = (C::SMEM <= 112 * 1024 && 2 * regs_per_cta <= 65536) ? 2 : 1;
   }
-  alignas(64) CUtensorMap mx, mw;
+  alignas(64) CUtensorMap mx, mw, mx1, mw1;
   if (!make_row_map(&mx, k.src0, k.n, k.hin, k.win, k.c0, C::HALO) || !make_w_map(&mw, k.weight, k.cout, k.K, CIN, BN)) {
     set_error("conv_strip: cuTensorMapEncodeTiled failed");
     return RCFD_ECUDA;
+  }
+  if (CIN1 > 0) {
+    if (!make_row_map(&mx1, k.src1, k.n, k.hin, k.win, k.c1, C::HALO) || !make_w_map(&mw1, k.weight, k.cout, k.K, CIN1, BN)) {
+      set_error("conv_strip: cuTensorMapEncodeTiled failed (second source)");
+      return RCFD_ECUDA;
+    }
+  } else {
+    mx1 = mx;
+    mw1 = mw;
   }
   const int ntile = ceil_div(k.cout, BN);
   int ctas = num_sms() * per_sm / ntile;                   // two CTAs per SM hide each other's barrier latencies
   if (ctas < 1) ctas = 1;
   if (ctas > t.num_items) ctas = t.num_items;
   dim3 grid(ctas, ntile);
-  conv_strip_kernel<BN, CIN, STATS, KS><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  conv_strip_kernel<BN, CIN, STATS, KS, CIN1><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, mx1, mw1, t);
   RCFD_CHECK_LAUNCH("conv_strip");
   return RCFD_OK;
 }
 
-template <int BN, int CIN, int KS = 3>
+template <int BN, int CIN, int KS = 3, int CIN1 = 0>
 int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
-  return t.ssum != nullptr ? launch_strip_s<BN, CIN, true, KS>(k, t, st) : launch_strip_s<BN, CIN, false, KS>(k, t, st);
+  return t.ssum != nullptr ? launch_strip_s<BN, CIN, true, KS, CIN1>(k, t, st) : launch_strip_s<BN, CIN, false, KS, CIN1>(k, t, st);
 }
 
 template <int BN, int CIN, bool STATS>
@@ -677,8 +717,24 @@ int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
   }
 }
 
+// concat pairs (c0 | c1) the kernel is instantiated for, with the cout tile that fits shared memory
+static int strip_dual_bn(const ConvKP& p) {
+  if (p.kh != 3) return 0;
+  if (p.c0 == 64 && p.c1 == 32) return p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 0);
+  if (p.c0 == 64 && p.c1 == 64) return p.cout % 32 == 0 ? 32 : 0;
+  if (p.c0 == 32 && p.c1 == 32) return p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 0);
+  return 0;
+}
+
 bool conv_strip_supported(const ConvKP& p, int dtype) {
-  if (dtype != RCFD_BF16 || p.up || p.dil != 1 || p.c1 != 0) return false;
+  if (dtype != RCFD_BF16 || p.up || p.dil != 1) return false;
+  if (p.c1 != 0) {
+    if (strip_dual_bn(p) == 0 || p.kw != 3 || p.stride != 1 || p.pad != 1 || p.ho != p.hin || p.wo != p.win) return false;
+    if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.src1) & 15) ||
+        (reinterpret_cast<uintptr_t>(p.weight) & 15))
+      return false;
+    return get_encode() != nullptr;
+  }
   const bool stem = p.kh == 4 && p.kw == 4 && p.stride == 1 && p.pad == 2 && p.c0 == 16 && (p.cout == 16 || p.cout == 32);
   if (!stem && (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1)) return false;
   if (p.c0 != 16 && p.c0 != 32 && p.c0 != 64) return false;
@@ -690,15 +746,18 @@ bool conv_strip_supported(const ConvKP& p, int dtype) {
 // worth it only where the 128-wide strips fit the image width reasonably and there is enough height
 bool conv_strip_preferred(const ConvKP& p, int dtype) {
   if (!conv_strip_supported(p, dtype)) return false;
+  if (p.c0 == 64 && p.c1 == 64) return false;      // cout tile 32 (two passes over the input): measured slower than the per-tap engine
   const int strips = ceil_div(p.wo, SW);
-  return p.ho >= 64 && (long)strips * SW * 100 <= (long)p.wo * (100 + g_strip_max_waste);   // default <= 50 % padded columns (176-wide maps: 2 strips)
+  // default <= 50 % padded columns (176-wide maps: 2 strips); many rows (RadarNet: 64 crops per image) tolerate 80 %
+  const int waste = (long)p.n * p.ho >= 4096 ? (g_strip_max_waste > 80 ? g_strip_max_waste : 80) : g_strip_max_waste;
+  return p.ho >= 64 && (long)strips * SW * 100 <= (long)p.wo * (100 + waste);
 }
 
 int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
   StripP t;
-  t.n = p.n; t.h = p.ho; t.w = p.wo; t.cin = p.c0; t.cout = p.cout;
+  t.n = p.n; t.h = p.ho; t.w = p.wo; t.cin = p.c0 + p.c1; t.cout = p.cout;
   t.strips = ceil_div(p.wo, SW);
-  const int bn = p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 16);
+  const int bn = p.c1 != 0 ? strip_dual_bn(p) : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 16));
   const int ntile = ceil_div(p.cout, bn);
   const int ctas = 2 * num_sms() / ntile > 0 ? 2 * num_sms() / ntile : 1;
   const int cols = p.n * t.strips;
@@ -712,6 +771,11 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
   t.desc_mode = g_strip_desc_mode;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
+  if (p.c1 != 0) {                  // conv over torch.cat([x, skip], 1): both sources streamed
+    if (p.c0 == 64 && p.c1 == 32) return bn == 64 ? launch_strip<64, 64, 3, 32>(p, t, st) : launch_strip<32, 64, 3, 32>(p, t, st);
+    if (p.c0 == 64 && p.c1 == 64) return launch_strip<32, 64, 3, 64>(p, t, st);
+    return bn == 64 ? launch_strip<64, 32, 3, 32>(p, t, st) : launch_strip<32, 32, 3, 32>(p, t, st);
+  }
   if (p.c0 == 64) {
     switch (bn) {
       case 64: return launch_strip<64, 64>(p, t, st);

@@ -333,6 +333,38 @@ def test_strip_conv(case, mode):
         ops.set_option('strip_desc_mode', 0)
 
 
+@pytest.mark.parametrize('case', [(1, 64, 32, 64, 12, 130), (2, 64, 32, 32, 9, 200), (1, 64, 64, 64, 17, 128),
+                                  (2, 32, 32, 32, 21, 70), (1, 32, 32, 64, 10, 140)])
+def test_strip_conv_concat(case):
+    """Row-streaming 3x3 conv over torch.cat([x, skip], 1) (decoder blocks, reference src/net_utils.py:565):
+    both sources ride in every ring slot; batch statistics and the folded-BN epilogue as in the single-source case."""
+    from rcfd import ops
+    n, c0, c1, cout, h, w = case
+    x0 = _q(_rand(n, c0, h, w, seed=61))
+    x1 = _q(_rand(n, c1, h, w, seed=62))
+    wt = _q(_rand(cout, c0 + c1, 3, 3, seed=63) / ((c0 + c1) * 9) ** 0.5)
+    raw = F.conv2d(torch.cat([x0, x1], 1), wt, None, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    ssq = torch.zeros_like(ssum)
+    y = ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), stats=(ssum, ssq), engine=ops.ENGINE_STRIP)
+    torch.cuda.synchronize()
+    err = relerr(_nchw(y), raw)
+    print('strip concat', case, 'relerr', err)
+    assert err < TOL
+    assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 1e-3 * (1 + float(raw.abs().sum() / (raw.sum(dim=(0, 2, 3)).abs().max() + 1e-9)))
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=64) * 0.1
+    ref = F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2)
+    z = ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), scale=scale.to(DEV), shift=shift.to(DEV), act=ops.ACT_LEAKY,
+                   engine=ops.ENGINE_STRIP)
+    assert relerr(_nchw(z), ref) < TOL
+    # same answer as the per-tap TMA engine on the same operands
+    z_tma = ops.conv2d(_nhwc(x0), wp, cout, 3, 1, x1=_nhwc(x1), scale=scale.to(DEV), shift=shift.to(DEV), act=ops.ACT_LEAKY,
+                       engine=ops.ENGINE_TMA)
+    assert relerr(_nchw(z), _nchw(z_tma)) < 2e-2
+
+
 @pytest.mark.parametrize('shape', [(2, 64, 32, 9, 70), (1, 32, 64, 20, 128), (1, 64, 64, 11, 200), (2, 32, 16, 5, 33)])
 def test_strip_upconv2x(shape):
     """Row-streaming variant of the sub-pixel up-conv: low-res rows in the shared-memory ring, four phase

@@ -297,17 +297,52 @@ def run_ours(args):
             launches = _lib.launch_count - l1
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the public API: pinned host -> device every step, result read back
+    # ---- end to end through the public API: pinned host -> device every step, result read back every step.
+    # The graphed entry points stage the host tensors on a copy stream (double buffered), so the copy of step i+1
+    # overlaps the compute of step i; the 4-byte result of step i is copied to pinned memory asynchronously and
+    # READ by the host while step i+1 runs (the reference reads loss.item() only at checkpoints, fusionnet_main.py:423).
+    res_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {'i': 0, 'last': None}
+
     def e2e_step():
-        if train:           # the graphed step copies straight from the pinned host tensors into its static buffers
+        if train:           # the graphed step copies straight from the pinned host tensors into its staging buffers
             inputs = host if args.graph else [t.to(dev, non_blocking=True) for t in host]
-        else:               # forward_graphed copies straight from the pinned host tensors into its static buffers
+        else:
             inputs = (host[:2] if args.graph else [t.to(dev, non_blocking=True) for t in host[:2]]) + [None, None]
         r = step(inputs)
-        return float(r) if train else float(r.sum())
+        i = state['i']
+        res_host[i % 2].copy_((r.detach() if train else r.sum()).reshape(1), non_blocking=True)
+        res_ev[i % 2].record()
+        if i > 0:                                   # read the previous step's result while this step runs
+            res_ev[(i - 1) % 2].synchronize()
+            state['last'] = float(res_host[(i - 1) % 2])
+        state['i'] = i + 1
+
+    def e2e_drain():
+        i = state['i']
+        if i > 0:
+            res_ev[(i - 1) % 2].synchronize()
+            state['last'] = float(res_host[(i - 1) % 2])
+
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    e2e_drain()
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_drain()                                     # the last result is read inside the timed region too
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t)
+    ms_e2e /= args.steps
 
     # ---- dominant kernel (conv engine) alone on the heaviest layer: decoder deconv0.deconv.conv
     # (64 -> 32, 3x3, nearest 2x up-sampling folded into the loads, output 352 x 704)

@@ -135,6 +135,37 @@ class FusionNetModel(object):
             out = _FusionNetFunction.apply(self, record, image, input_depth, *params)
         return [out] if return_multiscale else out
 
+    def _feed(self, entry, static, tensors):
+        """Bring this step's inputs into the graph's static buffers.  Device tensors: one device copy each.
+        Host tensors (pinned): the host->device copies run on a COPY stream into one of two staging sets, so the
+        copy of step i+1 overlaps the compute of step i (the host enqueues step i+1 while step i is running);
+        the graph's stream then only does a device-to-device copy (staging -> static) before the replay."""
+        if all(t.is_cuda for t in tensors):
+            for s, t in zip(static, tensors):
+                s.copy_(t, non_blocking=True)
+            return
+        main = torch.cuda.current_stream()
+        if 'stage' not in entry:
+            entry['stage'] = [[torch.empty_like(s) for s in static] for _ in range(2)]
+            entry['free'] = [torch.cuda.Event(), torch.cuda.Event()]
+            entry['copy_stream'] = torch.cuda.Stream()
+            entry['n'] = 0
+            for ev in entry['free']:
+                ev.record(main)
+        slot = entry['n'] % 2
+        entry['n'] += 1
+        cs = entry['copy_stream']
+        cs.wait_event(entry['free'][slot])              # the step that consumed this staging set has read it
+        with torch.cuda.stream(cs):
+            for s, t in zip(entry['stage'][slot], tensors):
+                s.copy_(t, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        main.wait_event(ready)
+        for s, g in zip(static, entry['stage'][slot]):
+            s.copy_(g, non_blocking=True)
+        entry['free'][slot].record(main)
+
     def forward_graphed(self, image, input_depth):
         """Inference forward replayed from a CUDA graph (captured once per input shape / precision):
         the ~150 kernel launches of one forward become one graph launch, so small batches are not
@@ -162,13 +193,11 @@ class FusionNetModel(object):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     s_out = self.forward(s_img, s_dep)
-            entry = (graph, s_img, s_dep, s_out)
+            entry = {'graph': graph, 'static': [s_img, s_dep], 'out': s_out}
             self._graphs[key] = entry
-        graph, s_img, s_dep, s_out = entry
-        s_img.copy_(image, non_blocking=True)
-        s_dep.copy_(input_depth, non_blocking=True)
-        graph.replay()
-        return s_out
+        self._feed(entry, entry['static'], (image, input_depth))
+        entry['graph'].replay()
+        return entry['out']
 
     def train_step_graphed(self, image, input_depth, ground_truth, lidar_map, optimizer, w_lidar_loss,
                            outlier_removal=None):
@@ -227,11 +256,10 @@ class FusionNetModel(object):
                 with torch.cuda.graph(graph):
                     loss, grads = body()
                 self.last_capture_launches = _lib.launch_count - l0 + 1      # + the eager Adam launch
-            entry = (graph, static, loss, grads)
+            entry = {'graph': graph, 'static': static, 'loss': loss, 'grads': grads}
             self._train_graphs[key] = entry
-        graph, static, loss, grads = entry
-        for s, t in zip(static, (image, input_depth, ground_truth, lidar_map)):
-            s.copy_(t, non_blocking=True)
+        graph, static, loss, grads = entry['graph'], entry['static'], entry['loss'], entry['grads']
+        self._feed(entry, static, (image, input_depth, ground_truth, lidar_map))
         graph.replay()
         if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
             self.grad_hook(grads)

@@ -194,10 +194,20 @@ def test_graphed_forward_matches_eager():
             eager = m.forward(image, depth).clone()
             graphed = m.forward_graphed(image, depth).clone()
         assert torch.equal(eager, graphed)
-    # pinned host inputs are copied straight into the graph's static buffers
-    hi, hd = image.cpu().pin_memory(), depth.cpu().pin_memory()
+    # pinned host inputs go through the double-buffered staging sets on the copy stream: a run of calls with
+    # different data, results read only afterwards (nothing synchronises between the calls)
+    hosts, outs, refs = [], [], []
+    for seed in (5, 6, 7, 8, 9):
+        image, depth = synth.fusionnet_inputs(2, 96, 160, seed, 'quasi_dense')
+        hosts.append((image.pin_memory(), depth.pin_memory()))
     with torch.no_grad():
-        assert torch.equal(m.forward_graphed(hi, hd), eager)
+        for hi, hd in hosts:
+            outs.append(m.forward_graphed(hi, hd).clone())
+        for hi, hd in hosts:
+            refs.append(m.forward(hi.to(DEV), hd.to(DEV)).clone())
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    image, depth = hosts[-1][0].to(DEV), hosts[-1][1].to(DEV)
     m.train()
     with pytest.raises(RuntimeError):
         m.forward_graphed(image, depth)

@@ -619,6 +619,8 @@ int launch_strip_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   const int ntile = ceil_div(k.cout, BN);
   int ctas = num_sms() * per_sm / ntile;                   // two CTAs per SM hide each other's barrier latencies
   if (ctas < 1) ctas = 1;
+  plan_row_chunks(t.h, t.n * t.strips, ctas, 6, 4, &t.rows_per_chunk, &t.chunks_per_col);
+  t.num_items = t.n * t.strips * t.chunks_per_col;
   if (ctas > t.num_items) ctas = t.num_items;
   dim3 grid(ctas, ntile);
   conv_strip_kernel<BN, CIN, STATS, KS, CIN1><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, mx1, mw1, t);
@@ -693,12 +695,7 @@ int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
   const int ntile = ceil_div(p.cout, bn);
   const int ctas = num_sms() / ntile > 0 ? num_sms() / ntile : 1;
   const int cols = p.n * t.strips;
-  int cpc = (2 * ctas + cols - 1) / cols;
-  if (cpc < 1) cpc = 1;
-  int rpc = ceil_div(p.h0, cpc);
-  if (rpc < 8) rpc = 8 < p.h0 ? 8 : p.h0;
-  t.rows_per_chunk = rpc;
-  t.chunks_per_col = ceil_div(p.h0, rpc);
+  plan_row_chunks(p.h0, cols, ctas, 6, 4, &t.rows_per_chunk, &t.chunks_per_col);
   t.num_items = cols * t.chunks_per_col;
   t.desc_mode = 0;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
@@ -759,15 +756,7 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
   t.strips = ceil_div(p.wo, SW);
   const int bn = p.c1 != 0 ? strip_dual_bn(p) : (p.cout % 64 == 0 ? 64 : (p.cout % 32 == 0 ? 32 : 16));
   const int ntile = ceil_div(p.cout, bn);
-  const int ctas = 2 * num_sms() / ntile > 0 ? 2 * num_sms() / ntile : 1;
-  const int cols = p.n * t.strips;
-  int cpc = (2 * ctas + cols - 1) / cols;              // aim at ~2 items per CTA
-  if (cpc < 1) cpc = 1;
-  int rpc = ceil_div(p.ho, cpc);
-  if (rpc < 8) rpc = 8 < p.ho ? 8 : p.ho;
-  t.rows_per_chunk = rpc;
-  t.chunks_per_col = ceil_div(p.ho, rpc);
-  t.num_items = cols * t.chunks_per_col;
+  (void)ntile;                      // the row chunks are planned in launch_strip_s, once the resident CTA count is known
   t.desc_mode = g_strip_desc_mode;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;

@@ -67,6 +67,26 @@ inline bool make_w_map(CUtensorMap* m, const void* ptr, int cout, int K, int bkc
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Row-streaming kernels: `cols` independent column strips of `h` rows are cut into chunks that `ctas` persistent
+// CTAs take round-robin.  Pick the chunk height that minimises  waves x (rows per chunk + per-item overhead rows):
+// a partly filled last wave costs a full chunk, and every chunk pays its halo rows and pipeline fill.
+inline void plan_row_chunks(int h, int cols, int ctas, int overhead_rows, int min_rows, int* rows_per_chunk,
+                            int* chunks_per_col) {
+  int best_rpc = h;
+  long best_cost = -1;
+  for (int cpc = 1; cpc <= h; ++cpc) {
+    const int rpc = (h + cpc - 1) / cpc;
+    if (cpc > 1 && rpc < min_rows) break;
+    const int chunks = (h + rpc - 1) / rpc;
+    const long items = (long)cols * chunks;
+    const long waves = (items + ctas - 1) / ctas;
+    const long cost = waves * (rpc + overhead_rows);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rpc = rpc; }
+  }
+  *rows_per_chunk = best_rpc;
+  *chunks_per_col = (h + best_rpc - 1) / best_rpc;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

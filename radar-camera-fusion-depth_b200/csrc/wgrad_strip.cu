@@ -275,12 +275,8 @@ inline bool make_dy_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w
 
 void plan_items(WgStripP& t, int ctas) {
   const int cols = t.n * t.strips;
-  int cpc = (2 * ctas + cols - 1) / cols;                // aim at ~2 items per CTA
-  if (cpc < 1) cpc = 1;
-  int rpc = ceil_div(t.h, cpc);
-  if (rpc < 16) rpc = 16 < t.h ? 16 : t.h;               // every chunk re-reads 2 halo rows
-  t.rows_per_chunk = rpc;
-  t.chunks_per_col = ceil_div(t.h, rpc);
+  // every chunk re-reads 2 halo rows and the CTA flushes its accumulators once at the end
+  plan_row_chunks(t.h, cols, ctas, 8, 8, &t.rows_per_chunk, &t.chunks_per_col);
   t.num_items = cols * t.chunks_per_col;
 }
 

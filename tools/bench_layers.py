@@ -80,7 +80,7 @@ def build(kind, cin, cout, h, w, o):
         wup = ops.pack_upconv2x_weight(w32, bf) if o.get('up') else None
         stats = (torch.zeros(cout, device=dev, dtype=torch.float64), torch.zeros(cout, device=dev, dtype=torch.float64)) \
             if o.get('stats') else None
-        kw = dict(x1=x1, stats=stats, weight_up2x=wup, pad=o.get('pad'))
+        kw = dict(x1=x1, stats=stats, weight_up2x=wup, pad=o.get('pad'), engine=int(os.environ.get('RCFD_ENGINE', '0')))
         if o.get('up'):
             kw['in_size'] = (h, w)
         if o.get('k') == 4:

@@ -198,6 +198,7 @@ __global__ void bn_act_fwd_wide(const T* __restrict__ y, const float* __restrict
   }
 }
 
+constexpr int BN_TRAIN_MAX_C = 1024;
 // Training-mode BatchNorm forward in ONE pass over the tensor: every thread derives scale / shift of its own
 // channel group from the batch sums (same fp64 formulas as bn_finalize_kernel, so the values are identical),
 // block 0 also publishes scale / shift / mean / invstd for the backward pass and updates the running statistics.
@@ -227,20 +228,23 @@ __global__ void bn_train_act_fwd_wide(const T* __restrict__ y, const double* __r
       }
     }
   }
+  // scale / shift of every channel once per block (fp64 divide + sqrt: not per thread), then registers
+  __shared__ float s_sc[BN_TRAIN_MAX_C], s_sh[BN_TRAIN_MAX_C];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = sum[c] / count;
+    double var = sqsum[c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    s_sc[c] = (float)((double)gamma[c] * invstd);
+    s_sh[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+  }
+  __syncthreads();
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i0 >= nvec) return;
   const int c0 = (int)(i0 % CV) * N;
   float sc[N], sh[N];
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const int c = c0 + k;
-    const double mean = sum[c] / count;
-    double var = sqsum[c] / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const double invstd = 1.0 / sqrt(var + (double)eps);
-    sc[k] = (float)((double)gamma[c] * invstd);
-    sh[k] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
-  }
+  for (int k = 0; k < N; ++k) { sc[k] = s_sc[c0 + k]; sh[k] = s_sh[c0 + k]; }
   for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float v[N], r[N];
     V16<T>::ld(y + i * N, v);
@@ -1007,7 +1011,7 @@ int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum,
                      channels > 0 && channels % 4 == 0,
                  "bn_train_act_fwd: bad args");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
-  if (channels % vw == 0 && NT % (channels / vw) == 0) {
+  if (channels % vw == 0 && NT % (channels / vw) == 0 && channels <= BN_TRAIN_MAX_C) {
     const int64_t nv = pixels * channels / vw;
     DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean,

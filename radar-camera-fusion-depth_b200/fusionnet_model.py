@@ -13,6 +13,8 @@ Extras that the reference does not have (all optional):
     the kernels (accumulation is always fp32).  'fp32' is the parity mode.
   * ``forward(..., return_logits=True)`` for tests.
 """
+import os
+
 import torch
 
 import fusionnet_losses as losses
@@ -59,7 +61,8 @@ class FusionNetModel(object):
         self.device = device
         self.compute_dtype = torch.float32
         self.conv_engine = ops.ENGINE_AUTO
-        self.multistream = True        # image branch / depth branch / fusion / weight gradients on parallel CUDA streams
+        # image branch / depth branch / fusion / weight gradients on parallel CUDA streams (RCFD_MULTISTREAM=0: one stream)
+        self.multistream = os.environ.get('RCFD_MULTISTREAM', '1') != '0'
         self._cache = {}
         self.grad_hook = None          # called with the list of (param, grad) after backward (DDP)
 

@@ -219,6 +219,13 @@ int rcfd_scatter_points_to_depth_map(const double* points_xy, const double* dept
 int rcfd_scatter_tiles_argmax(const float* crops, const float* points, int32_t k, int32_t ph,
                               int32_t pw, int32_t h, int32_t w, int32_t compat, int64_t* depth_i64,
                               float* depth_f32, float* response, void* stream);
+/* Stage-1 -> stage-2 bridge: RadarNet's quasi-dense depth (int64 in compat mode, else float) and
+ * response map -> FusionNet's input_depth (2 x h x w float: depth, response) without the PNG files the reference
+ * writes in between (setup/setup_dataset_nuscenes_radarnet.py:331-345).  quantize_png16 = 1 applies exactly what that
+ * round trip does to the values (src/data_utils.py:271-335: uint32(v * 256) resp. uint32(v * 2^14) stored as 16 bits,
+ * divided back on load, depth <= 0 -> 0), which is what FusionNet was trained on. */
+int rcfd_stage1_to_stage2(const int64_t* depth_i64, const float* depth_f32, const float* response,
+                          float* input_depth, int32_t h, int32_t w, int32_t quantize_png16, void* stream);
 
 /* torchvision.ops.roi_pool as called at src/networks.py:1232-1247 (NHWC, max over the
  * quantised bins; boxes: nbox x 5 float = (batch_index, x1, y1, x2, y2)). */

@@ -85,3 +85,17 @@ def s2_scatter(crops, points, image_width, patch_size, compat=True):
     else:
         depth = np.where(response == 0, np.float32(0), points[arg, 2]).astype(np.float32)
     return depth, response
+
+
+def png16_roundtrip(depth, response):
+    """What the reference's PNG files do to RadarNet's outputs on their way into FusionNet (TEST INFRASTRUCTURE):
+    save_depth / save_response (reference src/data_utils.py:271-286, 320-335: np.uint32(v * multiplier), mode 'I' -> 16-bit
+    PNG) followed by load_depth / load_response (:238-269, 288-318: / multiplier, depth <= 0 -> 0).
+    depth, response: numpy H x W (depth may be int64 as the reference produces it).  Returns float32 H x W each."""
+    import numpy as np
+    zd = np.uint32(np.float32(depth) * 256.0) & 0xffff          # PNG stores 16 bits
+    zr = np.uint32(np.float32(response) * 2 ** 14) & 0xffff
+    d = np.array(zd, dtype=np.float32) / 256.0
+    d[d <= 0] = 0.0
+    r = np.array(zr, dtype=np.float32) / 2 ** 14
+    return d, r

@@ -148,6 +148,26 @@ __global__ void roi_pool_scalar_kernel(const T* __restrict__ feat, const float* 
   }
 }
 
+// ---- stage-1 -> stage-2 bridge: what the 16-bit PNG round trip of the reference does to the quasi-dense depth and the
+// response map (save: uint32(v * multiplier) -> 16-bit PNG; load: / multiplier, depth <= 0 -> 0), written straight into
+// FusionNet's N x 2 x H x W input (channel 0 depth, channel 1 response).  float64 products like numpy's.
+__global__ void bridge_kernel(const long long* __restrict__ depth_i64, const float* __restrict__ depth_f32,
+                              const float* __restrict__ response, float* __restrict__ out, int64_t hw, int quantize,
+                              float mult_depth, float mult_response) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = depth_i64 ? (float)depth_i64[i] : depth_f32[i];
+    float r = response[i];
+    if (quantize) {
+      // numpy: np.uint32(float32 * python float) computes in float32 (NEP 50 weak scalar), truncates toward zero
+      uint32_t qd = (uint32_t)(d * mult_depth) & 0xffffu, qr = (uint32_t)(r * mult_response) & 0xffffu;
+      d = (float)qd / mult_depth;
+      r = (float)qr / mult_response;
+    }
+    out[i] = d <= 0.f ? 0.f : d;
+    out[hw + i] = r;
+  }
+}
+
 // out[r][j] = leaky(b[j] + sum_k x[r][k] * w[j][k]): shared-memory tiles (coalesced loads of both operands),
 // 32 output features x 64 rows per block, 8 rows per thread.
 constexpr int LIN_JT = 32, LIN_RT = 64, LIN_KT = 64;
@@ -221,6 +241,19 @@ int rcfd_scatter_tiles_argmax(const float* crops, const float* points, int32_t k
   s2_kernel<<<ceil_div((int64_t)h * w, 256), 256, 0, (cudaStream_t)stream>>>(
       crops, points, k, ph, pw, h, w, compat, reinterpret_cast<long long*>(depth_i64), depth_f32, response);
   RCFD_CHECK_LAUNCH("scatter_s2");
+  return RCFD_OK;
+}
+
+int rcfd_stage1_to_stage2(const int64_t* depth_i64, const float* depth_f32, const float* response, float* input_depth,
+                          int32_t h, int32_t w, int32_t quantize_png16, void* stream) {
+  RCFD_CHECK_ARG((depth_i64 != nullptr) != (depth_f32 != nullptr), "stage1_to_stage2: exactly one depth input");
+  RCFD_CHECK_ARG(response && input_depth && h > 0 && w > 0, "stage1_to_stage2: bad args");
+  const int64_t hw = (int64_t)h * w;
+  int64_t g = (hw + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  bridge_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(depth_i64), depth_f32, response,
+                                                         input_depth, hw, quantize_png16, 256.0f, 16384.0f);
+  RCFD_CHECK_LAUNCH("stage1_to_stage2");
   return RCFD_OK;
 }
 

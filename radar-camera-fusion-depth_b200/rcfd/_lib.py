@@ -65,6 +65,7 @@ _SIGS = {
     'rcfd_adam_step': [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, _P],
     'rcfd_scatter_points_to_depth_map': [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_scatter_tiles_argmax': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P],
+    'rcfd_stage1_to_stage2': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_roi_pool_fwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P],
     'rcfd_linear_leaky_fwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],

@@ -378,6 +378,18 @@ def scatter_tiles_argmax(crops, points, h, w, compat=True):
     return depth, response
 
 
+def stage1_to_stage2(depth, response, quantize_png16=True):
+    """(1 x H x W int64 or float32 depth, 1 x H x W float32 response) -> 1 x 2 x H x W float32 FusionNet input_depth."""
+    h, w = response.shape[-2:]
+    out = _empty((1, 2, h, w), device=response.device, dtype=torch.float32)
+    is_i64 = depth.dtype == torch.int64
+    if not is_i64:
+        depth = depth.float()
+    _lib.call('rcfd_stage1_to_stage2', _p(depth.contiguous()) if is_i64 else None, None if is_i64 else _p(depth.contiguous()),
+              _p(response.contiguous().float()), _p(out), h, w, 1 if quantize_png16 else 0, _stream())
+    return out
+
+
 def roi_pool(feat, boxes5, out_size, spatial_scale):
     """feat: NHWC; boxes5: [nbox, 5] float32 (batch_index, x1, y1, x2, y2)."""
     n, h, w, c = feat.shape

@@ -226,6 +226,31 @@ def s2_case(name, h, w, patch, k, seed, zs=None):
     print(name, 'ok  nonzero', int((depth != 0).sum()), 'dtype', depth.dtype)
 
 
+def png16_case(name, h, w, seed):
+    """The PNG round trip between the two stages, executed by the reference's own codec (src/data_utils.py:238-335)."""
+    import tempfile
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import data_utils as ref_du
+    sys.path[:] = saved
+    sys.modules.pop('data_utils', None)
+    rng = np.random.default_rng(seed)
+    depth_i64 = rng.integers(0, 100, (h, w)).astype(np.int64) * (rng.random((h, w)) < 0.3)
+    depth_f32 = (rng.random((h, w)) * 100).astype(np.float32) * (rng.random((h, w)) < 0.3)
+    response = rng.random((h, w)).astype(np.float32) * (rng.random((h, w)) < 0.3)
+    tmp = tempfile.mkdtemp()
+    out = dict(depth_i64=depth_i64, depth_f32=depth_f32, response=response)
+    for tag, dep in (('i64', depth_i64), ('f32', depth_f32)):
+        ref_du.save_depth(dep, os.path.join(tmp, 'd.png'))
+        ref_du.save_response(response, os.path.join(tmp, 'r.png'))
+        out['loaded_depth_' + tag] = ref_du.load_depth(os.path.join(tmp, 'd.png'))
+        out['loaded_response'] = ref_du.load_response(os.path.join(tmp, 'r.png'))
+        d_o, r_o = so.png16_roundtrip(dep, response)
+        assert np.array_equal(d_o, out['loaded_depth_' + tag]) and np.array_equal(r_o, out['loaded_response'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok (oracle == reference codec, bit exact)')
+
+
 if __name__ == '__main__':
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
@@ -235,4 +260,5 @@ if __name__ == '__main__':
                   1, 64, 128, 3, 2)
     s2_case('s2_compat_k6', 64, 160, (64, 64), 6, 11)
     s2_case('s2_compat_alias_k3', 32, 96, (32, 32), 3, 12, zs=[2.7, 2.2, 1.9])
+    png16_case('png16_roundtrip_48x64', 48, 64, 5)
     print('golden fixtures written to', OUT)

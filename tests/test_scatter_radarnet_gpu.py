@@ -115,3 +115,50 @@ def test_radarnet_forward_golden_and_s2():
                           boxes, return_logits=False)
     ref_d, ref_r = so.s2_scatter(crops.cpu().numpy(), pt.numpy(), w, (ph, pw), compat=True)
     assert np.array_equal(depth.cpu().numpy(), ref_d) and np.array_equal(resp.cpu().numpy(), ref_r)
+
+
+def test_stage1_to_stage2_bridge_kernel_bit_exact():
+    """rcfd_stage1_to_stage2 == the reference's PNG round trip (golden written by its own codec), for the int64 depth
+    of compat mode and for float depth; without quantisation the values pass through unchanged."""
+    from helpers import load_golden
+    from rcfd import ops
+    g = load_golden('png16_roundtrip_48x64')
+    resp = torch.from_numpy(g['response']).to(DEV)
+    for tag in ('i64', 'f32'):
+        dep = torch.from_numpy(g['depth_' + tag]).to(DEV)
+        out = ops.stage1_to_stage2(dep[None], resp[None]).cpu().numpy()
+        assert out.shape == (1, 2) + g['response'].shape
+        assert np.array_equal(out[0, 0], g['loaded_depth_' + tag])
+        assert np.array_equal(out[0, 1], g['loaded_response'])
+    raw = ops.stage1_to_stage2(torch.from_numpy(g['depth_f32']).to(DEV)[None], resp[None], quantize_png16=False).cpu().numpy()
+    assert np.array_equal(raw[0, 0], g['depth_f32']) and np.array_equal(raw[0, 1], g['response'])
+
+
+def test_image_and_radar_to_depth_end_to_end():
+    """One frame through both stages in memory == the same chain with the PNG quantisation done on the host by the
+    oracle between the stages (identical FusionNet input bits -> identical depth)."""
+    import fusionnet_model
+    import radarnet_main
+    import radarnet_model
+    import scatter_oracle as so
+    from rcfd import bridge, synth
+    torch.manual_seed(3)
+    h, w, k = 64, 128, 5
+    rn = radarnet_model.RadarNetModel(device=DEV, **dict(synth.CANONICAL_RADARNET, input_patch_size_image=(64, 64)))
+    rn.eval()
+    fn = fusionnet_model.FusionNetModel(device=DEV, **synth.SMALL_FUSIONNET)
+    fn.eval()
+    image = torch.rand(1, 3, h, w, device=DEV)
+    pts = synth.radar_points(k, h, w, 3).to(DEV)
+    depth, inp = bridge.image_and_radar_to_depth(rn, fn, image, pts)
+    assert depth.shape == (1, 1, h, w) and inp.shape == (1, 2, h, w)
+    # manual chain
+    p2, boxes = bridge.boxes_for_points(pts, 64, h)
+    with torch.no_grad():
+        d1, r1 = radarnet_main.forward(rn, image, p2, boxes, device=DEV)
+        dq, rq = so.png16_roundtrip(d1[0].cpu().numpy(), r1[0].cpu().numpy())
+        inp_ref = torch.from_numpy(np.stack([dq, rq])[None]).to(DEV)
+        depth_ref = fn.forward(image, inp_ref)
+    assert torch.equal(inp, inp_ref)
+    assert torch.equal(depth, depth_ref)
+    assert float(depth.min()) >= 0.99 and float(depth.max()) <= 100.0

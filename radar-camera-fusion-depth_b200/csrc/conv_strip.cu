@@ -385,11 +385,28 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 constexpr int NRU = 4;             // ring depth of the up-sampling variant (16 weight blocks need the room)
 
+// Sub-pixel phases of `3x3 after 2x nearest up-sampling`: phase (a, b), tap (t2, u) reads the input window
+// (row a + t2, column shift b + u) -- 9 distinct windows for 16 (phase, tap) pairs.  Pairs that share a window are issued
+// as ONE tcgen05.mma whose B operand stacks their weight blocks along N and whose D spans their (adjacent) phase
+// accumulators: 10 MMAs per 16-channel chunk instead of 16, i.e. 37 % fewer fetches of the 128-pixel A tile from shared
+// memory (the unit that binds this kernel, profiles/r1_ncu_summary.md).  Phase accumulators sit in TMEM in the order
+// 0, 1, 3, 2 so that three of the four two-phase windows are adjacent; the fourth is split.
+// Weight blocks in shared memory, slot -> (phase, tap):
+//   0-3 centre window (1,1): (0,3) (1,2) (3,0) (2,1)      4-5 window (0,1): (0,1) (1,0)      6-7 window (1,2): (1,3) (3,1)
+//   8-9 window (2,1): (3,2) (2,3)      10 / 11 window (1,0): (0,2) / (2,0)      12-15 corners: (0,0) (1,1) (2,2) (3,3)
+constexpr int8_t kUpSlotPhase[16] = {0, 1, 3, 2, 0, 1, 1, 3, 3, 2, 0, 2, 0, 1, 2, 3};
+constexpr int8_t kUpSlotTap[16] = {3, 2, 0, 1, 1, 0, 3, 1, 2, 3, 2, 0, 0, 1, 2, 3};
+// MMA list: window row, window column shift, first weight slot, blocks stacked along N, first TMEM phase position
+constexpr int8_t kUpMma[10][5] = {{1, 1, 0, 4, 0}, {0, 1, 4, 2, 0}, {1, 2, 6, 2, 1}, {2, 1, 8, 2, 2}, {1, 0, 10, 1, 0},
+                                              {1, 0, 11, 1, 3}, {0, 0, 12, 1, 0}, {0, 2, 13, 1, 1}, {2, 0, 14, 1, 3}, {2, 2, 15, 1, 2}};
+__device__ __forceinline__ int up_phase_pos(int ph) { return ph < 2 ? ph : 5 - ph; }     // TMEM order 0, 1, 3, 2
+
 template <int BN, int CIN>
 struct StripUpCfg {
   static constexpr int RB = CIN * 2;
   static constexpr int ROWBUF = ((HALO_W * RB + 1023) / 1024) * 1024;
   static constexpr int W_TAP = ((BN * RB + 1023) / 1024) * 1024;
+  static_assert(W_TAP == BN * RB, "stacked weight blocks must be contiguous (merged sub-pixel MMAs)");
   static constexpr int W_BYTES = 16 * W_TAP;
   static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;
   static constexpr int TMEM_COLS = 8 * BN;                   // 2 buffers x 4 phases
@@ -448,9 +465,9 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
       // resident weights: 4 phases x 4 taps x [BN][CIN]  (rcfd_pack_upconv2x_weight layout [ph][cout][tap][cin])
       mbar_expect_tx(wbar, (uint32_t)(16 * BN * C::RB));
-      for (int ph = 0; ph < 4; ++ph)
-        for (int tap = 0; tap < 4; ++tap)
-          tma_load_2d(sW + (ph * 4 + tap) * C::W_TAP, &map_w, wbar, tap * p.cin, ph * p.cout + n0);
+#pragma unroll
+      for (int slot = 0; slot < 16; ++slot)
+        tma_load_2d(sW + slot * C::W_TAP, &map_w, wbar, kUpSlotTap[slot] * p.cin, kUpSlotPhase[slot] * p.cout + n0);
       uint32_t L = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int ck = item % p.chunks_per_col;
@@ -487,24 +504,18 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (orow >= 2) mbar_wait(sBar + 8 * (2 * NRU + 2 + acc), ((orow >> 1) & 1) ^ 1);
         tc_fence_after();
         if (lane == 0) {
-          // phase (a, b): output pixel (2i+a, 2j+b) = 2x2 taps on low-res rows i-1+a, i+a and columns j-1+b, j+b
+          // phase (a, b): output pixel (2i+a, 2j+b) = 2x2 taps on low-res rows i-1+a, i+a and columns j-1+b, j+b;
+          // issued window by window (see kUpMma); the centre window comes first and overwrites all four accumulators
 #pragma unroll
-          for (int ph = 0; ph < 4; ++ph) {
-            const int pa = ph >> 1, pb = ph & 1;
-            const uint32_t d_tmem = tmem_base + (acc * 4 + ph) * BN;
+          for (int k = 0; k < CIN / 16; ++k) {
 #pragma unroll
-            for (int t2 = 0; t2 < 2; ++t2) {
-              const uint32_t rowbuf = sRing + ((L + t + pa + t2) % NRU) * C::ROWBUF;
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const uint32_t a0 = rowbuf + (pb + u) * C::RB;
-                const uint32_t b0 = sW + (ph * 4 + t2 * 2 + u) * C::W_TAP;
-#pragma unroll
-                for (int k = 0; k < CIN / 16; ++k) {
-                  umma_f16(d_tmem, umma_desc(a0 + k * 32, 16, sbo, C::LAYOUT), umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT), idesc,
-                           (uint32_t)((t2 | u | k) != 0));
-                }
-              }
+            for (int m = 0; m < 10; ++m) {
+              constexpr int dummy = 0; (void)dummy;
+              const int wr = kUpMma[m][0], wc = kUpMma[m][1], slot = kUpMma[m][2], nb = kUpMma[m][3], pos = kUpMma[m][4];
+              const uint32_t a0 = sRing + ((L + t + wr) % NRU) * C::ROWBUF + wc * C::RB;
+              const uint32_t b0 = sW + slot * C::W_TAP;
+              umma_f16(tmem_base + (acc * 4 + pos) * BN, umma_desc(a0 + k * 32, 16, sbo, C::LAYOUT),
+                       umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT), umma_idesc(nb * BN), (uint32_t)((m | k) != 0));
             }
           }
           umma_commit(sBar + 8 * (2 * NRU + acc));                  // accumulator of this output row complete
@@ -547,7 +558,7 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll 1
         for (int ph = 0; ph < 4; ++ph) {
           const size_t gm = ((size_t)img * (2 * p.h) + (2 * (y0 + t) + (ph >> 1))) * (2 * p.w) + (2 * ox + (ph & 1));
-          const uint32_t trow = tmem_base + (acc * 4 + ph) * BN + ((uint32_t)(q * 32) << 16);
+          const uint32_t trow = tmem_base + (acc * 4 + up_phase_pos(ph)) * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
           for (int cb = 0; cb < BN; cb += 16) {
             float v[16];

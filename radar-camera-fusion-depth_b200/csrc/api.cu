@@ -27,6 +27,7 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
 extern int g_tma_bn_cap;
 extern int g_strip_max_waste;
+extern int g_strip_input_stationary;
 extern int g_strip_up_max_waste;
 bool conv_tma_supported(const ConvKP& p, int dtype);
 int conv_tma_launch(const ConvKP& p, cudaStream_t st);
@@ -90,6 +91,7 @@ int rcfd_set_option(const char* key, int32_t value) {
   RCFD_CHECK_ARG(key != nullptr, "set_option: null key");
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
   if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
+  if (strcmp(key, "strip_input_stationary") == 0) { g_strip_input_stationary = value; return RCFD_OK; }
   if (strcmp(key, "strip_max_waste") == 0) { g_strip_max_waste = value; return RCFD_OK; }
   if (strcmp(key, "strip_up_max_waste") == 0) { g_strip_up_max_waste = value; return RCFD_OK; }
   set_error("set_option: unknown key %s", key);

@@ -394,10 +394,10 @@ constexpr int NRU = 4;             // ring depth of the up-sampling variant (16 
 // Weight blocks in shared memory, slot -> (phase, tap):
 //   0-3 centre window (1,1): (0,3) (1,2) (3,0) (2,1)      4-5 window (0,1): (0,1) (1,0)      6-7 window (1,2): (1,3) (3,1)
 //   8-9 window (2,1): (3,2) (2,3)      10 / 11 window (1,0): (0,2) / (2,0)      12-15 corners: (0,0) (1,1) (2,2) (3,3)
-constexpr int8_t kUpSlotPhase[16] = {0, 1, 3, 2, 0, 1, 1, 3, 3, 2, 0, 2, 0, 1, 2, 3};
-constexpr int8_t kUpSlotTap[16] = {3, 2, 0, 1, 1, 0, 3, 1, 2, 3, 2, 0, 0, 1, 2, 3};
+__device__ __constant__ int8_t kUpSlotPhase[16] = {0, 1, 3, 2, 0, 1, 1, 3, 3, 2, 0, 2, 0, 1, 2, 3};
+__device__ __constant__ int8_t kUpSlotTap[16] = {3, 2, 0, 1, 1, 0, 3, 1, 2, 3, 2, 0, 0, 1, 2, 3};
 // MMA list: window row, window column shift, first weight slot, blocks stacked along N, first TMEM phase position
-constexpr int8_t kUpMma[10][5] = {{1, 1, 0, 4, 0}, {0, 1, 4, 2, 0}, {1, 2, 6, 2, 1}, {2, 1, 8, 2, 2}, {1, 0, 10, 1, 0},
+__device__ __constant__ int8_t kUpMma[10][5] = {{1, 1, 0, 4, 0}, {0, 1, 4, 2, 0}, {1, 2, 6, 2, 1}, {2, 1, 8, 2, 2}, {1, 0, 10, 1, 0},
                                               {1, 0, 11, 1, 3}, {0, 0, 12, 1, 0}, {0, 2, 13, 1, 1}, {2, 0, 14, 1, 3}, {2, 2, 15, 1, 2}};
 __device__ __forceinline__ int up_phase_pos(int ph) { return ph < 2 ? ph : 5 - ph; }     // TMEM order 0, 1, 3, 2
 
@@ -510,7 +510,6 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int k = 0; k < CIN / 16; ++k) {
 #pragma unroll
             for (int m = 0; m < 10; ++m) {
-              constexpr int dummy = 0; (void)dummy;
               const int wr = kUpMma[m][0], wc = kUpMma[m][1], slot = kUpMma[m][2], nb = kUpMma[m][3], pos = kUpMma[m][4];
               const uint32_t a0 = sRing + ((L + t + wr) % NRU) * C::ROWBUF + wc * C::RB;
               const uint32_t b0 = sW + slot * C::W_TAP;
@@ -588,6 +587,234 @@ conv_strip_up_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// Input-stationary variant of the row-streaming 3x3 conv (single source).
+//
+// In the kernel above every output row issues 9 x CIN/16 MMAs of N = cout-tile, and each of them fetches its own
+// 128-pixel A window from shared memory: for cout tiles of 16-64 that operand fetch, not the MMA pipe, is the binding
+// unit (ncu: l1tex__data_pipe_tc_wavefronts_mem_shared ~50 % of peak at 19 % tensor-pipe activity).  Here the roles
+// are turned around: an INPUT row i (window shifted by the horizontal tap s) is multiplied ONCE with the weights of
+// the three vertical taps stacked along N ([W(r=2,s); W(r=1,s); W(r=0,s)], N = 3 x BN), and the three column blocks
+// of D land in the accumulators of output rows i-1, i, i+1, which live in a ring of S TMEM slots at columns
+// (o mod S) * BN.  3 x CIN/16 MMAs per row instead of 9 x CIN/16, one third of the A fetches.  Accumulators are always
+// accumulated into: the epilogue zeroes a slot (tcgen05.st) after draining it, before handing it back.
+// Chunk borders: input row j of a chunk only feeds the outputs t = j - r that lie inside the chunk, i.e. a sub-range of
+// the stacked blocks; a run that would wrap around the slot ring is split into two MMAs.
+constexpr int IS_SLOTS = 8;
+constexpr int IS_RING = 4;
+
+template <int BN, int CIN>
+struct StripIsCfg {
+  static constexpr int RB = CIN * 2;
+  static constexpr int HALO = SW + 2;
+  static constexpr int ROWBUF = ((HALO * RB + 1023) / 1024) * 1024;
+  static constexpr int W_BLK = BN * RB;                    // one (r, s) weight block; multiples of the swizzle atom (8 rows)
+  static constexpr int W_BYTES = ((9 * W_BLK + 1023) / 1024) * 1024;
+  static constexpr int RED_BYTES = 4 * BN * 2 * 4;
+  static constexpr int TMEM_COLS = IS_SLOTS * BN;          // 128 / 256 / 512
+  static constexpr int SMEM = IS_RING * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr uint32_t LAYOUT = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+};
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN, int CIN, bool STATS>
+__global__ void __launch_bounds__(NTHREADS)
+conv_strip_is_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
+  typedef StripIsCfg<BN, CIN> C;
+  constexpr int NRI = IS_RING, S = IS_SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sRing = base;
+  const uint32_t sW = base + NRI * C::ROWBUF;
+  const uint32_t sRed = sW + C::W_BYTES;
+  const uint32_t sBar = sRed + C::RED_BYTES;   // full[NRI], empty[NRI], tfull[S], tempty[S], wbar
+  const uint32_t bFull = sBar, bEmpty = sBar + 8 * NRI, bTfull = sBar + 8 * 2 * NRI, bTempty = bTfull + 8 * S;
+  const uint32_t wbar = bTempty + 8 * S;
+  const uint32_t sTmem = wbar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+  float* red = reinterpret_cast<float*>(gen_base + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < NRI; ++s) {
+      mbar_init(bFull + 8 * s, 1);
+      mbar_init(bEmpty + 8 * s, 1);
+    }
+    for (int a = 0; a < S; ++a) {
+      mbar_init(bTfull + 8 * a, 1);
+      mbar_init(bTempty + 8 * a, NEPI);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================================================== TMA PRODUCER
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      // resident weights, stacked per horizontal tap s as [r = 2; r = 1; r = 0] blocks of [BN][CIN]
+      mbar_expect_tx(wbar, (uint32_t)(9 * C::W_BLK));
+      for (int s = 0; s < 3; ++s)
+        for (int r = 0; r < 3; ++r)
+          tma_load_2d(sW + (s * 3 + (2 - r)) * C::W_BLK, &map_w, wbar, (r * 3 + s) * p.cin, n0);
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int ck = item % p.chunks_per_col;
+        int col = item / p.chunks_per_col;
+        const int strip = col % p.strips;
+        const int img = col / p.strips;
+        const int y0 = ck * p.rows_per_chunk;
+        const int rows = min(p.rows_per_chunk, p.h - y0);
+        for (int j = 0; j < rows + 2; ++j, ++L) {
+          const int s = L % NRI;
+          if (L >= (uint32_t)NRI) mbar_wait(bEmpty + 8 * s, ((L / NRI) & 1) ^ 1);
+          mbar_expect_tx(bFull + 8 * s, (uint32_t)(C::HALO * C::RB));
+          tma_load_4d(sRing + s * C::ROWBUF, &map_x, bFull + 8 * s, 0, strip * SW - 1, y0 - 1 + j, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA ISSUER
+    constexpr uint32_t sbo = 8 * C::RB;
+    mbar_wait(wbar, 0);
+    uint32_t L = 0, O = 0;                       // running input-row / output-row counters of this CTA
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      for (int j = 0; j < rows + 2; ++j, ++L) {
+        // input row j feeds outputs t = j - r, 0 <= t < rows
+        const int r_lo = max(0, j - rows + 1), r_hi = min(2, j);
+        if (j < rows) {                          // output t = j is touched for the first time: its slot must be free (and zeroed)
+          const uint32_t o = O + j;
+          mbar_wait(bTempty + 8 * (o % S), (o / S) & 1);
+        }
+        mbar_wait(bFull + 8 * (L % NRI), (L / NRI) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t rowbuf = sRing + (L % NRI) * C::ROWBUF;
+          // outputs in ascending order: o_first = O + j - r_hi ... o_last = O + j - r_lo; stacked blocks 2 - r, ascending too
+          const uint32_t o_first = O + j - r_hi;
+          const int nblk = r_hi - r_lo + 1;
+          const int slot0 = o_first % S;
+          const int run0 = min(nblk, S - slot0);            // blocks before the slot ring wraps
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint32_t a0 = rowbuf + s * C::RB;
+            const uint32_t b0 = sW + (s * 3 + (2 - r_hi)) * C::W_BLK;
+#pragma unroll
+            for (int k = 0; k < CIN / 16; ++k) {
+              umma_f16(tmem_base + slot0 * BN, strip_desc(a0 + k * 32, sbo, C::LAYOUT, 0), umma_desc(b0 + k * 32, 16, sbo, C::LAYOUT),
+                       umma_idesc(run0 * BN), 1u);
+              if (run0 < nblk)
+                umma_f16(tmem_base, strip_desc(a0 + k * 32, sbo, C::LAYOUT, 0),
+                         umma_desc(b0 + run0 * C::W_BLK + k * 32, 16, sbo, C::LAYOUT), umma_idesc((nblk - run0) * BN), 1u);
+            }
+          }
+          umma_commit(bEmpty + 8 * (L % NRI));                       // this input row has been consumed
+          if (j >= 2) umma_commit(bTfull + 8 * ((O + j - 2) % S));   // output t = j - 2 received its last contribution
+        }
+        __syncwarp();
+      }
+      O += rows;
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================== EPILOGUE (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // pixel within the strip == TMEM lane
+    const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
+    const int etid = tid - 64;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float ss[STATS ? BN : 1], sq[STATS ? BN : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) { ss[i] = 0.f; sq[i] = 0.f; }
+    }
+    // all slots start zeroed and free
+#pragma unroll 1
+    for (int a = 0; a < S; ++a) {
+#pragma unroll
+      for (int cb = 0; cb < BN; cb += 16) tmem_st16_zero(lane_base + a * BN + cb);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    for (int a = 0; a < S; ++a) mbar_arrive(bTempty + 8 * a);
+    uint32_t O = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      int col = item / p.chunks_per_col;
+      const int strip = col % p.strips;
+      const int img = col / p.strips;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      const int ox = strip * SW + r;
+      const bool mvalid = ox < p.w;
+      for (int t = 0; t < rows; ++t, ++O) {
+        const uint32_t slot = O % S;
+        const size_t gm = ((size_t)img * p.h + (y0 + t)) * p.w + ox;
+        mbar_wait(bTfull + 8 * slot, (O / S) & 1);
+        tc_fence_after();
+        const uint32_t trow = lane_base + slot * BN;
+        if constexpr (STATS) {
+#pragma unroll
+          for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            tmem_st16_zero(trow + cb);
+            if (mvalid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                ss[cb + i] += v[i];
+                sq[cb + i] = fmaf(v[i], v[i], sq[cb + i]);
+              }
+              strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            tmem_st16_zero(trow + cb);
+            if (mvalid) strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bTempty + 8 * slot);
+      }
+    }
+    if constexpr (STATS) strip_flush_stats<BN>(ss, sq, red, q, lane, etid, n0, p);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
 inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int halo = HALO_W) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
@@ -644,6 +871,43 @@ int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
   return t.ssum != nullptr ? launch_strip_s<BN, CIN, true, KS, CIN1>(k, t, st) : launch_strip_s<BN, CIN, false, KS, CIN1>(k, t, st);
 }
 
+
+template <int BN, int CIN, bool STATS>
+int launch_strip_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  typedef StripIsCfg<BN, CIN> C;
+  static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_is_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { set_error("conv_strip_is: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, conv_strip_is_kernel<BN, CIN, STATS>);
+    if (e != cudaSuccess) { set_error("conv_strip_is: attributes: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NTHREADS;
+    per_sm = (C::SMEM <= 112 * 1024 && 2 * regs_per_cta <= 65536 && 2 * C::TMEM_COLS <= 512) ? 2 : 1;
+  }
+  alignas(64) CUtensorMap mx, mw;
+  if (!make_row_map(&mx, k.src0, k.n, k.hin, k.win, k.c0, C::HALO) || !make_w_map(&mw, k.weight, k.cout, k.K, CIN, BN)) {
+    set_error("conv_strip_is: cuTensorMapEncodeTiled failed");
+    return RCFD_ECUDA;
+  }
+  const int ntile = ceil_div(k.cout, BN);
+  int ctas = num_sms() * per_sm / ntile;
+  if (ctas < 1) ctas = 1;
+  plan_row_chunks(t.h, t.n * t.strips, ctas, 6, 4, &t.rows_per_chunk, &t.chunks_per_col);
+  t.num_items = t.n * t.strips * t.chunks_per_col;
+  if (ctas > t.num_items) ctas = t.num_items;
+  dim3 grid(ctas, ntile);
+  conv_strip_is_kernel<BN, CIN, STATS><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  RCFD_CHECK_LAUNCH("conv_strip_is");
+  return RCFD_OK;
+}
+
+template <int BN, int CIN>
+int launch_strip_is(const ConvKP& k, StripP& t, cudaStream_t st) {
+  return t.ssum != nullptr ? launch_strip_is_s<BN, CIN, true>(k, t, st) : launch_strip_is_s<BN, CIN, false>(k, t, st);
+}
+
 template <int BN, int CIN, bool STATS>
 int launch_strip_up_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   typedef StripUpCfg<BN, CIN> C;
@@ -676,6 +940,7 @@ int launch_strip_up(const ConvKP& k, StripP& t, cudaStream_t st) {
 }  // namespace
 
 int g_strip_desc_mode = 0;
+int g_strip_input_stationary = 1;  // rcfd_set_option("strip_input_stationary"): 0 = output-stationary kernel for every 3x3 conv
 int g_strip_max_waste = 50;       // rcfd_set_option("strip_max_waste"): padded strip columns tolerated, percent of the map width
 int g_strip_up_max_waste = 30;    // same for the up-sampling variant (measured on the low-res width)
 
@@ -775,6 +1040,11 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
     if (p.c0 == 64 && p.c1 == 32) return bn == 64 ? launch_strip<64, 64, 3, 32>(p, t, st) : launch_strip<32, 64, 3, 32>(p, t, st);
     if (p.c0 == 64 && p.c1 == 64) return launch_strip<32, 64, 3, 64>(p, t, st);
     return bn == 64 ? launch_strip<64, 32, 3, 32>(p, t, st) : launch_strip<32, 32, 3, 32>(p, t, st);
+  }
+  if (g_strip_input_stationary && p.kh == 3 && p.c1 == 0) {       // one A fetch per horizontal tap, vertical taps stacked along N
+    if (p.c0 == 64) return bn == 64 ? launch_strip_is<64, 64>(p, t, st) : (bn == 32 ? launch_strip_is<32, 64>(p, t, st) : launch_strip_is<16, 64>(p, t, st));
+    if (p.c0 == 32) return bn == 64 ? launch_strip_is<64, 32>(p, t, st) : (bn == 32 ? launch_strip_is<32, 32>(p, t, st) : launch_strip_is<16, 32>(p, t, st));
+    if (p.c0 == 16) return bn == 64 ? launch_strip_is<64, 16>(p, t, st) : (bn == 32 ? launch_strip_is<32, 16>(p, t, st) : launch_strip_is<16, 16>(p, t, st));
   }
   if (p.c0 == 64) {
     switch (bn) {

@@ -815,6 +815,230 @@ conv_strip_is_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// Input-stationary variant of the sub-pixel up-conv (3x3 behind an exact 2x nearest up-sampling).
+//
+// Low-res input row j feeds the low-res output rows t = j - r, r = a + t2 in {0, 1, 2} (phase row a, vertical tap t2):
+// r = 2 -> (a=1, t2=1), r = 1 -> (a=0, t2=1) and (a=1, t2=0), r = 0 -> (a=0, t2=0).  For a fixed phase column b and
+// horizontal tap u (input window shifted by c = b + u pixels) those four (a, t2) weight blocks are stacked along N in the
+// order of the accumulators they feed -- [t=j-2: a=1 | t=j-1: a=0 | t=j-1: a=1 | t=j: a=0] -- and issued as ONE MMA
+// (N = 4 x BN): 4 MMAs per input row and 16-channel chunk (c = 0: b=0; c = 1: b=0 and b=1; c = 2: b=1) instead of 10.
+// TMEM: two rings (one per phase column b) of S slots, a slot = [a=0 | a=1] x BN columns of one output row.
+constexpr int UIS_SLOTS = 4;
+
+template <int BN, int CIN>
+struct StripUpIsCfg {
+  static constexpr int RB = CIN * 2;
+  static constexpr int HALO = SW + 2;
+  static constexpr int ROWBUF = ((HALO * RB + 1023) / 1024) * 1024;
+  static constexpr int W_BLK = BN * RB;
+  static constexpr int W_BYTES = ((16 * W_BLK + 1023) / 1024) * 1024;
+  static constexpr int RED_BYTES = 4 * BN * 2 * 4;
+  static constexpr int TMEM_COLS = UIS_SLOTS * 4 * BN;     // 2 rings x S slots x 2 phases rows x BN
+  static constexpr int SMEM = IS_RING * ROWBUF + W_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr uint32_t LAYOUT = RB == 128 ? 2u : (RB == 64 ? 4u : 6u);
+};
+
+template <int BN, int CIN, bool STATS>
+__global__ void __launch_bounds__(NTHREADS)
+conv_strip_up_is_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const StripP p) {
+  typedef StripUpIsCfg<BN, CIN> C;
+  constexpr int NRI = IS_RING, S = UIS_SLOTS;
+  static_assert(C::TMEM_COLS <= 512, "sub-pixel input-stationary kernel: cout tile too wide for TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sRing = base;
+  const uint32_t sW = base + NRI * C::ROWBUF;
+  const uint32_t sRed = sW + C::W_BYTES;
+  const uint32_t sBar = sRed + C::RED_BYTES;
+  const uint32_t bFull = sBar, bEmpty = sBar + 8 * NRI, bTfull = sBar + 8 * 2 * NRI, bTempty = bTfull + 8 * S;
+  const uint32_t wbar = bTempty + 8 * S;
+  const uint32_t sTmem = wbar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+  float* red = reinterpret_cast<float*>(gen_base + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < NRI; ++s) {
+      mbar_init(bFull + 8 * s, 1);
+      mbar_init(bEmpty + 8 * s, 1);
+    }
+    for (int a = 0; a < S; ++a) {
+      mbar_init(bTfull + 8 * a, 1);
+      mbar_init(bTempty + 8 * a, NEPI);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t RING1 = S * 2 * BN;            // first column of the b = 1 ring
+
+  if (warp == 0) {
+    // =========================================================== TMA PRODUCER
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      // weights (rcfd_pack_upconv2x_weight: [phase = a*2+b][cout][tap = t2*2+u][cin]); group g = b*2+u holds the four
+      // (a, t2) blocks in accumulator order (a,t2) = (1,1) (0,1) (1,0) (0,0)
+      mbar_expect_tx(wbar, (uint32_t)(16 * C::W_BLK));
+      for (int g = 0; g < 4; ++g) {
+        const int b = g >> 1, u = g & 1;
+        for (int blk = 0; blk < 4; ++blk) {
+          const int a = (blk == 0 || blk == 2) ? 1 : 0, t2 = blk < 2 ? 1 : 0;
+          tma_load_2d(sW + (g * 4 + blk) * C::W_BLK, &map_w, wbar, (t2 * 2 + u) * p.cin, (a * 2 + b) * p.cout + n0);
+        }
+      }
+      uint32_t L = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int ck = item % p.chunks_per_col;
+        int col = item / p.chunks_per_col;
+        const int strip = col % p.strips;
+        const int img = col / p.strips;
+        const int y0 = ck * p.rows_per_chunk;
+        const int rows = min(p.rows_per_chunk, p.h - y0);
+        for (int j = 0; j < rows + 2; ++j, ++L) {
+          const int s = L % NRI;
+          if (L >= (uint32_t)NRI) mbar_wait(bEmpty + 8 * s, ((L / NRI) & 1) ^ 1);
+          mbar_expect_tx(bFull + 8 * s, (uint32_t)(C::HALO * C::RB));
+          tma_load_4d(sRing + s * C::ROWBUF, &map_x, bFull + 8 * s, 0, strip * SW - 1, y0 - 1 + j, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA ISSUER
+    constexpr uint32_t sbo = 8 * C::RB;
+    mbar_wait(wbar, 0);
+    uint32_t L = 0, O = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      for (int j = 0; j < rows + 2; ++j, ++L) {
+        if (j < rows) {                          // output row t = j is touched for the first time
+          const uint32_t o = O + j;
+          mbar_wait(bTempty + 8 * (o % S), (o / S) & 1);
+        }
+        mbar_wait(bFull + 8 * (L % NRI), (L / NRI) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t rowbuf = sRing + (L % NRI) * C::ROWBUF;
+          // blocks 0..3 <-> (t, a) = (j-2, 1) (j-1, 0) (j-1, 1) (j, 0); the valid ones are a contiguous range
+          const int b_lo = j >= 2 ? 0 : (j >= 1 ? 1 : 3);
+          const int b_hi = j < rows ? 3 : (j - 1 < rows ? 2 : 0);
+          // column (within a ring) of block blk
+          uint32_t colv[4];
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) {
+            const int t = blk == 0 ? j - 2 : (blk == 3 ? j : j - 1);
+            const int a = (blk == 0 || blk == 2) ? 1 : 0;
+            colv[blk] = (uint32_t)(((O + t) % S) * 2 * BN + a * BN);      // only used for valid blocks
+          }
+          // first run: from b_lo while columns stay contiguous; a second run after the ring wrap
+          int run0 = 1;
+          while (b_lo + run0 <= b_hi && colv[b_lo + run0] == colv[b_lo + run0 - 1] + BN) ++run0;
+          const int nblk = b_hi - b_lo + 1;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int b = g >> 1, u = g & 1;
+            const uint32_t a0 = rowbuf + (b + u) * C::RB;
+            const uint32_t w0 = sW + (g * 4 + b_lo) * C::W_BLK;
+            const uint32_t d0 = tmem_base + (b ? RING1 : 0u);
+#pragma unroll
+            for (int k = 0; k < CIN / 16; ++k) {
+              umma_f16(d0 + colv[b_lo], umma_desc(a0 + k * 32, 16, sbo, C::LAYOUT), umma_desc(w0 + k * 32, 16, sbo, C::LAYOUT),
+                       umma_idesc(run0 * BN), 1u);
+              if (run0 < nblk)
+                umma_f16(d0 + colv[b_lo + run0], umma_desc(a0 + k * 32, 16, sbo, C::LAYOUT),
+                         umma_desc(w0 + run0 * C::W_BLK + k * 32, 16, sbo, C::LAYOUT), umma_idesc((nblk - run0) * BN), 1u);
+            }
+          }
+          umma_commit(bEmpty + 8 * (L % NRI));
+          if (j >= 2) umma_commit(bTfull + 8 * ((O + j - 2) % S));
+        }
+        __syncwarp();
+      }
+      O += rows;
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================== EPILOGUE (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
+    const int etid = tid - 64;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float ss[STATS ? BN : 1], sq[STATS ? BN : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) { ss[i] = 0.f; sq[i] = 0.f; }
+    }
+#pragma unroll 1
+    for (int cb = 0; cb < C::TMEM_COLS; cb += 16) tmem_st16_zero(lane_base + cb);
+    tmem_wait_st();
+    tc_fence_before();
+    for (int a = 0; a < S; ++a) mbar_arrive(bTempty + 8 * a);
+    uint32_t O = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int ck = item % p.chunks_per_col;
+      int col = item / p.chunks_per_col;
+      const int strip = col % p.strips;
+      const int img = col / p.strips;
+      const int y0 = ck * p.rows_per_chunk;
+      const int rows = min(p.rows_per_chunk, p.h - y0);
+      const int ox = strip * SW + r;
+      const bool mvalid = ox < p.w;
+      for (int t = 0; t < rows; ++t, ++O) {
+        const uint32_t slot = O % S;
+        mbar_wait(bTfull + 8 * slot, (O / S) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ph = 0; ph < 4; ++ph) {
+          const int a = ph >> 1, b = ph & 1;
+          const size_t gm = ((size_t)img * (2 * p.h) + (2 * (y0 + t) + a)) * (2 * p.w) + (2 * ox + b);
+          const uint32_t trow = lane_base + (b ? RING1 : 0u) + slot * 2 * BN + a * BN;
+#pragma unroll
+          for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(trow + cb, v);
+            tmem_st16_zero(trow + cb);
+            if (mvalid) {
+              if constexpr (STATS) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  ss[cb + i] += v[i];
+                  sq[cb + i] = fmaf(v[i], v[i], sq[cb + i]);
+                }
+              }
+              strip_store16(v, p, n0 + cb, gm * p.cout + n0 + cb, vector_epilogue);
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bTempty + 8 * slot);
+      }
+    }
+    if constexpr (STATS) strip_flush_stats<BN>(ss, sq, red, q, lane, etid, n0, p);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
 inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int halo = HALO_W) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
@@ -908,6 +1132,43 @@ int launch_strip_is(const ConvKP& k, StripP& t, cudaStream_t st) {
   return t.ssum != nullptr ? launch_strip_is_s<BN, CIN, true>(k, t, st) : launch_strip_is_s<BN, CIN, false>(k, t, st);
 }
 
+
+template <int BN, int CIN, bool STATS>
+int launch_strip_up_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  typedef StripUpIsCfg<BN, CIN> C;
+  static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(conv_strip_up_is_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { set_error("conv_strip_up_is: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, conv_strip_up_is_kernel<BN, CIN, STATS>);
+    if (e != cudaSuccess) { set_error("conv_strip_up_is: attributes: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NTHREADS;
+    per_sm = (C::SMEM <= 112 * 1024 && 2 * regs_per_cta <= 65536 && 2 * C::TMEM_COLS <= 512) ? 2 : 1;
+  }
+  alignas(64) CUtensorMap mx, mw;
+  if (!make_row_map(&mx, k.src0, k.n, k.h0, k.w0, k.c0) || !make_w_map(&mw, k.weight_up2x, 4 * k.cout, 4 * k.c0, CIN, BN)) {
+    set_error("conv_strip_up_is: cuTensorMapEncodeTiled failed");
+    return RCFD_ECUDA;
+  }
+  const int ntile = ceil_div(k.cout, BN);
+  int ctas = num_sms() * per_sm / ntile;
+  if (ctas < 1) ctas = 1;
+  plan_row_chunks(t.h, t.n * t.strips, ctas, 6, 4, &t.rows_per_chunk, &t.chunks_per_col);
+  t.num_items = t.n * t.strips * t.chunks_per_col;
+  if (ctas > t.num_items) ctas = t.num_items;
+  dim3 grid(ctas, ntile);
+  conv_strip_up_is_kernel<BN, CIN, STATS><<<grid, NTHREADS, C::SMEM, st>>>(mx, mw, t);
+  RCFD_CHECK_LAUNCH("conv_strip_up_is");
+  return RCFD_OK;
+}
+
+template <int BN, int CIN>
+int launch_strip_up_is(const ConvKP& k, StripP& t, cudaStream_t st) {
+  return t.ssum != nullptr ? launch_strip_up_is_s<BN, CIN, true>(k, t, st) : launch_strip_up_is_s<BN, CIN, false>(k, t, st);
+}
+
 template <int BN, int CIN, bool STATS>
 int launch_strip_up_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   typedef StripUpCfg<BN, CIN> C;
@@ -976,6 +1237,12 @@ int conv_strip_up_launch(const ConvKP& p, cudaStream_t st) {
   t.desc_mode = 0;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
+  // input-stationary variant (4 stacked MMAs per input row and chunk): measured faster only for 16-wide cout tiles (RadarNet's
+  // 352x288 up-conv); with 32 the window-merged kernel below wins (65.7 vs 85.6 us on deconv0.deconv).  2 = force, 1 = heuristic.
+  if ((g_strip_input_stationary == 2 && bn <= 32) || (g_strip_input_stationary == 1 && bn == 16)) {
+    if (p.c0 == 64) return bn == 32 ? launch_strip_up_is<32, 64>(p, t, st) : launch_strip_up_is<16, 64>(p, t, st);
+    return bn == 32 ? launch_strip_up_is<32, 32>(p, t, st) : launch_strip_up_is<16, 32>(p, t, st);
+  }
   if (p.c0 == 64) {
     switch (bn) {
       case 64: return launch_strip_up<64, 64>(p, t, st);

@@ -154,6 +154,13 @@ int rcfd_maxpool3x3s2_fwd(const void* x, void* out, int32_t n, int32_t h, int32_
                           int32_t dtype, void* stream);
 int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, int32_t h, int32_t w,
                           int32_t c, int32_t dtype, void* stream);
+/* Training variant: the forward also records the window position (dy * 3 + dx, first maximum in scan order like ATen,
+ * 255 = none) of every output element, one byte each; the backward reads dout + that byte instead of re-scanning x.
+ * Channels must fill 16-byte vectors (8 bf16 / 4 float). */
+int rcfd_maxpool3x3s2_fwd_idx(const void* x, void* out, uint8_t* idx, int32_t n, int32_t h, int32_t w,
+                              int32_t c, int32_t dtype, void* stream);
+int rcfd_maxpool3x3s2_bwd_idx(const void* dout, const uint8_t* idx, void* dx, int32_t n, int32_t h,
+                              int32_t w, int32_t c, int32_t dtype, void* stream);
 
 /* Backward of nearest up-sampling (src/net_utils.py:196): dsrc[n,sy,sx,c] = sum of
  * dup[n,y,x,c] over all (y,x) that map to (sy,sx). */

@@ -454,6 +454,111 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out,
   }
 }
 
+// Training forward: also records WHERE the maximum came from (window position dy * 3 + dx of the FIRST maximum in
+// row-major scan order, like ATen; 255 = empty / all -inf), one byte per output element, so that the backward pass
+// reads dout + one byte instead of re-scanning 9 inputs per window.  16-byte channel vectors.
+template <typename T>
+__global__ void maxpool_fwd_idx_kernel(const T* __restrict__ x, T* __restrict__ out, uint8_t* __restrict__ idx, int N, int H,
+                                       int W, int C, int HO, int WO) {
+  constexpr int NV = V16<T>::N;
+  const int CV = C / NV;
+  const int64_t total = (int64_t)N * HO * WO * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int ox = (int)(r % WO); r /= WO;
+    const int oy = (int)(r % HO);
+    const int n = (int)(r / HO);
+    float best[NV];
+    uint8_t arg[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) { best[c] = -INFINITY; arg[c] = 255; }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        float v[NV];
+        V16<T>::ld(x + (((size_t)(n * H + iy) * W + ix) * CV + cv) * NV, v);
+#pragma unroll
+        for (int c = 0; c < NV; ++c)
+          if (v[c] > best[c]) { best[c] = v[c]; arg[c] = (uint8_t)(dy * 3 + dx); }
+      }
+    }
+    V16<T>::st(out + i * NV, best);
+#pragma unroll
+    for (int c = 0; c < NV; c += 4)
+      *reinterpret_cast<uint32_t*>(idx + i * NV + c) = (uint32_t)arg[c] | ((uint32_t)arg[c + 1] << 8) | ((uint32_t)arg[c + 2] << 16) |
+                                                       ((uint32_t)arg[c + 3] << 24);
+  }
+}
+// Backward from the recorded positions: one thread owns a 2x2 block of input pixels x 16 bytes of channels and looks at
+// the <= 4 windows that touch it (dout vector + position bytes each).
+template <typename T>
+__global__ void maxpool_bwd_idx_kernel(const T* __restrict__ dout, const uint8_t* __restrict__ idx, T* __restrict__ dx, int N,
+                                       int H, int W, int C, int HO, int WO) {
+  constexpr int NV = V16<T>::N;
+  const int CV = C / NV;
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const int64_t total = (int64_t)N * HB * WB * CV;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int m = (int)(r % WB); r /= WB;
+    const int k = (int)(r % HB);
+    const int n = (int)(r / HB);
+    float g[4][NV];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) g[a][c] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy) {
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int oy = k + wy, ox = m + wx;
+        if (oy >= HO || ox >= WO) continue;
+        const size_t o = (((size_t)(n * HO + oy) * WO + ox) * CV + cv) * NV;
+        float d[NV];
+        V16<T>::ld(dout + o, d);
+        uint8_t arg[NV];
+#pragma unroll
+        for (int c = 0; c < NV; c += 4) {
+          const uint32_t pk = *reinterpret_cast<const uint32_t*>(idx + o + c);
+          arg[c] = pk & 0xff; arg[c + 1] = (pk >> 8) & 0xff; arg[c + 2] = (pk >> 16) & 0xff; arg[c + 3] = pk >> 24;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int dy = a + 1 - 2 * wy;
+          if (dy < 0) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int dxx = b + 1 - 2 * wx;
+            if (dxx < 0) continue;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (arg[c] == dy * 3 + dxx) g[a * 2 + b][c] += d[c];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int iy = 2 * k + a;
+      if (iy >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ix = 2 * m + b;
+        if (ix >= W) continue;
+        V16<T>::st(dx + (((size_t)(n * H + iy) * W + ix) * CV + cv) * NV, g[a * 2 + b]);
+      }
+    }
+  }
+}
+
 // gather form: one thread owns a 2x2 block of input pixels x 16 bytes of channels and recomputes the arg-max
 // (FIRST maximum in row-major window scan, like ATen) of the <= 4 windows that touch the block: rows 2k, 2k+1
 // lie in windows k (window rows 1, 2) and k+1 (window row 0, odd input row only), same for columns.
@@ -1121,6 +1226,30 @@ int rcfd_maxpool3x3s2_bwd(const void* x, const void* dout, void* dx, int32_t n, 
                           (const T*)x, (const T*)dout, (T*)dx, n, h, w, c, ho, wo)));
   }
   RCFD_CHECK_LAUNCH("maxpool_bwd");
+  return RCFD_OK;
+}
+
+int rcfd_maxpool3x3s2_fwd_idx(const void* x, void* out, uint8_t* idx, int32_t n, int32_t h, int32_t w, int32_t c,
+                              int32_t dtype, void* stream) {
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  RCFD_CHECK_ARG(x && out && idx && n > 0 && h > 0 && w > 0 && c > 0 && c % vw == 0, "maxpool_fwd_idx: bad args (channels %% 16 bytes)");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * ho * wo * (c / vw);
+  DISPATCH_T(dtype, (maxpool_fwd_idx_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, idx, n, h, w,
+                                                                                               c, ho, wo)));
+  RCFD_CHECK_LAUNCH("maxpool_fwd_idx");
+  return RCFD_OK;
+}
+
+int rcfd_maxpool3x3s2_bwd_idx(const void* dout, const uint8_t* idx, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
+                              int32_t dtype, void* stream) {
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  RCFD_CHECK_ARG(dout && idx && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % vw == 0, "maxpool_bwd_idx: bad args (channels %% 16 bytes)");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / vw);
+  DISPATCH_T(dtype, (maxpool_bwd_idx_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const T*)dout, idx, (T*)dx, n, h,
+                                                                                               w, c, ho, wo)));
+  RCFD_CHECK_LAUNCH("maxpool_bwd_idx");
   return RCFD_OK;
 }
 

@@ -51,6 +51,8 @@ _SIGS = {
     'rcfd_gate_fuse_bwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
     'rcfd_maxpool3x3s2_fwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_maxpool3x3s2_bwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_maxpool3x3s2_fwd_idx': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_maxpool3x3s2_bwd_idx': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_upsample_nearest_bwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_leaky_bwd': [_P, _P, _P, c_int64, c_int32, _P],
     'rcfd_add_inplace': [_P, _P, c_int64, c_int32, _P],

@@ -508,6 +508,19 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
 
 
 def max_pool(ctx, x):
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    if ctx.tape is not None and x.shape[3] % vec == 0 and hasattr(ops, 'maxpool3x3s2_idx'):
+        # training: record the arg-max positions (1 byte / element) so that the backward does not re-scan the input
+        out, idx = ops.maxpool3x3s2_idx(x)
+        tape = ctx.tape
+        hw = (x.shape[1], x.shape[2])
+
+        def bwd():
+            d = tape.grad_of(out)
+            if d is not None:
+                tape.add_grad(x, ops.maxpool3x3s2_bwd_idx(d, idx, hw))
+        tape.add_step(bwd)
+        return out
     out = ops.maxpool3x3s2(x)
     if ctx.tape is not None:
         tape = ctx.tape

@@ -264,6 +264,24 @@ def maxpool3x3s2_bwd(x, dout):
     return dx
 
 
+def maxpool3x3s2_idx(x):
+    """Training forward: (pooled, positions) -- positions feed maxpool3x3s2_bwd_idx."""
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1)
+    out = _empty((n, ho, wo, c), device=x.device, dtype=x.dtype)
+    idx = _empty((n, ho, wo, c), device=x.device, dtype=torch.uint8)
+    _lib.call('rcfd_maxpool3x3s2_fwd_idx', _p(x), _p(out), _p(idx), n, h, w, c, dt(x), _stream())
+    return out, idx
+
+
+def maxpool3x3s2_bwd_idx(dout, idx, in_hw):
+    n, ho, wo, c = dout.shape
+    h, w = in_hw
+    dx = _empty((n, h, w, c), device=dout.device, dtype=dout.dtype)
+    _lib.call('rcfd_maxpool3x3s2_bwd_idx', _p(dout), _p(idx), _p(dx), n, h, w, c, dt(dout), _stream())
+    return dx
+
+
 def upsample_nearest_bwd(dup, src_hw):
     n, hu, wu, c = dup.shape
     hs, ws = src_hw

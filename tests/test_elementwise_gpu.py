@@ -99,6 +99,11 @@ def test_maxpool_forward_backward(hw):
     assert torch.equal(_nchw(yd), y.detach())
     dx = ops.maxpool3x3s2_bwd(_nhwc(x.detach()), _nhwc(dy))
     assert relerr(_nchw(dx), x.grad) < 1e-6
+    # training variant: recorded arg-max positions instead of re-scanning the input
+    yi, idx = ops.maxpool3x3s2_idx(_nhwc(x.detach()))
+    assert torch.equal(_nchw(yi), y.detach())
+    dxi = ops.maxpool3x3s2_bwd_idx(_nhwc(dy), idx, hw)
+    assert torch.equal(dxi, dx)
 
 
 @pytest.mark.parametrize('src,dst', [((6, 11), (11, 22)), ((5, 9), (10, 18)), ((3, 4), (10, 9))])
@@ -129,6 +134,9 @@ def test_maxpool_upsample_backward_bf16(hw):
     dx = ops.maxpool3x3s2_bwd(xd, dyd)
     assert relerr(_nchw(dx), x.grad) < 1e-2          # sums of up to 4 bf16 values rounded to bf16
     assert torch.equal(_nchw(dx) != 0, x.grad != 0)  # the SAME winners
+    yi, idx = ops.maxpool3x3s2_idx(xd)
+    assert torch.equal(_nchw(yi), y.detach())
+    assert torch.equal(ops.maxpool3x3s2_bwd_idx(dyd, idx, hw), dx)
     u = _rand(2, 16, 2 * hw[0], 2 * hw[1], seed=14).bfloat16().float()
     ref = u.view(2, 16, hw[0], 2, hw[1], 2).sum(dim=(3, 5))
     du = ops.upsample_nearest_bwd(u.permute(0, 2, 3, 1).contiguous().to(DEV, bf), hw)

@@ -61,6 +61,9 @@ CASES = {
     'head_bwd': ('headbwd', 1, 16, 352, 704, dict()),
     'outlier': ('outlier', 1, 1, 352, 704, dict()),
     'maxpool_bwd': ('poolbwd', 32, 32, 176, 352, dict()),
+    'maxpool_bwd_idx': ('poolbwd', 32, 32, 176, 352, dict(idx=True)),
+    'maxpool_fwd_idx': ('poolfwd', 32, 32, 176, 352, dict(idx=True)),
+    'maxpool_fwd': ('poolfwd', 32, 32, 176, 352, dict()),
 }
 
 
@@ -125,9 +128,14 @@ def build(kind, cin, cout, h, w, o):
     if kind == 'outlier':
         d = torch.rand(B, 1, h, w, device=dev) * (torch.rand(B, 1, h, w, device=dev) < 0.3)
         return (lambda: ops.outlier_removal(d, 7, 1.5)), 0.0, B * h * w * 12
-    if kind == 'poolbwd':
+    if kind in ('poolbwd', 'poolfwd'):
         x = torch.randn(B, h, w, cin, device=dev).to(bf)
         d = torch.randn(B, h // 2, w // 2, cin, device=dev).to(bf)
+        if kind == 'poolfwd':
+            return (lambda: ops.maxpool3x3s2_idx(x)) if o.get('idx') else (lambda: ops.maxpool3x3s2(x)), 0.0, (x.numel() + d.numel()) * 2
+        if o.get('idx'):
+            _, idx = ops.maxpool3x3s2_idx(x)
+            return (lambda: ops.maxpool3x3s2_bwd_idx(d, idx, (h, w))), 0.0, (x.numel() + d.numel()) * 2 + d.numel()
         return (lambda: ops.maxpool3x3s2_bwd(x, d)), 0.0, (2 * x.numel() + d.numel()) * 2
     raise SystemExit('unknown kind ' + kind)
 

@@ -39,6 +39,7 @@ struct TmaConvP {
   const void* residual;
   double* ssum; double* ssq;
   int accumulate, dst_f32;
+  int debug_skip_b;         // rcfd_set_option("tma_debug_skip_b"): timing experiment, skips the weight loads after the first ring pass
   int phases;               // 1, or 4 = sub-pixel phases of a 2x nearest up-sampled 3x3 conv (2x2 taps each)
   int out_h, out_w, out_s;  // destination extent and pixel stride (out_s = 2 with phases)
 };
@@ -120,10 +121,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             if (it >= (uint32_t)C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / C::STAGES) & 1) ^ 1);
             const uint32_t full = sBar + 8 * s;
             const uint32_t a_dst = sStage + s * C::STAGE, b_dst = a_dst + C::A_BYTES;
-            mbar_expect_tx(full, (uint32_t)(a_bytes + b_bytes));
-            if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
-            else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
-            tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
+            // timing experiments only (wrong results): bit 0 skips the weight loads, bit 1 the activation loads, after the first ring pass
+            const bool skip_b = (p.debug_skip_b & 1) && it >= (uint32_t)C::STAGES;
+            const bool skip_a = (p.debug_skip_b & 2) && it >= (uint32_t)C::STAGES;
+            if (skip_a && skip_b) { mbar_arrive(full); continue; }
+            mbar_expect_tx(full, (uint32_t)((skip_a ? 0 : a_bytes) + (skip_b ? 0 : b_bytes)));
+            if (!skip_a) {
+              if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
+              else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+            }
+            if (!skip_b) tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
           }
         }
       }
@@ -313,6 +320,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
 }  // namespace
 extern int g_tma_bn_cap;
+extern int g_tma_debug_skip_b;
 namespace {
 
 template <int BN>
@@ -334,6 +342,7 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 
 }  // namespace
 
+int g_tma_debug_skip_b = 0;
 int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n
 
 // 2x nearest up-sampling folded into a 3x3 / stride-1 / pad-1 conv == four 2x2 convs (one per
@@ -365,6 +374,7 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   ConvKP p = pin;
   TmaConvP t;
   t.phases = 1; t.out_h = p.ho; t.out_w = p.wo; t.out_s = 1;
+  t.debug_skip_b = g_tma_debug_skip_b;
   if (conv_tma_up2x_supported(p, RCFD_BF16)) {
     // run on the low-res grid: 2x2 taps, per-phase weights, destination pixels (2i+a, 2j+b)
     t.phases = 4; t.out_s = 2;

@@ -281,7 +281,24 @@ __global__ void bn_bwd_reduce_wide(const T* __restrict__ dz, const T* __restrict
     float sc[N], sh[N], mu[N], is[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) { sc[k] = scale[c + k]; sh[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; }
-    for (int64_t p = pbeg + r0; p < pend; p += rstep) {
+    int64_t p = pbeg + r0;
+    for (; p + 3 * (int64_t)rstep < pend; p += 4 * (int64_t)rstep) {      // 8 independent 16-byte loads in flight per thread
+      float g[4][N], v[4][N];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        V16<T>::ld(dz + (p + u * (int64_t)rstep) * C + c, g[u]);
+        V16<T>::ld(y + (p + u * (int64_t)rstep) * C + c, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const float d = dact(fmaf(v[u][k], sc[k], sh[k]), g[u][k], act);
+          s[k] += d;
+          q[k] += d * (v[u][k] - mu[k]) * is[k];
+        }
+    }
+    for (; p < pend; p += rstep) {
       float g[N], v[N];
       V16<T>::ld(dz + p * C + c, g);
       V16<T>::ld(y + p * C + c, v);

@@ -153,9 +153,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_st = sStage + s * C::STAGE, b_st = a_st + C::A_BYTES;
-          for (int k = 0; k < p.bkc / 16; ++k) {
+          for (int k = 0; k < ((p.debug_skip_b & 8) ? 1 : p.bkc / 16); ++k) {     // bit 3: one MMA per k-step (timing experiment)
             umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
                      (uint32_t)((ks | k) != 0));
+          }
+          if (p.debug_skip_b & 4) {             // timing experiment: the same MMAs once more (wrong results)
+            for (int k = 0; k < p.bkc / 16; ++k)
+              umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc, 1u);
           }
           umma_commit(sBar + 8 * (C::STAGES + s));
           if (ks == p.ksteps - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));

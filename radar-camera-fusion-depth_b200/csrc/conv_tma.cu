@@ -39,6 +39,7 @@ struct TmaConvP {
   const void* residual;
   double* ssum; double* ssq;
   int accumulate, dst_f32;
+  int kpair;                // 1: two 64-channel chunks per k-step (one full barrier / one commit per PAIR of stages)
   int debug_skip_b;         // rcfd_set_option("tma_debug_skip_b"): timing experiment, skips the weight loads after the first ring pass
   int phases;               // 1, or 4 = sub-pixel phases of a 2x nearest up-sampled 3x3 conv (2x2 taps each)
   int out_h, out_w, out_s;  // destination extent and pixel stride (out_s = 2 with phases)
@@ -49,10 +50,11 @@ struct TmaCfg {
   static constexpr int A_BYTES = TM * 128;                  // sized for bkc = 64
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN <= 32 ? 8 : (BN <= 64 ? 6 : (BN <= 128 ? 5 : 3));
+  static constexpr int STAGES = BN <= 32 ? 10 : (BN <= 64 ? 8 : (BN <= 128 ? 6 : 4));     // even: stages can be consumed in pairs
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int RED_BYTES = 2 * 4 * BN * 2 * 4;      // [acc][warp][BN][sum, sq]
   static constexpr int SMEM = STAGES * STAGE + RED_BYTES + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024 && STAGES % 2 == 0, "per-tap engine: stage ring");
 };
 
 template <int BN>
@@ -114,6 +116,28 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         // phase (a, b) of the up-sampled conv reads rows i-1+a .. i+a: its "padding" is 1 - a
         const int x0 = tx * p.tw * p.stride - (p.pad - (ph & 1)), y0 = ty * p.th * p.stride - (p.pad - (ph >> 1));
         const int n0 = ph * p.cout + nt * BN;
+        if (p.kpair) {
+          // stages are filled and released in PAIRS (s, s+1): 8 MMAs per barrier round trip / commit instead of 4
+          constexpr uint32_t NP = C::STAGES / 2;
+          for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+            const int tr = tap / p.kw, ts = tap - tr * p.kw;
+            for (int ch = 0; ch < chunks; ch += 2, ++it) {
+              const uint32_t pr = it % NP, s = 2 * pr;
+              if (it >= NP) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / NP) & 1) ^ 1);
+              const uint32_t full = sBar + 8 * s;
+              mbar_expect_tx(full, (uint32_t)(2 * (a_bytes + b_bytes)));
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = ch + h;
+                const uint32_t a_dst = sStage + (s + h) * C::STAGE, b_dst = a_dst + C::A_BYTES;
+                if (c < chunks0) tma_load_4d(a_dst, &map_a0, full, c * p.bkc, x0 + ts, y0 + tr, img);
+                else tma_load_4d(a_dst, &map_a1, full, (c - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+                tma_load_2d(b_dst, &map_w, full, tap * ctot + c * p.bkc, n0);
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.kh * p.kw; ++tap) {
           const int tr = tap / p.kw, ts = tap - tr * p.kw;
           for (int ch = 0; ch < chunks; ++ch, ++it) {
@@ -147,6 +171,29 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (tcount >= 2) mbar_wait(sBar + 8 * (2 * C::STAGES + 2 + acc), ((tcount >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
+      if (p.kpair) {
+        constexpr uint32_t NP = C::STAGES / 2;
+        const int npairs = p.ksteps / 2;
+        for (int kp = 0; kp < npairs; ++kp, ++it) {
+          const uint32_t pr = it % NP, s = 2 * pr;
+          mbar_wait(sBar + 8 * s, (it / NP) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t a_st = sStage + (s + h) * C::STAGE, b_st = a_st + C::A_BYTES;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
+                         (uint32_t)((kp | h | k) != 0));
+            }
+            umma_commit(sBar + 8 * (C::STAGES + s));
+            if (kp == npairs - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(sBar + 8 * s, (it / C::STAGES) & 1);
@@ -325,6 +372,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 }  // namespace
 extern int g_tma_bn_cap;
 extern int g_tma_debug_skip_b;
+extern int g_tma_pair;
 namespace {
 
 template <int BN>
@@ -347,6 +395,7 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 }  // namespace
 
 int g_tma_debug_skip_b = 0;
+int g_tma_pair = 1;        // rcfd_set_option("tma_pair"): 0 = one 64-channel chunk per k-step (4 MMAs per commit)
 int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n
 
 // 2x nearest up-sampling folded into a 3x3 / stride-1 / pad-1 conv == four 2x2 convs (one per
@@ -379,6 +428,7 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   TmaConvP t;
   t.phases = 1; t.out_h = p.ho; t.out_w = p.wo; t.out_s = 1;
   t.debug_skip_b = g_tma_debug_skip_b;
+  t.kpair = 0;
   if (conv_tma_up2x_supported(p, RCFD_BF16)) {
     // run on the low-res grid: 2x2 taps, per-phase weights, destination pixels (2i+a, 2j+b)
     t.phases = 4; t.out_s = 2;
@@ -416,6 +466,9 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   t.tiles_n = ceil_div(p.cout, bn);
   t.num_tiles = p.n * t.tiles_y * t.tiles_x * t.tiles_n * t.phases;
   t.ksteps = p.kh * p.kw * ((p.c0 + p.c1) / t.bkc);
+  // 128 / 256-channel layers: consume the 64-channel chunks two at a time (needs an even chunk count per tap, and the
+  // split between the two sources on a pair boundary)
+  t.kpair = (g_tma_pair && t.bkc == 64 && ((p.c0 + p.c1) / 64) % 2 == 0 && (p.c0 / 64) % 2 == 0 && !t.debug_skip_b) ? 1 : 0;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
   alignas(64) CUtensorMap a0, a1, w;

@@ -251,6 +251,39 @@ def png16_case(name, h, w, seed):
     print(name, 'ok (oracle == reference codec, bit exact)')
 
 
+def transforms_case(name, seed):
+    """The on-device augmentation of the reference (src/fusionnet_transforms.py:46-178) on seeded inputs, executed by
+    the reference itself; the oracle must replay its random draws and reproduce every value bit for bit."""
+    import transforms_oracle as tro
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import fusionnet_transforms as ref_tr
+    sys.path[:] = saved
+    sys.modules.pop('fusionnet_transforms', None)
+    cfg = dict(random_brightness=[0.8, 1.2], random_contrast=[0.8, 1.2], random_saturation=[0.8, 1.2],
+               random_flip_type=['horizontal', 'vertical'])
+    out = {'meta': np.array([seed])}
+    for tag, scale, rng in (('u8_01', 255.0, [0, 1]), ('f_pm1', 1.0, [-1, 1])):
+        g = torch.Generator().manual_seed(seed)
+        img = torch.rand(5, 3, 18, 26, generator=g) * scale
+        if scale > 1.0:
+            img = img.round()
+        maps = [torch.rand(5, 1, 18, 26, generator=g) * 50, torch.rand(5, 2, 18, 26, generator=g)]
+        t = ref_tr.Transforms(normalized_image_range=rng, **cfg)
+        torch.manual_seed(seed + 1)
+        (ri,), rr = t.transform([img.clone()], [m.clone() for m in maps], random_transform_probability=0.9)
+        torch.manual_seed(seed + 1)
+        d = tro.draw_decisions(5, 0.9, cfg['random_brightness'], cfg['random_contrast'], cfg['random_saturation'],
+                               cfg['random_flip_type'])
+        oi, orr = tro.apply(img, maps, d, rng)
+        assert torch.equal(oi, ri) and all(torch.equal(a, b) for a, b in zip(orr, rr))
+        out[tag + '_image'] = ri.numpy()
+        out[tag + '_map0'] = rr[0].numpy()
+        out[tag + '_map1'] = rr[1].numpy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok (oracle == reference transforms, bit exact)')
+
+
 if __name__ == '__main__':
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
@@ -261,4 +294,5 @@ if __name__ == '__main__':
     s2_case('s2_compat_k6', 64, 160, (64, 64), 6, 11)
     s2_case('s2_compat_alias_k3', 32, 96, (32, 32), 3, 12, zs=[2.7, 2.2, 1.9])
     png16_case('png16_roundtrip_48x64', 48, 64, 5)
+    transforms_case('transforms_5x18x26', 21)
     print('golden fixtures written to', OUT)

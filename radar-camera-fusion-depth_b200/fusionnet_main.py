@@ -7,7 +7,8 @@ Outside this round's scope and handled explicitly:
   * dataset file I/O: batches come from ``rcfd.data.make_train_batches`` -- the reference's own
     ``datasets.FusionNetTrainingDataset`` when its ``src`` directory is importable, or seeded synthetic
     batches when ``train_image_path == 'synthetic'``;
-  * augmentation transforms, validation loop and TensorBoard summaries: skipped with a log line.
+  * augmentation: fusionnet_transforms.Transforms (the reference's draws and arithmetic, batched tensor expressions);
+  * validation loop and TensorBoard summaries: skipped.
 Multi-GPU: launch with ``torchrun``; ``model.data_parallel()`` attaches the NCCL gradient all-reduce.
 """
 import os
@@ -16,6 +17,7 @@ import time
 import torch
 
 from fusionnet_model import FusionNetModel
+from fusionnet_transforms import Transforms
 from net_utils import OutlierRemoval
 from rcfd import data as rcfd_data
 from rcfd import optim as rcfd_optim
@@ -95,9 +97,15 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
         outlier_removal = OutlierRemoval(ground_truth_outlier_removal_kernel_size, ground_truth_outlier_removal_threshold)
     if ground_truth_dilation_kernel_size > 1:
         raise NotImplementedError('ground_truth_dilation_kernel_size > 1 is not used by the shipped configs')
-    if any(p > 0 for p in augmentation_probabilities) and rank == 0:
-        log('NOTE: augmentation transforms are outside the accelerated path of this round (SURVEY 8f); '
-            'training runs without them', log_path)
+    # augmentation + normalisation exactly like the reference (:300-306, :343-345, :361-364), batched tensor expressions
+    train_transforms = Transforms(normalized_image_range=normalized_image_range,
+                                  random_brightness=augmentation_random_brightness,
+                                  random_contrast=augmentation_random_contrast,
+                                  random_saturation=augmentation_random_saturation,
+                                  random_flip_type=augmentation_random_flip_type)
+    augmentation_schedule_pos = 0
+    augmentation_probability = augmentation_probabilities[0]
+    synthetic = train_image_path == 'synthetic'          # synthetic images are already normalised floats in [0, 1)
     if rank == 0:
         log('Training FusionNet on {} GPU(s), {} steps/epoch, batch {} per GPU, precision {}'.format(
             world, n_train_step_per_epoch, batch_size, precision), log_path)
@@ -114,12 +122,19 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
             learning_rate = learning_rates[learning_schedule_pos]
             for g in optimizer.param_groups:
                 g['lr'] = learning_rate
+        if -1 not in augmentation_schedule and epoch > augmentation_schedule[augmentation_schedule_pos]:
+            augmentation_schedule_pos += 1
+            augmentation_probability = augmentation_probabilities[augmentation_schedule_pos]
         for image, input_depth, input_response, ground_truth, lidar_map in batches(epoch):
             train_step += 1
             image, input_depth, input_response, ground_truth, lidar_map = [
                 t.to(device, non_blocking=True) for t in (image, input_depth, input_response, ground_truth, lidar_map)]
-            if normalized_image_range[1] <= 1.0 and image.dtype != torch.float32:
-                image = image.float() / 255.0
+            if not synthetic or augmentation_probability > 0:
+                # the reference always goes through Transforms.transform ([0, 255] images in, normalised range out)
+                source = (image * 255.0).round() if synthetic else image
+                [image], [input_depth, input_response, ground_truth, lidar_map] = train_transforms.transform(
+                    images_arr=[source], range_maps_arr=[input_depth, input_response, ground_truth, lidar_map],
+                    random_transform_probability=augmentation_probability)
             net_input_depth = torch.cat([input_depth, input_response], dim=1)     # reference :366
             if graphed_step:
                 # canonical loss: forward + loss + backward replayed from one CUDA graph (same arithmetic)

@@ -167,3 +167,31 @@ def test_data_parallel_gradient_sync_gloo(tmp_path):
     assert n_none == 11
     used = sum(p.numel() for p, g in zip(r0['params'], r0['grads']) if g is not None)
     assert r0['payload'] == used * 4
+
+
+def test_batched_transforms_match_reference_fixture():
+    """fusionnet_transforms.Transforms (batched tensor expressions, same constructor / transform surface as the
+    reference) reproduces, bit for bit, what the reference's per-sample loop produced on the same seeded inputs and
+    random draws (tests/golden/transforms_5x18x26.npz, written by the reference)."""
+    import numpy as np
+    import fusionnet_transforms
+    from helpers import load_golden
+    g = load_golden('transforms_5x18x26')
+    seed = int(g['meta'][0])
+    cfg = dict(random_brightness=[0.8, 1.2], random_contrast=[0.8, 1.2], random_saturation=[0.8, 1.2],
+               random_flip_type=['horizontal', 'vertical'])
+    for tag, scale, rng in (('u8_01', 255.0, [0, 1]), ('f_pm1', 1.0, [-1, 1])):
+        gen = torch.Generator().manual_seed(seed)
+        img = torch.rand(5, 3, 18, 26, generator=gen) * scale
+        if scale > 1.0:
+            img = img.round()
+        maps = [torch.rand(5, 1, 18, 26, generator=gen) * 50, torch.rand(5, 2, 18, 26, generator=gen)]
+        t = fusionnet_transforms.Transforms(normalized_image_range=rng, **cfg)
+        torch.manual_seed(seed + 1)
+        (oi,), om = t.transform([img.clone()], [m.clone() for m in maps], random_transform_probability=0.9)
+        assert np.array_equal(oi.numpy(), g[tag + '_image'])
+        assert np.array_equal(om[0].numpy(), g[tag + '_map0']) and np.array_equal(om[1].numpy(), g[tag + '_map1'])
+    # images only -> a bare list, like the reference
+    t = fusionnet_transforms.Transforms(normalized_image_range=[0, 1])
+    out = t.transform([torch.rand(2, 3, 4, 4) * 255], random_transform_probability=0.0)
+    assert isinstance(out, list) and out[0].shape == (2, 3, 4, 4) and float(out[0].max()) <= 1.0

@@ -284,6 +284,48 @@ def transforms_case(name, seed):
     print(name, 'ok (oracle == reference transforms, bit exact)')
 
 
+def losses_case(name, seed):
+    """fusionnet_losses.* (src/fusionnet_losses.py) and the non-canonical branches of FusionNetModel.compute_loss
+    (src/fusionnet_model.py:172-302: l2 / smoothl1, first-order and Sobel smoothness, with and without the lidar term)
+    evaluated by the reference on seeded inputs."""
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import fusionnet_losses as ref_l
+    sys.path[:] = saved
+    sys.modules.pop('fusionnet_losses', None)
+    g = torch.Generator().manual_seed(seed)
+    n, h, w = 2, 24, 40
+    image = torch.rand(n, 3, h, w, generator=g)
+    pred = torch.rand(n, 1, h, w, generator=g) * 50 + 1
+    tgt = torch.rand(n, 1, h, w, generator=g) * 50 + 1
+    weights = (torch.rand(n, 1, h, w, generator=g) > 0.3).float()
+    gt = tgt * (torch.rand(n, 1, h, w, generator=g) < 0.4)
+    lidar = (torch.rand(n, 1, h, w, generator=g) * 50 + 1) * (torch.rand(n, 1, h, w, generator=g) < 0.05)
+    out = {'meta': np.array([seed, n, h, w])}
+    out['l1'] = ref_l.l1_loss(pred, tgt).numpy()
+    out['l2'] = ref_l.l2_loss(pred, tgt).numpy()
+    out['smoothl1'] = ref_l.smooth_l1_loss(pred, tgt).numpy()
+    out['smooth'] = ref_l.smoothness_loss_func(pred, image).numpy()
+    out['sobel7'] = ref_l.sobel_smoothness_loss_func(pred, image, weights, [1, 1, 7, 7]).numpy()
+    out['sobel3'] = ref_l.sobel_smoothness_loss_func(pred, image, weights, [1, 1, 3, 3]).numpy()
+    gx, gy = ref_l.sobel_filter([1, 1, 7, 7])
+    out['sobel_gx'], out['sobel_gy'] = gx.numpy(), gy.numpy()
+    dy, dx = ref_l.gradient_yx(pred)
+    out['grad_dy'], out['grad_dx'] = dy.numpy(), dx.numpy()
+    model, _ = build_fusionnet(synth.SMALL_FUSIONNET, 1)
+    combos = [('l1', 0.0, -1, 2.0), ('l2', 0.0, -1, 2.0), ('smoothl1', 0.0, -1, 0.0), ('l1', 0.5, -1, 2.0),
+              ('l1', 0.5, 7, 2.0), ('l2', 0.25, 3, 0.0)]
+    vals = []
+    for lf, ws, ks, wl in combos:
+        loss, _ = model.compute_loss(image=image, output_depth=pred, ground_truth=gt, lidar_map=lidar, loss_func=lf,
+                                     w_smoothness=ws, loss_smoothness_kernel_size=ks,
+                                     validity_map_loss_smoothness=weights, w_lidar_loss=wl)
+        vals.append(float(loss))
+    out['compute_loss'] = np.array(vals)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok', vals)
+
+
 if __name__ == '__main__':
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
@@ -295,4 +337,5 @@ if __name__ == '__main__':
     s2_case('s2_compat_alias_k3', 32, 96, (32, 32), 3, 12, zs=[2.7, 2.2, 1.9])
     png16_case('png16_roundtrip_48x64', 48, 64, 5)
     transforms_case('transforms_5x18x26', 21)
+    losses_case('losses_2x24x40', 31)
     print('golden fixtures written to', OUT)

@@ -195,3 +195,44 @@ def test_batched_transforms_match_reference_fixture():
     t = fusionnet_transforms.Transforms(normalized_image_range=[0, 1])
     out = t.transform([torch.rand(2, 3, 4, 4) * 255], random_transform_probability=0.0)
     assert isinstance(out, list) and out[0].shape == (2, 3, 4, 4) and float(out[0].max()) <= 1.0
+
+
+def test_losses_and_compute_loss_branches_match_reference_fixture():
+    """fusionnet_losses.* and the non-canonical branches of FusionNetModel.compute_loss (l2 / smoothl1, first-order and
+    Sobel smoothness, with / without the lidar term; tensor-op formulas) against values computed by the reference
+    (tests/golden/losses_2x24x40.npz)."""
+    import numpy as np
+    import fusionnet_losses as L
+    import fusionnet_model
+    from helpers import load_golden, relerr
+    g = load_golden('losses_2x24x40')
+    seed, n, h, w = [int(v) for v in g['meta']]
+    gen = torch.Generator().manual_seed(seed)
+    image = torch.rand(n, 3, h, w, generator=gen)
+    pred = torch.rand(n, 1, h, w, generator=gen) * 50 + 1
+    tgt = torch.rand(n, 1, h, w, generator=gen) * 50 + 1
+    weights = (torch.rand(n, 1, h, w, generator=gen) > 0.3).float()
+    gt = tgt * (torch.rand(n, 1, h, w, generator=gen) < 0.4)
+    lidar = (torch.rand(n, 1, h, w, generator=gen) * 50 + 1) * (torch.rand(n, 1, h, w, generator=gen) < 0.05)
+    tol = 1e-6
+    assert relerr(L.l1_loss(pred, tgt), g['l1']) < tol
+    assert relerr(L.l2_loss(pred, tgt), g['l2']) < tol
+    assert relerr(L.smooth_l1_loss(pred, tgt), g['smoothl1']) < tol
+    assert relerr(L.smoothness_loss_func(pred, image), g['smooth']) < tol
+    assert relerr(L.sobel_smoothness_loss_func(pred, image, weights, [1, 1, 7, 7]), g['sobel7']) < tol
+    assert relerr(L.sobel_smoothness_loss_func(pred, image, weights, [1, 1, 3, 3]), g['sobel3']) < tol
+    gx, gy = L.sobel_filter([1, 1, 7, 7])
+    assert np.array_equal(gx.numpy(), g['sobel_gx']) and np.array_equal(gy.numpy(), g['sobel_gy'])
+    dy, dx = L.gradient_yx(pred)
+    assert np.array_equal(dy.numpy(), g['grad_dy']) and np.array_equal(dx.numpy(), g['grad_dx'])
+    # compute_loss on CPU tensors takes the tensor-op branches (the fused kernel needs CUDA tensors)
+    m = fusionnet_model.FusionNetModel.__new__(fusionnet_model.FusionNetModel)
+    combos = [('l1', 0.0, -1, 2.0), ('l2', 0.0, -1, 2.0), ('smoothl1', 0.0, -1, 0.0), ('l1', 0.5, -1, 2.0),
+              ('l1', 0.5, 7, 2.0), ('l2', 0.25, 3, 0.0)]
+    for (lf, ws, ks, wl), ref in zip(combos, g['compute_loss']):
+        loss, info = m.compute_loss(image=image, output_depth=pred, ground_truth=gt, lidar_map=lidar, loss_func=lf,
+                                    w_smoothness=ws, loss_smoothness_kernel_size=ks,
+                                    validity_map_loss_smoothness=weights, w_lidar_loss=wl)
+        assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)), (lf, ws, ks, wl, float(loss), float(ref))
+    with pytest.raises(ValueError):
+        m.compute_loss(image, pred, gt, lidar, 'huber', 0.0, -1, weights, 0.0)

@@ -8,14 +8,17 @@ Outside this round's scope and handled explicitly:
     ``datasets.FusionNetTrainingDataset`` when its ``src`` directory is importable, or seeded synthetic
     batches when ``train_image_path == 'synthetic'``;
   * augmentation: fusionnet_transforms.Transforms (the reference's draws and arithmetic, batched tensor expressions);
-  * validation loop and TensorBoard summaries: skipped.
+  * validation: ``validate`` (the reference's metrics and best-result rule) runs at checkpoints when a validation set
+    is given (``val_image_path='synthetic'`` works too); TensorBoard summaries: skipped.
 Multi-GPU: launch with ``torchrun``; ``model.data_parallel()`` attaches the NCCL gradient all-reduce.
 """
 import os
 import time
 
+import numpy as np
 import torch
 
+import eval_utils
 from fusionnet_model import FusionNetModel
 from fusionnet_transforms import Transforms
 from net_utils import OutlierRemoval
@@ -105,6 +108,20 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
                                   random_flip_type=augmentation_random_flip_type)
     augmentation_schedule_pos = 0
     augmentation_probability = augmentation_probabilities[0]
+    # validation set (optional) and the reference's best-result bookkeeping (:134-152, :201-207)
+    val_dataloader = rcfd_data.make_val_batches(val_image_path, val_depth_path, val_response_path, val_ground_truth_path,
+                                                n_height, n_width) if rank == 0 else None
+    val_transforms = Transforms(normalized_image_range=normalized_image_range)
+    best_results = {'step': -1, 'mae': np.inf, 'rmse': np.inf, 'imae': np.inf, 'irmse': np.inf}
+
+    def run_validation(step, best):
+        model.eval()
+        with torch.no_grad():
+            best = validate(model=model, dataloader=val_dataloader, transforms=val_transforms, step=step,
+                            best_results=best, min_evaluate_depth=min_evaluate_depth,
+                            max_evaluate_depth=max_evaluate_depth, device=device, summary_writer=None, log_path=log_path)
+        model.train()
+        return best
     synthetic = train_image_path == 'synthetic'          # synthetic images are already normalised floats in [0, 1)
     if rank == 0:
         log('Training FusionNet on {} GPU(s), {} steps/epoch, batch {} per GPU, precision {}'.format(
@@ -145,6 +162,8 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
                     remain = (n_total - train_step) * elapsed / max(train_step, 1)
                     log('Step={:6}/{}  Loss={:.5f}  Time Elapsed={:.2f}h  Time Remaining={:.2f}h'.format(
                         train_step, n_total, float(loss), elapsed, remain), log_path)
+                    if val_dataloader is not None and train_step >= start_step_validation:
+                        best_results = run_validation(train_step, best_results)
                     model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
                 if max_steps is not None and train_step >= max_steps:
                     break
@@ -165,12 +184,60 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
                 remain = (n_total - train_step) * elapsed / max(train_step, 1)
                 log('Step={:6}/{}  Loss={:.5f}  Time Elapsed={:.2f}h  Time Remaining={:.2f}h'.format(
                     train_step, n_total, float(loss), elapsed, remain), log_path)
+                if val_dataloader is not None and train_step >= start_step_validation:
+                    best_results = run_validation(train_step, best_results)
                 model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
             if max_steps is not None and train_step >= max_steps:
                 break
         if max_steps is not None and train_step >= max_steps:
             break
     if rank == 0:
+        if val_dataloader is not None:                       # evaluate once more after training (reference :455-468)
+            best_results = run_validation(train_step, best_results)
         model.save_model(checkpoint_path.format(train_step), train_step, optimizer)
         log('Finished at step {} ({:.1f} s)'.format(train_step, time.time() - time_start), log_path)
     return model, optimizer, train_step
+
+
+def validate(model, dataloader, transforms, step, best_results, min_evaluate_depth, max_evaluate_depth, device,
+             summary_writer=None, n_summary_display=4, n_summary_display_interval=250, log_path=None):
+    """Validation pass with the reference's signature, metrics and best-result rule (reference
+    src/fusionnet_main.py:476-606): per sample MAE / RMSE in mm and iMAE / iRMSE in 1/km over the pixels with
+    min_evaluate_depth < ground truth < max_evaluate_depth, averaged over the samples; ``best_results`` is replaced
+    when more than two of the four metrics (rounded to 2 decimals) are at least as good.  TensorBoard summaries are
+    out of scope (``summary_writer`` is accepted and ignored).  The caller puts the model in eval mode."""
+    n_sample = len(dataloader)
+    mae, rmse, imae, irmse = np.zeros(n_sample), np.zeros(n_sample), np.zeros(n_sample), np.zeros(n_sample)
+    for idx, inputs in enumerate(dataloader):
+        image, depth, response, ground_truth = [in_.to(device) for in_ in inputs]
+        [image] = transforms.transform(images_arr=[image], random_transform_probability=0.0)
+        input_depth = torch.cat([depth, response], dim=1)
+        with torch.no_grad():
+            output_depth = model.forward(image=image, input_depth=input_depth)
+        output_depth = np.squeeze(output_depth.cpu().numpy())
+        ground_truth = np.squeeze(ground_truth.cpu().numpy())
+        mask = np.where(np.logical_and(ground_truth > 0, np.logical_and(ground_truth > min_evaluate_depth,
+                                                                         ground_truth < max_evaluate_depth)))
+        output_depth, ground_truth = output_depth[mask], ground_truth[mask]
+        mae[idx] = eval_utils.mean_abs_err(1000.0 * output_depth, 1000.0 * ground_truth)
+        rmse[idx] = eval_utils.root_mean_sq_err(1000.0 * output_depth, 1000.0 * ground_truth)
+        imae[idx] = eval_utils.inv_mean_abs_err(0.001 * output_depth, 0.001 * ground_truth)
+        irmse[idx] = eval_utils.inv_root_mean_sq_err(0.001 * output_depth, 0.001 * ground_truth)
+    mae, rmse, imae, irmse = np.mean(mae), np.mean(rmse), np.mean(imae), np.mean(irmse)
+    log_evaluation_results('Validation results', mae, rmse, imae, irmse, step=step, log_path=log_path)
+    n_improve = sum(int(np.round(new, 2) <= np.round(best_results[key], 2))
+                    for key, new in (('mae', mae), ('rmse', rmse), ('imae', imae), ('irmse', irmse)))
+    if n_improve > 2:
+        best_results['step'] = step
+        best_results['mae'], best_results['rmse'] = mae, rmse
+        best_results['imae'], best_results['irmse'] = imae, irmse
+    log_evaluation_results('Best results', best_results['mae'], best_results['rmse'], best_results['imae'],
+                           best_results['irmse'], step=best_results['step'], log_path=log_path)
+    return best_results
+
+
+def log_evaluation_results(title, mae, rmse, imae, irmse, step=-1, log_path=None):
+    """Same table as the reference (:1101-1120)."""
+    log(title + ':', log_path)
+    log('{:>8}  {:>8}  {:>8}  {:>8}  {:>8}'.format('Step', 'MAE', 'RMSE', 'iMAE', 'iRMSE'), log_path)
+    log('{:8}  {:8.3f}  {:8.3f}  {:8.3f}  {:8.3f}'.format(step, mae, rmse, imae, irmse), log_path)

@@ -40,3 +40,28 @@ def make_train_batches(image_path, depth_path, response_path, ground_truth_path,
             sampler.set_epoch(epoch)
         return iter(loader)
     return batches, len(loader)
+
+
+def make_val_batches(image_path, depth_path, response_path, ground_truth_path, n_height, n_width, synthetic_samples=4):
+    """Validation samples of batch 1 as (image in [0, 255], depth, response, ground_truth) CPU tensors, like the
+    reference's FusionNetInferenceDataset behind a DataLoader (reference src/fusionnet_main.py:134-152); None when no
+    validation set is given."""
+    if image_path is None or image_path == '':
+        return None
+    if image_path == 'synthetic':
+        samples = []
+        for i in range(synthetic_samples):
+            image, depth = synth.fusionnet_inputs(1, n_height, n_width, 5000 + i)
+            gt, _ = synth.training_targets(1, n_height, n_width, 5000 + i)
+            samples.append(((image * 255.0).round(), depth[:, 0:1].contiguous(), depth[:, 1:2].contiguous(), gt))
+        return samples
+    try:
+        import datasets
+        import data_utils
+    except ImportError as e:
+        raise ImportError("reading nuScenes-derived validation data needs the reference's datasets.py / data_utils.py on "
+                          "sys.path; use val_image_path='synthetic' or '' otherwise") from e
+    paths = [data_utils.read_paths(p) for p in (image_path, depth_path, response_path, ground_truth_path)]
+    dataset = datasets.FusionNetInferenceDataset(image_paths=paths[0], depth_paths=paths[1], response_paths=paths[2],
+                                                 ground_truth_paths=paths[3])
+    return torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=1, drop_last=False)

@@ -326,6 +326,50 @@ def losses_case(name, seed):
     print(name, 'ok', vals)
 
 
+class _DummyDepthModel(object):
+    """Stands in for FusionNetModel in the validate() fixture: a deterministic function of its inputs."""
+
+    def forward(self, image, input_depth):
+        return 1.0 + 40.0 * image.mean(dim=1, keepdim=True) + 0.5 * input_depth[:, 0:1]
+
+
+def validate_case(name, seed):
+    """The reference's validation loop, metrics and best-result rule (src/fusionnet_main.py:476-606,
+    src/eval_utils.py) on seeded samples with a dummy model; two passes so that the best-result update is exercised."""
+    import tempfile
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import fusionnet_main as ref_main
+    import fusionnet_transforms as ref_tr
+    sys.path[:] = saved
+    for m in ('fusionnet_main', 'fusionnet_transforms', 'fusionnet_model', 'networks', 'net_utils', 'fusionnet_losses',
+              'log_utils', 'datasets', 'data_utils', 'eval_utils'):
+        sys.modules.pop(m, None)
+    g = torch.Generator().manual_seed(seed)
+    loader = []
+    for _ in range(3):
+        image = (torch.rand(1, 3, 20, 32, generator=g) * 255).round()
+        depth = torch.rand(1, 1, 20, 32, generator=g) * 60 * (torch.rand(1, 1, 20, 32, generator=g) < 0.2)
+        response = torch.rand(1, 1, 20, 32, generator=g)
+        gt = torch.rand(1, 1, 20, 32, generator=g) * 90 * (torch.rand(1, 1, 20, 32, generator=g) < 0.5)
+        loader.append((image, depth, response, gt))
+    tr = ref_tr.Transforms(normalized_image_range=[0, 1])
+    log_path = os.path.join(tempfile.mkdtemp(), 'log.txt')
+    best = {'step': -1, 'mae': np.infty if hasattr(np, 'infty') else np.inf, 'rmse': np.inf, 'imae': np.inf, 'irmse': np.inf}
+    best = ref_main.validate(_DummyDepthModel(), loader, tr, step=10, best_results=best, min_evaluate_depth=1.0,
+                             max_evaluate_depth=80.0, device=torch.device('cpu'), summary_writer=None, log_path=log_path)
+    first = [best['step'], best['mae'], best['rmse'], best['imae'], best['irmse']]
+    worse = dict(best)
+    worse.update(mae=best['mae'] - 1.0, rmse=best['rmse'] - 1.0)          # 2 of 4 not better -> no update
+    second = ref_main.validate(_DummyDepthModel(), loader, tr, step=20, best_results=dict(worse), min_evaluate_depth=1.0,
+                               max_evaluate_depth=80.0, device=torch.device('cpu'), summary_writer=None, log_path=log_path)
+    out = dict(meta=np.array([seed]), first=np.array(first, dtype=np.float64),
+               second=np.array([second['step'], second['mae'], second['rmse'], second['imae'], second['irmse']], dtype=np.float64),
+               log=np.array(open(log_path).read()))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok', first, second['step'])
+
+
 if __name__ == '__main__':
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
@@ -338,4 +382,5 @@ if __name__ == '__main__':
     png16_case('png16_roundtrip_48x64', 48, 64, 5)
     transforms_case('transforms_5x18x26', 21)
     losses_case('losses_2x24x40', 31)
+    validate_case('validate_3x20x32', 41)
     print('golden fixtures written to', OUT)

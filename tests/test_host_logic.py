@@ -236,3 +236,41 @@ def test_losses_and_compute_loss_branches_match_reference_fixture():
         assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)), (lf, ws, ks, wl, float(loss), float(ref))
     with pytest.raises(ValueError):
         m.compute_loss(image, pred, gt, lidar, 'huber', 0.0, -1, weights, 0.0)
+
+
+class _DummyDepthModel(object):
+    def forward(self, image, input_depth):
+        return 1.0 + 40.0 * image.mean(dim=1, keepdim=True) + 0.5 * input_depth[:, 0:1]
+
+
+def test_validate_matches_reference_fixture(tmp_path):
+    """fusionnet_main.validate + eval_utils: the reference's metrics (mm, 1/km), masks and best-result rule, against
+    numbers and the log text produced by the reference's own validate() on the same seeded samples and dummy model
+    (tests/golden/validate_3x20x32.npz)."""
+    import numpy as np
+    import fusionnet_main
+    import fusionnet_transforms
+    from helpers import load_golden
+    g = load_golden('validate_3x20x32')
+    gen = torch.Generator().manual_seed(int(g['meta'][0]))
+    loader = []
+    for _ in range(3):
+        image = (torch.rand(1, 3, 20, 32, generator=gen) * 255).round()
+        depth = torch.rand(1, 1, 20, 32, generator=gen) * 60 * (torch.rand(1, 1, 20, 32, generator=gen) < 0.2)
+        response = torch.rand(1, 1, 20, 32, generator=gen)
+        gt = torch.rand(1, 1, 20, 32, generator=gen) * 90 * (torch.rand(1, 1, 20, 32, generator=gen) < 0.5)
+        loader.append((image, depth, response, gt))
+    tr = fusionnet_transforms.Transforms(normalized_image_range=[0, 1])
+    log_path = str(tmp_path / 'log.txt')
+    best = {'step': -1, 'mae': np.inf, 'rmse': np.inf, 'imae': np.inf, 'irmse': np.inf}
+    best = fusionnet_main.validate(_DummyDepthModel(), loader, tr, step=10, best_results=best, min_evaluate_depth=1.0,
+                                   max_evaluate_depth=80.0, device=torch.device('cpu'), summary_writer=None, log_path=log_path)
+    first = np.array([best['step'], best['mae'], best['rmse'], best['imae'], best['irmse']], dtype=np.float64)
+    assert np.allclose(first, g['first'], rtol=1e-9, atol=0)
+    worse = dict(best)
+    worse.update(mae=best['mae'] - 1.0, rmse=best['rmse'] - 1.0)
+    second = fusionnet_main.validate(_DummyDepthModel(), loader, tr, step=20, best_results=dict(worse), min_evaluate_depth=1.0,
+                                     max_evaluate_depth=80.0, device=torch.device('cpu'), summary_writer=None, log_path=log_path)
+    got = np.array([second['step'], second['mae'], second['rmse'], second['imae'], second['irmse']], dtype=np.float64)
+    assert np.allclose(got, g['second'], rtol=1e-9, atol=0) and int(second['step']) == 10
+    assert open(log_path).read() == str(g['log'])

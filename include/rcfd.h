@@ -35,6 +35,10 @@ const char* rcfd_arch(void);          /* "sm_100a" */
 const char* rcfd_last_error(void);
 /* tuning / debug knobs ("strip_desc_mode": 0 | 1). */
 int rcfd_set_option(const char* key, int32_t value);
+/* Host-only: the chunk plan of the row-streaming kernels (h rows x cols column strips over ctas persistent CTAs):
+ * minimises waves x (rows per chunk + overhead_rows); exported for tests / tools, launches nothing. */
+int rcfd_plan_row_chunks(int32_t h, int32_t cols, int32_t ctas, int32_t overhead_rows, int32_t min_rows,
+                         int32_t* rows_per_chunk, int32_t* chunks_per_col);
 
 /* ---------------------------------------------------------------------------------
  * Convolution as implicit GEMM.  Replaces torch.nn.Conv2d(bias=False, padding=k//2)

@@ -1338,3 +1338,17 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st) {
 }
 
 }  // namespace rcfd
+
+// Host-only helper exported for tests and tools: how the row-streaming kernels cut `h` rows of `cols` column strips into
+// chunks for `ctas` persistent CTAs (tma_common.cuh plan_row_chunks).  No device work.
+extern "C" int rcfd_plan_row_chunks(int32_t h, int32_t cols, int32_t ctas, int32_t overhead_rows, int32_t min_rows,
+                                    int32_t* rows_per_chunk, int32_t* chunks_per_col) {
+  RCFD_CHECK_ARG(h > 0 && cols > 0 && ctas > 0 && overhead_rows >= 0 && min_rows > 0 && rows_per_chunk && chunks_per_col,
+                 "plan_row_chunks: bad args");
+  int rpc = 0, cpc = 0;
+  rcfd::tma::plan_row_chunks(h, cols, ctas, overhead_rows, min_rows, &rpc, &cpc);
+  *rows_per_chunk = rpc;
+  *chunks_per_col = cpc;
+  return RCFD_OK;
+}
+

@@ -72,6 +72,7 @@ _SIGS = {
     'rcfd_linear_leaky_fwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
     'rcfd_set_option': [c_char_p, c_int32],
+    'rcfd_plan_row_chunks': [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P],
     'rcfd_version': [], 'rcfd_arch': [], 'rcfd_last_error': [],
 }
 _RESTYPE = {'rcfd_version': c_char_p, 'rcfd_arch': c_char_p, 'rcfd_last_error': c_char_p,

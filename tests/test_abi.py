@@ -51,3 +51,30 @@ def test_bad_descriptor_is_rejected_without_gpu(lib_path):
     d = _lib.ConvDesc()
     rc = lib.rcfd_conv2d_fwd(ctypes.byref(d), None)
     assert rc == -1 and b'conv' in lib.rcfd_last_error()
+
+
+def test_row_chunk_planner_balances_waves(lib_path):
+    """Host-only logic of the row-streaming kernels: chunks are chosen so that the persistent CTAs run full waves
+    (e.g. 352 rows x 48 strips over 296 CTAs -> 6 chunks of 59 rows = 288 items in ONE wave, not 13 chunks = 624 items
+    in 2.1 waves), every row is covered exactly once and the minimum chunk height is respected."""
+    import ctypes
+    from rcfd import _lib
+    lib = _lib.load()
+
+    def plan(h, cols, ctas, overhead=6, min_rows=4):
+        rpc, cpc = ctypes.c_int32(), ctypes.c_int32()
+        assert lib.rcfd_plan_row_chunks(h, cols, ctas, overhead, min_rows, ctypes.byref(rpc), ctypes.byref(cpc)) == 0
+        return rpc.value, cpc.value
+
+    assert plan(352, 48, 296) == (59, 6)                       # deconv0.conv, batch 8: one wave of 288 items
+    assert plan(88, 16, 148) == (10, 9)                        # blocks2, batch 8: 144 items, one wave
+    for h, cols, ctas in [(352, 48, 296), (176, 24, 148), (64, 2, 296), (7, 3, 148), (1000, 1, 5), (33, 200, 148)]:
+        rpc, cpc = plan(h, cols, ctas)
+        assert (cpc - 1) * rpc < h <= cpc * rpc                # chunks tile the rows exactly once
+        assert rpc >= min(4, h) or cpc == 1
+        items = cols * cpc
+        waves = -(-items // ctas)
+        # no other chunk count gives a cheaper schedule under the planner's own cost model
+        best = min((-(-(cols * -(-h // r)) // ctas)) * (r + 6) for r in range(min(4, h), h + 1))
+        assert waves * (rpc + 6) <= best
+    assert lib.rcfd_plan_row_chunks(0, 1, 1, 6, 4, None, None) != 0

@@ -6,8 +6,10 @@ bench.py's cpu_baseline leg may import this file.
 S1  points_to_depth_map / merge_radar_point_clouds
     setup/setup_dataset_nuscenes_with_denseGT.py:814-840 (plot), :644-656 (main sweep),
     :699-713 (z-buffer rule for extra sweeps), :771-782 (nonzero -> point list).
-    Parity status: UNPINNED by execution -- the defining script cannot be imported
-    (module-level nuScenes construction); this is a line-by-line restatement.
+    Parity status: PINNED.  The defining script cannot be imported (module-level nuScenes
+    construction), so tests/golden/make_golden.py parses it, EXECUTES the reference's
+    own statements of those line ranges (points_to_depth_map as a function) on seeded sweeps
+    and checks this restatement against them bit for bit (tests/golden/s1_merge_64x96.npz).
 
 S2  radarnet_main.forward's paste / max / arg-max / fill
     src/radarnet_main.py:563-591.  PINNED: tests/golden/make_golden.py runs the real

@@ -326,6 +326,69 @@ def losses_case(name, seed):
     print(name, 'ok', vals)
 
 
+def _reference_statements(path, func_name, first_line, last_line):
+    """The statements of ``func_name`` in the reference file ``path`` that lie entirely inside [first_line, last_line]
+    (outermost ones only), compiled as a module: lets a slice of a function that cannot be called as a whole (nuScenes
+    objects) be EXECUTED as it stands in the reference, on our own inputs."""
+    import ast
+    tree = ast.parse(open(path).read())
+    func = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == func_name)
+    picked = []
+
+    def visit(stmts):
+        for st in stmts:
+            if st.lineno >= first_line and st.end_lineno <= last_line:
+                picked.append(st)
+            elif st.lineno <= last_line and st.end_lineno >= first_line:
+                for field in ('body', 'orelse', 'finalbody'):
+                    visit(getattr(st, field, []) or [])
+    visit(func.body)
+    assert picked, (func_name, first_line, last_line)
+    return compile(ast.Module(body=picked, type_ignores=[]), path, 'exec')
+
+
+def s1_case(name, h, w, seed):
+    """Scatter S1 executed by the reference's own code: `points_to_depth_map` is called as a function; the main-sweep
+    plot, the z-buffer merge of a later sweep and the final nonzero -> point list are the reference's statements
+    (setup/setup_dataset_nuscenes_with_denseGT.py:641-659, :699-713, :771-782) run on seeded points."""
+    import ast
+    path = os.path.join(REF, 'setup', 'setup_dataset_nuscenes_with_denseGT.py')
+    tree = ast.parse(open(path).read())
+    fdef = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == 'points_to_depth_map')
+    ns = {'np': np}
+    exec(compile(ast.Module(body=[fdef], type_ignores=[]), path, 'exec'), ns)
+    rng = np.random.default_rng(seed)
+
+    def sweep(n):
+        xy = np.stack([rng.uniform(1, w - 2, n), rng.uniform(1, h - 2, n)])
+        xy[:, :4] = np.array([[10.5, 11.5, 30.5, 31.5], [20.5, 21.5, 7.5, 8.5]])[:, :min(4, n)]   # half-even ties
+        xy[:, 5] = xy[:, 4]                                                                   # duplicate pixel
+        return xy, rng.uniform(1, 80, n)
+    sweeps = [sweep(40), sweep(30), sweep(30)]
+    sweeps[1][0][:, :10] = sweeps[0][0][:, :10]             # collisions with the main sweep: closer / farther points
+    sweeps[1][1][:5] = sweeps[0][1][:5] * 0.5
+    sweeps[1][1][5:10] = sweeps[0][1][5:10] * 2.0
+    image = np.zeros((h, w, 3))
+    plot = ns['points_to_depth_map'](sweeps[0][0], sweeps[0][1], image)
+    assert np.array_equal(plot, so.s1_points_to_depth_map(sweeps[0][0], sweeps[0][1], h, w))
+    # merge_radar_point_clouds: main sweep
+    env = {'np': np, 'main_image': image, 'main_points_radar': sweeps[0][0], 'main_depth_radar': sweeps[0][1]}
+    exec(_reference_statements(path, 'merge_radar_point_clouds', 641, 659), env)
+    merge_code = _reference_statements(path, 'merge_radar_point_clouds', 699, 713)
+    for xy, z in sweeps[1:]:
+        env['next_points_radar_main'], env['next_depth_radar_main'] = xy, z
+        exec(merge_code, env)
+    exec(_reference_statements(path, 'merge_radar_point_clouds', 771, 780), env)
+    img_o, pts_o, dep_o = so.s1_merge(sweeps, h, w)
+    assert np.array_equal(env['main_radar_image'], img_o)
+    assert np.array_equal(env['return_points_radar'], pts_o) and np.array_equal(env['return_depth_radar'], dep_o)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), meta=np.array([h, w, seed]),
+                        **{'xy%d' % i: sw[0] for i, sw in enumerate(sweeps)}, **{'z%d' % i: sw[1] for i, sw in enumerate(sweeps)},
+                        plot=plot, merged=env['main_radar_image'], points=env['return_points_radar'],
+                        depth=env['return_depth_radar'])
+    print(name, 'ok (oracle == reference statements, bit exact); occupied pixels', int((env['main_radar_image'] > 0).sum()))
+
+
 class _DummyDepthModel(object):
     """Stands in for FusionNetModel in the validate() fixture: a deterministic function of its inputs."""
 
@@ -383,4 +446,5 @@ if __name__ == '__main__':
     transforms_case('transforms_5x18x26', 21)
     losses_case('losses_2x24x40', 31)
     validate_case('validate_3x20x32', 41)
+    s1_case('s1_merge_64x96', 64, 96, 51)
     print('golden fixtures written to', OUT)

@@ -35,6 +35,23 @@ def test_s1_scatter_bit_exact(k):
     assert np.array_equal(nz[:, 1].cpu().numpy(), ref_xy[0]) and np.array_equal(nz[:, 0].cpu().numpy(), ref_xy[1])
 
 
+def test_s1_scatter_reference_fixture_bit_exact():
+    """S1 kernels against the fixture written by executing the reference's own statements (three sweeps with rounding
+    ties, duplicates, closer / farther collisions): plot, z-buffer merges, nonzero -> point list."""
+    from rcfd import ops
+    g = load_golden('s1_merge_64x96')
+    h, w, _ = [int(v) for v in g['meta']]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    img = ops.scatter_points_to_depth_map(dev(g['xy0']), dev(g['z0']), h, w)
+    assert np.array_equal(img.cpu().numpy(), g['plot'])
+    for i in (1, 2):
+        ops.scatter_points_to_depth_map(dev(g['xy%d' % i]), dev(g['z%d' % i]), h, w, img=img)
+    assert np.array_equal(img.cpu().numpy(), g['merged'])
+    nz = torch.nonzero(img)
+    assert np.array_equal(nz[:, 1].cpu().numpy(), g['points'][0]) and np.array_equal(nz[:, 0].cpu().numpy(), g['points'][1])
+    assert np.array_equal(img[nz[:, 0], nz[:, 1]].cpu().numpy(), g['depth'])
+
+
 @pytest.mark.parametrize('name', ['s2_compat_k6', 's2_compat_alias_k3'])
 def test_s2_scatter_golden_bit_exact(name):
     from rcfd import ops

@@ -274,3 +274,33 @@ def test_validate_matches_reference_fixture(tmp_path):
     got = np.array([second['step'], second['mae'], second['rmse'], second['imae'], second['irmse']], dtype=np.float64)
     assert np.allclose(got, g['second'], rtol=1e-9, atol=0) and int(second['step']) == 10
     assert open(log_path).read() == str(g['log'])
+
+
+def test_train_cli_flag_surface_matches_reference():
+    """train_fusionnet.py exposes every flag of the reference's CLI (src/train_fusionnet.py:8-130; list taken from
+    the reference) plus --precision / --max_steps, and train() accepts every resulting keyword."""
+    import inspect
+    import fusionnet_main
+    import train_fusionnet
+    reference_flags = [
+        'activation_func', 'augmentation_probabilities', 'augmentation_random_brightness', 'augmentation_random_contrast',
+        'augmentation_random_crop_type', 'augmentation_random_flip_type', 'augmentation_random_saturation',
+        'augmentation_schedule', 'batch_size', 'checkpoint_dirpath', 'decoder_type', 'device', 'encoder_type', 'fusion_type',
+        'ground_truth_dilation_kernel_size', 'input_channels_depth', 'input_channels_image', 'learning_rates',
+        'learning_schedule', 'loss_func', 'loss_smoothness_kernel_size', 'max_evaluate_depth', 'max_predict_depth',
+        'min_evaluate_depth', 'min_predict_depth', 'n_filters_decoder', 'n_filters_encoder_depth', 'n_filters_encoder_image',
+        'n_height', 'n_resolutions_decoder', 'n_step_per_checkpoint', 'n_step_per_summary', 'n_thread', 'n_width',
+        'normalized_image_range', 'outlier_removal_kernel_size', 'outlier_removal_threshold', 'restore_path',
+        'start_step_validation', 'train_depth_path', 'train_ground_truth_path', 'train_image_path', 'train_lidar_map_path',
+        'train_response_path', 'val_depth_path', 'val_ground_truth_path', 'val_image_path', 'val_response_path',
+        'w_lidar_loss', 'w_smoothness', 'w_weight_decay', 'weight_initializer']
+    mine = {a.dest for a in train_fusionnet.parser._actions if a.dest != 'help'}
+    assert set(reference_flags) <= mine
+    assert mine - set(reference_flags) == {'precision', 'max_steps'}
+    args = vars(train_fusionnet.parser.parse_args([]))
+    args['ground_truth_outlier_removal_kernel_size'] = args.pop('outlier_removal_kernel_size')
+    args['ground_truth_outlier_removal_threshold'] = args.pop('outlier_removal_threshold')
+    params = inspect.signature(fusionnet_main.train).parameters
+    assert set(args) <= set(params)
+    required = {k for k, p in params.items() if p.default is inspect.Parameter.empty}
+    assert required <= set(args)                       # the CLI supplies every required keyword of train()

@@ -389,6 +389,19 @@ def s1_case(name, h, w, seed):
     print(name, 'ok (oracle == reference statements, bit exact); occupied pixels', int((env['main_radar_image'] > 0).sum()))
 
 
+def radarnet_loss_case(name, seed):
+    """RadarNetModel.compute_loss (weighted BCE over valid pixels, src/radarnet_model.py:126-167) evaluated by the reference."""
+    model = REFM['radarnet_model'].RadarNetModel(device=torch.device('cpu'),
+                                                 **dict(synth.CANONICAL_RADARNET, input_patch_size_image=(64, 64)))
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(3, 1, 64, 64, generator=g) * 3
+    gt = (torch.rand(3, 1, 64, 64, generator=g) < 0.2).float()
+    valid = (torch.rand(3, 1, 64, 64, generator=g) < 0.7).float()
+    vals = [float(model.compute_loss(logits, gt, valid, w_positive_class=w)[0]) for w in (1.0, 2.0, 5.5)]
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), meta=np.array([seed]), loss=np.array(vals))
+    print(name, 'ok', vals)
+
+
 class _DummyDepthModel(object):
     """Stands in for FusionNetModel in the validate() fixture: a deterministic function of its inputs."""
 
@@ -447,4 +460,5 @@ if __name__ == '__main__':
     losses_case('losses_2x24x40', 31)
     validate_case('validate_3x20x32', 41)
     s1_case('s1_merge_64x96', 64, 96, 51)
+    radarnet_loss_case('radarnet_loss_3x64x64', 61)
     print('golden fixtures written to', OUT)

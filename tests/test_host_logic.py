@@ -304,3 +304,19 @@ def test_train_cli_flag_surface_matches_reference():
     assert set(args) <= set(params)
     required = {k for k, p in params.items() if p.default is inspect.Parameter.empty}
     assert required <= set(args)                       # the CLI supplies every required keyword of train()
+
+
+def test_radarnet_compute_loss_matches_reference_fixture():
+    """RadarNetModel.compute_loss (weighted BCE over valid pixels, reference src/radarnet_model.py:126-167) against
+    values computed by the reference."""
+    import radarnet_model
+    from helpers import load_golden
+    g = load_golden('radarnet_loss_3x64x64')
+    gen = torch.Generator().manual_seed(int(g['meta'][0]))
+    logits = torch.randn(3, 1, 64, 64, generator=gen) * 3
+    gt = (torch.rand(3, 1, 64, 64, generator=gen) < 0.2).float()
+    valid = (torch.rand(3, 1, 64, 64, generator=gen) < 0.7).float()
+    m = radarnet_model.RadarNetModel.__new__(radarnet_model.RadarNetModel)
+    for w, ref in zip((1.0, 2.0, 5.5), g['loss']):
+        loss, info = m.compute_loss(logits, gt, valid, w_positive_class=w)
+        assert abs(float(loss) - float(ref)) < 1e-6 * abs(float(ref)) and 'loss' in info

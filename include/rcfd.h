@@ -249,6 +249,24 @@ int rcfd_roi_pool_fwd(const void* feat, const float* boxes, void* out, int32_t n
 int rcfd_linear_leaky_fwd(const float* x, const float* w, const float* b, float* out, int32_t rows,
                           int32_t in_features, int32_t out_features, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Tensor-core PARITY modes: the reference convolves in fp32 (src/net_utils.py:63-69,85).  The tcgen05 engines
+ * take bf16 operands, so a parity-grade result is several passes of the SAME kernels over bf16 splits of the
+ * fp32 operands,  x = x0 + x1 + x2,  accumulated in fp32 (TMEM, then the fp32 destination with accumulate = 1):
+ *   "bf16x3": x0.w0 + x1.w0 + x0.w1                          (~2^-16 per product)
+ *   "bf16x6": ... + x1.w1 + x2.w0 + x0.w2                    (~2^-23 per product: fp32-class)
+ * These are the HBM passes around those launches.
+ *   split      : p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) (p2 may be NULL)
+ *   stats      : per-channel sum / sum of squares of the fp32 conv output (training BatchNorm, :82)
+ *   epilogue   : out = act(y*scale+shift) [, leaky(out + residual)] in fp32, any channel count, with the
+ *                depth-head parameters (src/net_utils.py:86-91,323; src/fusionnet_model.py:162-165)
+ * --------------------------------------------------------------------------------- */
+int rcfd_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t count, void* stream);
+int rcfd_channel_stats(const float* y, double* stats_sum, double* stats_sqsum, int64_t pixels, int32_t channels,
+                       void* stream);
+int rcfd_epilogue_f32(const float* y, const float* scale, const float* shift, const float* residual, float* out,
+                      int64_t pixels, int32_t channels, int32_t act, float act_p0, float act_p1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1210,7 +1210,7 @@ bool conv_strip_up_supported(const ConvKP& p, int dtype) {
   if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
   if (p.hin != 2 * p.h0 || p.win != 2 * p.w0 || p.ho != p.hin || p.wo != p.win) return false;
   if (p.c0 != 32 && p.c0 != 64) return false;
-  if (p.cout % 16 != 0 || p.dst_f32 || p.act == RCFD_ACT_DEPTH_HEAD) return false;
+  if (p.cout % 16 != 0 || p.act == RCFD_ACT_DEPTH_HEAD) return false;      // dst_f32: scalar-store epilogue (parity mode)
   if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight_up2x) & 15)) return false;
   return get_encode() != nullptr;
 }

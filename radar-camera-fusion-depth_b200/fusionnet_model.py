@@ -9,8 +9,11 @@ autograd node whose backward replays the engine's tape (dgrad / wgrad / BN backw
 kernels) and fills ``parameter.grad``.
 
 Extras that the reference does not have (all optional):
-  * ``set_precision('fp32' | 'bf16')`` -- storage precision of activations / weights inside
-    the kernels (accumulation is always fp32).  'fp32' is the parity mode.
+  * ``set_precision('fp32' | 'bf16' | 'bf16x3' | 'bf16x6')`` -- arithmetic inside the kernels
+    (accumulation is always fp32).  'fp32': fp32 storage, SIMT FMA convolutions.  'bf16': bf16 storage,
+    tcgen05 engines (the fast path).  'bf16x3' / 'bf16x6': the tensor-core PARITY modes -- fp32 storage,
+    every convolution / weight gradient runs as 3 / 6 passes of the same tcgen05 engines over 2- / 3-part
+    bf16 splits of the fp32 operands (~2^-16 / ~2^-23 per product: 'bf16x6' is fp32-class; include/rcfd.h).
   * ``forward(..., return_logits=True)`` for tests.
 """
 import os
@@ -60,6 +63,8 @@ class FusionNetModel(object):
         self.max_predict_depth = max_predict_depth
         self.device = device
         self.compute_dtype = torch.float32
+        self.x3 = 0
+        self.precision = 'fp32'
         self.conv_engine = ops.ENGINE_AUTO
         # image branch / depth branch / fusion / weight gradients on parallel CUDA streams (RCFD_MULTISTREAM=0: one stream)
         self.multistream = os.environ.get('RCFD_MULTISTREAM', '1') != '0'
@@ -98,18 +103,25 @@ class FusionNetModel(object):
 
     # ------------------------------------------------------------------ precision / engine knobs
     def set_precision(self, precision):
-        self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[precision]
+        self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'bf16x3': torch.float32, 'bf16x6': torch.float32}[precision]
+        self.x3 = {'bf16x3': 2, 'bf16x6': 3}.get(precision, 0)
+        self.precision = precision
+        self._invalidate()
+        return self
+
+    def _invalidate(self):
+        """Drop everything derived from the parameters: packed weights, folded BatchNorm, and the captured CUDA
+        graphs (a graph holds raw pointers to the packed tensors of the pass it was captured from)."""
         self._cache.clear()
         self._graphs = {}
         self._train_graphs = {}
-        return self
 
     # ------------------------------------------------------------------ execution
     def _run(self, image, input_depth, record=False, return_logits=False, taps=None):
         # rcfd.ops refuses non-CUDA tensors: there is no CPU fallback behind this call
         with ops.hold_allocations():
             ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
-                                  record=record, engine=self.conv_engine, multistream=self.multistream)
+                                  record=record, engine=self.conv_engine, multistream=self.multistream, x3=self.x3)
             ectx.taps = taps
             # the layout conversion of each input is issued on its branch's stream
             latent, skips = engine.fusionnet_encoder(ectx, self.encoder, lambda: engine.stem_input(ectx, image),
@@ -176,7 +188,10 @@ class FusionNetModel(object):
         by the next call)."""
         if self.encoder.training:
             raise RuntimeError('forward_graphed is inference-only: call model.eval() first')
-        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine, self.multistream)
+        # eval graphs hold the packed weights / folded BatchNorm of the pass they were captured from: the key carries
+        # the parameter epoch (rcfd.optim.FusedAdam steps) and torch's version counters (optimizers, load_state_dict)
+        key = (tuple(image.shape), tuple(input_depth.shape), self.precision, self.conv_engine, self.multistream,
+               engine._PARAM_EPOCH[0], sum(t._version for t in self._state_tensors()))
         entry = self._graphs.get(key) if hasattr(self, '_graphs') else None
         if entry is None:
             if not hasattr(self, '_graphs'):
@@ -197,6 +212,8 @@ class FusionNetModel(object):
                 with torch.cuda.graph(graph):
                     s_out = self.forward(s_img, s_dep)
             entry = {'graph': graph, 'static': [s_img, s_dep], 'out': s_out}
+            for k in [k for k in self._graphs if k[:5] == key[:5]]:      # same shape / mode, older parameters
+                del self._graphs[k]
             self._graphs[key] = entry
         self._feed(entry, entry['static'], (image, input_depth))
         entry['graph'].replay()
@@ -219,7 +236,7 @@ class FusionNetModel(object):
             raise RuntimeError('train_step_graphed needs rcfd.optim.FusedAdam (gradients written in place into its flat buffer)')
         if not hasattr(self, '_train_graphs'):
             self._train_graphs = {}
-        key = (tuple(image.shape), tuple(input_depth.shape), self.compute_dtype, self.conv_engine, float(w_lidar_loss),
+        key = (tuple(image.shape), tuple(input_depth.shape), self.precision, self.conv_engine, float(w_lidar_loss),
                None if outlier_removal is None else (outlier_removal.kernel_size, outlier_removal.threshold),
                id(optimizer), self.multistream)
         entry = self._train_graphs.get(key)
@@ -324,6 +341,12 @@ class FusionNetModel(object):
                       'loss_lidar': loss_lidar}
 
     # ------------------------------------------------------------------ state management
+    def _state_tensors(self):
+        if getattr(self, '_state_list', None) is None:
+            self._state_list = [t for root in (self.encoder, self.decoder)
+                                for t in list(root.parameters()) + list(root.buffers())]
+        return self._state_list
+
     def parameters(self):
         """Encoder parameters then decoder parameters (reference :304-316; Adam state order)."""
         return list(self.encoder.parameters()) + list(self.decoder.parameters())
@@ -340,7 +363,7 @@ class FusionNetModel(object):
         self.device = device
         self.encoder.to(device)
         self.decoder.to(device)
-        self._cache.clear()
+        self._invalidate()
 
     def _modules_bare(self):
         enc = self.encoder.module if isinstance(self.encoder, torch.nn.DataParallel) else self.encoder
@@ -364,7 +387,8 @@ class FusionNetModel(object):
         checkpoint = torch.load(checkpoint_path, map_location=self.device, weights_only=False)
         self.encoder.load_state_dict(self._strip_module_prefix(checkpoint['encoder_state_dict']))
         self.decoder.load_state_dict(self._strip_module_prefix(checkpoint['decoder_state_dict']))
-        self._cache.clear()
+        self._invalidate()
+        engine.note_params_changed()
         if optimizer is not None:
             optimizer.load_state_dict(checkpoint['optimizer_state_dict'])
         return checkpoint['train_step'], optimizer

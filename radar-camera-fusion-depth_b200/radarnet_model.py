@@ -19,6 +19,8 @@ class RadarNetModel(object):
         self.input_patch_size_image = input_patch_size_image
         self.device = device
         self.compute_dtype = torch.float32
+        self.x3 = 0
+        self.precision = 'fp32'
         self.conv_engine = ops.ENGINE_AUTO
         self._cache = {}
         height, width = input_patch_size_image
@@ -44,7 +46,9 @@ class RadarNetModel(object):
         self.to(self.device)
 
     def set_precision(self, precision):
-        self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[precision]
+        self.compute_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'bf16x3': torch.float32, 'bf16x6': torch.float32}[precision]
+        self.x3 = {'bf16x3': 2, 'bf16x6': 3}.get(precision, 0)       # tensor-core parity mode (see FusionNetModel.set_precision)
+        self.precision = precision
         self._cache.clear()
         return self
 
@@ -54,7 +58,7 @@ class RadarNetModel(object):
         if self.encoder.training and torch.is_grad_enabled():
             raise NotImplementedError('RadarNet training (backward) is not part of this round; call under '
                                       'torch.no_grad() / model.eval() for stage-1 inference')
-        ctx = engine.Context(self.compute_dtype, False, image.device, cache=self._cache, engine=self.conv_engine)
+        ctx = engine.Context(self.compute_dtype, False, image.device, cache=self._cache, engine=self.conv_engine, x3=self.x3)
         img, s2d = engine.stem_input(ctx, image)
         latent, skips = engine.radarnet_encoder(ctx, self.encoder, img, point, bounding_boxes, stem_s2d=s2d)
         dec = self.decoder

@@ -70,6 +70,9 @@ _SIGS = {
     'rcfd_stage1_to_stage2': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_roi_pool_fwd': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P],
     'rcfd_linear_leaky_fwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_split_bf16': [_P, _P, _P, _P, c_int64, _P],
+    'rcfd_channel_stats': [_P, _P, _P, c_int64, c_int32, _P],
+    'rcfd_epilogue_f32': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, c_float, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
     'rcfd_set_option': [c_char_p, c_int32],
     'rcfd_plan_row_chunks': [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P],

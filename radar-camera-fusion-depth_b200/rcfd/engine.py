@@ -149,8 +149,13 @@ class Tape(object):
 class Context(object):
     """Per-forward state: dtype, mode, tape, BatchNorm scratch pool, packed-weight cache."""
 
-    def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO, multistream=False):
+    def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO, multistream=False,
+                 x3=False):
         self.dtype = dtype
+        # tensor-core parity modes: fp32 storage (dtype float32), every conv / wgrad = 3 or 6 bf16 tcgen05 passes over
+        # 2- or 3-part bf16 operand splits (rcfd/x3.py); x3 = number of parts (0: off), packed weights are tuples of parts
+        self.x3 = int(x3)
+        assert not self.x3 or dtype == torch.float32
         self.training = training
         self.device = device
         # multi-stream schedule: [caller's stream, DEPTH, FUSE, WG_MAIN, WG_DEPTH, PACK]
@@ -167,7 +172,7 @@ class Context(object):
         self.bn_counters = []
         self.taps = None
         self.prepacked = {}
-        self.plan = self.cache.setdefault(('pack_plan', dtype), {}) if (self.streams is not None and training) else None
+        self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (self.streams is not None and training) else None
         if self.streams is not None and training:
             self.stats(0)            # the zeroed statistics pool must exist before the streams fork
 
@@ -220,6 +225,8 @@ class Context(object):
     #    the model's pack plan; later steps replay the plan up front on the PACK stream (prepack), so the ~150
     #    tiny pack kernels leave the critical chains and each consumer just waits for its event.
     def packed(self, key, params, fn):
+        if self.x3 and not key[0].startswith('bn'):
+            fn = _split_after(fn, self.x3)       # pack in fp32 (self.dtype), then split the packed tensor into bf16 parts
         if self.training:
             hit = self.prepacked.pop(key, None)
             if hit is not None:
@@ -229,7 +236,7 @@ class Context(object):
             if self.plan is not None:
                 self.plan[key] = fn
             return fn()
-        ver = tuple(p._version for p in params) + (self.dtype, _PARAM_EPOCH[0])
+        ver = tuple(p._version for p in params) + (self.dtype, self.x3, _PARAM_EPOCH[0])
         hit = self.cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -273,7 +280,8 @@ class Context(object):
 
     def folded_bn(self, mod):
         bn = mod.batch_norm
-        ps = [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        # num_batches_tracked: the training kernels update the running statistics through raw pointers (no version bump)
+        ps = [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked]
 
         def make():
             scale = torch.empty(bn.num_features, device=self.device, dtype=torch.float32)
@@ -281,6 +289,10 @@ class Context(object):
             ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, scale, shift)
             return scale, shift
         return self.packed(('bn', id(mod)), ps, make)
+
+
+def _split_after(fn, parts):
+    return lambda: ops.split_bf16(fn(), parts)
 
 
 class _Role(object):
@@ -324,7 +336,7 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
     cin_data = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
     w = ctx.weight(mod, pad_to=cin_data if cin_data != mod.in_channels else None)   # 3/2-channel inputs live padded
     wup = None
-    if (in_size is not None and x1 is None and k == 3 and stride == 1 and ctx.dtype == torch.bfloat16
+    if (in_size is not None and x1 is None and k == 3 and stride == 1 and (ctx.dtype == torch.bfloat16 or ctx.x3)
             and int(in_size[0]) == 2 * x0.shape[1] and int(in_size[1]) == 2 * x0.shape[2] and x0.shape[3] % 16 == 0):
         wup = ctx.weight_up2x(mod)      # TMA engine: four 2x2 convs on the low-res source instead of a gather
     if head is not None:
@@ -333,7 +345,7 @@ def conv_unit(ctx, mod, x0, x1=None, in_size=None, residual=None, head=None, wan
         if ctx.tape is not None:
             _record_conv_backward(ctx, mod, x0, x1, in_size, out, None, want_input_grad,
                                   pre=lambda dd: ops.depth_head_bwd(dd, out, head[0], head[1], ctx.dtype,
-                                                                    cpad=CPAD_DY if ctx.dtype == torch.bfloat16 else 8))
+                                                                    cpad=CPAD_DY if (ctx.dtype == torch.bfloat16 or ctx.x3) else 8))
         return out
     if not mod.use_batch_norm:
         out = ops.conv2d(x0, w, cout, k, stride, x1=x1, in_size=in_size, act=act, residual=residual, engine=ctx.engine)
@@ -388,7 +400,7 @@ def _stem_s2d_unit(ctx, mod, x, act):
             gw = _grad_dst(mod.conv.weight)
 
             def wgrad():
-                dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine)      # [cout][16][CPAD]
+                dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine, x3=ctx.x3)      # [cout][16][CPAD]
                 ops.unpack_stem_s2d_wgrad(dw, gw)
             tape.side(wgrad)
             tape.param_grads.append((mod.conv.weight, gw))
@@ -432,7 +444,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         gw = _grad_dst(w_param)
 
         def wgrad():
-            dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine)
+            dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine, x3=ctx.x3)
             ops.unpack_wgrad(dw, gw)
         tape.side(wgrad)
         tape.param_grads.append((w_param, gw))
@@ -468,7 +480,8 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
             return scale, shift
         scale, shift = ctx.packed(('bncat', id(mod_w)),
                                   [bw.weight, bw.bias, bw.running_mean, bw.running_var,
-                                   bp.weight, bp.bias, bp.running_mean, bp.running_var], make)
+                                   bp.weight, bp.bias, bp.running_mean, bp.running_var,
+                                   bw.num_batches_tracked, bp.num_batches_tracked], make)
         y = ops.conv2d(dep, wcat, 2 * c, 1, 1, scale=scale, shift=shift, engine=ctx.engine)
         return ops.gate_fuse(y, None, None, img)
     ssum, ssq = ctx.stats(2 * c)
@@ -495,7 +508,7 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
             for bn, lo in ((bw, 0), (bp, c)):
                 tape.param_grads.append((bn.weight, dg[lo:lo + c]))
                 tape.param_grads.append((bn.bias, db[lo:lo + c]))
-            dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine)                         # [2c, 1, cd]
+            dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine, x3=ctx.x3)              # [2c, 1, cd]
             for wparam, lo in ((ww, 0), (wp, c)):
                 g = _grad_dst(wparam)
                 ops.unpack_wgrad(dw[lo:lo + c], g)
@@ -564,7 +577,7 @@ def stem_input(ctx, x_nchw):
     """NCHW float API tensor -> what the 7x7/s2 stem consumes: a space-to-depth NHWC tensor on the bf16 fast
     path (even H, W), else NHWC with channels zero-padded to CPAD.  Returns (tensor, is_s2d)."""
     h, w = x_nchw.shape[-2:]
-    if ctx.dtype == torch.bfloat16 and h % 2 == 0 and w % 2 == 0 and 4 * x_nchw.shape[1] <= CPAD:
+    if (ctx.dtype == torch.bfloat16 or ctx.x3) and h % 2 == 0 and w % 2 == 0 and 4 * x_nchw.shape[1] <= CPAD:
         return ops.nchw_to_s2d(x_nchw.float(), ctx.dtype, CPAD), True
     return ops.nchw_to_nhwc(x_nchw.float(), ctx.dtype, cpad=CPAD), False
 

@@ -4,6 +4,7 @@ Every function requires CUDA tensors and calls librcfd_b200.so; nothing here com
 PyTorch.  Activations are NHWC tensors [N, H, W, C] (float32 or bfloat16).
 """
 import ctypes
+import sys
 
 import torch
 
@@ -82,12 +83,42 @@ def conv_out_size(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
+def split_bf16(x, parts=2):
+    """float32 tensor -> ``parts`` (2 or 3) bfloat16 tensors of the same shape whose sum reproduces x to ~2^-17
+    (2 parts) / ~2^-25 (3 parts) relative: operand split of the tensor-core parity modes (include/rcfd.h)."""
+    x = x.contiguous()
+    assert x.dtype == torch.float32 and parts in (2, 3)
+    out = tuple(_empty(x.shape, device=x.device, dtype=torch.bfloat16) for _ in range(parts))
+    _lib.call('rcfd_split_bf16', _p(x), _p(out[0]), _p(out[1]), _p(out[2]) if parts == 3 else None, x.numel(), _stream())
+    return out
+
+
+def channel_stats(y, ssum, ssq):
+    """Per-channel sum / sum of squares of an fp32 NHWC tensor, ADDED to the float64 [C] tensors."""
+    c = y.shape[-1]
+    _lib.call('rcfd_channel_stats', _p(y), _p(ssum), _p(ssq), y.numel() // c, c, _stream())
+
+
+def epilogue_f32(y, scale, shift, act, act_params=(0.0, 0.0), residual=None, out=None):
+    """out = act(y * scale + shift) [, leaky(out + residual)] on fp32 NHWC tensors (any channel count)."""
+    c = y.shape[-1]
+    out = _empty_like(y) if out is None else out
+    _lib.call('rcfd_epilogue_f32', _p(y), _p(scale), _p(shift), _p(residual), _p(out), y.numel() // c, c, act,
+              float(act_params[0]), float(act_params[1]), _stream())
+    return out
+
+
 def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=None, shift=None,
            act=ACT_NONE, act_params=(0.0, 0.0), residual=None, stats=None, out=None, out_f32=False,
            accumulate=False, in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO, weight_up2x=None):
     """Implicit-GEMM convolution (see include/rcfd.h rcfd_conv2d_fwd).
     x0: [N, h0, w0, c0]; in_size: logical (H, W) the taps see (x0 is nearest-up-sampled to it);
-    x1: optional [N, H, W, c1] concat partner; stats: (sum, sqsum) float64 [cout] tensors."""
+    x1: optional [N, H, W, c1] concat partner; stats: (sum, sqsum) float64 [cout] tensors.
+    weight_packed given as a tuple of 2 / 3 bf16 parts selects the tensor-core parity mode (fp32 operands)."""
+    if isinstance(weight_packed, tuple):
+        from . import x3
+        return x3.conv2d_x3(sys.modules[__name__], x0, weight_packed, cout, k, stride, x1, in_size, scale, shift, act,
+                            act_params, residual, stats, out, accumulate, in_dilation, out_size, pad, engine, weight_up2x)
     for t in (x0, x1, weight_packed, scale, shift, residual, out):
         _p(t)                                   # CUDA + contiguity check
     n, h0, w0, c0 = x0.shape
@@ -130,8 +161,12 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     return out
 
 
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO):
-    """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above."""
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0):
+    """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above.  x3 = 2 | 3: tensor-core parity
+    mode (fp32 operands split into that many bf16 parts; 3 / 6 bf16 passes summed in fp32, rcfd/x3.py)."""
+    if x3:
+        from . import x3 as x3mod
+        return x3mod.wgrad_x3(sys.modules[__name__], int(x3), x0, dy, k, stride, x1, in_size, pad, engine)
     for t in (x0, x1, dy):
         _p(t)
     n, h0, w0, c0 = x0.shape

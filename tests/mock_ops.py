@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE ONLY: a torch-CPU emulation of rcfd.ops with the C-ABI's sem
 wiring, reverse-mode tape, gradient delivery, data-parallel sync) in the build container,
 which has no GPU.  Never imported by the product.
 """
+import sys
+
 import torch
 import torch.nn.functional as F
 
@@ -57,6 +59,10 @@ def _gather_input(x0, x1, in_size, in_dilation):
 def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=None, shift=None, act=ACT_NONE,
            act_params=(0.0, 0.0), residual=None, stats=None, out=None, out_f32=False, accumulate=False,
            in_dilation=1, out_size=None, pad=None, engine=ENGINE_AUTO, weight_up2x=None):
+    if isinstance(weight_packed, tuple):            # tensor-core parity mode: the REAL orchestration over mocked passes
+        from rcfd import x3
+        return x3.conv2d_x3(sys.modules[__name__], x0, weight_packed, cout, k, stride, x1, in_size, scale, shift, act,
+                            act_params, residual, stats, out, accumulate, in_dilation, out_size, pad, engine, weight_up2x)
     pad = k // 2 if pad is None else pad
     w = weight_packed.float().view(cout, k, k, -1).permute(0, 3, 1, 2)
     if in_dilation == 2:
@@ -69,7 +75,8 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     else:
         a = _gather_input(x0, x1, in_size, 1)
         y = F.conv2d(a, w, None, stride, pad)
-        if out_size is not None:
+        if out_size is not None:                    # even windows (space-to-depth stem, k = 4 / pad 2): first ho x wo outputs
+            y = y[:, :, :out_size[0], :out_size[1]]
             assert tuple(y.shape[-2:]) == tuple(out_size), (y.shape, out_size)
     if stats is not None:
         stats[0].add_(y.double().sum(dim=(0, 2, 3)))
@@ -86,12 +93,44 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     return res
 
 
+def split_bf16(x, parts=2):
+    out, r = [], x.float()
+    for _ in range(parts):
+        out.append(r.to(torch.bfloat16))
+        r = r - out[-1].float()
+    return tuple(out)
+
+
+def channel_stats(y, ssum, ssq):
+    c = y.shape[-1]
+    ssum.add_(y.double().reshape(-1, c).sum(0))
+    ssq.add_((y.double() ** 2).reshape(-1, c).sum(0))
+
+
+def epilogue_f32(y, scale, shift, act, act_params=(0.0, 0.0), residual=None, out=None):
+    v = y if scale is None else y * scale + shift
+    v = _act(v, act, act_params)
+    if residual is not None:
+        v = F.leaky_relu(v + residual, 0.2)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0):
+    if x3:
+        from rcfd import x3 as x3mod
+        return x3mod.wgrad_x3(sys.modules[__name__], int(x3), x0, dy, k, stride, x1, in_size, pad, engine)
+    return _conv2d_wgrad(x0, dy, k, stride, x1, in_size, pad)
+
+
 @torch.enable_grad()
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO):
+def _conv2d_wgrad(x0, dy, k, stride, x1, in_size, pad):
     a = _gather_input(x0, x1, in_size, 1)
     cout = dy.shape[3]
     w = torch.zeros(cout, a.shape[1], k, k, requires_grad=True)   # a already carries any channel padding
-    y = F.conv2d(a, w, None, stride, k // 2 if pad is None else pad)
+    y = F.conv2d(a, w, None, stride, k // 2 if pad is None else pad)[:, :, :dy.shape[1], :dy.shape[2]]
     y.backward(_nchw(dy))
     return w.grad.permute(0, 2, 3, 1).reshape(cout, k * k, -1).contiguous()
 
@@ -239,7 +278,35 @@ def nchw_to_nhwc(x, dtype, cpad=None):
 
 
 def nchw_to_s2d(x, dtype, cpad=16):
-    raise NotImplementedError('the mock runs the fp32 path only')
+    n, c, h, w = x.shape
+    y = x.view(n, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, h // 2, w // 2, 4 * c)
+    return F.pad(y, (0, cpad - 4 * c)).contiguous().to(dtype)
+
+
+def pack_stem_s2d_weight(w_oihw, dtype, cpad=16):
+    # include/rcfd.h: w'[ty][tx][(dy*2+dx)*c + ch] = w[2ty+dy-1][2tx+dx-1] (zero outside the 7x7 window)
+    cout, c, _, _ = w_oihw.shape
+    out = torch.zeros(cout, 4, 4, cpad)
+    for ty in range(4):
+        for tx in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    r, q = 2 * ty + dy - 1, 2 * tx + dx - 1
+                    if 0 <= r < 7 and 0 <= q < 7:
+                        out[:, ty, tx, (dy * 2 + dx) * c:(dy * 2 + dx + 1) * c] = w_oihw[:, :, r, q]
+    return out.view(cout, 16, cpad).to(dtype)
+
+
+def unpack_stem_s2d_wgrad(dw_packed, grad_oihw):
+    cout, c, _, _ = grad_oihw.shape
+    d = dw_packed.view(-1, 4, 4, dw_packed.shape[2])
+    for ty in range(4):
+        for tx in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    r, q = 2 * ty + dy - 1, 2 * tx + dx - 1
+                    if 0 <= r < 7 and 0 <= q < 7:
+                        grad_oihw[:, :, r, q] = d[:cout, ty, tx, (dy * 2 + dx) * c:(dy * 2 + dx + 1) * c]
 
 
 def nhwc_to_nchw(x):

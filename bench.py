@@ -1,20 +1,31 @@
 #!/usr/bin/env python
 """
-bench.py -- FusionNet depth-maps/s @352x704 on N B200s (BASELINE.json metric).
+bench.py -- FusionNet depth-maps/s @352x704 on N B200s (BASELINE.json metric) and the other BASELINE configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode train|infer] [--batch B]
-                    [--precision bf16|fp32] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode train|infer|radarnet] [--batch B]
+                    [--precision bf16|fp32|bf16x3|bf16x6] [--impl ours|reference|cudnn]
 
 One "step" is one pass of the hot path over one synthetic batch:
-  train (default, BASELINE configs[1]): forward + masked-L1 loss + backward + Adam, batch 8 / GPU, bf16;
-  infer                               : eval-mode forward, batch 8 / GPU.
-`value` is whole-job depth-maps/s with inputs resident in HBM; `e2e` is the same step through
-the public API with pinned-host inputs copied H2D and the loss / a depth checksum read back D2H
-inside the timed region.  N > 1: launched by torchrun, one rank per GPU, gradients all-reduced
-over NCCL (train) or independent replicas (infer); weak scaling.
+  train    (default, BASELINE configs[1]): forward + masked-L1 loss + backward + Adam, batch 8 / GPU, bf16;
+  infer    (configs[4])                  : eval-mode forward, batch B / GPU;
+  radarnet (configs[2])                  : RadarNet stage-1 forward + S2 scatter, 16 images x 64 radar points / GPU.
+`value` is whole-job throughput with inputs resident in HBM; `e2e` is the same step through the public API with
+pinned-host inputs copied H2D and the result (loss / depth maps / depth + response maps) read back D2H inside the
+timed region.  N > 1: launched by torchrun, one rank per GPU, gradients all-reduced over NCCL (train) or independent
+replicas (infer, radarnet); weak scaling.
 
---impl reference times the reference's own CPU path (the oracle port: same algorithm, fp32,
-torch CPU ops on all host threads) on a bounded sample of the same workload.
+The default run prints ONE JSON line for the train step; at N = 1 that line also carries
+  `roofline`     the time-dominant kernel of the step (found by timing every C-ABI call of one step alone with CUDA
+                 events, rcfd/census.py), algorithmic and executed FLOP/s against the measured peak, plus `kernels`
+                 (top kernels by share) and `step_breakdown`;
+  `cpu_baseline` the reference's CPU path (oracle port) timed on the box's host cores at the SAME batch;
+  `gpu_baseline` PyTorch eager + cuDNN running the reference graph on this GPU (fp32/TF32 and autocast bf16 +
+                 channels_last; tools/eager_fusionnet.py) -- the library path the reference itself would use here;
+  `also`         the same measurement object for the other BASELINE configs (infer batch 8, radarnet 16 x 64);
+  `parity`       the recorded deviation of this arithmetic from the fp32 oracle (profiles/r2_bf16_deviation.json).
+
+--impl reference times the reference's own CPU path (the oracle port: same algorithm, fp32, torch CPU ops on the host
+threads a probe finds fastest) on the same config; --impl cudnn prints the eager + cuDNN arm alone.
 """
 import argparse
 import json
@@ -30,9 +41,26 @@ sys.path.insert(0, os.path.join(ROOT, 'radar-camera-fusion-depth_b200'))
 import torch  # noqa: E402
 
 H, W = 352, 704
+K_POINTS = 64
+PATCH = (352, 288)
 FWD_GFLOP = 57.10            # per depth map, SURVEY.md 8d / BASELINE.md section 2
 TRAIN_GFLOP = 170.5
 ACT_MB_BF16 = 240.8          # conv activation traffic per depth map, bf16 (fwd)
+RADAR_GFLOP = 14.35 + 8.20 * K_POINTS          # per image at K = 64
+
+METRIC = {'train': ('FusionNet depth-maps/sec @352x704', 'depth-maps/s'),
+          'infer': ('FusionNet depth-maps/sec @352x704', 'depth-maps/s'),
+          'radarnet': ('RadarNet stage-1 images/sec @352x704, 64 radar points per image', 'images/s')}
+
+
+def workload_config(mode, batch, world):
+    """The `config` object: identical for every arm (--impl ours | reference | cudnn) of the same workload."""
+    name = {'train': 'FusionNet training step (fwd + masked-L1 + bwd + Adam), 352x704, batch %d per GPU (BASELINE configs[1])',
+            'infer': 'FusionNet eval forward, 352x704, batch %d per GPU (BASELINE configs[4])',
+            'radarnet': 'RadarNet stage-1 forward + S2 scatter, 352x704, %d images x 64 radar points per GPU, patch 352x288 '
+                        '(BASELINE configs[2])'}[mode] % batch
+    return {'workload': name, 'batch_per_gpu': batch, 'global_batch': world * batch, 'parallelism': 'dp%d' % world,
+            'l2': 'no flush needed: the per-step working set (> 1 GB of activations) exceeds the 126 MB L2'}
 
 
 def read_peaks():
@@ -42,6 +70,26 @@ def read_peaks():
         return dict(hbm=d['hbm_gbs'], tc_burst=d['bf16_tflops'], tc_sustained=d['bf16_tflops_sustained'],
                     source='measured (MEASURED_PEAKS.json)')
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def read_parity(precision):
+    p = os.path.join(ROOT, 'profiles', 'r2_bf16_deviation.json')
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    step = d.get('train_step_352x704_b2', {})
+    out = {'source': 'profiles/r2_bf16_deviation.json (tests/test_tc_parity_gpu.py, vs the fp32 CPU oracle)',
+           'tolerance': 'north star 1e-3 relative: met by the tensor-core parity modes bf16x3 / bf16x6 and by fp32; '
+                        'the bf16 fast mode is NOT inside it (deviation below)'}
+    key = precision if precision in step else None
+    if key:
+        out['train_step_352x704_b2'] = step[key]
+    if 'bf16x6' in step and precision != 'bf16x6':
+        out['train_step_352x704_b2_parity_mode_bf16x6'] = step['bf16x6']
+    for k in ('config1_bf16x3', 'config1_bf16x6', 'radarnet_352x704_k64'):
+        if k in d:
+            out[k] = d[k]
+    return out
 
 
 class ClockSampler(object):
@@ -100,10 +148,25 @@ def synthetic_batch(batch, seed):
     return image, depth, gt.float(), lidar.float()
 
 
+def radarnet_batch(n_img, seed):
+    """configs[2] inputs: images 3 x 352 x 704, 64 radar points each (x, y, z) and their column boxes
+    (reference src/radarnet_main.py:980-990: x +- patch_width / 2 in edge-padded pixel coordinates)."""
+    from rcfd import synth
+    pad = PATCH[1] // 2
+    g = torch.Generator().manual_seed(2000 + seed)
+    images = torch.rand(n_img, 3, H, W, generator=g)
+    pts, boxes = [], []
+    for b in range(n_img):
+        pt = synth.radar_points(K_POINTS, H, W, seed * 1000 + b)
+        pt[:, 0] += pad
+        pts.append(pt)
+        boxes.append(torch.stack([pt[:, 0] - pad, torch.zeros(K_POINTS), pt[:, 0] + pad,
+                                  torch.full((K_POINTS,), float(H))], 1))
+    return images, torch.stack(pts), torch.stack(boxes)
+
+
 # ----------------------------------------------------------------------------- reference arm (CPU oracle port)
-def oracle_step_fn(mode, batch, seed=0):
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import fusionnet_oracle as fo
+def _oracle_state(seed=0):
     from rcfd import synth
     import networks  # parameter containers only (CPU)
     cfg = synth.CANONICAL_FUSIONNET
@@ -117,6 +180,15 @@ def oracle_step_fn(mode, batch, seed=0):
     for k, v in dec.state_dict().items():
         p['decoder.' + k] = v.detach().clone()
     synth.fill_state_dict_(p, seed)
+    return p
+
+
+def oracle_step_fn(mode, batch, seed=0):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    if mode == 'radarnet':
+        return oracle_radarnet_step_fn(batch, seed)
+    import fusionnet_oracle as fo
+    p = _oracle_state(seed)
     image, depth, gt, lidar = synthetic_batch(batch, seed)
     if mode == 'infer':
         def step():
@@ -143,7 +215,35 @@ def oracle_step_fn(mode, batch, seed=0):
             fo.adam_step([p[k] for k in names], [p[k].grad for k in names], m, v, state['t'])
             for k, val in stats.items():
                 p[k].copy_(val)
-        return float(loss)
+        return float(loss.detach())
+    return step
+
+
+def oracle_radarnet_step_fn(n_img, seed=0):
+    import radarnet_oracle as ro
+    import scatter_oracle as so
+    import radarnet_model
+    from rcfd import synth
+    m = radarnet_model.RadarNetModel(device=torch.device('cpu'), **synth.CANONICAL_RADARNET)
+    p = {}
+    for k, v in m.encoder.state_dict().items():
+        p['encoder.' + k] = v
+    for k, v in m.decoder.state_dict().items():
+        p['decoder.' + k] = v
+    synth.fill_state_dict_(p, seed)
+    images, pts, boxes = radarnet_batch(n_img, seed)
+    pad = PATCH[1] // 2
+
+    def step():
+        tot = 0.0
+        with torch.no_grad():
+            for b in range(n_img):
+                img = torch.nn.functional.pad(images[b:b + 1], (pad, pad, 0, 0), mode='replicate')
+                crops = ro.radarnet_forward(p, img, pts[b], [boxes[b]], PATCH, return_logits=False,
+                                            roi_pool=ro.roi_pool_vectorised)
+                d, r = so.s2_scatter(crops.numpy(), pts[b].numpy(), W, PATCH, compat=True)
+                tot += float(r.sum())
+        return tot
     return step
 
 
@@ -162,11 +262,11 @@ def pick_cpu_threads():
         if best_t is None or dt < best_t:
             best, best_t = nt, dt
     torch.set_num_threads(best)
-    return best
+    return best, ncpu
 
 
 def time_cpu(mode, batch, steps, warmup):
-    pick_cpu_threads()
+    threads, ncpu = pick_cpu_threads()
     step = oracle_step_fn(mode, batch)
     for _ in range(warmup):
         step()
@@ -174,52 +274,178 @@ def time_cpu(mode, batch, steps, warmup):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt
+    return {'value': batch / dt, 'unit': METRIC[mode][1], 'cores': threads, 'host_cpus': ncpu,
+            'os_cpu_count': os.cpu_count(), 'kind': 'port', 'ms_per_step': dt * 1e3,
+            'sample': '%d timed %s steps of batch %d at 352x704 (+%d warm-up): the SAME batch as the GPU arm; oracle port '
+                      '(functional restatement of the reference, torch CPU fp32), thread count = fastest of a probe over '
+                      '{all, 1/2, 1/4, 1/8} of the %d host CPUs' % (steps, mode, batch, warmup, ncpu)}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch = 1 if args.mode == 'train' else 2
-    value, dt = time_cpu(args.mode, batch, args.steps, args.warmup)
-    cores = torch.get_num_threads()
+    batch = args.batch
+    if args.mode == 'radarnet':
+        batch = min(batch, 1)            # one image x 64 point columns per step: ~0.5 TFLOP of CPU convolution
+    steps = args.steps if args.mode != 'radarnet' else min(args.steps, 3)
+    warmup = min(args.warmup, 2)
+    cpu = time_cpu(args.mode, batch, steps, warmup)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    cfg = workload_config(args.mode, args.batch, world)
     line = {
-        'impl': 'reference', 'metric': 'FusionNet depth-maps/sec @352x704', 'value': value, 'unit': 'depth-maps/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+        'impl': 'reference', 'metric': METRIC[args.mode][0], 'value': cpu['value'], 'unit': METRIC[args.mode][1],
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cpu['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'FusionNet %s step 352x704 (CPU reference path, oracle port of the reference '
-                               'algorithm, torch CPU fp32)' % args.mode, 'batch_per_step': batch},
-        'cpu_baseline': {'value': value, 'unit': 'depth-maps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d timed %s steps of batch %d at 352x704 (+%d warm-up), all host threads'
-                                   % (args.steps, args.mode, batch, args.warmup)},
-        'e2e': {'value': value, 'unit': 'depth-maps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': cfg, 'timed_steps': steps, 'timed_batch': batch,
+        'cpu_baseline': cpu,
+        'e2e': {'value': cpu['value'], 'unit': METRIC[args.mode][1], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch.distributed as dist
-    from rcfd import synth, ops, _lib
-    import fusionnet_model
-    import net_utils
+# ----------------------------------------------------------------------------- library arm (torch eager + cuDNN on the GPU)
+def time_cudnn(mode, batch, dev, steps=5, warmup=3, seed=0):
+    """The reference graph in PyTorch eager + cuDNN on this GPU (tools/eager_fusionnet.py): depth-maps/s for
+    fp32 (TF32 convolutions allowed = torch's cuDNN default, what the unmodified reference would run) and for
+    autocast(bf16) + channels_last."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import eager_fusionnet as ef
+    state = {k: v.to(dev) for k, v in _oracle_state(seed).items()}
+    tensors = [t.to(dev) for t in synthetic_batch(batch, seed)]
+    out = {'kind': 'PyTorch %s eager + cuDNN %s, reference graph restated with the same ATen calls '
+                   '(tools/eager_fusionnet.py); none of this repo\'s kernels' % (torch.__version__, torch.backends.cudnn.version()),
+           'batch': batch, 'mode': mode, 'unit': 'depth-maps/s', 'steps': steps, 'warmup': warmup,
+           'cudnn_allow_tf32': bool(torch.backends.cudnn.allow_tf32)}
+    torch.backends.cudnn.benchmark = True
+    for variant in ('fp32', 'bf16_cl'):
+        step = ef.make_step(state, mode, tensors, variant)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out['fp32_tf32_eager' if variant == 'fp32' else 'bf16_autocast_channels_last'] = {'value': batch / ms * 1e3, 'ms_per_step': ms}
+        del step
+        torch.cuda.empty_cache()
+    return out
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+def run_cudnn(args):
     rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    peaks = read_peaks()
-    batch = args.batch
+    if rank != 0:
+        return
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    mode = 'train' if args.mode == 'radarnet' else args.mode
+    res = time_cudnn(mode, args.batch, dev, steps=args.steps, warmup=max(args.warmup, 3))
+    best = max(res['fp32_tf32_eager']['value'], res['bf16_autocast_channels_last']['value'])
+    print(json.dumps({'impl': 'cudnn', 'metric': METRIC[mode][0], 'value': best, 'unit': METRIC[mode][1], 'n_gpus': 1,
+                      'steps': args.steps, 'warmup': max(args.warmup, 3), 'higher_is_better': True, 'data': 'synthetic',
+                      'config': workload_config(mode, args.batch, 1), 'gpu_baseline': res}))
 
+
+# ----------------------------------------------------------------------------- our arm
+class Timer(object):
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, drain=None):
+        """K steps bracketed by barrier + synchronize; CUDA events on the current stream; max over ranks."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if drain is not None:
+            drain()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+
+class ResultReader(object):
+    """The step's result is copied D2H into one of two pinned buffers and READ by the host while the next step runs
+    (the last one inside the timed region too)."""
+
+    def __init__(self, like):
+        self.host = [torch.zeros(like.shape, dtype=like.dtype).pin_memory() for _ in range(2)]
+        self.ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i, self.last = 0, None
+        self.bytes = like.numel() * like.element_size()
+
+    def push(self, t):
+        i = self.i
+        self.host[i % 2].copy_(t, non_blocking=True)
+        self.ev[i % 2].record()
+        if i > 0:
+            self.drain_one(i - 1)
+        self.i = i + 1
+
+    def drain_one(self, j):
+        self.ev[j % 2].synchronize()
+        self.last = float(self.host[j % 2].flatten()[0])
+
+    def drain(self):
+        if self.i > 0:
+            self.drain_one(self.i - 1)
+
+
+def build_workload(args, mode, batch, dev, rank, world):
+    """Returns dict(step(inputs), resident, host, result(t) -> tensor copied back, h2d_bytes, model, census_step)."""
+    from rcfd import synth, ops
+    import net_utils
     torch.manual_seed(0)
+    if mode == 'radarnet':
+        import radarnet_model
+        import radarnet_main
+        model = radarnet_model.RadarNetModel(device=dev, **synth.CANONICAL_RADARNET)
+        model.set_precision(args.precision)
+        model.eval()
+        images, pts, boxes = radarnet_batch(batch, rank)
+        host = [t.pin_memory() for t in (images, pts, boxes)]
+        resident = [t.to(dev) for t in host]
+
+        def step(inputs):
+            img, pt, bx = inputs
+            if not img.is_cuda:
+                img, pt, bx = [t.to(dev, non_blocking=True) for t in (img, pt, bx)]
+            depth, resp = [], []
+            with torch.no_grad():
+                for b in range(img.shape[0]):          # the reference's entry point is per image (radarnet_main.forward)
+                    d, r = radarnet_main.forward(model, img[b:b + 1], pt[b], [bx[b]], device=dev)
+                    depth.append(d)
+                    resp.append(r)
+            return torch.stack(depth), torch.stack(resp)
+
+        def result(out):            # depth (int64, the reference's dtype) + response maps
+            return torch.cat([out[0].reshape(-1).view(torch.float32), out[1].reshape(-1)])
+        return dict(step=step, resident=resident, host=host, result=result, model=model, opt=None,
+                    h2d_bytes=sum(t.numel() * t.element_size() for t in host), eager=step)
+
+    import fusionnet_model
     model = fusionnet_model.FusionNetModel(device=dev, **synth.CANONICAL_FUSIONNET)
     model.set_precision(args.precision)
     model.multistream = args.multistream
-    train = args.mode == 'train'
+    train = mode == 'train'
+    opt = outlier = None
     if train:
         model.train()
         if world > 1:
@@ -230,16 +456,14 @@ def run_ours(args):
         outlier = net_utils.OutlierRemoval(7, 1.5)
     else:
         model.eval()
-
     host = [t.pin_memory() for t in synthetic_batch(batch, rank)]
-    h2d_bytes = sum(t.numel() * 4 for t in (host if train else host[:2]))
+    if not train:
+        host = host[:2]
     resident = [t.to(dev) for t in host]
 
-    def step(inputs):
-        image, depth, gt, lidar = inputs
-        if train and args.graph:
-            return model.train_step_graphed(image, depth, gt, lidar, opt, 2.0, outlier_removal=outlier)
+    def eager(inputs):
         if train:
+            image, depth, gt, lidar = [t if t.is_cuda else t.to(dev, non_blocking=True) for t in inputs]
             out = model.forward(image, depth)
             gt_c = outlier.remove_outliers(gt)
             loss, _ = model.compute_loss(image=image, output_depth=out, ground_truth=gt_c, lidar_map=lidar,
@@ -248,176 +472,179 @@ def run_ours(args):
             opt.zero_grad()
             loss.backward()
             opt.step()
-            return loss
+            return loss.detach()
+        image, depth = [t if t.is_cuda else t.to(dev, non_blocking=True) for t in inputs]
         with torch.no_grad():
-            return model.forward_graphed(image, depth) if args.graph else model.forward(image, depth)
+            return model.forward(image, depth)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step(inputs):
+        if not args.graph:
+            return eager(inputs)
+        if train:       # the graphed entry points stage pinned-host tensors on a copy stream themselves
+            return model.train_step_graphed(inputs[0], inputs[1], inputs[2], inputs[3], opt, 2.0, outlier_removal=outlier)
+        with torch.no_grad():
+            return model.forward_graphed(inputs[0], inputs[1])
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms / steps
+    def result(out):
+        return out.detach().reshape(-1) if not train else out.detach().reshape(1)
+    return dict(step=step, resident=resident, host=host, result=result, model=model, opt=opt,
+                h2d_bytes=sum(t.numel() * t.element_size() for t in host), eager=eager)
+
+
+def measure(args, mode, batch, dev, rank, world, peaks, want_census, want_cpu):
+    from rcfd import _lib, census
+    timer = Timer(world, dev)
+    wl = build_workload(args, mode, batch, dev, rank, world)
+    step, model = wl['step'], wl['model']
+    train = mode == 'train'
 
     # ---- device-resident timing
     for _ in range(args.warmup):
-        step(resident)
-    if args.profile_step:            # for ncu launch lists: one more step, nothing else
+        step(wl['resident'])
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ms = timer.timed(lambda: step(wl['resident']), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- kernels per step: count the C-ABI calls of one eagerly issued step (what the CUDA graph replays)
+    l0 = _lib.launch_count
+    if mode == 'radarnet' or not args.graph:
+        step(wl['resident'])
+        launches = _lib.launch_count - l0
+    elif train:
+        launches = getattr(model, 'last_capture_launches', 0)
+    else:
+        with torch.no_grad():
+            model.forward(wl['resident'][0], wl['resident'][1])
+        launches = _lib.launch_count - l0
+
+    # ---- end to end through the public API: pinned host -> device every step, result read back every step
+    probe = wl['result'](step(wl['resident']))
+    reader = ResultReader(probe)
+
+    def e2e_step():
+        reader.push(wl['result'](step(wl['host'])))
+    for _ in range(2):
+        e2e_step()
+    reader.drain()
+    ms_e2e = timer.timed(e2e_step, args.steps, drain=reader.drain)
+
+    per_unit_gflop = {'train': TRAIN_GFLOP, 'infer': FWD_GFLOP, 'radarnet': RADAR_GFLOP}[mode]
+    value = world * batch / (ms * 1e-3)
+    line = {
+        'metric': METRIC[mode][0], 'value': value, 'unit': METRIC[mode][1],
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'bf16': 'bf16', 'fp32': 'f32'}.get(args.precision, args.precision), 'data': 'synthetic',
+        'config': workload_config(mode, batch, world),
+        'engine': {'precision': args.precision, 'cuda_graph': bool(args.graph) and mode != 'radarnet',
+                   'multistream': bool(args.multistream) and mode != 'radarnet'},
+        'clocks': clocks,
+        'e2e': {'value': world * batch / (ms_e2e * 1e-3), 'unit': METRIC[mode][1], 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': wl['h2d_bytes'], 'd2h_bytes_per_step': reader.bytes},
+        'gpu_launches': launches,
+        'step_roofline': {'tensor_frac': value / world * per_unit_gflop * 1e9 / (peaks['tc_sustained'] * 1e12),
+                          'gflop_per_unit': per_unit_gflop, 'tflops': value / world * per_unit_gflop / 1e3,
+                          'peak_tflops_sustained': peaks['tc_sustained'], 'peaks': peaks['source']},
+    }
+    if mode != 'radarnet':
+        line['step_roofline']['hbm_frac_fwd_activations'] = value / world * ACT_MB_BF16 * 1e6 / (peaks['hbm'] * 1e9)
+
+    # ---- roofline of the time-dominant kernel: every C-ABI call of one step timed alone (CUDA events, L2 flushed)
+    if want_census and rank == 0:
+        ms_flag = getattr(model, 'multistream', False)
+        if hasattr(model, 'multistream'):
+            model.multistream = False
+        with census.record() as rec:
+            wl['eager'](wl['resident'])
+        torch.cuda.synchronize()
+        rows = census.replay(rec.calls, reps=2)
+        rec.release()
+        if hasattr(model, 'multistream'):
+            model.multistream = ms_flag
+        kernels = census.by_kernel(rows)
+        convs = [k for k in kernels if k['flops'] > 0]
+        dom = convs[0]
+        total_ms = sum(k['ms'] for k in kernels)
+        tf = dom['flops'] / (dom['ms'] * 1e-3) / 1e12
+        gbs = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
+        tensor_bound = tf / peaks['tc_burst'] >= gbs / peaks['hbm']
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_kernel_traffic.json')
+        if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)
+            tj = json.load(open(tp))
+            ent = tj.get('kernels', {}).get('%s|%s|%d' % (dom['kernel'], mode, batch))
+            traffic = ent.get('dram_bytes_per_launch') if ent else None
+        line['roofline'] = {
+            'bound': 'tensor' if tensor_bound else 'hbm',
+            'achieved': tf if tensor_bound else gbs, 'peak': peaks['tc_burst'] if tensor_bound else peaks['hbm'],
+            'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
+            'frac': (tf / peaks['tc_burst']) if tensor_bound else (gbs / peaks['hbm']),
+            'traffic': traffic,
+            'kernel': dom['kernel'], 'launches_per_step': dom['launches'], 'share_of_step_kernel_time': dom['share'],
+            'kernel_ms_per_step': dom['ms'], 'avg_launch_us': dom['ms'] / dom['launches'] * 1e3,
+            'algorithmic_gflop_per_step': dom['flops'] / 1e9, 'executed_gflop_per_step': dom['executed_flops'] / 1e9,
+            'achieved_tflops': tf, 'executed_tflops': dom['executed_flops'] / (dom['ms'] * 1e-3) / 1e12,
+            'algorithmic_mb_per_step': dom['bytes'] / 1e6, 'achieved_gbs': gbs, 'peaks': peaks['source'],
+            'how': 'time-dominant conv kernel of the step; every C-ABI call of one eagerly issued step re-issued alone between '
+                   'CUDA events on its launch stream, L2 flushed before each (rcfd/census.py); achieved = sum of the algorithmic '
+                   'FLOPs of its launches / sum of their durations; peak = burst figure (kernel timed alone)'}
+        line['kernels'] = [{'kernel': k['kernel'], 'launches': k['launches'], 'ms': round(k['ms'], 4), 'share': round(k['share'], 4),
+                            'tflops': (k['flops'] / (k['ms'] * 1e-3) / 1e12) if k['flops'] else None} for k in kernels[:12]]
+        line['step_breakdown'] = {'serialised_kernel_ms': total_ms, 'calls': len(rows), 'by_category': census.by_category(rows)}
+    if want_cpu and rank == 0 and world == 1:
+        line['cpu_baseline'] = time_cpu(mode, batch if mode != 'radarnet' else 1, 3 if mode != 'radarnet' else 1, 1)
+    line['parity'] = read_parity(args.precision)
+    # free this workload before the next one
+    del wl, step, model
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = read_peaks()
+    batch = args.batch if args.batch > 0 else {'train': 8, 'infer': 8, 'radarnet': 16}[args.mode]
+
+    if args.profile_step:            # for ncu launch lists: warm up, one more step, nothing else
+        wl = build_workload(args, args.mode, batch, dev, rank, world)
+        for _ in range(max(args.warmup, 1)):
+            wl['step'](wl['resident'])
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_push('profile_step')
-        step(resident)
+        wl['step'](wl['resident'])
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_pop()
         return
-    sampler = ClockSampler(local)
+
+    solo = world == 1
+    line = measure(args, args.mode, batch, dev, rank, world, peaks, want_census=solo and not args.no_census,
+                   want_cpu=not args.no_cpu)
+    if solo and args.mode == 'train' and not args.no_also:
+        # the other BASELINE configs, same measurement object each (driver-visible in the one JSON line)
+        also = {}
+        for mode, b in (('infer', 8), ('radarnet', 16)):
+            sub = measure(args, mode, b, dev, rank, world, peaks, want_census=not args.no_census, want_cpu=False)
+            sub.pop('parity', None)
+            also['%s_b%d' % (mode, b)] = sub
+        line['also'] = also
+    if solo and args.mode in ('train', 'infer') and not args.no_gpu_baseline:
+        gb = {args.mode: time_cudnn(args.mode, batch, dev)}
+        if args.mode == 'train' and not args.no_also:
+            gb['infer'] = time_cudnn('infer', 8, dev)
+        for k, v in gb.items():
+            ours = line['value'] if k == args.mode else line['also']['infer_b8']['value']
+            v['ours_over_best_library'] = ours / max(v['fp32_tf32_eager']['value'], v['bf16_autocast_channels_last']['value'])
+        line['gpu_baseline'] = gb
     if rank == 0:
-        sampler.start()
-    l0 = _lib.launch_count
-    ms = timed(lambda: step(resident), args.steps)
-    launches = (_lib.launch_count - l0) // args.steps
-    if args.graph:                        # replayed from a CUDA graph: count the kernels captured in it
-        launches = getattr(model, 'last_capture_launches', launches)
-        if not train:
-            l1 = _lib.launch_count
-            with torch.no_grad():
-                model.forward(resident[0], resident[1])
-            launches = _lib.launch_count - l1
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- end to end through the public API: pinned host -> device every step, result read back every step.
-    # The graphed entry points stage the host tensors on a copy stream (double buffered), so the copy of step i+1
-    # overlaps the compute of step i; the 4-byte result of step i is copied to pinned memory asynchronously and
-    # READ by the host while step i+1 runs (the reference reads loss.item() only at checkpoints, fusionnet_main.py:423).
-    res_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    res_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {'i': 0, 'last': None}
-
-    def e2e_step():
-        if train:           # the graphed step copies straight from the pinned host tensors into its staging buffers
-            inputs = host if args.graph else [t.to(dev, non_blocking=True) for t in host]
-        else:
-            inputs = (host[:2] if args.graph else [t.to(dev, non_blocking=True) for t in host[:2]]) + [None, None]
-        r = step(inputs)
-        i = state['i']
-        res_host[i % 2].copy_((r.detach() if train else r.sum()).reshape(1), non_blocking=True)
-        res_ev[i % 2].record()
-        if i > 0:                                   # read the previous step's result while this step runs
-            res_ev[(i - 1) % 2].synchronize()
-            state['last'] = float(res_host[(i - 1) % 2])
-        state['i'] = i + 1
-
-    def e2e_drain():
-        i = state['i']
-        if i > 0:
-            res_ev[(i - 1) % 2].synchronize()
-            state['last'] = float(res_host[(i - 1) % 2])
-
-    for _ in range(2):
-        e2e_step()
-    e2e_drain()
-
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_drain()                                     # the last result is read inside the timed region too
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t)
-    ms_e2e /= args.steps
-
-    # ---- dominant kernel (conv engine) alone on the heaviest layer: decoder deconv0.deconv.conv
-    # (64 -> 32, 3x3, nearest 2x up-sampling folded into the loads, output 352 x 704)
-    roof = None
-    if rank == 0:
-        cdt = model.compute_dtype
-        x = torch.randn(batch, H // 2, W // 2, 64, device=dev).to(cdt)
-        w32 = torch.randn(32, 64, 3, 3, device=dev) * 0.05
-        wt = ops.pack_weight(w32, cdt)
-        # same call the model makes for this layer: bf16 -> row-streaming sub-pixel engine (needs the phase weights)
-        wup = ops.pack_upconv2x_weight(w32, cdt) if cdt == torch.bfloat16 else None
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
-        out = None
-        for _ in range(3):
-            out = ops.conv2d(x, wt, 32, 3, 1, in_size=(H, W), out=out, engine=model.conv_engine, weight_up2x=wup)
-        reps, tot = 5, 0.0
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            ops.conv2d(x, wt, 32, 3, 1, in_size=(H, W), out=out, engine=model.conv_engine, weight_up2x=wup)
-            b.record()
-            torch.cuda.synchronize()
-            tot += a.elapsed_time(b)
-        k_ms = tot / reps
-        esz = 2 if cdt == torch.bfloat16 else 4
-        flops = 2.0 * batch * H * W * 32 * 9 * 64
-        bytes_ = batch * ((H // 2) * (W // 2) * 64 + H * W * 32) * esz + 32 * 9 * 64 * esz
-        tf = flops / (k_ms * 1e-3) / 1e12
-        gbs = bytes_ / (k_ms * 1e-3) / 1e9
-        if tf / peaks['tc_burst'] >= gbs / peaks['hbm']:
-            roof = {'bound': 'tensor', 'achieved': tf, 'peak': peaks['tc_burst'], 'unit': 'TFLOP/s',
-                    'frac': tf / peaks['tc_burst']}
-        else:
-            roof = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm']}
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'roofline_kernel_traffic.json')
-        if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel (ncu --set full, batch 8)
-            tj = json.load(open(tp))
-            if tj.get('batch') == batch and tj.get('precision') == args.precision:
-                traffic = tj.get('dram_bytes_per_launch')
-        roof.update({'traffic': traffic, 'executed_gflop': flops / 1e9 * (4.0 / 9.0 if wup is not None else 1.0), 'kernel': 'implicit-GEMM conv, decoder deconv0.deconv (64->32 3x3, fused 2x nearest '
-                     'up-sample), batch %d' % batch, 'kernel_ms': k_ms, 'algorithmic_gflop': flops / 1e9,
-                     'algorithmic_mb': bytes_ / 1e6, 'achieved_gbs': gbs, 'achieved_tflops': tf, 'peaks': peaks['source']})
-
-    value = world * batch / (ms * 1e-3)
-    e2e_value = world * batch / (ms_e2e * 1e-3)
-    if rank == 0:
-        cpu_batch = 1 if train else 2
-        cpu_value, cpu_dt = time_cpu(args.mode, cpu_batch, 1, 1) if (world == 1 and not args.no_cpu) else (None, None)
-        gflop = TRAIN_GFLOP if train else FWD_GFLOP
-        line = {
-            'metric': 'FusionNet depth-maps/sec @352x704', 'value': value, 'unit': 'depth-maps/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-            'config': {'workload': 'FusionNet %s, 352x704, batch %d per GPU (BASELINE configs[%d])'
-                                   % ('training step (fwd + masked-L1 + bwd + Adam)' if train else 'eval forward', batch,
-                                      1 if train else 4),
-                       'global_batch': world * batch, 'parallelism': 'dp%d' % world,
-                       'l2': 'no flush needed: per-step activation working set (>1 GB) exceeds the 126 MB L2',
-                       'precision': args.precision, 'cuda_graph': bool(args.graph), 'multistream': bool(args.multistream)},
-            'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'depth-maps/s', 'ms_per_step': ms_e2e,
-                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
-            'gpu_launches': launches,
-            'roofline': roof,
-            'step_roofline': {'tensor_frac': value / world * gflop * 1e9 / (peaks['tc_sustained'] * 1e12),
-                              'hbm_frac_fwd_activations': value / world * ACT_MB_BF16 * 1e6 / (peaks['hbm'] * 1e9),
-                              'gflop_per_map': gflop, 'peaks': peaks['source']},
-            'cpu_baseline': None if cpu_value is None else {
-                'value': cpu_value, 'unit': 'depth-maps/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                'sample': '1 timed %s step of batch %d at 352x704 (+1 warm-up), oracle port, thread count picked by a probe'
-                          % (args.mode, cpu_batch)},
-        }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -428,17 +655,26 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--mode', choices=['train', 'infer'], default='train')
-    ap.add_argument('--batch', type=int, default=8)
-    ap.add_argument('--precision', choices=['bf16', 'fp32'], default='bf16')
-    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--mode', choices=['train', 'infer', 'radarnet'], default='train')
+    ap.add_argument('--batch', type=int, default=0, help='per GPU; default 8 (train, infer) / 16 images (radarnet)')
+    ap.add_argument('--precision', choices=['bf16', 'fp32', 'bf16x3', 'bf16x6'], default='bf16')
+    ap.add_argument('--impl', choices=['ours', 'reference', 'cudnn'], default='ours')
     ap.add_argument('--profile-step', dest='profile_step', action='store_true', help='warm up, run ONE step, exit (for ncu)')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch kernels one by one instead of replaying a CUDA graph')
     ap.add_argument('--no-multistream', dest='multistream', action='store_false', help='issue every kernel on one stream')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-also', dest='no_also', action='store_true', help='skip the other BASELINE configs in the default run')
+    ap.add_argument('--no-census', dest='no_census', action='store_true', help='skip the per-kernel timing / roofline leg')
+    ap.add_argument('--no-gpu-baseline', dest='no_gpu_baseline', action='store_true', help='skip the torch eager + cuDNN leg')
     args = ap.parse_args()
     if args.impl == 'reference':
+        if args.batch <= 0:
+            args.batch = {'train': 8, 'infer': 8, 'radarnet': 16}[args.mode]
         run_reference(args)
+    elif args.impl == 'cudnn':
+        if args.batch <= 0:
+            args.batch = 8
+        run_cudnn(args)
     else:
         if args.warmup < 3 and not args.profile_step:
             args.warmup = 3

@@ -33,6 +33,9 @@ enum rcfd_engine { RCFD_ENGINE_AUTO = 0, RCFD_ENGINE_SIMT = 1, RCFD_ENGINE_TCGEN
 const char* rcfd_version(void);
 const char* rcfd_arch(void);          /* "sm_100a" */
 const char* rcfd_last_error(void);
+/* Name of the kernel the calling thread's last rcfd_conv2d_fwd / rcfd_conv2d_wgrad launched, e.g.
+ * "conv_tma_kernel<128>" (measurement: bench.py groups its per-call timings by it). */
+const char* rcfd_last_kernel(void);
 /* tuning / debug knobs ("strip_desc_mode": 0 | 1). */
 int rcfd_set_option(const char* key, int32_t value);
 /* Host-only: the chunk plan of the row-streaming kernels (h rows x cols column strips over ctas persistent CTAs):

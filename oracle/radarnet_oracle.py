@@ -54,6 +54,41 @@ def roi_pool(feat, boxes_list, spatial_scale, output_size):
     return torch.stack(outs, dim=0)
 
 
+def roi_pool_vectorised(feat, boxes_list, spatial_scale, output_size):
+    """Same values as ``roi_pool`` above (checked against it in tests/test_oracle_golden.py), with the bin loops
+    replaced by gathers: a bin is at most (mh x mw) pixels, so the max runs over mh * mw shifted gathers.  Used at the
+    BASELINE configs[2] size, where the scalar loops take minutes."""
+    n, c, h, w = feat.shape
+    ph, pw = output_size
+    outs = []
+    f32 = np.float32
+    for b, boxes in enumerate(boxes_list):
+        for box in boxes:
+            x1, y1, x2, y2 = [f32(v) * f32(spatial_scale) for v in box.tolist()]
+            sw, sh, ew, eh = (_round_half_away(x1), _round_half_away(y1), _round_half_away(x2), _round_half_away(y2))
+            bh = f32(max(eh - sh + 1, 1)) / f32(ph)
+            bw = f32(max(ew - sw + 1, 1)) / f32(pw)
+            i = np.arange(ph, dtype=np.float32)
+            j = np.arange(pw, dtype=np.float32)
+            hs = np.clip(np.floor(i * bh).astype(np.int64) + sh, 0, h)
+            he = np.clip(np.ceil((i + f32(1)) * bh).astype(np.int64) + sh, 0, h)
+            ws = np.clip(np.floor(j * bw).astype(np.int64) + sw, 0, w)
+            we = np.clip(np.ceil((j + f32(1)) * bw).astype(np.int64) + sw, 0, w)
+            mh, mw = int(max((he - hs).max(), 0)), int(max((we - ws).max(), 0))
+            out = torch.full((c, ph, pw), float('-inf'), dtype=feat.dtype)
+            for dy in range(mh):
+                rows = torch.from_numpy(np.minimum(hs + dy, h - 1))
+                rok = torch.from_numpy(hs + dy < he)
+                for dx in range(mw):
+                    cols = torch.from_numpy(np.minimum(ws + dx, w - 1))
+                    cok = torch.from_numpy(ws + dx < we)
+                    v = feat[b][:, rows][:, :, cols]
+                    ok = (rok[:, None] & cok[None, :])[None]
+                    out = torch.where(ok, torch.maximum(out, v), out)
+            outs.append(torch.where(torch.isinf(out), torch.zeros_like(out), out))
+    return torch.stack(outs, dim=0)
+
+
 def resnet_encoder(p, x, n_filters, use_bn, training, pre):
     """src/networks.py:232-268 (ResNetEncoder.forward)."""
     layers = [conv_block(p, pre + 'conv1', x, 2, 'leaky_relu', use_bn, training)]
@@ -74,7 +109,7 @@ def mlp_encoder(p, points, pre, n_layers=6):
 
 
 def radarnet_forward(p, image, points, boxes_list, patch_size, n_filters_image=(32, 64, 128, 128, 128),
-                     n_neuron_latent=128, training=False, return_logits=True):
+                     n_neuron_latent=128, training=False, return_logits=True, roi_pool=roi_pool):
     """src/radarnet_model.py:102-124 + src/networks.py:1203-1256."""
     ph, pw = patch_size
     lat_h, lat_w = int(ph // 32.0), int(pw // 32.0)

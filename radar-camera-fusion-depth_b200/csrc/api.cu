@@ -14,6 +14,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local char g_kernel[96] = "";
+
+void note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
+  va_end(ap);
+}
+
 int conv_simt_launch(const ConvKP& p, int dtype, cudaStream_t st);
 int conv_wgrad_simt_launch(const ConvKP& p, float* dw, int dtype, cudaStream_t st);
 bool conv_tc_supported(const ConvKP& p, int dtype);
@@ -51,6 +60,7 @@ extern "C" {
 const char* rcfd_version(void) { return "rcfd-b200 0.1.0"; }
 const char* rcfd_arch(void) { return "sm_100a"; }
 const char* rcfd_last_error(void) { return g_err; }
+const char* rcfd_last_kernel(void) { return g_kernel; }
 
 int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
   ConvKP p;
@@ -86,6 +96,7 @@ int rcfd_conv2d_fwd(const rcfd_conv_desc* d, void* stream) {
     return conv_tc_launch(p, st);
   }
   if (engine != RCFD_ENGINE_SIMT) { set_error("conv: bad engine %d", engine); return RCFD_EINVAL; }
+  note_kernel("conv_simt_kernel");
   return conv_simt_launch(p, d->dtype, st);
 }
 
@@ -146,6 +157,7 @@ int rcfd_conv2d_wgrad(const rcfd_conv_desc* d, float* dw, void* workspace, int64
     }
     return wgrad_tc_launch(p, dw, (cudaStream_t)stream);
   }
+  note_kernel("conv_wgrad_simt_kernel");
   return conv_wgrad_simt_launch(p, dw, d->dtype, (cudaStream_t)stream);
 }
 

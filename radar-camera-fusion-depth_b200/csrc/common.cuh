@@ -9,6 +9,7 @@
 namespace rcfd {
 
 void set_error(const char* fmt, ...);
+void note_kernel(const char* fmt, ...);   // name of the kernel the last conv / wgrad call launched (rcfd_last_kernel)
 
 #define RCFD_CHECK_ARG(cond, ...)                 \
   do {                                            \

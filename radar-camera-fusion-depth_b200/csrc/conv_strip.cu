@@ -1051,6 +1051,7 @@ inline bool make_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, i
 
 template <int BN, int CIN, bool STATS, int KS, int CIN1>
 int launch_strip_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  note_kernel("conv_strip_kernel<%d,%d,%d,%d,%d>", BN, CIN, (int)STATS, KS, CIN1);
   typedef StripCfg<BN, CIN, KS, CIN1> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
   static int per_sm = 0;                 // resident CTAs per SM (shared memory AND registers: the statistics variant is wide)
@@ -1098,6 +1099,7 @@ int launch_strip(const ConvKP& k, StripP& t, cudaStream_t st) {
 
 template <int BN, int CIN, bool STATS>
 int launch_strip_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  note_kernel("conv_strip_is_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripIsCfg<BN, CIN> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
   static int per_sm = 0;
@@ -1135,6 +1137,7 @@ int launch_strip_is(const ConvKP& k, StripP& t, cudaStream_t st) {
 
 template <int BN, int CIN, bool STATS>
 int launch_strip_up_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  note_kernel("conv_strip_up_is_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripUpIsCfg<BN, CIN> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
   static int per_sm = 0;
@@ -1171,6 +1174,7 @@ int launch_strip_up_is(const ConvKP& k, StripP& t, cudaStream_t st) {
 
 template <int BN, int CIN, bool STATS>
 int launch_strip_up_s(const ConvKP& k, StripP& t, cudaStream_t st) {
+  note_kernel("conv_strip_up_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripUpCfg<BN, CIN> C;
   static bool attr_set = false;
   if (!attr_set) {

@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const ConvKP p) {
 
 template <int BN>
 int launch_tc(const ConvKP& p, cudaStream_t st) {
+  note_kernel("conv_tc_kernel<%d>", BN);
   typedef TcCfg<BN> C;
   static bool attr_set = false;
   if (!attr_set) {

@@ -378,6 +378,7 @@ namespace {
 template <int BN>
 int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                cudaStream_t st) {
+  note_kernel("conv_tma_kernel<%d>", BN);
   typedef TmaCfg<BN> C;
   static bool attr_set = false;
   if (!attr_set) {

@@ -283,6 +283,7 @@ void plan_items(WgStripP& t, int ctas) {
 template <int BN, int CIN, bool UP>
 int launch_wg_strip(const void* x, int n, int hx, int wx, const void* dy, int hd, int wd, int cout, WgStripP& t, float* dst,
                     cudaStream_t st) {
+  note_kernel("wgrad_strip_kernel<%d,%d,%d>", BN, CIN, (int)UP);
   typedef WgStripCfg<BN, CIN, UP> C;
   static bool attr_set = false;
   if (!attr_set) {

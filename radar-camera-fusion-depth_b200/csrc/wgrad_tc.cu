@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const ConvKP p, floa
 
 template <int BN>
 int launch_wg(const ConvKP& p, float* dw, cudaStream_t st) {
+  note_kernel("wgrad_tc_kernel<%d>", BN);
   typedef WgCfg<BN> C;
   static bool attr_set = false;
   if (!attr_set) {

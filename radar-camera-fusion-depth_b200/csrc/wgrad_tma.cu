@@ -177,6 +177,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 template <int BN>
 int launch_wg_tma(const WgTmaP& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dy, float* dw,
                   cudaStream_t st) {
+  note_kernel("wgrad_tma_kernel<%d>", BN);
   typedef WgTmaCfg<BN> C;
   static bool attr_set = false;
   if (!attr_set) {

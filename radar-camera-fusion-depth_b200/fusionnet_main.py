@@ -174,7 +174,9 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
             loss, loss_info = model.compute_loss(
                 image=image, output_depth=output_depth, ground_truth=ground_truth, lidar_map=lidar_map,
                 loss_func=loss_func, w_smoothness=w_smoothness, loss_smoothness_kernel_size=loss_smoothness_kernel_size,
-                validity_map_loss_smoothness=torch.ones_like(ground_truth) if w_smoothness > 0 else None,
+                # the smoothness term only acts where there is no supervision (reference :379-382)
+                validity_map_loss_smoothness=torch.where(ground_truth > 0, torch.zeros_like(ground_truth),
+                                                         torch.ones_like(ground_truth)) if w_smoothness > 0 else None,
                 w_lidar_loss=w_lidar_loss)
             optimizer.zero_grad()
             loss.backward()

@@ -370,12 +370,21 @@ class FusionNetModel(object):
         dec = self.decoder.module if isinstance(self.decoder, torch.nn.DataParallel) else self.decoder
         return enc, dec
 
+    # The reference always wraps encoder / decoder in torch.nn.DataParallel before it saves or restores
+    # (src/fusionnet_main.py:198, 727-731), so its checkpoints carry 'module.'-prefixed keys and its strict
+    # load_state_dict expects them.  True: write that format (loadable by the reference's run / train scripts);
+    # restore_model accepts both.
+    REFERENCE_CHECKPOINT_KEYS = True
+
     def save_model(self, checkpoint_path, step, optimizer):
-        """Same checkpoint dictionary as the reference (:347-368)."""
+        """Same checkpoint dictionary as the reference (:347-368), 'module.'-prefixed keys like the files the reference
+        writes (see REFERENCE_CHECKPOINT_KEYS); the optimizer state is torch.optim.Adam's layout."""
+        pre = 'module.' if self.REFERENCE_CHECKPOINT_KEYS else ''
+        enc, dec = self._modules_bare()
         torch.save({'train_step': step,
                     'optimizer_state_dict': optimizer.state_dict(),
-                    'encoder_state_dict': self.encoder.state_dict(),
-                    'decoder_state_dict': self.decoder.state_dict()}, checkpoint_path)
+                    'encoder_state_dict': {pre + k: v for k, v in enc.state_dict().items()},
+                    'decoder_state_dict': {pre + k: v for k, v in dec.state_dict().items()}}, checkpoint_path)
 
     @staticmethod
     def _strip_module_prefix(state):

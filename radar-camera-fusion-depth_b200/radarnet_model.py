@@ -109,11 +109,13 @@ class RadarNetModel(object):
         self._cache.clear()
 
     def save_model(self, checkpoint_path, step, optimizer):
-        """Reference key names (:212-233)."""
+        """Reference key names (:212-233); 'module.'-prefixed like the files the reference writes after data_parallel()
+        (src/radarnet_main.py:203), restore_model accepts both."""
         torch.save({'train_step': step,
                     'radarnet_optimizer_state_dict': optimizer.state_dict(),
-                    'radarnet_encoder_state_dict': self.encoder.state_dict(),
-                    'radarnet_decoder_state_dict': self.decoder.state_dict()}, checkpoint_path)
+                    'radarnet_encoder_state_dict': {'module.' + k: v for k, v in self.encoder.state_dict().items()},
+                    'radarnet_decoder_state_dict': {'module.' + k: v for k, v in self.decoder.state_dict().items()}},
+                   checkpoint_path)
 
     def restore_model(self, checkpoint_path, optimizer=None):
         strip = lambda sd: {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}

@@ -76,15 +76,16 @@ _SIGS = {
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
     'rcfd_set_option': [c_char_p, c_int32],
     'rcfd_plan_row_chunks': [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P],
-    'rcfd_version': [], 'rcfd_arch': [], 'rcfd_last_error': [],
+    'rcfd_version': [], 'rcfd_arch': [], 'rcfd_last_error': [], 'rcfd_last_kernel': [],
 }
-_RESTYPE = {'rcfd_version': c_char_p, 'rcfd_arch': c_char_p, 'rcfd_last_error': c_char_p,
+_RESTYPE = {'rcfd_version': c_char_p, 'rcfd_arch': c_char_p, 'rcfd_last_error': c_char_p, 'rcfd_last_kernel': c_char_p,
             'rcfd_conv2d_wgrad_workspace': c_int64}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)
 
 _lib = None
 launch_count = 0      # number of C-ABI kernel-launching calls made (bench: gpu_launches evidence)
+census = None         # list collecting (name, args, kernel) while rcfd.census.record() is active
 
 
 class RcfdError(RuntimeError):
@@ -120,5 +121,8 @@ def call(name, *args):
     lib = _lib if _lib is not None else load()
     rc = getattr(lib, name)(*args)
     launch_count += 1
+    if census is not None:                # rcfd.census.record(): (entry point, arguments, kernel label) of every call
+        conv = name in ('rcfd_conv2d_fwd', 'rcfd_conv2d_wgrad')
+        census.append((name, args, lib.rcfd_last_kernel().decode() if conv else name))
     if rc != 0:
         raise RcfdError('%s failed (%d): %s' % (name, rc, lib.rcfd_last_error().decode()))

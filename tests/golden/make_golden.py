@@ -446,7 +446,78 @@ def validate_case(name, seed):
     print(name, 'ok', first, second['step'])
 
 
+TINY_FUSIONNET = dict(synth.CANONICAL_FUSIONNET, n_filters_encoder_image=[8, 8, 16, 16, 16, 16],
+                      n_filters_encoder_depth=[8, 8, 8, 8, 8, 8], n_filters_decoder=[16, 16, 16, 8, 8, 8])
+
+
+def checkpoint_case(name, seed):
+    """Checkpoint interop in both directions.  (1) The unmodified reference -- wrapped in
+    torch.nn.DataParallel like src/fusionnet_main.py:198 does before it saves -- takes one Adam step and writes
+    tests/golden/<name>.pth with its own save_model; the product model + rcfd.optim.FusedAdam restore it.  (2) A
+    checkpoint written by the product's save_model with FusedAdam's state loads into the reference's restore_model
+    (strict DataParallel keys) and its torch.optim.Adam, which can then step."""
+    import tempfile
+    import fusionnet_model as prod_fm
+    from rcfd import optim as prod_optim
+    torch.manual_seed(seed)
+    ref = REFM['fusionnet_model'].FusionNetModel(device=torch.device('cpu'), **TINY_FUSIONNET)
+    synth.fill_state_dict_(flat_state(ref), seed)
+    ref.train()
+    ref.data_parallel()
+    opt = torch.optim.Adam([{'params': ref.parameters(), 'weight_decay': 0.0}], lr=1e-3)
+    image, depth = synth.fusionnet_inputs(2, 64, 128, seed, 'quasi_dense')
+    gt, lidar = synth.training_targets(2, 64, 128, seed)
+    out = ref.forward(image, depth)
+    loss, _ = ref.compute_loss(image=image, output_depth=out, ground_truth=gt, lidar_map=lidar, loss_func='l1',
+                               w_smoothness=0.0, loss_smoothness_kernel_size=-1,
+                               validity_map_loss_smoothness=torch.ones_like(gt), w_lidar_loss=2.0)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    path = os.path.join(OUT, name + '.pth')
+    ref.save_model(path, 7, opt)
+    ck = torch.load(path, weights_only=False)
+    assert all(k.startswith('module.') for k in ck['encoder_state_dict'])
+    # (1) reference file -> product
+    prod = prod_fm.FusionNetModel(device=torch.device('cpu'), **TINY_FUSIONNET)
+    popt = prod_optim.FusedAdam([{'params': prod.parameters(), 'weight_decay': 0.0}], lr=5e-4)
+    step, popt = prod.restore_model(path, optimizer=popt)
+    assert step == 7 and popt.step_count == 1 and popt.param_groups[0]['lr'] == 1e-3
+    for a, b in zip(prod.parameters(), ref.parameters()):
+        assert torch.equal(a, b)
+    sd_ref = opt.state_dict()
+    sd_prod = popt.state_dict()
+    assert set(sd_prod['state']) == set(sd_ref['state']), (len(sd_prod['state']), len(sd_ref['state']))
+    for i, st in sd_ref['state'].items():
+        assert torch.equal(sd_prod['state'][i]['exp_avg'], st['exp_avg']) and float(sd_prod['state'][i]['step']) == float(st['step'])
+    assert set(sd_ref['param_groups'][0]) <= set(sd_prod['param_groups'][0]), set(sd_ref['param_groups'][0]) - set(sd_prod['param_groups'][0])
+    # (2) product file -> reference
+    with tempfile.TemporaryDirectory() as tmp:
+        p2 = os.path.join(tmp, 'model-9.pth')
+        prod.save_model(p2, 9, popt)
+        ref2 = REFM['fusionnet_model'].FusionNetModel(device=torch.device('cpu'), **TINY_FUSIONNET)
+        ref2.data_parallel()
+        opt2 = torch.optim.Adam([{'params': ref2.parameters(), 'weight_decay': 0.0}], lr=1e-3)
+        step2, opt2 = ref2.restore_model(p2, optimizer=opt2)
+        assert step2 == 9
+        for a, b in zip(ref2.parameters(), ref.parameters()):
+            assert torch.equal(a, b)
+        ref2.train()
+        out2 = ref2.forward(image, depth)
+        loss2, _ = ref2.compute_loss(image=image, output_depth=out2, ground_truth=gt, lidar_map=lidar, loss_func='l1',
+                                     w_smoothness=0.0, loss_smoothness_kernel_size=-1,
+                                     validity_map_loss_smoothness=torch.ones_like(gt), w_lidar_loss=2.0)
+        opt2.zero_grad()
+        loss2.backward()
+        opt2.step()                       # the restored Adam state is usable
+        assert int(float(opt2.state_dict()['state'][0]['step'])) == 2
+    print(name, 'ok: reference checkpoint', os.path.getsize(path), 'bytes, both directions load')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'checkpoint':
+        checkpoint_case('reference_checkpoint_tiny', 71)
+        sys.exit(0)
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
     fusionnet_case('fusionnet_canonical_2x96x160', synth.CANONICAL_FUSIONNET, 2, 96, 160, 1, 'quasi_dense', False)
@@ -461,4 +532,5 @@ if __name__ == '__main__':
     validate_case('validate_3x20x32', 41)
     s1_case('s1_merge_64x96', 64, 96, 51)
     radarnet_loss_case('radarnet_loss_3x64x64', 61)
+    checkpoint_case('reference_checkpoint_tiny', 71)
     print('golden fixtures written to', OUT)

@@ -143,9 +143,13 @@ def test_checkpoint_surface_roundtrip(tmp_path, mocked):
     m.save_model(path, 5, opt)
     ck = torch.load(path, weights_only=False)
     assert set(ck) == {'train_step', 'optimizer_state_dict', 'encoder_state_dict', 'decoder_state_dict'}
-    # the reference saves after data_parallel(): 'module.'-prefixed keys must load too
-    ck['encoder_state_dict'] = {'module.' + k: v for k, v in ck['encoder_state_dict'].items()}
-    ck['decoder_state_dict'] = {'module.' + k: v for k, v in ck['decoder_state_dict'].items()}
+    # written like the reference does after data_parallel(): 'module.'-prefixed keys
+    assert all(k.startswith('module.') for part in ('encoder_state_dict', 'decoder_state_dict') for k in ck[part])
+    m3 = _model(synth.SMALL_FUSIONNET, synth_fusionnet_state(synth.SMALL_FUSIONNET, 9))
+    assert m3.restore_model(path)[0] == 5
+    # bare keys (a checkpoint saved without DataParallel) must load too
+    ck['encoder_state_dict'] = {k[len('module.'):]: v for k, v in ck['encoder_state_dict'].items()}
+    ck['decoder_state_dict'] = {k[len('module.'):]: v for k, v in ck['decoder_state_dict'].items()}
     torch.save(ck, path)
     m2 = _model(synth.SMALL_FUSIONNET, synth_fusionnet_state(synth.SMALL_FUSIONNET, 8))
     step, _ = m2.restore_model(path, torch.optim.Adam(m2.parameters(), lr=1e-3))
@@ -158,6 +162,62 @@ def test_checkpoint_surface_roundtrip(tmp_path, mocked):
     with pytest.raises(ValueError):
         m.compute_loss(None, torch.ones(1, 1, 2, 2), torch.ones(1, 1, 2, 2), torch.ones(1, 1, 2, 2), 'bogus', 0.0, -1,
                        None, 0.0)
+
+
+def test_reference_checkpoint_interop(tmp_path, mocked):
+    """tests/golden/reference_checkpoint_tiny.pth was written by the UNMODIFIED reference (DataParallel-wrapped model,
+    torch.optim.Adam after one step; tests/golden/make_golden.py checkpoint_case, which also checks on the spot that the
+    reference loads a checkpoint written here).  It restores into the product model + FusedAdam, the round trip through
+    the product's save_model reproduces the reference file's structure ('module.' keys, torch.optim.Adam layout), and
+    FusedAdam <-> torch.optim.Adam state dicts interchange."""
+    from rcfd import optim
+    import fusionnet_model
+    cfg = dict(synth.CANONICAL_FUSIONNET, n_filters_encoder_image=[8, 8, 16, 16, 16, 16],
+               n_filters_encoder_depth=[8, 8, 8, 8, 8, 8], n_filters_decoder=[16, 16, 16, 8, 8, 8])
+    ref_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_checkpoint_tiny.pth')
+    ref_ck = torch.load(ref_path, weights_only=False)
+    m = fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg)
+    opt = optim.FusedAdam([{'params': m.parameters(), 'weight_decay': 0.0}], lr=5e-4)
+    step, opt = m.restore_model(ref_path, optimizer=opt)
+    assert step == 7 and opt.step_count == 1
+    ref_state = ref_ck['optimizer_state_dict']['state']
+    params = m.parameters()
+    off = 0
+    for i, p in enumerate(params):
+        n = p.numel()
+        if i in ref_state:
+            assert torch.equal(opt.exp_avg[off:off + n].view(p.shape), ref_state[i]['exp_avg'])
+            assert torch.equal(opt.exp_avg_sq[off:off + n].view(p.shape), ref_state[i]['exp_avg_sq'])
+        else:                                    # never-used projection weights: torch's Adam has no state for them
+            assert not bool(opt.exp_avg[off:off + n].any())
+        assert torch.equal(p, ref_ck['encoder_state_dict' if i < len(list(m.encoder.parameters())) else 'decoder_state_dict'][
+            'module.' + dict((id(q), k) for root in (m.encoder, m.decoder) for k, q in root.named_parameters())[id(p)]])
+        off += n
+    assert len(params) - 14 <= len(ref_state) < len(params)      # identity-shortcut projections never get Adam state
+    # product save -> same structure as the reference's file
+    out = str(tmp_path / 'model-9.pth')
+    m.save_model(out, 9, opt)
+    ck = torch.load(out, weights_only=False)
+    assert set(ck) == set(ref_ck)
+    for part in ('encoder_state_dict', 'decoder_state_dict'):
+        assert list(ck[part]) == list(ref_ck[part])
+        for k in ck[part]:
+            assert ck[part][k].shape == ref_ck[part][k].shape and torch.equal(ck[part][k], ref_ck[part][k]), k
+    sd, rsd = ck['optimizer_state_dict'], ref_ck['optimizer_state_dict']
+    assert set(sd['state']) == set(rsd['state'])
+    assert set(rsd['param_groups'][0]) <= set(sd['param_groups'][0])
+    assert sd['param_groups'][0]['params'] == rsd['param_groups'][0]['params']
+    # torch.optim.Adam accepts FusedAdam's state and vice versa
+    plain = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    adam = torch.optim.Adam([{'params': plain, 'weight_decay': 0.0}], lr=1e-3)
+    adam.load_state_dict(sd)
+    assert torch.equal(adam.state_dict()['state'][0]['exp_avg'], ref_state[0]['exp_avg'])
+    m2 = fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg)
+    opt2 = optim.FusedAdam(m2.parameters(), lr=1e-3)
+    opt2.load_state_dict(adam.state_dict())
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq) and opt2.step_count == 1
+    # a fresh FusedAdam (no step yet) has an empty per-parameter state, like torch's
+    assert optim.FusedAdam(fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg).parameters()).state_dict()['state'] == {}
 
 
 def _ddp_worker(rank, world, port, tmp):

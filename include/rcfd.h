@@ -270,6 +270,41 @@ int rcfd_channel_stats(const float* y, double* stats_sum, double* stats_sqsum, i
 int rcfd_epilogue_f32(const float* y, const float* scale, const float* shift, const float* residual, float* out,
                       int64_t pixels, int32_t channels, int32_t act, float act_p0, float act_p1, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Batched on-device augmentation: Transforms.transform of src/fusionnet_transforms.py:46-178 --
+ * brightness / contrast / saturation blends (torchvision `_blend` semantics for the dtype the reference feeds it:
+ * images whose maximum exceeds 1.0 are treated as int32, truncating after every op), normalisation, and the
+ * horizontal / vertical flips of the image AND of up to four range maps -- for the whole batch in one apply kernel
+ * (plus a max and a per-sample grey-mean reduction; no host synchronisation, unlike the reference's torch.max at :82).
+ * image / image_out: n x 3 x h x w float NCHW (NULL: range maps only).  maps / maps_out / map_channels: HOST arrays
+ * of n_maps (<= 4) device pointers / channel counts.  params: device, n x 11 floats per sample
+ * [do_b, f_b, 1-f_b, do_c, f_c, 1-f_c, do_s, f_s, 1-f_s, hflip, vflip] from the reference's torch.rand draws.
+ * scratch_max: 1 int32, scratch_sums: n doubles.  norm_mode: 0 = [0, 255], 1 = [0, 1], 2 = [-1, 1].
+ * --------------------------------------------------------------------------------- */
+int rcfd_transform_batch(const float* image, float* image_out, const float* const* maps, float* const* maps_out,
+                         const int32_t* map_channels, int32_t n_maps, const float* params, int32_t* scratch_max,
+                         double* scratch_sums, int32_t n, int32_t h, int32_t w, int32_t norm_mode, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * RadarNet stage-1 TRAINING step (src/radarnet_main.py:320-403): what autograd does behind
+ * torchvision.ops.roi_pool (src/networks.py:1232-1247), the point MLP (src/networks.py:1033-1063) and
+ * RadarNetModel.compute_loss (src/radarnet_model.py:126-167).
+ *   roi_pool_bwd : dfeat_f32 (n x h x w x c floats, zeroed by the call) += dout routed to each bin's arg-max
+ *                  (first maximum in scan order); cast_f32 converts the accumulator to the storage dtype.
+ *   linear_leaky_bwd : y = leaky(x w^T + b) -> dpre = dy * leaky'(y); db = sum_k dpre; dw = dpre^T x;
+ *                  dx = dpre w (dx may be NULL for the first layer); dpre_scratch: rows x out floats.
+ *   bce_logits_loss : L = sum(v * bce_with_logits(x, t, pos_weight)) / sum(v), dlogits = dL/dx (may be NULL);
+ *                  accum: 2 doubles (zeroed by the call), loss: 1 float.  Sync-free.
+ * --------------------------------------------------------------------------------- */
+int rcfd_roi_pool_bwd(const void* feat, const float* boxes, const void* dout, float* dfeat_f32, int32_t n, int32_t h,
+                      int32_t w, int32_t c, int32_t nbox, int32_t ph, int32_t pw, float spatial_scale, int32_t dtype,
+                      void* stream);
+int rcfd_cast_f32(const float* src, void* dst, int64_t count, int32_t dtype, void* stream);
+int rcfd_linear_leaky_bwd(const float* x, const float* w, const float* y, const float* dy, float* dpre_scratch, float* dx,
+                          float* dw, float* db, int32_t rows, int32_t in_features, int32_t out_features, void* stream);
+int rcfd_bce_logits_loss(const float* logits, const float* target, const float* validity, float pos_weight, double* accum,
+                         float* loss, float* dlogits, int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

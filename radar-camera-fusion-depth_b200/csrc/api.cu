@@ -35,7 +35,6 @@ bool conv_strip_preferred(const ConvKP& p, int dtype);
 int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
 extern int g_tma_bn_cap;
-extern int g_tma_debug_skip_b;
 extern int g_tma_pair;
 extern int g_strip_max_waste;
 extern int g_strip_input_stationary;
@@ -105,7 +104,6 @@ int rcfd_set_option(const char* key, int32_t value) {
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
   if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
   if (strcmp(key, "tma_pair") == 0) { g_tma_pair = value; return RCFD_OK; }
-  if (strcmp(key, "tma_debug_skip_loads") == 0) { g_tma_debug_skip_b = value; return RCFD_OK; }
   if (strcmp(key, "strip_input_stationary") == 0) { g_strip_input_stationary = value; return RCFD_OK; }
   if (strcmp(key, "strip_max_waste") == 0) { g_strip_max_waste = value; return RCFD_OK; }
   if (strcmp(key, "strip_up_max_waste") == 0) { g_strip_up_max_waste = value; return RCFD_OK; }

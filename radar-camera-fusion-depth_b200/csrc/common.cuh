@@ -119,4 +119,11 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// index of the current device (function attributes such as the dynamic shared-memory limit are per device)
+inline int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 15;
+}
+
 }  // namespace rcfd

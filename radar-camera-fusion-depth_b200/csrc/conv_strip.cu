@@ -1054,7 +1054,7 @@ int launch_strip_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   note_kernel("conv_strip_kernel<%d,%d,%d,%d,%d>", BN, CIN, (int)STATS, KS, CIN1);
   typedef StripCfg<BN, CIN, KS, CIN1> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
-  static int per_sm = 0;                 // resident CTAs per SM (shared memory AND registers: the statistics variant is wide)
+  static int per_sm_dev[16] = {}; int& per_sm = per_sm_dev[cur_dev()];                 // resident CTAs per SM (shared memory AND registers: the statistics variant is wide)
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<BN, CIN, STATS, KS, CIN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
@@ -1102,7 +1102,7 @@ int launch_strip_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   note_kernel("conv_strip_is_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripIsCfg<BN, CIN> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
-  static int per_sm = 0;
+  static int per_sm_dev[16] = {}; int& per_sm = per_sm_dev[cur_dev()];
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_strip_is_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip_is: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
@@ -1140,7 +1140,7 @@ int launch_strip_up_is_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   note_kernel("conv_strip_up_is_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripUpIsCfg<BN, CIN> C;
   static_assert(C::SMEM <= 227 * 1024, "row-streaming configuration exceeds shared memory");
-  static int per_sm = 0;
+  static int per_sm_dev[16] = {}; int& per_sm = per_sm_dev[cur_dev()];
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_strip_up_is_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip_up_is: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
@@ -1176,7 +1176,7 @@ template <int BN, int CIN, bool STATS>
 int launch_strip_up_s(const ConvKP& k, StripP& t, cudaStream_t st) {
   note_kernel("conv_strip_up_kernel<%d,%d,%d>", BN, CIN, (int)STATS);
   typedef StripUpCfg<BN, CIN> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_strip_up_kernel<BN, CIN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_strip_up: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }

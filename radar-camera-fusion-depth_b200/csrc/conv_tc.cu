@@ -338,7 +338,7 @@ template <int BN>
 int launch_tc(const ConvKP& p, cudaStream_t st) {
   note_kernel("conv_tc_kernel<%d>", BN);
   typedef TcCfg<BN> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_tc: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }

@@ -40,7 +40,6 @@ struct TmaConvP {
   double* ssum; double* ssq;
   int accumulate, dst_f32;
   int kpair;                // 1: two 64-channel chunks per k-step (one full barrier / one commit per PAIR of stages)
-  int debug_skip_b;         // rcfd_set_option("tma_debug_skip_b"): timing experiment, skips the weight loads after the first ring pass
   int phases;               // 1, or 4 = sub-pixel phases of a 2x nearest up-sampled 3x3 conv (2x2 taps each)
   int out_h, out_w, out_s;  // destination extent and pixel stride (out_s = 2 with phases)
 };
@@ -145,16 +144,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             if (it >= (uint32_t)C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / C::STAGES) & 1) ^ 1);
             const uint32_t full = sBar + 8 * s;
             const uint32_t a_dst = sStage + s * C::STAGE, b_dst = a_dst + C::A_BYTES;
-            // timing experiments only (wrong results): bit 0 skips the weight loads, bit 1 the activation loads, after the first ring pass
-            const bool skip_b = (p.debug_skip_b & 1) && it >= (uint32_t)C::STAGES;
-            const bool skip_a = (p.debug_skip_b & 2) && it >= (uint32_t)C::STAGES;
-            if (skip_a && skip_b) { mbar_arrive(full); continue; }
-            mbar_expect_tx(full, (uint32_t)((skip_a ? 0 : a_bytes) + (skip_b ? 0 : b_bytes)));
-            if (!skip_a) {
-              if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
-              else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
-            }
-            if (!skip_b) tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
+            mbar_expect_tx(full, (uint32_t)(a_bytes + b_bytes));
+            if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
+            else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+            tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
           }
         }
       }
@@ -200,13 +193,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_st = sStage + s * C::STAGE, b_st = a_st + C::A_BYTES;
-          for (int k = 0; k < ((p.debug_skip_b & 8) ? 1 : p.bkc / 16); ++k) {     // bit 3: one MMA per k-step (timing experiment)
+          for (int k = 0; k < p.bkc / 16; ++k) {
             umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
                      (uint32_t)((ks | k) != 0));
-          }
-          if (p.debug_skip_b & 4) {             // timing experiment: the same MMAs once more (wrong results)
-            for (int k = 0; k < p.bkc / 16; ++k)
-              umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc, 1u);
           }
           umma_commit(sBar + 8 * (C::STAGES + s));
           if (ks == p.ksteps - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
@@ -371,7 +360,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
 }  // namespace
 extern int g_tma_bn_cap;
-extern int g_tma_debug_skip_b;
 extern int g_tma_pair;
 namespace {
 
@@ -380,7 +368,7 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
                cudaStream_t st) {
   note_kernel("conv_tma_kernel<%d>", BN);
   typedef TmaCfg<BN> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_tma: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
@@ -395,7 +383,6 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 
 }  // namespace
 
-int g_tma_debug_skip_b = 0;
 int g_tma_pair = 1;        // rcfd_set_option("tma_pair"): 0 = one 64-channel chunk per k-step (4 MMAs per commit)
 int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n
 
@@ -428,7 +415,6 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   ConvKP p = pin;
   TmaConvP t;
   t.phases = 1; t.out_h = p.ho; t.out_w = p.wo; t.out_s = 1;
-  t.debug_skip_b = g_tma_debug_skip_b;
   t.kpair = 0;
   if (conv_tma_up2x_supported(p, RCFD_BF16)) {
     // run on the low-res grid: 2x2 taps, per-phase weights, destination pixels (2i+a, 2j+b)
@@ -469,7 +455,7 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   t.ksteps = p.kh * p.kw * ((p.c0 + p.c1) / t.bkc);
   // 128 / 256-channel layers: consume the 64-channel chunks two at a time (needs an even chunk count per tap, and the
   // split between the two sources on a pair boundary)
-  t.kpair = (g_tma_pair && t.bkc == 64 && ((p.c0 + p.c1) / 64) % 2 == 0 && (p.c0 / 64) % 2 == 0 && !t.debug_skip_b) ? 1 : 0;
+  t.kpair = (g_tma_pair && t.bkc == 64 && ((p.c0 + p.c1) / 64) % 2 == 0 && (p.c0 / 64) % 2 == 0) ? 1 : 0;
   t.dst = p.dst; t.scale = p.scale; t.shift = p.shift; t.act = p.act; t.p0 = p.p0; t.p1 = p.p1;
   t.residual = p.residual; t.ssum = p.ssum; t.ssq = p.ssq; t.accumulate = p.accumulate; t.dst_f32 = p.dst_f32;
   alignas(64) CUtensorMap a0, a1, w;

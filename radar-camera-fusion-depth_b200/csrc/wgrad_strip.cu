@@ -285,7 +285,7 @@ int launch_wg_strip(const void* x, int n, int hx, int wx, const void* dy, int hd
                     cudaStream_t st) {
   note_kernel("wgrad_strip_kernel<%d,%d,%d>", BN, CIN, (int)UP);
   typedef WgStripCfg<BN, CIN, UP> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_strip_kernel<BN, CIN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("wgrad_strip: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }

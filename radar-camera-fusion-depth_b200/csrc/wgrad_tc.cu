@@ -204,14 +204,16 @@ template <int BN>
 int launch_wg(const ConvKP& p, float* dw, cudaStream_t st) {
   note_kernel("wgrad_tc_kernel<%d>", BN);
   typedef WgCfg<BN> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     attr_set = true;
   }
   const int gx = ceil_div(p.K, TM), gy = ceil_div(p.cout, BN);
-  int splits = (148 * 2 + gx * gy - 1) / (gx * gy);
+  // one wave of resident CTAs: two per SM fit only for the 64-wide tile (96 KB of stages), the wider ones take an SM each
+  const int capacity = 148 * (C::SMEM <= 113 * 1024 ? 2 : 1);
+  int splits = capacity / (gx * gy);
   const int max_splits = (p.M + 4 * PB - 1) / (4 * PB);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -179,14 +179,16 @@ int launch_wg_tma(const WgTmaP& t, const CUtensorMap& a0, const CUtensorMap& a1,
                   cudaStream_t st) {
   note_kernel("wgrad_tma_kernel<%d>", BN);
   typedef WgTmaCfg<BN> C;
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("wgrad_tma: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     attr_set = true;
   }
   const int gx = ceil_div(t.K, TM), gy = ceil_div(t.cout, BN);
-  int splits = (num_sms() + gx * gy - 1) / (gx * gy);
+  // one wave: every CTA occupies a whole SM (shared memory), so a 149th CTA would run alone after the others (ncu: 162 CTAs
+  // for 256 -> 256 @22x44 = 1.09 waves, SMs busy 50 % of the kernel's duration)
+  int splits = num_sms() / (gx * gy);
   const int max_splits = (t.num_ptiles + 3) / 4;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -12,16 +12,24 @@ written by the reference itself):
     image dtype), saturation with the grey image;
   * normalisation to [0, 1] / [-1, 1] / [0, 255], then horizontal / vertical flips of images AND range maps.
 
-This is SURVEY.md 8f row 2 ("next"): tensor-op formulas for now; a single fused CUDA kernel is the follow-up.
+CUDA tensors go through ONE fused apply kernel for the whole batch (rcfd_transform_batch: blends + normalisation +
+flips of the image and of every range map, preceded by a max and a per-sample grey-mean reduction; no host
+synchronisation, unlike the reference's `torch.max(images) > 1.0` at :82).  CPU tensors take the equivalent tensor
+expressions below (host-side tests).  The only arithmetic difference between the two: the contrast partner (mean of the
+grey image) is summed exactly in float64 by the kernel and in float32 by torch.mean, which can move a blended value
+across an integer boundary on isolated pixels (bounded by one grey level; tests/test_dataops_gpu.py).
 """
 import torch
+
+from rcfd import ops
 
 
 class Transforms(object):
 
     def __init__(self, normalized_image_range=[0, 255], random_brightness=[-1], random_contrast=[-1],
-                 random_saturation=[-1], random_flip_type=['none']):
+                 random_saturation=[-1], random_flip_type=['none'], rand_device=None):
         self.normalized_image_range = normalized_image_range
+        self.rand_device = rand_device          # where the torch.rand draws are made (None: the data's device)
         self.do_random_brightness = -1 not in random_brightness
         self.random_brightness = random_brightness
         self.do_random_contrast = -1 not in random_contrast
@@ -54,7 +62,10 @@ class Transforms(object):
         n_batch = images_arr[0].shape[0]
         images_arr = list(images_arr)
         range_maps_arr = list(range_maps_arr)
-        rand = lambda: torch.rand(n_batch, device=device)
+        rand_device = device if self.rand_device is None else self.rand_device
+        rand = lambda: torch.rand(n_batch, device=rand_device)
+        if device.type == 'cuda':
+            return self._transform_cuda(images_arr, range_maps_arr, random_transform_probability, rand, device)
         do_random_transform = rand() <= random_transform_probability
 
         for idx, images in enumerate(images_arr):
@@ -95,6 +106,44 @@ class Transforms(object):
             outputs.append(images_arr)
         if len(range_maps_arr) > 0:
             outputs.append(range_maps_arr)
+        return outputs[0] if len(outputs) == 1 else outputs
+
+    def _transform_cuda(self, images_arr, range_maps_arr, probability, rand, device):
+        """Same draws (same sequence of torch.rand(n_batch) calls as the reference), arithmetic in rcfd_transform_batch."""
+        n_batch = images_arr[0].shape[0]
+        do_t = rand() <= probability
+        zeros = torch.zeros(n_batch, device=do_t.device)
+        cols = []
+        for enabled, limits in ((self.do_random_brightness, self.random_brightness),
+                                (self.do_random_contrast, self.random_contrast),
+                                (self.do_random_saturation, self.random_saturation)):
+            if not enabled:
+                cols += [zeros, zeros, zeros]
+                continue
+            do = torch.logical_and(do_t, rand() <= 0.50)
+            lo, hi = limits
+            factors = (hi - lo) * rand() + lo
+            cols += [do.float(), factors, (1.0 - factors.double()).float()]      # (1 - f) in double like the python float
+        for enabled in (self.do_random_horizontal_flip, self.do_random_vertical_flip):
+            cols.append(torch.logical_and(do_t, rand() <= 0.50).float() if enabled else zeros)
+        params = torch.stack(cols, dim=1).to(device=device, dtype=torch.float32)
+        rng = list(self.normalized_image_range)
+        if rng not in ([0, 255], [0, 1], [-1, 1]):
+            raise ValueError('Unsupported normalization range: {}'.format(self.normalized_image_range))
+        norm_mode = {(0, 255): 0, (0, 1): 1, (-1, 1): 2}[tuple(rng)]
+        images_out, maps_out = [], [m.float() for m in range_maps_arr]
+        for idx, images in enumerate(images_arr):
+            img, maps = ops.transform_batch(images.float(), maps_out if idx == 0 else [], params, norm_mode)
+            images_out.append(img)
+            if idx == 0:
+                maps_out = maps
+        if len(images_arr) == 0 and maps_out:
+            _, maps_out = ops.transform_batch(None, maps_out, params, norm_mode)
+        outputs = []
+        if len(images_out) > 0:
+            outputs.append(images_out)
+        if len(maps_out) > 0:
+            outputs.append(maps_out)
         return outputs[0] if len(outputs) == 1 else outputs
 
     def normalize_images(self, images_arr, normalized_image_range=[0, 1]):

@@ -73,6 +73,11 @@ _SIGS = {
     'rcfd_split_bf16': [_P, _P, _P, _P, c_int64, _P],
     'rcfd_channel_stats': [_P, _P, _P, c_int64, c_int32, _P],
     'rcfd_epilogue_f32': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, c_float, _P],
+    'rcfd_transform_batch': [_P, _P, _P, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_roi_pool_bwd': [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, _P],
+    'rcfd_cast_f32': [_P, _P, c_int64, c_int32, _P],
+    'rcfd_linear_leaky_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_bce_logits_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
     'rcfd_set_option': [c_char_p, c_int32],
     'rcfd_plan_row_chunks': [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P],

@@ -65,3 +65,35 @@ def make_val_batches(image_path, depth_path, response_path, ground_truth_path, n
     dataset = datasets.FusionNetInferenceDataset(image_paths=paths[0], depth_paths=paths[1], response_paths=paths[2],
                                                  ground_truth_paths=paths[3])
     return torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=1, drop_last=False)
+
+
+def make_radarnet_batches(image_path, radar_path, ground_truth_path, batch_size, patch_size, total_points_sampled, n_height,
+                          n_width, rank=0, world=1, synthetic_steps=4):
+    """Batches of the RadarNet stage-1 training step (reference src/radarnet_main.py:336-340): (image N x 3 x H x (W + pw)
+    edge-padded, radar points N x K x 3 with x in padded-image pixels, column boxes N x K x 4, lidar depth of every
+    point's crop N x K x 1 x ph x pw).  'synthetic' paths give seeded synthetic batches (SURVEY 8d); the reference's
+    nuScenes-derived files are data preparation outside the B200 hot path."""
+    if image_path != 'synthetic':
+        raise NotImplementedError("RadarNet training data files are outside the B200 hot path: use train_image_path='synthetic'")
+    ph, pw = patch_size
+    pad = pw // 2
+    k = total_points_sampled
+
+    def batches(epoch):
+        for i in range(synthetic_steps):
+            seed = 3000 + i * world + rank              # the same few synthetic batches every epoch
+            g = torch.Generator().manual_seed(seed)
+            image = torch.rand(batch_size, 3, n_height, n_width + 2 * pad, generator=g)
+            pts = torch.stack([synth.radar_points(k, n_height, n_width, seed * 131 + b) for b in range(batch_size)])
+            pts[..., 0] += pad
+            boxes = torch.stack([pts[..., 0] - pad, torch.zeros(batch_size, k), pts[..., 0] + pad,
+                                 torch.full((batch_size, k), float(n_height))], dim=-1)
+            # sparse lidar returns in every crop; a band of them lies within the correspondence distance of the radar depth
+            z = pts[..., 2].view(batch_size, k, 1, 1, 1)
+            noise = (torch.rand(batch_size, k, 1, ph, pw, generator=g) - 0.5) * 6.0
+            far = torch.rand(batch_size, k, 1, ph, pw, generator=g) * 79 + 1
+            near = torch.rand(batch_size, k, 1, ph, pw, generator=g) < 0.3
+            mask = torch.rand(batch_size, k, 1, ph, pw, generator=g) < 0.05
+            gt = torch.where(near, (z + noise).clamp_min(0.5), far) * mask
+            yield [t.pin_memory() for t in (image, pts, boxes, gt.float())]
+    return batches, synthetic_steps

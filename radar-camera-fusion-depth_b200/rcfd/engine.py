@@ -711,22 +711,56 @@ def boxes_to_rois(boxes_list, device):
     return torch.cat(rows, dim=0).contiguous()
 
 
+def _roi_pool(ctx, feat, rois, out_size, scale):
+    out = ops.roi_pool(feat, rois, out_size, scale)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            d = tape.grad_of(out)
+            if d is not None:
+                tape.add_grad(feat, ops.roi_pool_bwd(feat, rois, d, out_size, scale))
+        tape.add_step(bwd)
+    return out
+
+
 def radarnet_encoder(ctx, enc, image, points, boxes_list, stem_s2d=False):
-    """networks.RadarNetV1Encoder.forward (reference src/networks.py:1203-1256); image NHWC."""
+    """networks.RadarNetV1Encoder.forward (reference src/networks.py:1203-1256); image NHWC.  With a tape (training,
+    reference src/radarnet_main.py:392-399) every piece records its backward: roi_pool -> arg-max scatter, the point MLP ->
+    rcfd_linear_leaky_bwd per layer, the latent concat -> channel split."""
     ph, pw = enc.input_patch_size_image
     lat_h, lat_w = int(ph // 32.0), int(pw // 32.0)
     scales = [1 / 2.0, 1 / 4.0, 1 / 8.0, 1 / 16.0, 1 / 32.0, 1 / 64.0, 1 / 128.0]
     latent_img, skips_img = resnet_encoder(ctx, enc.encoder_image, image, stem_s2d=stem_s2d)
     rois = boxes_to_rois(boxes_list, image.device)
-    latent_pooled = ops.roi_pool(latent_img, rois, (lat_h, lat_w), 1 / 32.0)
-    skips = [ops.roi_pool(s, rois, (int(ph * scales[i]), int(pw * scales[i])), scales[i])
+    latent_pooled = _roi_pool(ctx, latent_img, rois, (lat_h, lat_w), 1 / 32.0)
+    skips = [_roi_pool(ctx, s, rois, (int(ph * scales[i]), int(pw * scales[i])), scales[i])
              for i, s in enumerate(skips_img)]
     x = points.to(device=image.device, dtype=torch.float32).contiguous()
+    acts = [x]
     for fc in enc.encoder_depth.mlp:
         x = ops.linear_leaky(x, fc.fully_connected.weight.detach(), fc.fully_connected.bias.detach())
+        acts.append(x)
     k = x.shape[0]
     cl = enc.n_neuron_latent_depth
     # reference views the MLP output as (K, C, h, w) NCHW (src/networks.py:1252) -> NHWC
     lat_d = ops.nchw_to_nhwc(x.view(k, cl, lat_h, lat_w), ctx.dtype)
     latent = torch.cat([latent_pooled, lat_d], dim=3).contiguous()      # channel concat of two small tensors
+    if ctx.tape is not None:
+        tape = ctx.tape
+        c_img = latent_pooled.shape[3]
+        layers = list(enc.encoder_depth.mlp)
+
+        def bwd():
+            d = tape.grad_of(latent)
+            if d is None:
+                return
+            tape.add_grad(latent_pooled, d[..., :c_img].contiguous())
+            g = ops.nhwc_to_nchw(d[..., c_img:].contiguous()).view(k, -1)          # float32, the MLP's (K, C*h*w) order
+            for i in range(len(layers) - 1, -1, -1):
+                fc = layers[i].fully_connected
+                g, dw, db = ops.linear_leaky_bwd(acts[i], fc.weight.detach(), acts[i + 1], g, want_dx=i > 0)
+                tape.param_grads.append((fc.weight, dw))
+                tape.param_grads.append((fc.bias, db))
+        tape.add_step(bwd)
     return latent, skips

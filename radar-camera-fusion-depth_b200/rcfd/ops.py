@@ -459,3 +459,66 @@ def linear_leaky(x, w, b):
     out = _empty((rows, fout), device=x.device, dtype=torch.float32)
     _lib.call('rcfd_linear_leaky_fwd', _p(x.contiguous()), _p(w), _p(b), _p(out), rows, fin, fout, _stream())
     return out
+
+
+def transform_batch(image, range_maps, params, norm_mode):
+    """Batched augmentation (include/rcfd.h rcfd_transform_batch).  image: N x 3 x H x W float or None; range_maps: list
+    of N x c x H x W float tensors; params: N x 11 float (see the header).  Returns (image_out, [maps_out])."""
+    ref = image if image is not None else range_maps[0]
+    n, _, h, w = ref.shape
+    image = image.contiguous() if image is not None else None
+    range_maps = [m.contiguous() for m in range_maps]
+    for t in [image] + range_maps:
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError('transform_batch takes float32 tensors')
+    image_out = _empty_like(image) if image is not None else None
+    maps_out = [_empty_like(m) for m in range_maps]
+    scratch_max = _empty(1, device=ref.device, dtype=torch.int32)
+    scratch_sums = _empty(n, device=ref.device, dtype=torch.float64)
+    params = params.contiguous()
+    for first in range(0, max(len(range_maps), 1), 4):
+        chunk, chunk_out = range_maps[first:first + 4], maps_out[first:first + 4]
+        k = len(chunk)
+        src = (ctypes.c_void_p * 4)(*([m.data_ptr() for m in chunk] + [None] * (4 - k)))
+        dst = (ctypes.c_void_p * 4)(*([m.data_ptr() for m in chunk_out] + [None] * (4 - k)))
+        chs = (ctypes.c_int32 * 4)(*([m.shape[1] for m in chunk] + [0] * (4 - k)))
+        img = image if first == 0 else None
+        _lib.call('rcfd_transform_batch', _p(img), _p(image_out) if img is not None else None, src, dst, chs, k, _p(params),
+                  _p(scratch_max), _p(scratch_sums), n, h, w, int(norm_mode), _stream())
+    return image_out, maps_out
+
+
+def roi_pool_bwd(feat, boxes5, dout, out_size, spatial_scale):
+    """Gradient of roi_pool w.r.t. ``feat`` (NHWC, storage dtype of feat); dout: [nbox, ph, pw, c]."""
+    n, h, w, c = feat.shape
+    acc = _empty((n, h, w, c), device=feat.device, dtype=torch.float32)
+    _lib.call('rcfd_roi_pool_bwd', _p(feat), _p(boxes5.contiguous()), _p(dout.contiguous()), _p(acc), n, h, w, c,
+              boxes5.shape[0], out_size[0], out_size[1], float(spatial_scale), dt(feat), _stream())
+    if feat.dtype == torch.float32:
+        return acc
+    out = _empty((n, h, w, c), device=feat.device, dtype=feat.dtype)
+    _lib.call('rcfd_cast_f32', _p(acc), _p(out), acc.numel(), dt(feat), _stream())
+    return out
+
+
+def linear_leaky_bwd(x, w, y, dy, want_dx=True):
+    """Backward of y = leaky(x w^T + b): returns (dx or None, dw, db), all float32."""
+    rows, fin = x.shape
+    fout = w.shape[0]
+    dpre = _empty((rows, fout), device=x.device, dtype=torch.float32)
+    dx = _empty((rows, fin), device=x.device, dtype=torch.float32) if want_dx else None
+    dw = _empty((fout, fin), device=x.device, dtype=torch.float32)
+    db = _empty((fout,), device=x.device, dtype=torch.float32)
+    _lib.call('rcfd_linear_leaky_bwd', _p(x.contiguous()), _p(w), _p(y.contiguous()), _p(dy.contiguous()), _p(dpre), _p(dx),
+              _p(dw), _p(db), rows, fin, fout, _stream())
+    return dx, dw, db
+
+
+def bce_logits_loss(logits, target, validity, pos_weight, want_grad=True):
+    """sum(v * BCEWithLogits(x, t, pos_weight)) / sum(v) and its gradient w.r.t. the logits (sync-free)."""
+    accum = _empty(2, device=logits.device, dtype=torch.float64)
+    loss = _empty(1, device=logits.device, dtype=torch.float32)
+    dl = _empty_like(logits) if want_grad else None
+    _lib.call('rcfd_bce_logits_loss', _p(logits.contiguous()), _p(target.contiguous()), _p(validity.contiguous()),
+              float(pos_weight), _p(accum), _p(loss), _p(dl), logits.numel(), _stream())
+    return loss, dl

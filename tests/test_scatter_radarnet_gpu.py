@@ -179,3 +179,95 @@ def test_image_and_radar_to_depth_end_to_end():
     assert torch.equal(inp, inp_ref)
     assert torch.equal(depth, depth_ref)
     assert float(depth.min()) >= 0.99 and float(depth.max()) <= 100.0
+
+
+def _radarnet_train_case(precision, tol_logit, tol_grad):
+    """One RadarNet training step (forward -> weighted BCE -> backward) vs the oracle's autograd: logits, loss and
+    EVERY parameter gradient (image encoder through roi_pool's arg-max routing, point MLP, decoder)."""
+    import radarnet_main
+    import radarnet_model
+    h, w, k, ph, pw, seed = 64, 128, 5, 64, 64, 9
+    cfg = dict(synth.CANONICAL_RADARNET, input_patch_size_image=(ph, pw))
+    m = radarnet_model.RadarNetModel(device=DEV, **cfg)
+    p = {}
+    for kk, v in m.encoder.state_dict().items():
+        p['encoder.' + kk] = v
+    for kk, v in m.decoder.state_dict().items():
+        p['decoder.' + kk] = v
+    synth.fill_state_dict_(p, seed)
+    p_cpu = {kk: v.detach().cpu().clone() for kk, v in p.items()}
+    m.set_precision(precision)
+    m.train()
+    pad = pw // 2
+    gen = torch.Generator().manual_seed(seed)
+    n = 2
+    image = torch.rand(n, 3, h, w + 2 * pad, generator=gen)
+    pts = torch.stack([synth.radar_points(k, h, w, seed + b) for b in range(n)])
+    pts[..., 0] += pad
+    boxes = torch.stack([pts[..., 0] - pad, torch.zeros(n, k), pts[..., 0] + pad, torch.full((n, k), float(h))], dim=-1)
+    gt = (torch.rand(n, k, 1, ph, pw, generator=gen) * 60 + 1) * (torch.rand(n, k, 1, ph, pw, generator=gen) < 0.2)
+    gt = torch.where(torch.rand(n, k, 1, ph, pw, generator=gen) < 0.3, pts[..., 2].view(n, k, 1, 1, 1).expand_as(gt) + 0.2, gt) * (gt > 0)
+    # ---- oracle: autograd through the CPU restatement
+    po = {kk: v.clone().requires_grad_('running' not in kk and v.is_floating_point()) for kk, v in p_cpu.items()}
+    flat_pts = pts.view(n * k, 3)
+    label, validity = radarnet_main.make_labels(gt.view(n * k, 1, ph, pw), flat_pts[:, 2].view(-1, 1, 1, 1), 0.4, False)
+    logits_o = ro.radarnet_forward(po, image, flat_pts, [boxes[b] for b in range(n)], (ph, pw), training=True,
+                                   roi_pool=ro.roi_pool_vectorised)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(logits_o, label, reduction='none', pos_weight=torch.tensor(3.0))
+    loss_o = torch.sum(validity * bce) / torch.sum(validity)
+    loss_o.backward()
+    # ---- product
+    logits = m.forward(image.to(DEV), flat_pts.to(DEV), [boxes[b].to(DEV) for b in range(n)], return_logits=True)
+    loss, _ = m.compute_loss(logits, label.to(DEV), validity.to(DEV), w_positive_class=3.0)
+    loss.backward()
+    assert relerr(logits.detach().cpu(), logits_o.detach()) < tol_logit
+    assert abs(float(loss) - float(loss_o)) < tol_logit * abs(float(loss_o))
+    named = dict([('encoder.' + kk, v) for kk, v in m.encoder.named_parameters()] +
+                 [('decoder.' + kk, v) for kk, v in m.decoder.named_parameters()])
+    worst = []
+    for kk, v in named.items():
+        go = po[kk].grad
+        assert (v.grad is None) == (go is None), kk
+        if go is not None:
+            worst.append((relerr(v.grad.cpu(), go), kk))
+    worst.sort(reverse=True)
+    print(precision, 'radarnet train step: worst gradient deviations', ['%.1e %s' % e for e in worst[:4]])
+    assert worst[0][0] < tol_grad, worst[:4]
+    assert any('encoder_depth.mlp.0' in kk for _, kk in worst) and any('encoder_image.conv1' in kk for _, kk in worst)
+
+
+def test_radarnet_train_step_vs_oracle_fp32():
+    _radarnet_train_case('fp32', 1e-3, 5e-3)
+
+
+def test_radarnet_train_step_vs_oracle_tensor_core_parity():
+    _radarnet_train_case('bf16x6', 1e-3, 5e-3)
+
+
+def test_radarnet_train_entry_point_synthetic(tmp_path):
+    """radarnet_main.train with the reference's keyword surface on the synthetic workload: FusedAdam steps in bf16 lower
+    the loss on a repeated batch; checkpoints carry the reference's key names."""
+    import radarnet_main
+    torch.manual_seed(0)
+    kw = dict(train_image_path='synthetic', train_radar_path='synthetic', train_ground_truth_path='synthetic',
+              val_image_path='', val_radar_path='', val_ground_truth_path='', batch_size=2, patch_size=(64, 64),
+              total_points_sampled=4, sample_probability_of_lidar=0.1, normalized_image_range=[0, 1],
+              encoder_type=['radarnetv1', 'batch_norm'], n_filters_encoder_image=[32, 64, 128, 128, 128],
+              n_neurons_encoder_depth=[32, 64, 128, 128, 128], decoder_type=['multiscale', 'batch_norm'],
+              n_filters_decoder=[256, 128, 64, 32, 16], weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+              learning_rates=[1e-3], learning_schedule=[3], augmentation_probabilities=[0.0], augmentation_schedule=[-1],
+              augmentation_random_brightness=[-1, -1], augmentation_random_contrast=[-1, -1],
+              augmentation_random_saturation=[-1, -1], augmentation_random_noise_type=['none'],
+              augmentation_random_noise_spread=-1, augmentation_random_flip_type=['none'], w_weight_decay=0.0,
+              w_positive_class=2.0, max_distance_correspondence=0.4, set_invalid_to_negative_class=False,
+              checkpoint_dirpath=str(tmp_path), n_step_per_summary=100, n_step_per_checkpoint=4,
+              start_step_validation=1000, restore_path='', precision='bf16', n_height=64, n_width=128)
+    model, opt, step = radarnet_main.train(**kw)
+    assert step == 12
+    text = open(str(tmp_path / 'results.txt')).read()
+    losses = [float(l.split('Loss=')[1].split()[0]) for l in text.splitlines() if l.startswith('Loss=')]
+    assert len(losses) == 3 and losses[2] < losses[0], losses
+    ck = torch.load(str(tmp_path / 'model-12.pth'), weights_only=False)
+    assert set(ck) == {'train_step', 'radarnet_optimizer_state_dict', 'radarnet_encoder_state_dict', 'radarnet_decoder_state_dict'}
+    kw.update(restore_path=str(tmp_path / 'model-12.pth'), max_steps=13)
+    assert radarnet_main.train(**kw)[2] == 13

@@ -161,8 +161,8 @@ def test_train_step_352x704_b2_tensor_core_parity():
         value of the same algorithm).  At this size the reference's own fp32 gradient deviates from the float64 one by
         4e-3 (median over the 209 tensors, max-norm relative) up to 3e-2 -- BatchNorm backward cancels large sums over
         5e5 pixels -- so "within 5e-3 of the fp32 oracle" is below the reference's own rounding noise.  The assertion is
-        therefore made against the float64 gradient: per tensor <= 5e-3 or <= 3x the fp32 oracle's own deviation for
-        that tensor, and in aggregate (median) <= 1.5x the fp32 oracle's.
+        therefore made against the float64 gradient, distribution against distribution: median, 90th percentile and
+        maximum of the per-tensor deviations each <= 1.5x the fp32 oracle's own, every tensor <= 6e-2 and cosine > 0.9995.
     The fp32 SIMT mode is held to the same bar; the bf16 fast mode's deviation on the same step is measured, bounded at
     a stated value and recorded."""
     n, h, w, seed = 2, 352, 704, 21
@@ -201,9 +201,13 @@ def test_train_step_352x704_b2_tensor_core_parity():
         sp, ep = summary[prec], all_errs[prec]
         assert sp['depth_relerr'] < TOL and sp['depth_mae_m'] < 1e-3 and sp['loss_relerr'] < TOL, (prec, sp)
         assert sp['bn_running_relerr_max'] < TOL, (prec, sp)
-        bad = [(k, ep[k], e_ref[k]) for k in ep if not (ep[k] < 5e-3 or ep[k] < 3.0 * e_ref[k])]
-        assert not bad, (prec, bad[:8])
-        assert sp['grad_relerr_vs_float64_median'] < max(1.5 * ref_med, 2e-3), (prec, sp, ref_med)
+        # the two noise realisations are independent, so they are compared as distributions over the 209 tensors
+        # (median, 90th percentile, maximum: each <= 1.5x the fp32 oracle's own), with a per-tensor cap and a direction check
+        ours, theirs = sorted(ep.values()), ref_sorted
+        for q in (0.5, 0.9, 1.0):
+            i = min(int(q * len(ours)), len(ours) - 1)
+            assert ours[i] < max(1.5 * theirs[i], 2e-3), (prec, q, ours[i], theirs[i])
+        assert ours[-1] < 6e-2 and sp['grad_cosine_min'] > 0.9995, (prec, sp)
     # fast mode: recorded above; stated bounds (bf16 rounding of activations and weights, ~35 layers deep)
     sb = summary['bf16']
     assert sb['depth_mae_m'] < 0.06 and sb['loss_relerr'] < 1e-2 and sb['grad_cosine_median'] > 0.9 and sb['grad_cosine_min'] > 0.8

@@ -305,6 +305,21 @@ int rcfd_linear_leaky_bwd(const float* x, const float* w, const float* y, const 
 int rcfd_bce_logits_loss(const float* logits, const float* target, const float* validity, float pos_weight, double* accum,
                          float* loss, float* dlogits, int64_t count, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Data path on the device: the value codec of the reference's 16-bit PNG depth / response files and
+ * the crop of src/datasets.py:19-109, batched, from the on-disk sample types.
+ *   decode_crop : src = n rasters of src_h x src_w x channels samples (src_bits 8: uint8 HWC image as PIL decodes it;
+ *                 16: uint16 map, channels = 1); dst[n][c][y][x] = max(float(src[n][y + y0][x + x0][c]) / multiplier, 0)
+ *                 (load_image / load_depth / load_response, src/data_utils.py:238-269, 288-318); crop_yx: device, n x 2
+ *                 int32 (y0, x0) per sample or NULL; dst_batch_stride (elements) lets depth and response land in the two
+ *                 channels of FusionNet's input_depth (src/fusionnet_main.py:366).
+ *   encode_u16  : the reference's save_depth / save_response quantisation, uint16(uint32(v * multiplier) & 0xffff).
+ * --------------------------------------------------------------------------------- */
+int rcfd_decode_crop(const void* src, int32_t src_bits, float* dst, const int32_t* crop_yx, int32_t n, int32_t src_h,
+                     int32_t src_w, int32_t channels, int32_t out_h, int32_t out_w, float multiplier,
+                     int64_t dst_batch_stride, void* stream);
+int rcfd_encode_u16(const float* src, uint16_t* dst, float multiplier, int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,12 +135,69 @@ __global__ void xform_apply_kernel(const float* __restrict__ img, float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 16-bit PNG value codec + crop
+// What the reference's data path does between the decoded PNG raster and the network input (src/data_utils.py:238-269,
+// 288-318: np.array(Image.open(path), float32) / multiplier, depth <= 0 -> 0; src/datasets.py:19-109: crop every tensor of
+// the sample at the same (y0, x0); load_image: HWC uint8 -> CHW float): here for the whole batch, from the on-disk sample
+// types (uint16 rasters, uint8 HWC images), so the host ships 2 / 1 bytes per value instead of 4.
+template <typename S>
+__global__ void decode_crop_kernel(const S* __restrict__ src, float* __restrict__ dst, const int* __restrict__ crop_yx, int N,
+                                   int SH, int SW, int C, int OH, int OW, float multiplier, int64_t dst_batch_stride) {
+  const int64_t total = (int64_t)N * C * OH * OW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OW);
+    int64_t r = i / OW;
+    const int y = (int)(r % OH); r /= OH;
+    const int c = (int)(r % C);
+    const int n = (int)(r / C);
+    const int y0 = crop_yx ? crop_yx[2 * n] : 0, x0 = crop_yx ? crop_yx[2 * n + 1] : 0;
+    const S v = src[(((int64_t)n * SH + (y + y0)) * SW + (x + x0)) * C + c];          // HWC raster (C = 1 for the maps)
+    float f = __fdiv_rn((float)v, multiplier);
+    if (f <= 0.f) f = 0.f;
+    dst[(int64_t)n * dst_batch_stride + ((int64_t)c * OH + y) * OW + x] = f;
+  }
+}
+
+// save_depth / save_response (src/data_utils.py:271-286, 320-335): np.uint32(v * multiplier) stored as a 16-bit PNG sample
+__global__ void encode_u16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, float multiplier, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __fmul_rn(src[i], multiplier);
+    const unsigned int u = v > 0.f ? (unsigned int)fminf(v, 4294967040.f) : 0u;       // C cast: truncation toward zero
+    dst[i] = (uint16_t)(u & 0xffffu);
+  }
+}
+
 }  // namespace
 }  // namespace rcfd
 
 using namespace rcfd;
 
 extern "C" {
+
+int rcfd_decode_crop(const void* src, int32_t src_bits, float* dst, const int32_t* crop_yx, int32_t n, int32_t src_h,
+                     int32_t src_w, int32_t channels, int32_t out_h, int32_t out_w, float multiplier,
+                     int64_t dst_batch_stride, void* stream) {
+  RCFD_CHECK_ARG(src && dst && n > 0 && channels > 0 && out_h > 0 && out_w > 0 && src_h >= out_h && src_w >= out_w,
+                 "decode_crop: bad args");
+  RCFD_CHECK_ARG((src_bits == 8 || src_bits == 16) && multiplier > 0.f, "decode_crop: src_bits 8 | 16, multiplier > 0");
+  RCFD_CHECK_ARG(dst_batch_stride >= (int64_t)channels * out_h * out_w, "decode_crop: dst_batch_stride");
+  const int64_t total = (int64_t)n * channels * out_h * out_w;
+  if (src_bits == 8)
+    decode_crop_kernel<uint8_t><<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>((const uint8_t*)src, dst, crop_yx, n, src_h, src_w,
+                                                                                   channels, out_h, out_w, multiplier, dst_batch_stride);
+  else
+    decode_crop_kernel<uint16_t><<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst, crop_yx, n, src_h, src_w,
+                                                                                    channels, out_h, out_w, multiplier, dst_batch_stride);
+  RCFD_CHECK_LAUNCH("decode_crop");
+  return RCFD_OK;
+}
+
+int rcfd_encode_u16(const float* src, uint16_t* dst, float multiplier, int64_t count, void* stream) {
+  RCFD_CHECK_ARG(src && dst && count > 0 && multiplier > 0.f, "encode_u16: bad args");
+  encode_u16_kernel<<<blocks_for(count), NT, 0, (cudaStream_t)stream>>>(src, dst, multiplier, count);
+  RCFD_CHECK_LAUNCH("encode_u16");
+  return RCFD_OK;
+}
 
 int rcfd_transform_batch(const float* image, float* image_out, const float* const* maps, float* const* maps_out,
                          const int32_t* map_channels, int32_t n_maps, const float* params, int32_t* scratch_max,

@@ -4,9 +4,9 @@ src/fusionnet_main.py:13-474).  What is accelerated is the step body (reference 
 forward, ground-truth outlier removal, masked L1 loss, backward, Adam -- all on librcfd_b200.so.
 
 Outside this round's scope and handled explicitly:
-  * dataset file I/O: batches come from ``rcfd.data.make_train_batches`` -- the reference's own
-    ``datasets.FusionNetTrainingDataset`` when its ``src`` directory is importable, or seeded synthetic
-    batches when ``train_image_path == 'synthetic'``;
+  * dataset files: ``rcfd.data.make_train_batches`` reads the reference's path lists / PNG files itself (Pillow for the
+    inflate), keeps the on-disk sample types (uint8 / uint16) across PCIe and decodes + crops on the device
+    (rcfd_decode_crop); ``train_image_path == 'synthetic'`` gives seeded synthetic batches;
   * augmentation: fusionnet_transforms.Transforms (the reference's draws and arithmetic, batched tensor expressions);
   * validation: ``validate`` (the reference's metrics and best-result rule) runs at checkpoints when a validation set
     is given (``val_image_path='synthetic'`` works too); TensorBoard summaries: skipped.
@@ -142,10 +142,14 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
         if -1 not in augmentation_schedule and epoch > augmentation_schedule[augmentation_schedule_pos]:
             augmentation_schedule_pos += 1
             augmentation_probability = augmentation_probabilities[augmentation_schedule_pos]
-        for image, input_depth, input_response, ground_truth, lidar_map in batches(epoch):
+        for batch in batches(epoch):
             train_step += 1
-            image, input_depth, input_response, ground_truth, lidar_map = [
-                t.to(device, non_blocking=True) for t in (image, input_depth, input_response, ground_truth, lidar_map)]
+            if getattr(batches, 'raw', False):
+                # on-disk sample types (uint8 image, uint16 maps) from pinned memory: value codec, layout and crop on the device
+                image, input_depth, input_response, ground_truth, lidar_map = rcfd_data.decode_fusionnet_batch(
+                    batch, device, shape=(n_height, n_width))
+            else:
+                image, input_depth, input_response, ground_truth, lidar_map = [t.to(device, non_blocking=True) for t in batch]
             if not synthetic or augmentation_probability > 0:
                 # the reference always goes through Transforms.transform ([0, 255] images in, normalised range out)
                 source = (image * 255.0).round() if synthetic else image

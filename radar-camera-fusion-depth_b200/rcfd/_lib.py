@@ -78,6 +78,8 @@ _SIGS = {
     'rcfd_cast_f32': [_P, _P, c_int64, c_int32, _P],
     'rcfd_linear_leaky_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_bce_logits_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],
+    'rcfd_decode_crop': [_P, c_int32, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int64, _P],
+    'rcfd_encode_u16': [_P, _P, c_float, c_int64, _P],
     'rcfd_conv2d_wgrad_workspace': [POINTER(ConvDesc)],
     'rcfd_set_option': [c_char_p, c_int32],
     'rcfd_plan_row_chunks': [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P],

@@ -522,3 +522,32 @@ def bce_logits_loss(logits, target, validity, pos_weight, want_grad=True):
     _lib.call('rcfd_bce_logits_loss', _p(logits.contiguous()), _p(target.contiguous()), _p(validity.contiguous()),
               float(pos_weight), _p(accum), _p(loss), _p(dl), logits.numel(), _stream())
     return loss, dl
+
+
+def decode_crop(src, multiplier, out_hw=None, crop_yx=None, out=None, out_channel=0):
+    """On-disk samples -> network input (include/rcfd.h rcfd_decode_crop).  src: uint8 [N, H, W, C] (image as decoded
+    from the file) or uint16 / int16-viewed [N, H, W] raster of a 16-bit PNG map; returns float32 [N, C, oh, ow] =
+    max(src / multiplier, 0) cropped at crop_yx ([N, 2] int32 (y0, x0) on the device) or at the origin.  With ``out``
+    ([N, C_total, oh, ow]) the result is written into channels [out_channel, out_channel + C) of it."""
+    if src.dtype == torch.uint8:
+        bits, (n, sh, sw, c) = 8, src.shape
+    elif src.dtype in (torch.uint16, torch.int16):
+        bits, (n, sh, sw), c = 16, src.shape, 1
+    else:
+        raise RuntimeError('decode_crop takes uint8 images or uint16 maps')
+    oh, ow = (sh, sw) if out_hw is None else out_hw
+    if out is None:
+        out = _empty((n, c, oh, ow), device=src.device, dtype=torch.float32)
+        out_channel = 0
+    assert out.shape[0] == n and out.shape[2:] == (oh, ow) and out_channel + c <= out.shape[1] and out.is_contiguous()
+    dst = ctypes.c_void_p(out.data_ptr() + 4 * out_channel * oh * ow)
+    _lib.call('rcfd_decode_crop', _p(src.contiguous()), bits, dst, _p(crop_yx), n, sh, sw, c, oh, ow, float(multiplier),
+              out.shape[1] * oh * ow, _stream())
+    return out
+
+
+def encode_u16(x, multiplier):
+    """float32 tensor -> uint16 samples of the reference's 16-bit PNG files: uint32(x * multiplier) & 0xffff."""
+    out = _empty(x.shape, device=x.device, dtype=torch.uint16)
+    _lib.call('rcfd_encode_u16', _p(x.contiguous().float()), _p(out), float(multiplier), x.numel(), _stream())
+    return out

@@ -446,6 +446,35 @@ def validate_case(name, seed):
     print(name, 'ok', first, second['step'])
 
 
+CROP_TYPES = (['none'], ['center'], ['left', 'top'], ['right', 'bottom'], ['horizontal'], ['horizontal', 'anchored'],
+              ['horizontal', 'vertical'], ['horizontal', 'vertical', 'anchored'], ['bottom', 'horizontal'])
+
+
+def crop_case(name):
+    """Crop origins chosen by the reference's own random_crop (src/datasets.py:19-109) for every crop type under seeded
+    numpy draws; rcfd.data.crop_origin must make the same decisions (checked here and in tests/test_host_logic.py)."""
+    saved = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'src'))
+    import datasets as ref_ds
+    sys.path[:] = saved
+    for m in ('datasets', 'data_utils'):
+        sys.modules.pop(m, None)
+    from rcfd import data as prod_data
+    oh, ow, nh, nw = 90, 160, 35, 70
+    index = np.arange(oh * ow, dtype=np.float32).reshape(1, oh, ow)
+    origins = np.zeros((len(CROP_TYPES), 8, 2), dtype=np.int32)
+    for ci, crop_type in enumerate(CROP_TYPES):
+        for seed in range(8):
+            np.random.seed(100 + seed)
+            [out] = ref_ds.random_crop([index], (nh, nw), crop_type)
+            y0, x0 = divmod(int(out[0, 0, 0]), ow)
+            origins[ci, seed] = (y0, x0)
+            got = prod_data.crop_origin(oh, ow, nh, nw, crop_type, rng=np.random.RandomState(100 + seed))
+            assert got == (y0, x0), (crop_type, seed, got, (y0, x0))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), origins=origins, meta=np.array([oh, ow, nh, nw]))
+    print(name, 'ok (crop_origin == reference random_crop for', len(CROP_TYPES), 'crop types x 8 seeds)')
+
+
 TINY_FUSIONNET = dict(synth.CANONICAL_FUSIONNET, n_filters_encoder_image=[8, 8, 16, 16, 16, 16],
                       n_filters_encoder_depth=[8, 8, 8, 8, 8, 8], n_filters_decoder=[16, 16, 16, 8, 8, 8])
 
@@ -518,6 +547,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'checkpoint':
         checkpoint_case('reference_checkpoint_tiny', 71)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'crop':
+        crop_case('crop_origins_90x160')
+        sys.exit(0)
     fusionnet_case('fusionnet_small_2x64x96', synth.SMALL_FUSIONNET, 2, 64, 96, 3, 'quasi_dense', True)
     fusionnet_case('fusionnet_canonical_1x64x128', synth.CANONICAL_FUSIONNET, 1, 64, 128, 0, 'sparse', False, train=False)
     fusionnet_case('fusionnet_canonical_2x96x160', synth.CANONICAL_FUSIONNET, 2, 96, 160, 1, 'quasi_dense', False)
@@ -533,4 +565,5 @@ if __name__ == '__main__':
     s1_case('s1_merge_64x96', 64, 96, 51)
     radarnet_loss_case('radarnet_loss_3x64x64', 61)
     checkpoint_case('reference_checkpoint_tiny', 71)
+    crop_case('crop_origins_90x160')
     print('golden fixtures written to', OUT)

@@ -56,3 +56,44 @@ def test_batched_transforms_kernel_matches_reference_fixture():
         for b in range(4):
             c = (m_in[b], m_in[b].flip(-1), m_in[b].flip(-2), m_in[b].flip(-1).flip(-2))[which[b]]
             assert torch.equal(m_out[b], c)
+
+
+def test_decode_crop_and_encode_kernels():
+    """rcfd_decode_crop / rcfd_encode_u16 vs the reference's value codec restated in numpy (load_image / load_depth /
+    load_response: raster / multiplier, <= 0 -> 0; save_*: uint32(v * multiplier) as 16 bits; src/data_utils.py:167-335)
+    and its crop (src/datasets.py:101-109), bit exact; depth and response land in the two channels of input_depth."""
+    from rcfd import data, ops
+    rng = np.random.RandomState(5)
+    n, h0, w0, oh, ow = 3, 37, 61, 24, 40
+    img = rng.randint(0, 256, (n, h0, w0, 3)).astype(np.uint8)
+    z = (rng.rand(n, h0, w0) * 65535 * (rng.rand(n, h0, w0) < 0.5)).astype(np.uint16)
+    r = (rng.rand(n, h0, w0) * 16384).astype(np.uint16)
+    origin = np.stack([rng.randint(0, h0 - oh + 1, n), rng.randint(0, w0 - ow + 1, n)], 1).astype(np.int32)
+    d_img, d_z, d_r = torch.from_numpy(img).to(DEV), torch.from_numpy(z.view(np.int16)).to(DEV), torch.from_numpy(r.view(np.int16)).to(DEV)
+    d_o = torch.from_numpy(origin).to(DEV)
+    crop = lambda a, i: a[i, origin[i, 0]:origin[i, 0] + oh, origin[i, 1]:origin[i, 1] + ow]
+    out = ops.decode_crop(d_img, 1.0, (oh, ow), d_o).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(out[i], np.transpose(crop(img, i).astype(np.float32), (2, 0, 1)))
+    both = torch.full((n, 2, oh, ow), -1.0, device=DEV)
+    ops.decode_crop(d_z, 256.0, (oh, ow), d_o, out=both, out_channel=0)
+    ops.decode_crop(d_r, 2.0 ** 14, (oh, ow), d_o, out=both, out_channel=1)
+    both = both.cpu().numpy()
+    for i in range(n):
+        ref_z = crop(z, i).astype(np.float32) / 256.0
+        ref_z[ref_z <= 0] = 0.0
+        assert np.array_equal(both[i, 0], ref_z) and np.array_equal(both[i, 1], crop(r, i).astype(np.float32) / 2 ** 14)
+    # no crop: whole rasters
+    assert np.array_equal(ops.decode_crop(d_z, 256.0).cpu().numpy()[:, 0], z.astype(np.float32) / 256.0)
+    # encode: save_depth / save_response quantisation, and the round trip through file precision
+    v = torch.rand(2, 1, 9, 13) * 300.0          # beyond 255.99: the 16-bit store wraps like the PNG does
+    enc = ops.encode_u16(v.to(DEV), 256.0).cpu().numpy()
+    assert np.array_equal(enc, (np.uint32(v.numpy() * np.float32(256.0)) & 0xffff).astype(np.uint16))
+    # the five tensors of a training batch from on-disk sample types == the float batch in file precision
+    image = (torch.rand(2, 3, 16, 24) * 255).round()
+    maps = [torch.rand(2, 1, 16, 24) * 80 * (torch.rand(2, 1, 16, 24) < 0.5) for _ in range(4)]
+    raw = data.encode_raw_batch(image, *maps)
+    dec = data.decode_fusionnet_batch([t.pin_memory() for t in raw], DEV)
+    assert torch.equal(dec[0].cpu(), image)
+    for got, want in zip(dec[1:], maps):
+        assert torch.equal(got.cpu(), torch.floor(want * 256.0) / 256.0)

@@ -428,3 +428,70 @@ def test_radarnet_compute_loss_matches_reference_fixture():
     for w, ref in zip((1.0, 2.0, 5.5), g['loss']):
         loss, info = m.compute_loss(logits, gt, valid, w_positive_class=w)
         assert abs(float(loss) - float(ref)) < 1e-6 * abs(float(ref)) and 'loss' in info
+
+
+def test_data_path_host_side(tmp_path):
+    """rcfd.data without the reference on sys.path: path lists, 16-bit PNG rasters (written here with Pillow the way the
+    reference's save_depth does, src/data_utils.py:271-286), the raw dataset's on-disk sample types, and crop_origin's
+    draws against the decisions of the reference's random_crop (src/datasets.py:19-109) replayed from the same seed."""
+    import numpy as np
+    from PIL import Image
+    from rcfd import data
+    rng = np.random.RandomState(3)
+    h0, w0 = 40, 70
+    files = {k: [] for k in ('image', 'depth', 'response', 'gt', 'lidar')}
+    truth = []
+    for i in range(3):
+        img = rng.randint(0, 256, (h0, w0, 3)).astype(np.uint8)
+        Image.fromarray(img).save(str(tmp_path / ('im%d.png' % i)))
+        files['image'].append(str(tmp_path / ('im%d.png' % i)))
+        maps = {}
+        for k in ('depth', 'response', 'gt', 'lidar'):
+            z = (rng.rand(h0, w0) * 80 * (rng.rand(h0, w0) < 0.4)).astype(np.float32)
+            Image.fromarray(np.uint32(z * 256.0), mode='I').save(str(tmp_path / ('%s%d.png' % (k, i))))     # save_depth
+            files[k].append(str(tmp_path / ('%s%d.png' % (k, i))))
+            maps[k] = z
+        truth.append((img, maps))
+    for k, v in files.items():
+        with open(str(tmp_path / (k + '.txt')), 'w') as f:
+            f.write('\n'.join(v) + '\n')
+    paths = {k: data.read_paths(str(tmp_path / (k + '.txt'))) for k in files}
+    assert paths['image'] == files['image'] and len(paths['gt']) == 3
+    z16 = data.load_png16(files['depth'][1])
+    assert z16.dtype == np.uint16 and np.array_equal(z16, np.uint32(truth[1][1]['depth'] * 256.0).astype(np.uint16))
+    # load_depth of the reference == raster / 256 with <= 0 -> 0
+    ref = np.array(Image.open(files['depth'][1]), dtype=np.float32) / 256.0
+    ref[ref <= 0] = 0.0
+    assert np.array_equal(z16.astype(np.float32) / 256.0, ref)
+    ds = data.FusionNetRawDataset(paths['image'], paths['depth'], paths['response'], paths['gt'], paths['lidar'],
+                                  shape=(24, 32), random_crop_type=['horizontal', 'vertical'])
+    np.random.seed(11)
+    sample = ds[2]
+    assert sample[0].dtype == torch.uint8 and tuple(sample[0].shape) == (24, 32, 3)
+    assert sample[1].dtype == torch.int16 and tuple(sample[1].shape) == (24, 32) and tuple(sample[5]) == (0, 0)
+    np.random.seed(11)
+    y0, x0 = data.crop_origin(h0, w0, 24, 32, ['horizontal', 'vertical'])
+    assert np.array_equal(sample[0].numpy(), truth[2][0][y0:y0 + 24, x0:x0 + 32])
+    full = data.FusionNetRawDataset(paths['image'], paths['depth'], paths['response'], paths['gt'], paths['lidar'],
+                                    shape=(24, 32), random_crop_type=['horizontal', 'vertical'], crop_on_host=False)
+    np.random.seed(11)
+    s2 = full[2]
+    assert tuple(s2[0].shape) == (h0, w0, 3) and tuple(int(v) for v in s2[5]) == (y0, x0)
+    # crop decisions: origins chosen by the reference's own random_crop (tests/golden/crop_origins_90x160.npz, written by
+    # make_golden.py crop_case from src/datasets.py:19-109) for every crop type under the same seeded draws
+    from helpers import load_golden
+    g = load_golden('crop_origins_90x160')
+    oh, ow, nh, nw = [int(v) for v in g['meta']]
+    crop_types = (['none'], ['center'], ['left', 'top'], ['right', 'bottom'], ['horizontal'], ['horizontal', 'anchored'],
+                  ['horizontal', 'vertical'], ['horizontal', 'vertical', 'anchored'], ['bottom', 'horizontal'])
+    for ci, crop_type in enumerate(crop_types):
+        for seed in range(8):
+            got = data.crop_origin(oh, ow, nh, nw, crop_type, rng=np.random.RandomState(100 + seed))
+            assert got == tuple(int(v) for v in g['origins'][ci, seed]), (crop_type, seed)
+    # synthetic batch -> file precision -> back (what bench.py's end-to-end leg ships over PCIe)
+    image = (torch.rand(2, 3, 8, 12) * 255).round()
+    maps = [torch.rand(2, 1, 8, 12) * 80 * (torch.rand(2, 1, 8, 12) < 0.5) for _ in range(4)]
+    raw = data.encode_raw_batch(image, *maps)
+    assert raw[0].dtype == torch.uint8 and tuple(raw[0].shape) == (2, 8, 12, 3) and raw[1].dtype == torch.int16
+    back = raw[1].view(torch.uint16).to(torch.int32).float() / 256.0
+    assert float((back - maps[0][:, 0]).abs().max()) <= 1.0 / 256.0

@@ -112,6 +112,33 @@ int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int
                            int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t accumulate,
                            void* stream);
 
+/* All weight (un)packing of one training step in ONE launch each.  The reference keeps its parameters
+ * OIHW float (state_dict layout, src/net_utils.py:63-69) and so does this library; the kernels want the
+ * packed layouts above, so a step used to issue ~150 pack and ~75 unpack launches.  `items` is a DEVICE
+ * array of n descriptors sorted by block0 (block b serves the item with block0 <= b < block0 + nblocks,
+ * RCFD_PACK_BLOCK_ELEMS destination elements per block); total_blocks = sum of nblocks.
+ *   RCFD_PACK_FWD      = rcfd_pack_conv_weight mode 0       RCFD_PACK_UP2X = rcfd_pack_upconv2x_weight
+ *   RCFD_PACK_DGRAD    = rcfd_pack_conv_weight mode 1, written at column col_off of rows dst_cols wide
+ *                        (the stacked 1x1 fusion weights share one destination; padding columns are
+ *                        never written: zero the destination once)
+ *   RCFD_PACK_STEM_S2D = rcfd_pack_stem_s2d_weight (cin = c, cpad = cpad)
+ *   RCFD_UNPACK_CONV / RCFD_UNPACK_STEM_S2D = rcfd_unpack_conv_wgrad (overwrite) / rcfd_unpack_stem_s2d_wgrad;
+ *                        src = packed float gradient, dst = OIHW float gradient. */
+#define RCFD_PACK_BLOCK_ELEMS 2048
+enum { RCFD_PACK_FWD = 0, RCFD_PACK_DGRAD = 1, RCFD_PACK_UP2X = 2, RCFD_PACK_STEM_S2D = 3,
+       RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5 };
+typedef struct rcfd_pack_item {
+  const float* src;
+  void* dst;
+  int64_t total;                      /* destination elements of this item */
+  int32_t kind, dtype;                /* dtype of dst for the pack kinds (unpack: float) */
+  int32_t cout, cin, taps;
+  int32_t cin_off, cin_cnt, cpad;
+  int32_t col_off, dst_cols;
+  int32_t block0, nblocks;
+} rcfd_pack_item;
+int rcfd_pack_batch(const rcfd_pack_item* items, int32_t n, int32_t total_blocks, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * BatchNorm2d, training mode (src/net_utils.py:82,86; torch.nn.BatchNorm2d eps 1e-5,
  * momentum 0.1).  finalize: batch mean / biased var from the conv epilogue's sums ->

@@ -41,6 +41,7 @@ _SIGS = {
     'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_pack_upconv2x_weight': [_P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_pack_batch': [_P, c_int32, c_int32, _P],
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
     'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],
     'rcfd_bn_act_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],

@@ -69,6 +69,7 @@ class Tape(object):
         self.param_grads = []        # (parameter, grad tensor float32 in the parameter's layout)
         self.streams = streams       # None = single stream
         self.sid = MAIN              # role being recorded (forward) / replayed (backward)
+        self.finalizers = []         # run on the caller's stream once the backward streams have joined
 
     def add_step(self, fn):
         self.steps.append((fn, self.sid))
@@ -141,6 +142,9 @@ class Tape(object):
                 self.sid = MAIN
                 for s in self.streams[1:]:
                     main.wait_stream(s)
+                for fn in self.finalizers:
+                    fn()
+        self.finalizers = []
         self.steps = []
         self.grads = {}
         self.keep = []
@@ -173,6 +177,16 @@ class Context(object):
         self.taps = None
         self.prepacked = {}
         self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (self.streams is not None and training) else None
+        # batched weight (un)packing (training, multi-stream, plain dtypes): ONE rcfd_pack_batch launch per step packs every
+        # weight the step uses into persistent buffers, another one unpacks every weight gradient at the end of backward
+        self.unpack = None
+        if self.plan is not None and not self.x3 and self.tape is not None:
+            self.unpack = self.cache.setdefault(('unpack_state', dtype), {'bufs': {}, 'items': {}, 'batch': None, 'dirty': False})
+            _validate_unpack(self.unpack)
+            self.tape.finalizers.append(lambda: _finish_unpack(self.unpack, self.device))
+            # the pack table of the NEXT step is built here, at the end of the step that recorded the plan (eagerly: a
+            # capture that follows, FusionNetModel.train_step_graphed, then already replays the batched form)
+            self.tape.finalizers.append(lambda: _pack_batch_for(self.cache, self.plan, self.dtype, self.device))
         if self.streams is not None and training:
             self.stats(0)            # the zeroed statistics pool must exist before the streams fork
 
@@ -224,9 +238,12 @@ class Context(object):
     #    Training under the multi-stream schedule: the first step records every pack call (key -> closure) in
     #    the model's pack plan; later steps replay the plan up front on the PACK stream (prepack), so the ~150
     #    tiny pack kernels leave the critical chains and each consumer just waits for its event.
-    def packed(self, key, params, fn):
+    def packed(self, key, params, fn, spec=None):
+        """spec: callable returning the ops.spec_pack_* description of what fn does (lets the step's packs run as one
+        batched launch, see prepack)."""
         if self.x3 and not key[0].startswith('bn'):
             fn = _split_after(fn, self.x3)       # pack in fp32 (self.dtype), then split the packed tensor into bf16 parts
+            spec = None
         if self.training:
             hit = self.prepacked.pop(key, None)
             if hit is not None:
@@ -234,7 +251,7 @@ class Context(object):
                 torch.cuda.current_stream().wait_event(ev)
                 return val
             if self.plan is not None:
-                self.plan[key] = fn
+                self.plan[key] = (fn, spec)
             return fn()
         ver = tuple(p._version for p in params) + (self.dtype, self.x3, _PARAM_EPOCH[0])
         hit = self.cache.get(key)
@@ -251,7 +268,16 @@ class Context(object):
         pk, main = self.streams[PACK], self.streams[MAIN]
         pk.wait_stream(main)
         with torch.cuda.stream(pk):
-            for key, fn in self.plan.items():
+            batch = _pack_batch_for(self.cache, self.plan, self.dtype, self.device)
+            if batch is not None:
+                batch['table'].run()
+                ev = torch.cuda.Event()
+                ev.record(pk)
+                for key, out in batch['outputs'].items():
+                    self.prepacked[key] = (out, ev)
+            for key, (fn, spec) in self.plan.items():
+                if batch is not None and key in batch['outputs']:
+                    continue
                 val = fn()
                 ev = torch.cuda.Event()
                 ev.record(pk)
@@ -260,23 +286,28 @@ class Context(object):
     def weight(self, mod, pad_to=None):
         """Packed [cout][taps][cin_pad] weights; pad_to = channel count of the (zero-padded) input."""
         w, dtype = mod.conv.weight, self.dtype          # the closures outlive this context (pack plan): no self in them
-        return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), dtype, pad_to=pad_to))
+        return self.packed(('w', id(mod), pad_to), [w], lambda: ops.pack_weight(w.detach(), dtype, pad_to=pad_to),
+                           spec=lambda: ops.spec_pack_weight(w.detach(), dtype, pad_to=pad_to))
 
     def weight_stem_s2d(self, mod):
         """7x7/s2 stem weights rearranged for the space-to-depth (4x4/s1) formulation."""
         w, dtype = mod.conv.weight, self.dtype
-        return self.packed(('ws2d', id(mod)), [w], lambda: ops.pack_stem_s2d_weight(w.detach(), dtype, CPAD))
+        return self.packed(('ws2d', id(mod)), [w], lambda: ops.pack_stem_s2d_weight(w.detach(), dtype, CPAD),
+                           spec=lambda: ops.spec_pack_stem_s2d_weight(w.detach(), dtype, CPAD))
 
     def weight_up2x(self, mod):
         """Sub-pixel phase weights for a 3x3 conv behind an exact 2x nearest up-sampling (bf16 fast path)."""
         w, dtype = mod.conv.weight, self.dtype
-        return self.packed(('wup', id(mod)), [w], lambda: ops.pack_upconv2x_weight(w.detach(), dtype))
+        return self.packed(('wup', id(mod)), [w], lambda: ops.pack_upconv2x_weight(w.detach(), dtype),
+                           spec=lambda: ops.spec_pack_upconv2x_weight(w.detach(), dtype))
 
     def weight_dgrad(self, mod, off, cnt, pad_to):
         """Packed [cin_cnt][taps][cout_pad] weights of the data-gradient convolution (one concat source)."""
         w, dtype = mod.conv.weight, self.dtype
         return self.packed(('wd', id(mod), off, cnt, pad_to), [w],
-                           lambda: ops.pack_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, dgrad=True, pad_to=pad_to))
+                           lambda: ops.pack_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, dgrad=True, pad_to=pad_to),
+                           spec=lambda: ops.spec_pack_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, dgrad=True,
+                                                             pad_to=pad_to))
 
     def folded_bn(self, mod):
         bn = mod.batch_norm
@@ -293,6 +324,82 @@ class Context(object):
 
 def _split_after(fn, parts):
     return lambda: ops.split_bf16(fn(), parts)
+
+
+def _pack_batch_for(cache, plan, dtype, device):
+    """The batched form of a pack plan: persistent destination tensors + one device table (rcfd_pack_batch), built once
+    per model / dtype outside graph capture and reused while the plan and the parameters' storage stay the same."""
+    key = ('pack_batch', dtype)
+    batch = cache.get(key)
+    if batch is not None and (batch['n_plan'] != len(plan) or any(t.data_ptr() != ptr for t, ptr in batch['srcs'])):
+        batch = None                     # the plan grew, or a parameter moved (model.to(), a new state_dict storage)
+    if batch is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                  # table upload and allocations belong outside a capture: per-item path this time
+        table, outputs, srcs = ops.PackBatch(), {}, []
+        for k, (fn, spec) in plan.items():
+            if spec is None:
+                continue
+            shape, dt_, zero, items = spec()
+            out = (torch.zeros if zero else torch.empty)(shape, device=device, dtype=dt_)
+            for it in items:
+                it = dict(it)
+                src = it.pop('src')
+                table.add(it.pop('kind'), src, out, **it)
+                srcs.append((src, src.data_ptr()))
+            outputs[k] = out
+        if not outputs:
+            return None
+        batch = {'table': table.finalize(device), 'outputs': outputs, 'srcs': srcs, 'n_plan': len(plan)}
+        cache[key] = batch
+    return batch
+
+
+def _validate_unpack(st):
+    """Drop the batched-unpack table when a gradient destination moved (new optimiser / flat buffer)."""
+    if st['batch'] is not None and any(p.grad is None or p.grad.data_ptr() != ptr for p, ptr in st['batch']['checks']):
+        st['batch'] = None
+        st['items'].clear()
+        st['bufs'].clear()
+
+
+def _wgrad_slot(ctx, key, shape, param, gw):
+    """Persistent packed-gradient buffer for the batched unpack, or None when this gradient takes the per-layer path
+    (no flat destination, parity modes).  Returns (buffer, deferred): deferred = the step's batch unpacks it."""
+    st = ctx.unpack
+    if st is None or gw is not param.grad or not getattr(param, '_rcfd_flat', False):
+        return None, False
+    buf = st['bufs'].get(key)
+    if buf is None or tuple(buf.shape) != tuple(shape):
+        buf = torch.empty(shape, device=ctx.device, dtype=torch.float32)
+        st['bufs'][key] = buf
+        st['dirty'] = True
+    batch = st['batch']
+    return buf, batch is not None and key in batch['keys']
+
+
+def _finish_unpack(st, device):
+    """End of backward (streams joined): the one batched unpack; (re)build the table after a recording step."""
+    if st['batch'] is not None:
+        st['batch']['table'].run()
+    if st['dirty'] and not torch.cuda.is_current_stream_capturing():
+        table, checks = ops.PackBatch(), []
+        for key, items in st['items'].items():
+            for kind, src, src_off, dst, param, f in items:
+                table.add(kind, src, dst, src_off=src_off, **f)
+                checks.append((param, dst.data_ptr()))
+        st['batch'] = {'table': table.finalize(device), 'keys': set(st['items']), 'checks': checks} if checks else None
+        st['dirty'] = False
+
+
+def _unpack_conv(ctx, key, dw, gw, param, src_off=0, rows=None):
+    """Register (first time) the unpack of packed gradient ``dw`` (persistent) into ``gw`` for the batch."""
+    st = ctx.unpack
+    cout, cin, kh, kw = gw.shape
+    cpad = dw.shape[2]
+    f = dict(total=cout * min(cpad, cin) * kh * kw, cout=cout, cin=cin, taps=kh * kw, cin_off=0, cin_cnt=min(cpad, cin),
+             cpad=cpad)
+    st['items'].setdefault(key, []).append((ops.UNPACK_CONV, dw, src_off, gw, param, f))
 
 
 class _Role(object):
@@ -400,8 +507,15 @@ def _stem_s2d_unit(ctx, mod, x, act):
             gw = _grad_dst(mod.conv.weight)
 
             def wgrad():
-                dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine, x3=ctx.x3)      # [cout][16][CPAD]
-                ops.unpack_stem_s2d_wgrad(dw, gw)
+                ukey = ('dws2d', id(mod))
+                buf, deferred = _wgrad_slot(ctx, ukey, (cout, 16, x.shape[3]), mod.conv.weight, gw)
+                dw = ops.conv2d_wgrad(x, dy, 4, 1, pad=2, engine=ctx.engine, x3=ctx.x3, out=buf)      # [cout][16][CPAD]
+                if not deferred:
+                    ops.unpack_stem_s2d_wgrad(dw, gw)
+                    if buf is not None and ukey not in ctx.unpack['items']:
+                        c = gw.shape[1]
+                        ctx.unpack['items'][ukey] = [(ops.UNPACK_STEM_S2D, dw, 0, gw, mod.conv.weight,
+                                                      dict(total=cout * c * 49, cout=cout, cin=c, taps=16, cpad=dw.shape[2]))]
             tape.side(wgrad)
             tape.param_grads.append((mod.conv.weight, gw))
         tape.add_step(bwd)
@@ -444,8 +558,14 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         gw = _grad_dst(w_param)
 
         def wgrad():
-            dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine, x3=ctx.x3)
-            ops.unpack_wgrad(dw, gw)
+            ukey = ('dw', id(mod))
+            cin_tot = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
+            buf, deferred = _wgrad_slot(ctx, ukey, (dy.shape[3], k * k, cin_tot), w_param, gw)   # d(logit) rows are padded
+            dw = ops.conv2d_wgrad(x0, dy, k, stride, x1=x1, in_size=in_size, engine=ctx.engine, x3=ctx.x3, out=buf)
+            if not deferred:
+                ops.unpack_wgrad(dw, gw)
+                if buf is not None and ukey not in ctx.unpack['items']:
+                    _unpack_conv(ctx, ukey, dw, gw, w_param)
         tape.side(wgrad)
         tape.param_grads.append((w_param, gw))
         if not want_input_grad:
@@ -469,7 +589,8 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
     ww, wp = mod_w.conv.weight, mod_p.conv.weight
     dtype = ctx.dtype
     wcat = ctx.packed(('wcat', id(mod_w)), [ww, wp],
-                      lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype))
+                      lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype),
+                      spec=lambda: ops.spec_pack_stacked_1x1([ww.detach(), wp.detach()], dtype))
     bw, bp = mod_w.batch_norm, mod_p.batch_norm
     if not ctx.training:
         def make():
@@ -508,13 +629,21 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
             for bn, lo in ((bw, 0), (bp, c)):
                 tape.param_grads.append((bn.weight, dg[lo:lo + c]))
                 tape.param_grads.append((bn.bias, db[lo:lo + c]))
-            dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine, x3=ctx.x3)              # [2c, 1, cd]
-            for wparam, lo in ((ww, 0), (wp, c)):
-                g = _grad_dst(wparam)
-                ops.unpack_wgrad(dw[lo:lo + c], g)
+            ukey = ('dwcat', id(mod_w))
+            gs = [_grad_dst(ww), _grad_dst(wp)]
+            buf, deferred = _wgrad_slot(ctx, ukey, (2 * c, 1, dep.shape[3]), ww, gs[0])
+            if buf is not None and (gs[1] is not wp.grad or not getattr(wp, '_rcfd_flat', False)):
+                buf, deferred = None, False
+            dw = ops.conv2d_wgrad(dep, dy, 1, 1, engine=ctx.engine, x3=ctx.x3, out=buf)              # [2c, 1, cd]
+            for (wparam, lo), g in zip(((ww, 0), (wp, c)), gs):
+                if not deferred:
+                    ops.unpack_wgrad(dw[lo:lo + c], g)
+                    if buf is not None and len(ctx.unpack['items'].get(ukey, ())) < 2:
+                        _unpack_conv(ctx, ukey, dw, g, wparam, src_off=lo * dw.shape[2])
                 tape.param_grads.append((wparam, g))
             wd = ctx.packed(('wcatd', id(mod_w)), [ww, wp],
-                            lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype, dgrad=True))
+                            lambda: ops.pack_weight(torch.cat([ww.detach(), wp.detach()], 0), dtype, dgrad=True),
+                            spec=lambda: ops.spec_pack_stacked_1x1([ww.detach(), wp.detach()], dtype, dgrad=True))
             tape.add_grad(dep, ops.conv2d(dy, wd, dep.shape[3], 1, 1, engine=ctx.engine))
         tape.add_step(bwd)
     return out

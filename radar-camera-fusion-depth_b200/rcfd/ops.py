@@ -161,10 +161,12 @@ def conv2d(x0, weight_packed, cout, k, stride=1, x1=None, in_size=None, scale=No
     return out
 
 
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0):
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0, out=None):
     """Packed float weight gradient [cout][k*k][c0+c1] of the convolution above.  x3 = 2 | 3: tensor-core parity
-    mode (fp32 operands split into that many bf16 parts; 3 / 6 bf16 passes summed in fp32, rcfd/x3.py)."""
+    mode (fp32 operands split into that many bf16 parts; 3 / 6 bf16 passes summed in fp32, rcfd/x3.py).
+    out: destination to overwrite (the persistent buffers of the batched unpack)."""
     if x3:
+        assert out is None
         from . import x3 as x3mod
         return x3mod.wgrad_x3(sys.modules[__name__], int(x3), x0, dy, k, stride, x1, in_size, pad, engine)
     for t in (x0, x1, dy):
@@ -181,7 +183,8 @@ def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=EN
     d.hin, d.win = hin, win
     d.src0, d.h0, d.w0, d.c0 = x0.data_ptr(), h0, w0, c0
     d.src1, d.c1 = (x1.data_ptr() if x1 is not None else None), c1
-    dw = _empty((cout, k * k, c0 + c1), device=x0.device, dtype=torch.float32)
+    dw = _empty((cout, k * k, c0 + c1), device=x0.device, dtype=torch.float32) if out is None else out
+    assert dw.shape == (cout, k * k, c0 + c1) and dw.dtype == torch.float32 and dw.is_contiguous()
     d.weight = dw.data_ptr()       # unused by wgrad, must be non-null
     d.dst = dy.data_ptr()
     d.dtype = dt(x0)
@@ -223,6 +226,96 @@ def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None
     cin_cnt = min(cin_pad, cin - cin_off) if cin_cnt is None else cin_cnt
     _lib.call('rcfd_unpack_conv_wgrad', _p(dw_packed), _p(grad_oihw), cout, cin, kh, kw, cin_off, cin_cnt, cin_pad,
               1 if accumulate else 0, _stream())
+
+
+# ---------------------------------------------------------------------------------- batched (un)packing
+PACK_FWD, PACK_DGRAD, PACK_UP2X, PACK_STEM_S2D, UNPACK_CONV, UNPACK_STEM_S2D = 0, 1, 2, 3, 4, 5
+PACK_BLOCK_ELEMS = 2048
+
+
+def spec_pack_weight(w, dtype, cin_off=0, cin_cnt=None, dgrad=False, pad_to=None):
+    """What pack_weight(w, ...) would do, as data: (shape, dtype, needs_zero_init, [item fields]) for PackBatch."""
+    cout, cin, kh, kw = w.shape
+    taps = kh * kw
+    cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
+    inner = cout if dgrad else cin_cnt
+    pad = inner if pad_to is None else max(inner, int(pad_to))
+    if dgrad:
+        item = dict(kind=PACK_DGRAD, src=w, off=0, total=cin_cnt * taps * cout, cout=cout, cin=cin, taps=taps,
+                    cin_off=cin_off, cin_cnt=cin_cnt, cpad=pad, col_off=0, dst_cols=pad)
+        return (cin_cnt, taps, pad), dtype, pad > cout, [item]
+    item = dict(kind=PACK_FWD, src=w, off=0, total=cout * taps * pad, cout=cout, cin=cin, taps=taps, cin_off=cin_off,
+                cin_cnt=cin_cnt, cpad=pad)
+    return (cout, taps, pad), dtype, False, [item]
+
+
+def spec_pack_stacked_1x1(ws, dtype, dgrad=False):
+    """pack_weight(torch.cat(ws, 0), dtype, dgrad=dgrad) for 1x1 weights without the cat: one item per weight."""
+    cin = ws[0].shape[1]
+    ctot = sum(w.shape[0] for w in ws)
+    items, row = [], 0
+    for w in ws:
+        c = w.shape[0]
+        assert w.shape[1] == cin and w.shape[2] == 1 and w.shape[3] == 1
+        if dgrad:
+            items.append(dict(kind=PACK_DGRAD, src=w, off=0, total=cin * c, cout=c, cin=cin, taps=1, cin_off=0,
+                              cin_cnt=cin, cpad=ctot, col_off=row, dst_cols=ctot))
+        else:
+            items.append(dict(kind=PACK_FWD, src=w, off=row * cin, total=c * cin, cout=c, cin=cin, taps=1, cin_off=0,
+                              cin_cnt=cin, cpad=cin))
+        row += c
+    return ((cin, 1, ctot) if dgrad else (ctot, 1, cin)), dtype, False, items
+
+
+def spec_pack_upconv2x_weight(w, dtype):
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    return (4, cout, 4, cin), dtype, False, [dict(kind=PACK_UP2X, src=w, off=0, total=16 * cout * cin, cout=cout, cin=cin,
+                                                  taps=9)]
+
+
+def spec_pack_stem_s2d_weight(w, dtype, cpad=16):
+    cout, c, kh, kw = w.shape
+    assert kh == 7 and kw == 7 and 4 * c <= cpad
+    return (cout, 16, cpad), dtype, False, [dict(kind=PACK_STEM_S2D, src=w, off=0, total=cout * 16 * cpad, cout=cout,
+                                                 cin=c, taps=16, cpad=cpad)]
+
+
+class PackBatch(object):
+    """Device table of rcfd_pack_item for rcfd_pack_batch (include/rcfd.h): ONE launch packs every weight of a training
+    step, another one unpacks every weight gradient.  add() takes the fields of one item; src / dst are tensors (kept
+    alive here), off = element offset into dst."""
+
+    def __init__(self):
+        self.rows = []
+        self.keep = []
+        self.table = None
+        self.total_blocks = 0
+
+    def add(self, kind, src, dst, off=0, total=0, cout=0, cin=0, taps=0, cin_off=0, cin_cnt=0, cpad=0, col_off=0,
+            dst_cols=0, src_off=0):
+        assert self.table is None and total > 0
+        for t in (src, dst):
+            _p(t)
+        nblocks = (total + PACK_BLOCK_ELEMS - 1) // PACK_BLOCK_ELEMS
+        self.rows.append((src.data_ptr() + src_off * src.element_size(), dst.data_ptr() + off * dst.element_size(), total,
+                          kind, _DT[dst.dtype], cout, cin, taps, cin_off, cin_cnt, cpad, col_off, dst_cols,
+                          self.total_blocks, nblocks))
+        self.total_blocks += nblocks
+        self.keep += [src, dst]
+
+    def finalize(self, device):
+        import numpy as np
+        rec = np.dtype([('src', '<u8'), ('dst', '<u8'), ('total', '<i8')] +
+                       [(n, '<i4') for n in ('kind', 'dtype', 'cout', 'cin', 'taps', 'cin_off', 'cin_cnt', 'cpad', 'col_off',
+                                             'dst_cols', 'block0', 'nblocks')])
+        assert rec.itemsize == 72           # sizeof(rcfd_pack_item)
+        arr = np.array(self.rows, dtype=rec)
+        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        return self
+
+    def run(self):
+        _lib.call('rcfd_pack_batch', _p(self.table), len(self.rows), self.total_blocks, _stream())
 
 
 def bn_finalize(ssum, ssq, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, count):

@@ -118,7 +118,8 @@ def epilogue_f32(y, scale, shift, act, act_params=(0.0, 0.0), residual=None, out
     return v
 
 
-def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0):
+def conv2d_wgrad(x0, dy, k, stride=1, x1=None, in_size=None, pad=None, engine=ENGINE_AUTO, x3=0, out=None):
+    assert out is None          # persistent buffers belong to the multi-stream (CUDA) schedule
     if x3:
         from rcfd import x3 as x3mod
         return x3mod.wgrad_x3(sys.modules[__name__], int(x3), x0, dy, k, stride, x1, in_size, pad, engine)

@@ -115,7 +115,8 @@ int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int
 /* All weight (un)packing of one training step in ONE launch each.  The reference keeps its parameters
  * OIHW float (state_dict layout, src/net_utils.py:63-69) and so does this library; the kernels want the
  * packed layouts above, so a step used to issue ~150 pack and ~75 unpack launches.  `items` is a DEVICE
- * array of n descriptors sorted by block0 (block b serves the item with block0 <= b < block0 + nblocks,
+ * array of n descriptors sorted by block0 (block b serves the item with block0 <= b < block0 + nblocks);
+ * nblocks of an item = rcfd_pack_item_blocks(item) (host helper: one block per staged K-row / tile, or
  * RCFD_PACK_BLOCK_ELEMS destination elements per block); total_blocks = sum of nblocks.
  *   RCFD_PACK_FWD      = rcfd_pack_conv_weight mode 0       RCFD_PACK_UP2X = rcfd_pack_upconv2x_weight
  *   RCFD_PACK_DGRAD    = rcfd_pack_conv_weight mode 1, written at column col_off of rows dst_cols wide
@@ -126,7 +127,7 @@ int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int
  *                        src = packed float gradient, dst = OIHW float gradient. */
 #define RCFD_PACK_BLOCK_ELEMS 2048
 enum { RCFD_PACK_FWD = 0, RCFD_PACK_DGRAD = 1, RCFD_PACK_UP2X = 2, RCFD_PACK_STEM_S2D = 3,
-       RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5 };
+       RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5, RCFD_COPY_F32 = 6 /* dst[i] = src[i], float */ };
 typedef struct rcfd_pack_item {
   const float* src;
   void* dst;
@@ -137,7 +138,10 @@ typedef struct rcfd_pack_item {
   int32_t col_off, dst_cols;
   int32_t block0, nblocks;
 } rcfd_pack_item;
-int rcfd_pack_batch(const rcfd_pack_item* items, int32_t n, int32_t total_blocks, void* stream);
+int32_t rcfd_pack_item_blocks(const rcfd_pack_item* item);      /* host only; 0 = invalid item */
+/* block_item: optional DEVICE array [total_blocks] = index of the item each block serves (saves the per-block search) */
+int rcfd_pack_batch(const rcfd_pack_item* items, const int32_t* block_item, int32_t n, int32_t total_blocks,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------
  * BatchNorm2d, training mode (src/net_utils.py:82,86; torch.nn.BatchNorm2d eps 1e-5,
@@ -169,6 +173,11 @@ int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum,
 int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, const float* shift,
                            const float* mean, const float* invstd, double* sums, int64_t pixels,
                            int32_t channels, int32_t act, int32_t dtype, void* stream);
+/* The same without zeroing `sums` first (the caller hands out slices of one pool zeroed once per step: ~60 memset
+ * nodes less on the backward chains of a training step). */
+int rcfd_bn_act_bwd_reduce_acc(const void* dz, const void* y, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, double* sums, int64_t pixels,
+                               int32_t channels, int32_t act, int32_t dtype, void* stream);
 int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, const float* shift,
                           const float* mean, const float* invstd, const double* sums, void* dy,
                           float* dgamma, float* dbeta, int64_t pixels, int32_t channels, int32_t act,

@@ -1149,13 +1149,15 @@ int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum,
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, const float* shift,
-                           const float* mean, const float* invstd, double* sums, int64_t pixels,
-                           int32_t channels, int32_t act, int32_t dtype, void* stream) {
+static int bn_bwd_reduce_impl(const void* dz, const void* y, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, double* sums, int64_t pixels,
+                              int32_t channels, int32_t act, int32_t dtype, void* stream, bool zero_first) {
   RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && sums, "bn_bwd_reduce: null");
   RCFD_CHECK_ARG(channels % 4 == 0 && channels <= 1024 && channels > 0 && pixels > 0, "bn_bwd_reduce: channels");
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, (cudaStream_t)stream);
-  if (e != cudaSuccess) { set_error("bn_bwd_reduce memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("bn_bwd_reduce memset: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+  }
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   const bool wide = channels % vw == 0;
   const int CVP = next_pow2(channels / (wide ? vw : 4));
@@ -1174,6 +1176,18 @@ int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, co
   }
   RCFD_CHECK_LAUNCH("bn_bwd_reduce");
   return RCFD_OK;
+}
+
+int rcfd_bn_act_bwd_reduce(const void* dz, const void* y, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, double* sums, int64_t pixels,
+                           int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  return bn_bwd_reduce_impl(dz, y, scale, shift, mean, invstd, sums, pixels, channels, act, dtype, stream, true);
+}
+
+int rcfd_bn_act_bwd_reduce_acc(const void* dz, const void* y, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, double* sums, int64_t pixels,
+                               int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  return bn_bwd_reduce_impl(dz, y, scale, shift, mean, invstd, sums, pixels, channels, act, dtype, stream, false);
 }
 
 int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, const float* shift,

@@ -121,7 +121,8 @@ class FusionNetModel(object):
         # rcfd.ops refuses non-CUDA tensors: there is no CPU fallback behind this call
         with ops.hold_allocations():
             ectx = engine.Context(self.compute_dtype, self.encoder.training, image.device, cache=self._cache,
-                                  record=record, engine=self.conv_engine, multistream=self.multistream, x3=self.x3)
+                                  record=record, engine=self.conv_engine, multistream=self.multistream, x3=self.x3,
+                                  external_pack=getattr(self, '_external_pack', False))
             ectx.taps = taps
             # the layout conversion of each input is issued on its branch's stream
             latent, skips = engine.fusionnet_encoder(ectx, self.encoder, lambda: engine.stem_input(ectx, image),
@@ -271,12 +272,22 @@ class FusionNetModel(object):
                 for b, s in zip(buffers, saved):
                     b.copy_(s)
                 from rcfd import _lib
+                # the eager pass recorded the step's weight packs and built their batched form (rcfd_pack_batch): that one
+                # launch stays OUTSIDE the graph, issued right after every optimiser step, where it overlaps the launch
+                # latency of the next replay instead of delaying the first convolutions
+                pack = self._cache.get(('pack_batch', self.compute_dtype)) if self.multistream and not self.x3 else None
+                if pack is not None:
+                    pack['table'].run()
                 l0 = _lib.launch_count
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    loss, grads = body()
-                self.last_capture_launches = _lib.launch_count - l0 + 1      # + the eager Adam launch
-            entry = {'graph': graph, 'static': static, 'loss': loss, 'grads': grads}
+                self._external_pack = pack is not None
+                try:
+                    with torch.cuda.graph(graph):
+                        loss, grads = body()
+                finally:
+                    self._external_pack = False
+                self.last_capture_launches = _lib.launch_count - l0 + 1 + (1 if pack is not None else 0)      # + Adam (+ pack)
+            entry = {'graph': graph, 'static': static, 'loss': loss, 'grads': grads, 'pack': pack}
             self._train_graphs[key] = entry
         graph, static, loss, grads = entry['graph'], entry['static'], entry['loss'], entry['grads']
         self._feed(entry, static, (image, input_depth, ground_truth, lidar_map))
@@ -284,6 +295,8 @@ class FusionNetModel(object):
         if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
             self.grad_hook(grads)
         optimizer.step()
+        if entry.get('pack') is not None:
+            entry['pack']['table'].run()            # next step's packed weights (the graph reads the persistent buffers)
         return loss
 
     def _deliver_grads(self, param_grads, hook=True):

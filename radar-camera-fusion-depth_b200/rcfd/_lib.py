@@ -33,6 +33,13 @@ class ConvDesc(Structure):
     ]
 
 
+class PackItem(Structure):
+    """rcfd_pack_item (include/rcfd.h)."""
+    _fields_ = [('src', c_void_p), ('dst', c_void_p), ('total', c_int64), ('kind', c_int32), ('dtype', c_int32),
+                ('cout', c_int32), ('cin', c_int32), ('taps', c_int32), ('cin_off', c_int32), ('cin_cnt', c_int32),
+                ('cpad', c_int32), ('col_off', c_int32), ('dst_cols', c_int32), ('block0', c_int32), ('nblocks', c_int32)]
+
+
 # name -> argtypes (all return int32 status unless listed in _RESTYPE)
 _P = c_void_p
 _SIGS = {
@@ -41,12 +48,14 @@ _SIGS = {
     'rcfd_pack_conv_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_pack_upconv2x_weight': [_P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
-    'rcfd_pack_batch': [_P, c_int32, c_int32, _P],
+    'rcfd_pack_batch': [_P, _P, c_int32, c_int32, _P],
+    'rcfd_pack_item_blocks': [POINTER(PackItem)],
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],
     'rcfd_bn_fold': [_P, _P, _P, _P, _P, _P, c_int32, c_float, _P],
     'rcfd_bn_act_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_train_act_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, c_float, c_int32, _P],
     'rcfd_bn_act_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_act_bwd_reduce_acc': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_act_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_gate_fuse_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
     'rcfd_gate_fuse_bwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],

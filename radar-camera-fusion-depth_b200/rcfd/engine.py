@@ -154,7 +154,7 @@ class Context(object):
     """Per-forward state: dtype, mode, tape, BatchNorm scratch pool, packed-weight cache."""
 
     def __init__(self, dtype, training, device, cache=None, record=False, engine=ops.ENGINE_AUTO, multistream=False,
-                 x3=False):
+                 x3=False, external_pack=False):
         self.dtype = dtype
         # tensor-core parity modes: fp32 storage (dtype float32), every conv / wgrad = 3 or 6 bf16 tcgen05 passes over
         # 2- or 3-part bf16 operand splits (rcfd/x3.py); x3 = number of parts (0: off), packed weights are tuples of parts
@@ -176,6 +176,9 @@ class Context(object):
         self.bn_counters = []
         self.taps = None
         self.prepacked = {}
+        # external_pack: the caller runs the batched pack launch itself before this step (FusionNetModel.train_step_graphed
+        # issues it right after the optimiser step, where it overlaps the launch latency of the next graph replay)
+        self.external_pack = external_pack
         self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (self.streams is not None and training) else None
         # batched weight (un)packing (training, multi-stream, plain dtypes): ONE rcfd_pack_batch launch per step packs every
         # weight the step uses into persistent buffers, another one unpacks every weight gradient at the end of backward
@@ -223,6 +226,14 @@ class Context(object):
         self._off_stats += 2 * c
         return s[:c], s[c:]
 
+    def zeroed_sums(self, c):
+        """Zeroed float64 [2c] scratch for a BatchNorm backward reduction (multi-stream training: a slice of the step's
+        one zeroed pool, so the backward chains carry no memset nodes), else None (the kernel call zeroes its own)."""
+        if self.streams is None or not self.training:
+            return None
+        a, b = self.stats(c)
+        return self._pool_stats[a.storage_offset():a.storage_offset() + 2 * c]
+
     def aff(self, c, k=4):
         n = k * c
         if self._pool_aff is None or self._off_aff + n > self._pool_aff.numel():
@@ -248,7 +259,8 @@ class Context(object):
             hit = self.prepacked.pop(key, None)
             if hit is not None:
                 val, ev = hit
-                torch.cuda.current_stream().wait_event(ev)
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
                 return val
             if self.plan is not None:
                 self.plan[key] = (fn, spec)
@@ -270,9 +282,11 @@ class Context(object):
         with torch.cuda.stream(pk):
             batch = _pack_batch_for(self.cache, self.plan, self.dtype, self.device)
             if batch is not None:
-                batch['table'].run()
-                ev = torch.cuda.Event()
-                ev.record(pk)
+                ev = None
+                if not self.external_pack:
+                    batch['table'].run()
+                    ev = torch.cuda.Event()
+                    ev.record(pk)
                 for key, out in batch['outputs'].items():
                     self.prepacked[key] = (out, ev)
             for key, (fn, spec) in self.plan.items():
@@ -501,7 +515,7 @@ def _stem_s2d_unit(ctx, mod, x, act):
             if dz is None:
                 return
             dgamma, dbeta = _grad_dst(bn.weight), _grad_dst(bn.bias)
-            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
+            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=ctx.zeroed_sums(cout))
             tape.param_grads.append((bn.weight, dgamma))
             tape.param_grads.append((bn.bias, dbeta))
             gw = _grad_dst(mod.conv.weight)
@@ -548,7 +562,7 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
             bn = mod.batch_norm
             dgamma = _grad_dst(bn.weight)
             dbeta = _grad_dst(bn.bias)
-            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta)
+            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=ctx.zeroed_sums(y.shape[3]))
             if residual is not None:
                 tape.add_grad(residual, dz)             # published after its last read here (Tape.add_grad)
             tape.param_grads.append((bn.weight, dgamma))
@@ -623,12 +637,34 @@ def fusion_level(ctx, mod_w, mod_p, dep, img):
                 return
             dzy = ops.gate_fuse_bwd(dout, y, scale, shift)
             tape.add_grad(img, dout)
-            dg = torch.empty(2 * c, device=ctx.device, dtype=torch.float32)
-            db = torch.empty_like(dg)
-            dy = ops.bn_act_bwd(dzy, y, scale, shift, mean, invstd, ACT_NONE, dg, db)
+            # d(gamma) / d(beta) of the stacked pair land in one [2][2c] buffer; with flat gradient destinations the four
+            # slices are copied by the step's batched unpack launch instead of four captured memcpys per level
+            st, gkey = ctx.unpack, ('dgcat', id(mod_w))
+            flat = st is not None and all(getattr(q, '_rcfd_flat', False) and q.grad is not None
+                                          for q in (bw.weight, bw.bias, bp.weight, bp.bias))
+            if flat:
+                gbuf = st['bufs'].get(gkey)
+                if gbuf is None:
+                    gbuf = st['bufs'][gkey] = torch.empty(2, 2 * c, device=ctx.device, dtype=torch.float32)
+                    st['dirty'] = True
+                dg, db = gbuf[0], gbuf[1]
+                gdeferred = st['batch'] is not None and gkey in st['batch']['keys']
+            else:
+                dg = torch.empty(2 * c, device=ctx.device, dtype=torch.float32)
+                db = torch.empty_like(dg)
+                gdeferred = False
+            dy = ops.bn_act_bwd(dzy, y, scale, shift, mean, invstd, ACT_NONE, dg, db, sums=ctx.zeroed_sums(2 * c))
             for bn, lo in ((bw, 0), (bp, c)):
+                if gdeferred:
+                    tape.param_grads.append((bn.weight, bn.weight.grad))
+                    tape.param_grads.append((bn.bias, bn.bias.grad))
+                    continue
                 tape.param_grads.append((bn.weight, dg[lo:lo + c]))
                 tape.param_grads.append((bn.bias, db[lo:lo + c]))
+                if flat and len(st['items'].get(gkey, ())) < 4:
+                    st['items'].setdefault(gkey, []).extend([
+                        (ops.COPY_F32, gbuf, lo, bn.weight.grad, bn.weight, dict(total=c)),
+                        (ops.COPY_F32, gbuf, 2 * c + lo, bn.bias.grad, bn.bias, dict(total=c))])
             ukey = ('dwcat', id(mod_w))
             gs = [_grad_dst(ww), _grad_dst(wp)]
             buf, deferred = _wgrad_slot(ctx, ukey, (2 * c, 1, dep.shape[3]), ww, gs[0])

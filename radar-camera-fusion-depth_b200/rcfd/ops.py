@@ -229,8 +229,7 @@ def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None
 
 
 # ---------------------------------------------------------------------------------- batched (un)packing
-PACK_FWD, PACK_DGRAD, PACK_UP2X, PACK_STEM_S2D, UNPACK_CONV, UNPACK_STEM_S2D = 0, 1, 2, 3, 4, 5
-PACK_BLOCK_ELEMS = 2048
+PACK_FWD, PACK_DGRAD, PACK_UP2X, PACK_STEM_S2D, UNPACK_CONV, UNPACK_STEM_S2D, COPY_F32 = 0, 1, 2, 3, 4, 5, 6
 
 
 def spec_pack_weight(w, dtype, cin_off=0, cin_cnt=None, dgrad=False, pad_to=None):
@@ -284,7 +283,7 @@ def spec_pack_stem_s2d_weight(w, dtype, cpad=16):
 class PackBatch(object):
     """Device table of rcfd_pack_item for rcfd_pack_batch (include/rcfd.h): ONE launch packs every weight of a training
     step, another one unpacks every weight gradient.  add() takes the fields of one item; src / dst are tensors (kept
-    alive here), off = element offset into dst."""
+    alive here), off / src_off = element offsets into dst / src."""
 
     def __init__(self):
         self.rows = []
@@ -297,25 +296,28 @@ class PackBatch(object):
         assert self.table is None and total > 0
         for t in (src, dst):
             _p(t)
-        nblocks = (total + PACK_BLOCK_ELEMS - 1) // PACK_BLOCK_ELEMS
-        self.rows.append((src.data_ptr() + src_off * src.element_size(), dst.data_ptr() + off * dst.element_size(), total,
-                          kind, _DT[dst.dtype], cout, cin, taps, cin_off, cin_cnt, cpad, col_off, dst_cols,
-                          self.total_blocks, nblocks))
-        self.total_blocks += nblocks
+        it = _lib.PackItem(src.data_ptr() + src_off * src.element_size(), dst.data_ptr() + off * dst.element_size(), total,
+                           kind, _DT[dst.dtype], cout, cin, taps, cin_off, cin_cnt, cpad, col_off, dst_cols,
+                           self.total_blocks, 0)
+        it.nblocks = int(_lib.load().rcfd_pack_item_blocks(ctypes.byref(it)))
+        if it.nblocks <= 0:
+            raise _lib.RcfdError('rcfd_pack_item_blocks: invalid item')
+        self.rows.append(it)
+        self.total_blocks += it.nblocks
         self.keep += [src, dst]
 
     def finalize(self, device):
         import numpy as np
-        rec = np.dtype([('src', '<u8'), ('dst', '<u8'), ('total', '<i8')] +
-                       [(n, '<i4') for n in ('kind', 'dtype', 'cout', 'cin', 'taps', 'cin_off', 'cin_cnt', 'cpad', 'col_off',
-                                             'dst_cols', 'block0', 'nblocks')])
-        assert rec.itemsize == 72           # sizeof(rcfd_pack_item)
-        arr = np.array(self.rows, dtype=rec)
-        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        assert ctypes.sizeof(_lib.PackItem) == 72           # sizeof(rcfd_pack_item)
+        arr = (_lib.PackItem * len(self.rows))(*self.rows)
+        host = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(host).to(device)
+        owner = np.repeat(np.arange(len(self.rows), dtype=np.int32), [it.nblocks for it in self.rows])
+        self.block_item = torch.from_numpy(owner).to(device)
         return self
 
     def run(self):
-        _lib.call('rcfd_pack_batch', _p(self.table), len(self.rows), self.total_blocks, _stream())
+        _lib.call('rcfd_pack_batch', _p(self.table), _p(self.block_item), len(self.rows), self.total_blocks, _stream())
 
 
 def bn_finalize(ssum, ssq, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, count):
@@ -350,11 +352,15 @@ def bn_train_act(y, ssum, ssq, bn_weight, bn_bias, running_mean, running_var, sc
 
 
 def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None):
+    """sums: optional ZEROED float64 [2c] scratch (a slice of a pool zeroed once per step); default: a fresh buffer
+    zeroed by the call."""
     c = y.shape[-1]
     pixels = y.numel() // c
+    entry = 'rcfd_bn_act_bwd_reduce_acc'
     if sums is None:
         sums = _empty(2 * c, device=y.device, dtype=torch.float64)
-    _lib.call('rcfd_bn_act_bwd_reduce', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), pixels, c,
+        entry = 'rcfd_bn_act_bwd_reduce'
+    _lib.call(entry, _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), pixels, c,
               act, dt(y), _stream())
     dy = _empty_like(y)
     _lib.call('rcfd_bn_act_bwd_apply', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), _p(dy),

@@ -22,13 +22,15 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
+    # RCFD_TRACE=1: experiment build with in-kernel clock stamps (tools/trace_tma.py); never shipped
+    extra = ['-DRCFD_TRACE'] if os.environ.get('RCFD_TRACE') == '1' else []
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for s in SOURCES:
         o = os.path.join(HERE, 'build', s.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, s), '-o', o]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, s), '-o', o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:

@@ -22,8 +22,19 @@ namespace {
 
 using namespace tc;
 using namespace tma;
-constexpr int NTHREADS = 192;
-constexpr int NEPI = 128;
+constexpr int EPI_GROUPS = 2;     // epilogue warps per TMEM lane quarter (each takes every 4th column chunk)
+constexpr int NEPI = 128 * EPI_GROUPS;
+constexpr int NTHREADS = 64 + NEPI;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
+
+// Build with -DRCFD_TRACE (tools/trace_tma.py) to stamp clock64() at the phases of a CTA's life; compiled out of the product.
+#ifdef RCFD_TRACE
+__device__ long long g_trace[148 * 32];
+#define TRACE(slot) do { if (blockIdx.x < 148) g_trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+#define TRACE_VAL(slot, v) do { if (blockIdx.x < 148) g_trace[blockIdx.x * 32 + (slot)] = (long long)(v); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define TRACE_VAL(slot, v) do { } while (0)
+#endif
 
 struct TmaConvP {
   int n, ho, wo, cout;
@@ -72,6 +83,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   float* red = reinterpret_cast<float*>(gen_base + (sRed - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TRACE(0);
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -93,6 +105,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TRACE(1);
 
   const int a_bytes = TM * p.bkc * 2, b_bytes = BN * p.bkc * 2;
   const int chunks0 = p.c0 / p.bkc, chunks = (p.c0 + p.c1) / p.bkc;
@@ -105,6 +118,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
       if (p.c1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
       uint32_t it = 0;
+      TRACE(2);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int ph = tile % p.phases;
         int sp = tile / p.phases;
@@ -151,6 +165,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
         }
       }
+      TRACE(3);
     }
   } else if (warp == 1) {
     // =========================================================== MMA ISSUER
@@ -171,6 +186,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           const uint32_t pr = it % NP, s = 2 * pr;
           mbar_wait(sBar + 8 * s, (it / NP) & 1);
           tc_fence_after();
+          if (lane == 0 && it == 0) TRACE(4);
+          if (lane == 0 && it == 1) TRACE(14);
+          if (lane == 0 && it == 2) TRACE(15);
           if (lane == 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -182,6 +200,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             }
             umma_commit(sBar + 8 * (C::STAGES + s));
             if (kp == npairs - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+            if (kp == npairs - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
           }
           __syncwarp();
         }
@@ -199,21 +218,30 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
           umma_commit(sBar + 8 * (C::STAGES + s));
           if (ks == p.ksteps - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+          if (it == 0) TRACE(4);
+          if (ks == p.ksteps - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
         }
         __syncwarp();
       }
     }
     tc_fence_before();
   } else {
-    // =========================================================== EPILOGUE (warps 2..5)
+    // =========================================================== EPILOGUE (warps 2..9)
+    // EPI_GROUPS warps per TMEM lane quarter, each taking every EPI_GROUPS-th CW-column chunk of its 32 tile rows; BatchNorm statistics
+    // by a butterfly transpose-reduce over CW = 32 columns at a time (31 exchange steps leave lane l with the total of
+    // column l: half the shuffles of the first version's 16-column form).  In-kernel clock stamps
+    // (profiles/r2_conv_tma_trace.txt) had shown 3.9 us per 128 x 128 tile for the 4-warp epilogue: as long as half the
+    // k-loop of a 256-channel 3x3 layer, and not overlapped when a CTA owns one tile (every level <= 22x44 at batch 8).
+    constexpr int CW = BN >= 64 ? 32 : 16;     // columns per chunk
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;           // which chunks of the row this warp takes
     const int r = q * 32 + lane;               // tile row == TMEM lane
     const int th = r / p.tw, tw_ = r - th * p.tw;
     const bool want_stats = p.ssum != nullptr;
     const bool vector_epilogue = (p.cout % 16 == 0) && !p.dst_f32 && p.act != RCFD_ACT_DEPTH_HEAD;
     const bf16* R = reinterpret_cast<const bf16*>(p.residual);
     bf16* D = reinterpret_cast<bf16*>(p.dst);
-    const int etid = tid - 64;                 // 0..127 within the epilogue group
+    const int etid = tid - 64;                 // index within the epilogue group
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1;
@@ -230,112 +258,127 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       float* redt = red + acc * (4 * BN * 2);
       mbar_wait(sBar + 8 * (2 * C::STAGES + acc), (tcount >> 1) & 1);
       tc_fence_after();
+      if (tid == 64 && tcount == 0) TRACE(7);
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 16) {
-        float v[16];
-        tmem_ld16(trow + cb, v);
+      for (int cb = grp * CW; cb < BN; cb += EPI_GROUPS * CW) {
+        float v[CW];
+        {
+          uint32_t raw[CW];
+#pragma unroll
+          for (int j = 0; j < CW; j += 16) tmem_ld16_nowait(trow + cb + j, raw + j);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
+        }
         if (want_stats) {
-          float s16[16], q16[16];
+          float s_[CW], q_[CW];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const float x = mvalid ? v[i] : 0.f;        // rows outside the image carry partial sums of real taps
-            s16[i] = x;
-            q16[i] = x * x;
+            s_[i] = x;
+            q_[i] = x * x;
+          }
+          if (CW == 16) {                               // 16 columns on 32 lanes: fold the two half-warps first
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+              s_[i] += __shfl_xor_sync(0xffffffffu, s_[i], 16);
+              q_[i] += __shfl_xor_sync(0xffffffffu, q_[i], 16);
+            }
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            s16[i] += __shfl_xor_sync(0xffffffffu, s16[i], 16);
-            q16[i] += __shfl_xor_sync(0xffffffffu, q16[i], 16);
-          }
-#pragma unroll
-          for (int w = 8; w >= 1; w >>= 1) {
+          for (int w = CW / 2; w >= 1; w >>= 1) {
             const bool hi = (lane & w) != 0;
 #pragma unroll
             for (int i = 0; i < w; ++i) {
-              const float send_s = hi ? s16[i] : s16[i + w];
-              const float keep_s = hi ? s16[i + w] : s16[i];
-              s16[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-              const float send_q = hi ? q16[i] : q16[i + w];
-              const float keep_q = hi ? q16[i + w] : q16[i];
-              q16[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+              const float send_s = hi ? s_[i] : s_[i + w];
+              const float keep_s = hi ? s_[i + w] : s_[i];
+              s_[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+              const float send_q = hi ? q_[i] : q_[i + w];
+              const float keep_q = hi ? q_[i + w] : q_[i];
+              q_[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
             }
           }
-          if (lane < 16) {
-            redt[(q * BN + cb + lane) * 2 + 0] = s16[0];
-            redt[(q * BN + cb + lane) * 2 + 1] = q16[0];
+          if (lane < CW) {
+            redt[(q * BN + cb + lane) * 2 + 0] = s_[0];
+            redt[(q * BN + cb + lane) * 2 + 1] = q_[0];
           }
         }
         if (mvalid) {
-          const int nb = n0 + cb;
-          const size_t o = gm * p.cout + nb;
-          if (!vector_epilogue) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = nb + i;
-              if (n < p.cout) {
-                float x = v[i];
-                if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
-                x = apply_act(x, p.act, p.p0, p.p1);
-                if (R) x = leaky(x + __bfloat162float(R[o + i]));
-                if (p.dst_f32) {
-                  float* Df = reinterpret_cast<float*>(p.dst);
-                  Df[o + i] = p.accumulate ? Df[o + i] + x : x;
-                } else {
-                  D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+          for (int c16 = 0; c16 < CW; c16 += 16) {
+            const int nb = n0 + cb + c16;
+            const size_t o = gm * p.cout + nb;
+            float* v16 = v + c16;
+            if (!vector_epilogue) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = nb + i;
+                if (n < p.cout) {
+                  float x = v16[i];
+                  if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+                  x = apply_act(x, p.act, p.p0, p.p1);
+                  if (R) x = leaky(x + __bfloat162float(R[o + i]));
+                  if (p.dst_f32) {
+                    float* Df = reinterpret_cast<float*>(p.dst);
+                    Df[o + i] = p.accumulate ? Df[o + i] + x : x;
+                  } else {
+                    D[o + i] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(D[o + i]) + x : x);
+                  }
                 }
               }
-            }
-          } else if (nb < p.cout) {
-            if (p.scale) {
+            } else if (nb < p.cout) {
+              if (p.scale) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
-            }
-            if (p.act == RCFD_ACT_LEAKY) {
+                for (int i = 0; i < 16; ++i) v16[i] = fmaf(v16[i], __ldg(p.scale + nb + i), __ldg(p.shift + nb + i));
+              }
+              if (p.act == RCFD_ACT_LEAKY) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-            } else if (p.act == RCFD_ACT_SIGMOID) {
+                for (int i = 0; i < 16; ++i) v16[i] = leaky(v16[i]);
+              } else if (p.act == RCFD_ACT_SIGMOID) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = sigmoid_precise(v[i]);
-            }
-            if (R) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                for (int i = 0; i < 16; ++i) v16[i] = sigmoid_precise(v16[i]);
+              }
+              if (R) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(R + o);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(R + o + 8);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                  v16[2 * i] = leaky(v16[2 * i] + f.x);
+                  v16[2 * i + 1] = leaky(v16[2 * i + 1] + f.y);
+                }
+              }
+              if (p.accumulate) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                  v16[2 * i] += f.x;
+                  v16[2 * i + 1] += f.y;
+                }
+              }
+              uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                v[2 * i] = leaky(v[2 * i] + f.x);
-                v[2 * i + 1] = leaky(v[2 * i + 1] + f.y);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v16[2 * i], v16[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
               }
+              *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-            if (p.accumulate) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(D + o);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(D + o + 8);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(D + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(D + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(sBar + 8 * (2 * C::STAGES + 2 + acc));
+      if (tid == 64 && tcount == 0) TRACE(8);
       if (want_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
         for (int c = etid; c < BN; c += NEPI) {
           if (n0 + c < p.cout) {
             double s = 0.0, qq = 0.0;
@@ -349,9 +392,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
         }
       }
+      if (tid == 64) { if (tcount == 0) TRACE(9); TRACE(10); TRACE_VAL(12, tcount + 1); TRACE_VAL(13, p.ksteps); }
     }
   }
   __syncthreads();
+  if (tid == 0) TRACE(11);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -382,6 +427,16 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
 }
 
 }  // namespace
+
+#ifdef RCFD_TRACE
+extern "C" int rcfd_debug_read_trace(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+extern "C" int rcfd_debug_clear_trace() {
+  static long long zeros[148 * 32] = {};
+  return cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int g_tma_pair = 1;        // rcfd_set_option("tma_pair"): 0 = one 64-channel chunk per k-step (4 MMAs per commit)
 int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n

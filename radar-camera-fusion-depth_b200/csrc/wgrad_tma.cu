@@ -22,6 +22,15 @@ using namespace tma;
 constexpr int PB = 64;            // pixels per reduction step
 constexpr int NTHREADS = 192;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 
+#ifdef RCFD_TRACE
+__device__ long long g_wtrace[148 * 32];
+#define TRACE(slot) do { const int b_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (b_ < 148) g_wtrace[b_ * 32 + (slot)] = clock64(); } while (0)
+#define TRACE_VAL(slot, v) do { const int b_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (b_ < 148) g_wtrace[b_ * 32 + (slot)] = (long long)(v); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define TRACE_VAL(slot, v) do { } while (0)
+#endif
+
 struct WgTmaP {
   int n, ho, wo, cout;
   int kh, kw, stride, pad;
@@ -59,6 +68,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   const int k0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
   const int split = blockIdx.z, nsplit = gridDim.z;
   const int my_tiles = (p.num_ptiles - split + nsplit - 1) / nsplit;    // tiles split, split+nsplit, ...
+  if (tid == 0) { TRACE(0); TRACE_VAL(12, my_tiles); }
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -77,6 +87,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TRACE(1);
 
   const int ctot = p.c0 + p.c1;
   const int ablocks = 128 / p.bkc;                  // input boxes per stage
@@ -95,6 +106,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       int b_live = 0;
       for (int b = 0; b < nblocks; ++b) b_live += (n0 + b * p.bnb) < p.cout ? 1 : 0;
       const uint32_t tx_bytes = (uint32_t)(a_live * a_blk_bytes + b_live * b_blk_bytes);
+      TRACE(2);
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % C::STAGES;
         if (i >= C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((i / C::STAGES) & 1) ^ 1);
@@ -121,6 +133,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           tma_load_4d(b_dst + b * b_blk_bytes, &map_dy, full, co, ox0, oy0, img);
         }
       }
+      TRACE(3);
     }
   } else if (warp == 1) {
     // both operands MN-major; swizzle span = box row bytes
@@ -131,6 +144,10 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       const int s = i % C::STAGES;
       mbar_wait(sBar + 8 * s, (i / C::STAGES) & 1);
       tc_fence_after();
+      if (lane == 0 && i == 0) TRACE(4);
+      if (lane == 0 && i == 1) TRACE(14);
+      if (lane == 0 && i == 2) TRACE(15);
+      if (lane == 0 && i == my_tiles - 1) TRACE(6);
       if (lane == 0) {
         const uint32_t a_st = sStage + s * C::STAGE, b_st = a_st + C::A_BYTES;
 #pragma unroll
@@ -150,6 +167,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       const int q = warp & 3;
       mbar_wait(sBar + 8 * (2 * C::STAGES), 0);
       tc_fence_after();
+      if (tid == 64) TRACE(7);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       const int k = k0 + q * 32 + lane;
 #pragma unroll 1
@@ -165,14 +183,24 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
       }
     }
+    if (tid == 64) TRACE(10);
     tc_fence_before();
   }
   __syncthreads();
+  if (tid == 0) TRACE(11);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
+
+#ifdef RCFD_TRACE
+}  // namespace
+extern "C" int rcfd_debug_read_wtrace(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_wtrace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+namespace {
+#endif
 
 template <int BN>
 int launch_wg_tma(const WgTmaP& t, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dy, float* dw,

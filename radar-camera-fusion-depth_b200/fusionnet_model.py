@@ -210,7 +210,7 @@ class FusionNetModel(object):
                         self.forward(s_img, s_dep)
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=engine.capture_stream(dev)):
                     s_out = self.forward(s_img, s_dep)
             entry = {'graph': graph, 'static': [s_img, s_dep], 'out': s_out}
             for k in [k for k in self._graphs if k[:5] == key[:5]]:      # same shape / mode, older parameters
@@ -282,7 +282,7 @@ class FusionNetModel(object):
                 graph = torch.cuda.CUDAGraph()
                 self._external_pack = pack is not None
                 try:
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, stream=engine.capture_stream(dev)):
                         loss, grads = body()
                 finally:
                     self._external_pack = False

@@ -53,8 +53,26 @@ def side_streams(device):
     """The five side streams of a device (created once, outside any graph capture)."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(5)]
+        # DEPTH / FUSE carry the step's dependency chains: high priority, so that their CTAs are scheduled before those
+        # of the weight-gradient / packing kernels (nothing waits for those before the optimiser), which otherwise fill
+        # all 148 SMs in front of a critical-path kernel.  RCFD_STREAM_PRIORITY=0 switches it off.
+        import os
+        hi = -1 if os.environ.get('RCFD_STREAM_PRIORITY', '1') != '0' else 0
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device, priority=hi if i < 2 else 0) for i in range(5)]
     return _SIDE_STREAMS[key]
+
+
+_CAPTURE_STREAMS = {}
+
+
+def capture_stream(device):
+    """High-priority stream to capture the step graphs on (the MAIN role of a captured step)."""
+    import os
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        hi = -1 if os.environ.get('RCFD_STREAM_PRIORITY', '1') != '0' else 0
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device, priority=hi)
+    return _CAPTURE_STREAMS[key]
 
 
 class Tape(object):

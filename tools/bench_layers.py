@@ -140,24 +140,25 @@ def build(kind, cin, cout, h, w, o):
     raise SystemExit('unknown kind ' + kind)
 
 
-names = sys.argv[1:] or list(CASES)
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-reps = int(os.environ.get('RCFD_REPS', '5'))
-for name in names:
-    run, flops, byts = build(*CASES[name])
-    try:
-        for _ in range(2):
-            run()
-        tot = 0.0
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            run()
-            b.record()
-            torch.cuda.synchronize()
-            tot += a.elapsed_time(b)
-        us = tot / reps * 1e3
-        print('%-20s %9.1f us  %7.1f TF/s  %7.1f GB/s' % (name, us, flops / us / 1e6, byts / us / 1e3), flush=True)
-    except Exception as e:  # noqa: BLE001
-        print('%-20s FAILED %s' % (name, e), flush=True)
+if __name__ == '__main__':
+    names = sys.argv[1:] or list(CASES)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    reps = int(os.environ.get('RCFD_REPS', '5'))
+    for name in names:
+        run, flops, byts = build(*CASES[name])
+        try:
+            for _ in range(2):
+                run()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                run()
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            us = tot / reps * 1e3
+            print('%-20s %9.1f us  %7.1f TF/s  %7.1f GB/s' % (name, us, flops / us / 1e6, byts / us / 1e3), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print('%-20s FAILED %s' % (name, e), flush=True)

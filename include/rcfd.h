@@ -106,6 +106,13 @@ int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32
  * taps that hit the same low-res pixel.  packed: [4 = a*2+b][cout][4 = t*2+u][cin] in dtype. */
 int rcfd_pack_upconv2x_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t dtype,
                               void* stream);
+/* Phase weights of the data gradient of a 3x3 / stride-2 / pad-1 convolution (autograd of src/net_utils.py:63-69 for the
+ * first conv of every down-sampling ResNet block, src/net_utils.py:270-279): dx[2i+a][2j+b] = sum over 2x2 taps (t, u) of
+ * W'[a,b][t,u] . dy[i-1+a+t][j-1+b+u], W'[a,b][t,u] = w[r][s] with (a,t) -> r: (0,1) -> 1, (1,0) -> 2, (1,1) -> 0, (0,0) -> none
+ * (same for b, u -> s).  packed: [4 = a*2+b][cin_cnt][4 = t*2+u][cout_pad] in dtype; passed as `weight_up2x` of a conv
+ * descriptor with in_dilation = 2 it selects the zero-insertion-free dgrad of the TMA engine. */
+int rcfd_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t cin_off,
+                              int32_t cin_cnt, int32_t cout_pad, int32_t dtype, void* stream);
 /* packed float [>=cout][kh*kw][cin_pad] gradient -> OIHW float slice (+= if accumulate); only the
  * first cin_cnt channels of every tap and the first cout rows are read. */
 int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh,
@@ -127,7 +134,8 @@ int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int
  *                        src = packed float gradient, dst = OIHW float gradient. */
 #define RCFD_PACK_BLOCK_ELEMS 2048
 enum { RCFD_PACK_FWD = 0, RCFD_PACK_DGRAD = 1, RCFD_PACK_UP2X = 2, RCFD_PACK_STEM_S2D = 3,
-       RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5, RCFD_COPY_F32 = 6 /* dst[i] = src[i], float */ };
+       RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5, RCFD_COPY_F32 = 6 /* dst[i] = src[i], float */,
+       RCFD_PACK_DGRAD_S2 = 7 /* rcfd_pack_dgrad_s2_weight (cpad = cout_pad) */ };
 typedef struct rcfd_pack_item {
   const float* src;
   void* dst;

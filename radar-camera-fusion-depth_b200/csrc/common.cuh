@@ -117,6 +117,17 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
   return s < in_size - 1 ? s : in_size - 1;
 }
 
+// Phase weight of the stride-2 / 3x3 / pad-1 data gradient: destination pixel (2i + a, 2j + b) = sum over the 2x2 taps
+// (t, u) on dy rows i-1+a+t, columns j-1+b+u of W'[a,b][t,u] = w[r(a,t)][s(b,u)]:  a = 0: (t=0: none, t=1: r=1);
+// a = 1: (t=0: r=2, t=1: r=0); same for columns.  w is OIHW [cout][cin][3][3]; (ci, co) = (row, column) of the dgrad GEMM.
+__host__ __device__ inline float dgrad_s2_weight(const float* w, int cout, int cin, int ci, int co, int ph, int tap) {
+  const int a = ph >> 1, b = ph & 1, t = tap >> 1, u = tap & 1;
+  const int r = a == 0 ? (t == 0 ? -1 : 1) : (t == 0 ? 2 : 0);
+  const int s = b == 0 ? (u == 0 ? -1 : 1) : (u == 0 ? 2 : 0);
+  if (r < 0 || s < 0 || co >= cout) return 0.f;
+  return w[((size_t)co * cin + ci) * 9 + r * 3 + s];
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // index of the current device (function attributes such as the dynamic shared-memory limit are per device)

@@ -252,7 +252,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const int ty = sp % p.tiles_y;
       const int img = sp / p.tiles_y;
       const int oy = ty * p.th + th, ox = tx * p.tw + tw_;
-      const bool mvalid = oy < p.ho && ox < p.wo;
+      // phases: destination pixel (2 oy + a, 2 ox + b); an odd destination extent (stride-2 dgrad of 11 -> 6 rows) drops the last one
+      const bool mvalid = oy < p.ho && ox < p.wo && (oy * p.out_s + (ph >> 1)) < p.out_h && (ox * p.out_s + (ph & 1)) < p.out_w;
       const size_t gm = ((size_t)img * p.out_h + (oy * p.out_s + (ph >> 1))) * p.out_w + (ox * p.out_s + (ph & 1));
       const int n0 = nt * BN;
       float* redt = red + acc * (4 * BN * 2);
@@ -453,8 +454,21 @@ bool conv_tma_up2x_supported(const ConvKP& p, int dtype) {
   return get_encode() != nullptr;
 }
 
+// Data gradient of a 3x3 / stride-2 / pad-1 convolution WITHOUT zero insertion: the destination pixel (2i + a, 2j + b)
+// only sees the taps of matching parity, i.e. phase (a, b) is a 2x2 convolution over dy rows i-1+a .. i+a (the same
+// geometry as the sub-pixel up-conv above) with the phase weights of rcfd_pack_dgrad_s2_weight: 16 tap GEMMs on the
+// dy grid instead of 9 on the 4x larger zero-inserted grid through the gather engine.
+bool conv_tma_dgrad_s2_supported(const ConvKP& p, int dtype) {
+  if (dtype != RCFD_BF16 || p.dil != 2 || p.weight_up2x == nullptr || p.up) return false;
+  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1 || p.c1 != 0) return false;
+  if (p.c0 % 16 != 0 || p.cout % 16 != 0) return false;
+  if (!(p.ho == 2 * p.h0 || p.ho == 2 * p.h0 - 1) || !(p.wo == 2 * p.w0 || p.wo == 2 * p.w0 - 1)) return false;
+  if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.weight_up2x) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
 bool conv_tma_supported(const ConvKP& p, int dtype) {
-  if (conv_tma_up2x_supported(p, dtype)) return true;
+  if (conv_tma_up2x_supported(p, dtype) || conv_tma_dgrad_s2_supported(p, dtype)) return true;
   if (dtype != RCFD_BF16) return false;
   if (p.up || p.dil != 1) return false;
   if (p.stride != 1 && p.stride != 2) return false;
@@ -471,9 +485,9 @@ int conv_tma_launch(const ConvKP& pin, cudaStream_t st) {
   TmaConvP t;
   t.phases = 1; t.out_h = p.ho; t.out_w = p.wo; t.out_s = 1;
   t.kpair = 0;
-  if (conv_tma_up2x_supported(p, RCFD_BF16)) {
+  if (conv_tma_up2x_supported(p, RCFD_BF16) || conv_tma_dgrad_s2_supported(p, RCFD_BF16)) {
     // run on the low-res grid: 2x2 taps, per-phase weights, destination pixels (2i+a, 2j+b)
-    t.phases = 4; t.out_s = 2;
+    t.phases = 4; t.out_s = 2; p.dil = 1;
     p.ho = p.h0; p.wo = p.w0; p.hin = p.h0; p.win = p.w0;
     p.kh = 2; p.kw = 2; p.K = 4 * p.c0;
     p.weight = p.weight_up2x;

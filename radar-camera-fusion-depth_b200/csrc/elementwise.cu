@@ -1057,6 +1057,20 @@ __global__ void pack_up2x_kernel(const float* __restrict__ w, T* __restrict__ ou
     out[i] = from_f<T>(acc);
   }
 }
+// phase weights of the stride-2 data gradient (conv_tma_dgrad_s2_supported): out[phase a*2+b][ci][tap t*2+u][co < copad]
+template <typename T>
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int cin_off,
+                                     int cin_cnt, int copad) {
+  const int64_t total = (int64_t)16 * cin_cnt * copad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % copad);
+    int64_t r = i / copad;
+    const int tap = (int)(r % 4); r /= 4;
+    const int ci = (int)(r % cin_cnt);
+    const int ph = (int)(r / cin_cnt);
+    out[i] = from_f<T>(dgrad_s2_weight(w, cout, cin, cin_off + ci, co, ph, tap));
+  }
+}
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout,
                                     int cin, int kh, int kw, int cin_off, int cin_cnt, int cpad, int accumulate) {
   const int taps = kh * kw;
@@ -1446,6 +1460,17 @@ int rcfd_pack_upconv2x_weight(const float* w_oihw, void* packed, int32_t cout, i
   const int64_t total = (int64_t)16 * cout * cin;
   DISPATCH_T(dtype, (pack_up2x_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(w_oihw, (T*)packed, cout, cin)));
   RCFD_CHECK_LAUNCH("pack_upconv2x");
+  return RCFD_OK;
+}
+
+int rcfd_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t cin_off,
+                              int32_t cin_cnt, int32_t cout_pad, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin_cnt > 0 && cin_off >= 0 && cin_off + cin_cnt <= cin && cout_pad >= cout,
+                 "pack_dgrad_s2_weight: bad args");
+  const int64_t total = (int64_t)16 * cin_cnt * cout_pad;
+  DISPATCH_T(dtype, (pack_dgrad_s2_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                        w_oihw, (T*)packed, cout, cin, cin_off, cin_cnt, cout_pad)));
+  RCFD_CHECK_LAUNCH("pack_dgrad_s2_weight");
   return RCFD_OK;
 }
 

@@ -71,6 +71,14 @@ __device__ __forceinline__ void pack_one(const rcfd_pack_item& it, uint32_t i) {
       out[i] = from_f<T>(acc);
       break;
     }
+    case RCFD_PACK_DGRAD_S2: {                 // out[phase][ci][2x2 tap][co < cpad]
+      const uint32_t co = i % it.cpad;
+      uint32_t r = i / it.cpad;
+      const uint32_t tap = r % 4; r /= 4;
+      const uint32_t ci = r % it.cin_cnt, ph = r / it.cin_cnt;
+      out[i] = from_f<T>(dgrad_s2_weight(w, it.cout, it.cin, it.cin_off + ci, co, ph, tap));
+      break;
+    }
     default: {                                 // RCFD_PACK_STEM_S2D: out[co][4x4 tap][cpad], 7x7 window on the s2d tensor
       const uint32_t C = it.cin, CP = it.cpad;
       const uint32_t ch = i % CP, r = i / CP;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(PB_THREADS) pack_batch_kernel(const rcfd_pack_
   const uint32_t beg = (uint32_t)blk * RCFD_PACK_BLOCK_ELEMS;
   uint32_t end = beg + RCFD_PACK_BLOCK_ELEMS;
   if (end > (uint32_t)it.total) end = (uint32_t)it.total;
-  if (it.kind >= RCFD_UNPACK_CONV) {
+  if (it.kind >= RCFD_UNPACK_CONV && it.kind <= RCFD_COPY_F32) {
     for (uint32_t i = beg + threadIdx.x; i < end; i += PB_THREADS) unpack_one(it, i);
   } else if (bf) {
     for (uint32_t i = beg + threadIdx.x; i < end; i += PB_THREADS) pack_one<bf16>(it, i);

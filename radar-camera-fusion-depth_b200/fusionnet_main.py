@@ -205,6 +205,123 @@ def train(train_image_path, train_depth_path, train_response_path, train_ground_
     return model, optimizer, train_step
 
 
+def run(restore_path, image_path, depth_path, response_path, ground_truth_path,
+        # Input settings
+        input_channels_image, input_channels_depth, normalized_image_range,
+        # Network settings
+        encoder_type, n_filters_encoder_image, n_filters_encoder_depth, fusion_type, decoder_type, n_filters_decoder,
+        n_resolutions_decoder, min_predict_depth, max_predict_depth,
+        # Weight settings
+        weight_initializer, activation_func,
+        # Output settings
+        output_dirpath, save_outputs, keep_input_filenames, verbose=True,
+        # Evaluation settings
+        min_evaluate_depth=0.0, max_evaluate_depth=100.0,
+        # B200 path
+        precision='fp32'):
+    """Inference / evaluation over a list of frames with the reference's keyword surface (reference
+    src/fusionnet_main.py:608-896): restore a checkpoint (the reference's own files load: 'module.' keys), run every frame
+    through the graphed eval forward, evaluate MAE / RMSE (mm) and iMAE / iRMSE (1/km) against the ground truth when it
+    is given, optionally save image / ground truth / fused depth / radar depth / radar response with the reference's
+    16-bit PNG codecs (src/data_utils.py:271-335).  ``'synthetic'`` as image_path evaluates seeded synthetic frames.
+    Returns the dict of mean metrics (None without ground truth).  File reading / writing is host work (Pillow) outside
+    the hot path; the depth maps come from the sm_100a kernels (precision: 'fp32' parity mode, 'bf16' fast mode)."""
+    device = torch.device('cuda')
+    os.makedirs(output_dirpath, exist_ok=True)
+    log_path = os.path.join(output_dirpath, 'results.txt')
+    ground_truth_available = ground_truth_path is not None and (ground_truth_path == 'synthetic' or os.path.exists(ground_truth_path))
+    synthetic = image_path == 'synthetic'
+    if synthetic:
+        samples = rcfd_data.make_val_batches('synthetic', None, None, None, 352, 704, synthetic_samples=4)
+        image_paths = ['synthetic_%d' % i for i in range(len(samples))]
+        dataloader = samples if ground_truth_available else [s[:3] for s in samples]
+    else:
+        image_paths = rcfd_data.read_paths(image_path)
+        n = len(image_paths)
+        other = [rcfd_data.read_paths(pth) for pth in (depth_path, response_path)]
+        gt_paths = rcfd_data.read_paths(ground_truth_path) if ground_truth_available else None
+        for paths in other + ([gt_paths] if gt_paths is not None else []):
+            assert n == len(paths)
+        dataloader = rcfd_data.make_val_batches(image_path, depth_path, response_path,
+                                                ground_truth_path if ground_truth_available else None, None, None)
+    n_sample = len(image_paths)
+    transforms = Transforms(normalized_image_range=normalized_image_range)
+    out_dirs = {}
+    if save_outputs:
+        for name in ('image', 'ground_truth', 'output_depth_fusion', 'output_depth_radar', 'output_response_radar'):
+            out_dirs[name] = os.path.join(output_dirpath, name)
+            os.makedirs(out_dirs[name], exist_ok=True)
+
+    model = FusionNetModel(
+        input_channels_image=input_channels_image, input_channels_depth=input_channels_depth, encoder_type=encoder_type,
+        n_filters_encoder_image=n_filters_encoder_image, n_filters_encoder_depth=n_filters_encoder_depth,
+        fusion_type=fusion_type, decoder_type=decoder_type, n_resolution_decoder=n_resolutions_decoder,
+        n_filters_decoder=n_filters_decoder, deconv_type='up', activation_func=activation_func,
+        weight_initializer=weight_initializer, min_predict_depth=min_predict_depth, max_predict_depth=max_predict_depth,
+        device=device)
+    model.set_precision(precision)
+    model.eval()
+    model.data_parallel()
+    step = -1
+    if restore_path:
+        step, _ = model.restore_model(restore_path)
+
+    log('Evaluation input paths:', log_path)
+    for pth in [image_path, depth_path, response_path] + ([ground_truth_path] if ground_truth_available else []):
+        log(str(pth), log_path)
+    log('', log_path)
+    log('Network settings: encoder {} decoder {} fusion {} filters {} / {} / {} resolutions {} depth [{}, {}] precision {}'.format(
+        encoder_type, decoder_type, fusion_type, n_filters_encoder_image, n_filters_encoder_depth, n_filters_decoder,
+        n_resolutions_decoder, min_predict_depth, max_predict_depth, precision), log_path)
+    log('Evaluation settings: min_evaluate_depth={} max_evaluate_depth={} restore_path={}'.format(
+        min_evaluate_depth, max_evaluate_depth, restore_path), log_path)
+
+    mae, rmse, imae, irmse = [np.zeros(n_sample) for _ in range(4)]
+    with torch.no_grad():
+        for idx, data in enumerate(dataloader):
+            data = [datum.to(device) for datum in data]
+            if ground_truth_available:
+                image, depth, response, ground_truth = data
+            else:
+                image, depth, response = data[:3]
+            [image] = transforms.transform(images_arr=[image], random_transform_probability=0.0)
+            input_depth = torch.cat([depth, response], dim=1)
+            output_depth = model.forward_graphed(image, input_depth)          # one CUDA graph per frame shape
+            output_depth_fusion = np.squeeze(output_depth.cpu().numpy())
+            if verbose:
+                print('Processed {}/{} samples'.format(idx + 1, n_sample), end='\r')
+            if ground_truth_available:
+                gt = np.squeeze(ground_truth.cpu().numpy())
+                mask = np.where(np.logical_and(gt > 0, np.logical_and(gt > min_evaluate_depth, gt < max_evaluate_depth)))
+                mae[idx] = eval_utils.mean_abs_err(1000.0 * output_depth_fusion[mask], 1000.0 * gt[mask])
+                rmse[idx] = eval_utils.root_mean_sq_err(1000.0 * output_depth_fusion[mask], 1000.0 * gt[mask])
+                imae[idx] = eval_utils.inv_mean_abs_err(0.001 * output_depth_fusion[mask], 0.001 * gt[mask])
+                irmse[idx] = eval_utils.inv_root_mean_sq_err(0.001 * output_depth_fusion[mask], 0.001 * gt[mask])
+            if save_outputs:
+                from PIL import Image
+                if keep_input_filenames:
+                    filename = os.path.splitext(os.path.basename(image_paths[idx]))[0] + '.png'
+                else:
+                    filename = '{:010d}.png'.format(idx)
+                output_image = np.transpose(np.squeeze(image.cpu().numpy()), (1, 2, 0))
+                Image.fromarray((255 * output_image).astype(np.uint8)).save(os.path.join(out_dirs['image'], filename))
+                rcfd_data.save_png16(output_depth_fusion, os.path.join(out_dirs['output_depth_fusion'], filename),
+                                     rcfd_data.DEPTH_MULTIPLIER)
+                rcfd_data.save_png16(np.squeeze(depth.cpu().numpy()), os.path.join(out_dirs['output_depth_radar'], filename),
+                                     rcfd_data.DEPTH_MULTIPLIER)
+                rcfd_data.save_png16(np.squeeze(response.cpu().numpy()),
+                                     os.path.join(out_dirs['output_response_radar'], filename), rcfd_data.RESPONSE_MULTIPLIER)
+                if ground_truth_available:
+                    rcfd_data.save_png16(gt, os.path.join(out_dirs['ground_truth'], filename), rcfd_data.DEPTH_MULTIPLIER)
+    if not ground_truth_available:
+        return None
+    results = {'mae': float(np.mean(mae)), 'rmse': float(np.mean(rmse)), 'imae': float(np.mean(imae)),
+               'irmse': float(np.mean(irmse)), 'step': step}
+    log_evaluation_results('Evaluation results', results['mae'], results['rmse'], results['imae'], results['irmse'],
+                           step=step, log_path=log_path)
+    return results
+
+
 def validate(model, dataloader, transforms, step, best_results, min_evaluate_depth, max_evaluate_depth, device,
              summary_writer=None, n_summary_display=4, n_summary_display_interval=250, log_path=None):
     """Validation pass with the reference's signature, metrics and best-result rule (reference

@@ -46,6 +46,13 @@ def load_png16(path):
     return z.astype(np.uint16)
 
 
+def save_png16(z, path, multiplier):
+    """The reference's save_depth / save_response (src/data_utils.py:271-286, 320-335): uint32(z * multiplier) written as a
+    Pillow mode-'I' PNG."""
+    from PIL import Image
+    Image.fromarray(np.uint32(np.asarray(z, dtype=np.float32) * multiplier), mode='I').save(path)
+
+
 def crop_origin(o_height, o_width, n_height, n_width, crop_type, rng=np.random):
     """(y_start, x_start) of the reference's random_crop (src/datasets.py:19-109), drawing from ``rng`` in the same order
     (horizontal first, then the vertical coin flip and position)."""

@@ -341,6 +341,14 @@ class Context(object):
                            spec=lambda: ops.spec_pack_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, dgrad=True,
                                                              pad_to=pad_to))
 
+    def weight_dgrad_s2(self, mod, off, cnt, pad_to):
+        """Phase weights of the zero-insertion-free data gradient of a 3x3 / stride-2 conv (bf16 fast path)."""
+        w, dtype = mod.conv.weight, self.dtype
+        return self.packed(('wds2', id(mod), off, cnt, pad_to), [w],
+                           lambda: ops.pack_dgrad_s2_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, pad_to=pad_to),
+                           spec=lambda: ops.spec_pack_dgrad_s2_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt,
+                                                                      pad_to=pad_to))
+
     def folded_bn(self, mod):
         bn = mod.batch_norm
         # num_batches_tracked: the training kernels update the running statistics through raw pointers (no version bump)
@@ -606,8 +614,16 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         hin, win = (x0.shape[1], x0.shape[2]) if in_size is None else in_size
         pad_d = k - 1 - k // 2
         for (src, off, cnt) in ((x0, 0, c0),) + (((x1, c0, x1.shape[3]),) if x1 is not None else ()):
-            wd = ctx.weight_dgrad(mod, off, cnt, dy.shape[3])
-            dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine)
+            if (stride == 2 and k == 3 and x1 is None and ctx.dtype == torch.bfloat16 and not ctx.x3
+                    and dy.shape[3] % 16 == 0 and cnt % 16 == 0 and ctx.engine == ops.ENGINE_AUTO):
+                # TMA engine: four 2x2 convs on the dy grid (one per destination parity) instead of 9 taps on the
+                # zero-inserted grid through the gather engine
+                wd = ctx.weight_dgrad_s2(mod, off, cnt, dy.shape[3])
+                dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine,
+                                  weight_up2x=wd)
+            else:
+                wd = ctx.weight_dgrad(mod, off, cnt, dy.shape[3])
+                dsrc = ops.conv2d(dy, wd, cnt, k, 1, pad=pad_d, in_dilation=stride, out_size=(hin, win), engine=ctx.engine)
             if src is x0 and (hin, win) != (x0.shape[1], x0.shape[2]):
                 dsrc = ops.upsample_nearest_bwd(dsrc, (x0.shape[1], x0.shape[2]))
             tape.add_grad(src, dsrc)

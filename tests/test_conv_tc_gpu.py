@@ -112,6 +112,44 @@ def test_tc_dgrad(case):
     assert relerr(_nchw(dx), x.grad) < TOL
 
 
+@pytest.mark.parametrize('case', [(2, 32, 64, 12, 20), (1, 64, 128, 11, 22), (2, 128, 256, 22, 44), (1, 16, 32, 9, 13),
+                                  (3, 64, 64, 6, 11)])
+def test_tma_dgrad_stride2_phases(case):
+    """Zero-insertion-free data gradient of a 3x3 / stride-2 / pad-1 conv on the TMA engine (four 2x2 phase convs on the
+    dy grid, rcfd_pack_dgrad_s2_weight) vs autograd, even and odd input extents (11 -> 6 drops the last phase row), plus
+    the batched pack of the same weights."""
+    from rcfd import ops
+    n, cin, cout, h, w = case
+    x = _q(_rand(n, cin, h, w, seed=21)).requires_grad_(True)
+    wt = _q(_rand(cout, cin, 3, 3, seed=22) / (cin * 9) ** 0.5)
+    y = F.conv2d(x, wt, None, 2, 1)
+    dy = _q(_rand(*y.shape, seed=23))
+    y.backward(dy)
+    wd2 = ops.pack_dgrad_s2_weight(wt.to(DEV), BF)
+    assert wd2.shape == (4, cin, 4, cout)
+    dx = ops.conv2d(_nhwc(dy), wd2, cin, 3, 1, pad=1, in_dilation=2, out_size=(h, w), weight_up2x=wd2)
+    assert ops._lib.load().rcfd_last_kernel().decode().startswith('conv_tma_kernel')
+    assert relerr(_nchw(dx), x.grad) < TOL
+    # the gather engine on the zero-inserted grid computes the same thing
+    wd = ops.pack_weight(wt.to(DEV), BF, dgrad=True)
+    old = ops.conv2d(_nhwc(dy), wd, cin, 3, 1, pad=1, in_dilation=2, out_size=(h, w), engine=ops.ENGINE_TCGEN05)
+    assert relerr(_nchw(dx), _nchw(old)) < 2e-2
+    # batched pack == single pack (also with a channel slice and padded dy channels)
+    t = ops.PackBatch()
+    outs = []
+    for kw in (dict(), dict(cin_off=cin // 2, cin_cnt=cin // 2, pad_to=cout + 16)):
+        shape, dt_, zero, items = ops.spec_pack_dgrad_s2_weight(wt.to(DEV), BF, **kw)
+        out = torch.full(shape, 3.0, device=DEV, dtype=dt_)
+        for it in items:
+            it = dict(it)
+            t.add(it.pop('kind'), it.pop('src'), out, **it)
+        outs.append((out, ops.pack_dgrad_s2_weight(wt.to(DEV), BF, **kw)))
+    t.finalize(DEV).run()
+    torch.cuda.synchronize()
+    for got, ref in outs:
+        assert torch.equal(got, ref)
+
+
 def test_tc_rejects_unsupported():
     from rcfd import ops, _lib
     x = torch.zeros(1, 4, 4, 8, device=DEV)          # fp32 -> not a tcgen05 case

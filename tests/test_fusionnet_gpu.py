@@ -1,6 +1,8 @@
 """GPU parity of the whole FusionNet path (FusionNetModel on librcfd_b200.so, fp32 parity
 mode) against the CPU oracle and the golden fixtures produced by the unmodified reference.
 Tolerance (north star): 1e-3 relative in fp32 terms, stated per assertion."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -394,3 +396,40 @@ def test_train_entry_point_synthetic(tmp_path):
     kw.update(restore_path=str(tmp_path / 'model-12.pth'), learning_schedule=[1], learning_rates=[1e-3], max_steps=14)
     _, _, step2 = fusionnet_main.train(**kw)
     assert step2 == 14
+
+
+def test_run_entry_point_synthetic(tmp_path):
+    """fusionnet_main.run with the reference's keyword surface: restores a checkpoint written by save_model (the
+    reference's key format), evaluates the synthetic frames through the graphed forward, writes the reference's output
+    tree; the metrics equal a by-hand evaluation of model.forward on the same frames."""
+    import numpy as np
+    import eval_utils
+    import fusionnet_main
+    from rcfd import data
+    cfg = synth.SMALL_FUSIONNET
+    m = make_model(cfg, synth_fusionnet_state(cfg, 21))
+    ckpt = str(tmp_path / 'model.pth')
+    m.save_model(ckpt, 7, torch.optim.Adam(m.parameters(), lr=1e-3))
+    kw = dict(cfg)
+    kw['n_resolutions_decoder'] = kw.pop('n_resolution_decoder')
+    kw.pop('deconv_type')
+    out = str(tmp_path / 'out')
+    res = fusionnet_main.run(restore_path=ckpt, image_path='synthetic', depth_path='synthetic', response_path='synthetic',
+                             ground_truth_path='synthetic', normalized_image_range=[0, 1], output_dirpath=out,
+                             save_outputs=True, keep_input_filenames=False, verbose=False, min_evaluate_depth=0.0,
+                             max_evaluate_depth=100.0, **kw)
+    assert res['step'] == 7
+    m.eval()
+    maes = []
+    for image, depth, response, gt in data.make_val_batches('synthetic', None, None, None, 352, 704, synthetic_samples=4):
+        with torch.no_grad():
+            d = m.forward((image / 255.0).to(DEV), torch.cat([depth, response], 1).to(DEV)).cpu().numpy().squeeze()
+        g = gt.numpy().squeeze()
+        mask = np.where(g > 0)
+        maes.append(eval_utils.mean_abs_err(1000.0 * d[mask], 1000.0 * g[mask]))
+    assert abs(res['mae'] - float(np.mean(maes))) < 1e-3 * abs(res['mae'])
+    files = sorted(os.listdir(os.path.join(out, 'output_depth_fusion')))
+    assert files == ['%010d.png' % i for i in range(4)]
+    back = data.load_png16(os.path.join(out, 'output_depth_fusion', files[-1])).astype(np.float32) / 256.0
+    assert np.abs(back - d).max() <= 1.0 / 256.0 + 1e-6
+    assert 'Evaluation results' in open(os.path.join(out, 'results.txt')).read()

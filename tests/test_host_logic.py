@@ -414,6 +414,39 @@ def test_train_cli_flag_surface_matches_reference():
     assert required <= set(args)                       # the CLI supplies every required keyword of train()
 
 
+def test_run_cli_flag_surface_matches_reference():
+    """run_fusionnet.py exposes every flag of the reference's CLI (src/run_fusionnet.py:8-67; list taken from the
+    reference) plus --precision, and run() accepts every resulting keyword in the reference's order."""
+    import inspect
+    import fusionnet_main
+    import run_fusionnet
+    reference_flags = [
+        'restore_path', 'image_path', 'depth_path', 'response_path', 'ground_truth_path', 'input_channels_image',
+        'input_channels_depth', 'normalized_image_range', 'encoder_type', 'n_filters_encoder_image',
+        'n_filters_encoder_depth', 'fusion_type', 'decoder_type', 'n_filters_decoder', 'n_resolutions_decoder',
+        'min_predict_depth', 'max_predict_depth', 'weight_initializer', 'activation_func', 'output_dirpath', 'save_outputs',
+        'keep_input_filenames', 'verbose', 'min_evaluate_depth', 'max_evaluate_depth']
+    mine = [a.dest for a in run_fusionnet.parser._actions if a.dest != 'help']
+    assert mine == reference_flags + ['precision']
+    params = list(inspect.signature(fusionnet_main.run).parameters)
+    assert params == reference_flags + ['precision']         # the reference passes everything by keyword; same names, same order
+    required = {a.dest for a in run_fusionnet.parser._actions if a.required}
+    assert required == {'restore_path', 'image_path', 'depth_path', 'response_path', 'output_dirpath'}
+
+
+def test_png16_writer_matches_reference_codec(tmp_path):
+    """rcfd.data.save_png16 == the reference's save_depth / save_response (uint32(z * multiplier) as a mode-'I' PNG):
+    the file decodes to what the reference's loaders return."""
+    import numpy as np
+    from PIL import Image
+    from rcfd import data
+    z = (np.random.RandomState(0).rand(12, 20).astype(np.float32) * 90) * (np.random.RandomState(1).rand(12, 20) < 0.5)
+    data.save_png16(z, str(tmp_path / 'd.png'), data.DEPTH_MULTIPLIER)
+    back = np.array(Image.open(str(tmp_path / 'd.png')), dtype=np.float32) / 256.0        # load_depth (src/data_utils.py:254-257)
+    assert np.array_equal(back, np.floor(z * 256.0) / 256.0)
+    assert np.array_equal(data.load_png16(str(tmp_path / 'd.png')), np.uint16(np.uint32(z * 256.0)))
+
+
 def test_radarnet_compute_loss_matches_reference_fixture():
     """RadarNetModel.compute_loss (weighted BCE over valid pixels, reference src/radarnet_model.py:126-167) against
     values computed by the reference."""

@@ -113,6 +113,12 @@ int rcfd_pack_upconv2x_weight(const float* w_oihw, void* packed, int32_t cout, i
  * descriptor with in_dilation = 2 it selects the zero-insertion-free dgrad of the TMA engine. */
 int rcfd_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t cin_off,
                               int32_t cin_cnt, int32_t cout_pad, int32_t dtype, void* stream);
+/* Data gradient of `3x3 conv after exact 2x nearest up-sampling` (autograd of src/net_utils.py:196-197) w.r.t. the low-res
+ * source as ONE 4x4 / stride-2 / pad-1 convolution over dy (instead of a 3x3 dgrad at the up-sampled resolution followed by
+ * a 2x2 sum): dsrc[i][j] = sum_{k,l} W4[k][l] . dy[2i-1+k][2j-1+l], W4[k][l] = sum of w[r][s] with k+r, l+s in {2, 3}.
+ * packed: [cin_cnt][16 = k*4+l][cout_pad] in dtype = forward-packed weights of that convolution (cout' = cin_cnt). */
+int rcfd_pack_upconv2x_dgrad_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t cin_off,
+                                    int32_t cin_cnt, int32_t cout_pad, int32_t dtype, void* stream);
 /* packed float [>=cout][kh*kw][cin_pad] gradient -> OIHW float slice (+= if accumulate); only the
  * first cin_cnt channels of every tap and the first cout rows are read. */
 int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int32_t cin, int32_t kh,
@@ -135,7 +141,8 @@ int rcfd_unpack_conv_wgrad(const float* packed, float* g_oihw, int32_t cout, int
 #define RCFD_PACK_BLOCK_ELEMS 2048
 enum { RCFD_PACK_FWD = 0, RCFD_PACK_DGRAD = 1, RCFD_PACK_UP2X = 2, RCFD_PACK_STEM_S2D = 3,
        RCFD_UNPACK_CONV = 4, RCFD_UNPACK_STEM_S2D = 5, RCFD_COPY_F32 = 6 /* dst[i] = src[i], float */,
-       RCFD_PACK_DGRAD_S2 = 7 /* rcfd_pack_dgrad_s2_weight (cpad = cout_pad) */ };
+       RCFD_PACK_DGRAD_S2 = 7 /* rcfd_pack_dgrad_s2_weight (cpad = cout_pad) */,
+       RCFD_PACK_UPCONV_DGRAD = 8 /* rcfd_pack_upconv2x_dgrad_weight (cpad = cout_pad) */ };
 typedef struct rcfd_pack_item {
   const float* src;
   void* dst;

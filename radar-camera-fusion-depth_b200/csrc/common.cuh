@@ -128,6 +128,21 @@ __host__ __device__ inline float dgrad_s2_weight(const float* w, int cout, int c
   return w[((size_t)co * cin + ci) * 9 + r * 3 + s];
 }
 
+// Data gradient of `3x3 / pad-1 conv after exact 2x nearest up-sampling` w.r.t. the LOW-RES source, as one 4x4 / stride-2 /
+// pad-1 convolution over dy:  dsrc[i][j] = sum_{k,l in 0..3} W4[k][l] . dy[2i-1+k][2j-1+l],  W4[k][l] = sum of w[r][s] over the
+// taps with k + r in {2, 3} and l + s in {2, 3} (the up-sampled pixels 2i, 2i+1 that source pixel i feeds).
+__host__ __device__ inline float upconv_dgrad_weight(const float* w, int cout, int cin, int ci, int co, int tap) {
+  if (co >= cout) return 0.f;
+  const int k = tap >> 2, l = tap & 3;
+  const int r0 = k == 0 ? 2 : (k == 1 ? 1 : 0), r1 = k == 0 ? 2 : (k == 1 ? 2 : (k == 2 ? 1 : 0));
+  const int s0 = l == 0 ? 2 : (l == 1 ? 1 : 0), s1 = l == 0 ? 2 : (l == 1 ? 2 : (l == 2 ? 1 : 0));
+  const float* wp = w + ((size_t)co * cin + ci) * 9;
+  float acc = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int s = s0; s <= s1; ++s) acc += wp[r * 3 + s];
+  return acc;
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // index of the current device (function attributes such as the dynamic shared-memory limit are per device)

@@ -1071,6 +1071,16 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, T* __restrict_
     out[i] = from_f<T>(dgrad_s2_weight(w, cout, cin, cin_off + ci, co, ph, tap));
   }
 }
+template <typename T>
+__global__ void pack_upconv_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int cin_off,
+                                         int cin_cnt, int copad) {
+  const int64_t total = (int64_t)cin_cnt * 16 * copad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % copad);
+    const int64_t r = i / copad;
+    out[i] = from_f<T>(upconv_dgrad_weight(w, cout, cin, cin_off + (int)(r / 16), co, (int)(r % 16)));
+  }
+}
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int cout,
                                     int cin, int kh, int kw, int cin_off, int cin_cnt, int cpad, int accumulate) {
   const int taps = kh * kw;
@@ -1471,6 +1481,17 @@ int rcfd_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int32_t cout, i
   DISPATCH_T(dtype, (pack_dgrad_s2_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
                         w_oihw, (T*)packed, cout, cin, cin_off, cin_cnt, cout_pad)));
   RCFD_CHECK_LAUNCH("pack_dgrad_s2_weight");
+  return RCFD_OK;
+}
+
+int rcfd_pack_upconv2x_dgrad_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t cin_off,
+                                    int32_t cin_cnt, int32_t cout_pad, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin_cnt > 0 && cin_off >= 0 && cin_off + cin_cnt <= cin && cout_pad >= cout,
+                 "pack_upconv2x_dgrad_weight: bad args");
+  const int64_t total = (int64_t)cin_cnt * 16 * cout_pad;
+  DISPATCH_T(dtype, (pack_upconv_dgrad_kernel<T><<<grid_for(total), NT, 0, (cudaStream_t)stream>>>(
+                        w_oihw, (T*)packed, cout, cin, cin_off, cin_cnt, cout_pad)));
+  RCFD_CHECK_LAUNCH("pack_upconv2x_dgrad_weight");
   return RCFD_OK;
 }
 

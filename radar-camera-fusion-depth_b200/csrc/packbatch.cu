@@ -71,6 +71,13 @@ __device__ __forceinline__ void pack_one(const rcfd_pack_item& it, uint32_t i) {
       out[i] = from_f<T>(acc);
       break;
     }
+    case RCFD_PACK_UPCONV_DGRAD: {             // out[ci][4x4 tap][co < cpad]
+      const uint32_t co = i % it.cpad;
+      const uint32_t r = i / it.cpad;
+      const uint32_t tap = r % 16, ci = r / 16;
+      out[i] = from_f<T>(upconv_dgrad_weight(w, it.cout, it.cin, it.cin_off + ci, co, tap));
+      break;
+    }
     case RCFD_PACK_DGRAD_S2: {                 // out[phase][ci][2x2 tap][co < cpad]
       const uint32_t co = i % it.cpad;
       uint32_t r = i / it.cpad;

@@ -49,6 +49,7 @@ _SIGS = {
     'rcfd_pack_upconv2x_weight': [_P, _P, c_int32, c_int32, c_int32, _P],
     'rcfd_unpack_conv_wgrad': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_pack_dgrad_s2_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
+    'rcfd_pack_upconv2x_dgrad_weight': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_pack_batch': [_P, _P, c_int32, c_int32, _P],
     'rcfd_pack_item_blocks': [POINTER(PackItem)],
     'rcfd_bn_finalize': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int64, c_float, c_float, _P],

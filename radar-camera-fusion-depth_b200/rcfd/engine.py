@@ -26,6 +26,10 @@ from .ops import ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_DEPTH_HEAD
 
 _ACT = {'linear': ACT_NONE, 'leaky_relu': ACT_LEAKY, 'sigmoid': ACT_SIGMOID}
 CPAD = 16    # RGB image / depth+response are stored with 16 channels (TMA boxes and UMMA K need 32 B rows)
+# the per-tap engine needs >= 64 dy channels per tap to beat `dgrad at the up-sampled resolution + 2x2 sum` (32-channel taps
+# are 12 KB loads behind a full barrier round: measured no gain on deconv0)
+import os as _os
+UPCONV_DGRAD_MIN_C = int(_os.environ.get('RCFD_UPCONV_DGRAD_MIN_C', '64'))
 CPAD_DY = 16  # d(logit) of the 1-channel head: 16 channels (32-byte rows) so its dgrad / wgrad stream through the row engines
 
 
@@ -349,6 +353,14 @@ class Context(object):
                            spec=lambda: ops.spec_pack_dgrad_s2_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt,
                                                                       pad_to=pad_to))
 
+    def weight_upconv_dgrad(self, mod, off, cnt, pad_to):
+        """4x4 / stride-2 weights of the data gradient of an exact-2x up-conv w.r.t. its low-res source (bf16 fast path)."""
+        w, dtype = mod.conv.weight, self.dtype
+        return self.packed(('wupd', id(mod), off, cnt, pad_to), [w],
+                           lambda: ops.pack_upconv2x_dgrad_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt, pad_to=pad_to),
+                           spec=lambda: ops.spec_pack_upconv2x_dgrad_weight(w.detach(), dtype, cin_off=off, cin_cnt=cnt,
+                                                                            pad_to=pad_to))
+
     def folded_bn(self, mod):
         bn = mod.batch_norm
         # num_batches_tracked: the training kernels update the running statistics through raw pointers (no version bump)
@@ -614,6 +626,14 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
         hin, win = (x0.shape[1], x0.shape[2]) if in_size is None else in_size
         pad_d = k - 1 - k // 2
         for (src, off, cnt) in ((x0, 0, c0),) + (((x1, c0, x1.shape[3]),) if x1 is not None else ()):
+            if (src is x0 and (hin, win) == (2 * x0.shape[1], 2 * x0.shape[2]) and k == 3 and stride == 1
+                    and ctx.dtype == torch.bfloat16 and not ctx.x3 and dy.shape[3] % UPCONV_DGRAD_MIN_C == 0 and cnt % 16 == 0
+                    and ctx.engine == ops.ENGINE_AUTO):
+                # gradient w.r.t. the low-res source of an exact-2x up-conv in one 4x4 / stride-2 conv over dy (no dgrad at
+                # the up-sampled resolution, no 2x2 sum pass)
+                w4 = ctx.weight_upconv_dgrad(mod, off, cnt, dy.shape[3])
+                tape.add_grad(src, ops.conv2d(dy, w4, cnt, 4, 2, pad=1, engine=ctx.engine))
+                continue
             if (stride == 2 and k == 3 and x1 is None and ctx.dtype == torch.bfloat16 and not ctx.x3
                     and dy.shape[3] % 16 == 0 and cnt % 16 == 0 and ctx.engine == ops.ENGINE_AUTO):
                 # TMA engine: four 2x2 convs on the dy grid (one per destination parity) instead of 9 taps on the

@@ -230,6 +230,18 @@ def pack_dgrad_s2_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, pad_to=None):
     return out
 
 
+def pack_upconv2x_dgrad_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, pad_to=None):
+    """[cin_cnt][4x4 taps][cout_pad]: forward-packed weights of the 4x4 / stride-2 conv over dy that is the data gradient of a
+    3x3 conv behind an exact 2x nearest up-sampling w.r.t. its low-res source (include/rcfd.h)."""
+    cout, cin, kh, kw = w_oihw.shape
+    assert kh == 3 and kw == 3
+    cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
+    pad = cout if pad_to is None else max(cout, int(pad_to))
+    out = _empty((cin_cnt, 16, pad), device=w_oihw.device, dtype=dtype)
+    _lib.call('rcfd_pack_upconv2x_dgrad_weight', _p(w_oihw), _p(out), cout, cin, cin_off, cin_cnt, pad, _DT[dtype], _stream())
+    return out
+
+
 def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None):
     """packed float [>=cout][taps][cin_pad] -> OIHW slice; cin_cnt defaults to the packed width."""
     cout, cin, kh, kw = grad_oihw.shape
@@ -240,7 +252,7 @@ def unpack_wgrad(dw_packed, grad_oihw, cin_off=0, accumulate=False, cin_cnt=None
 
 
 # ---------------------------------------------------------------------------------- batched (un)packing
-PACK_FWD, PACK_DGRAD, PACK_UP2X, PACK_STEM_S2D, UNPACK_CONV, UNPACK_STEM_S2D, COPY_F32, PACK_DGRAD_S2 = 0, 1, 2, 3, 4, 5, 6, 7
+PACK_FWD, PACK_DGRAD, PACK_UP2X, PACK_STEM_S2D, UNPACK_CONV, UNPACK_STEM_S2D, COPY_F32, PACK_DGRAD_S2, PACK_UPCONV_DGRAD = range(9)
 
 
 def spec_pack_weight(w, dtype, cin_off=0, cin_cnt=None, dgrad=False, pad_to=None):
@@ -291,6 +303,15 @@ def spec_pack_dgrad_s2_weight(w, dtype, cin_off=0, cin_cnt=None, pad_to=None):
     pad = cout if pad_to is None else max(cout, int(pad_to))
     return (4, cin_cnt, 4, pad), dtype, False, [dict(kind=PACK_DGRAD_S2, src=w, off=0, total=16 * cin_cnt * pad, cout=cout,
                                                      cin=cin, taps=9, cin_off=cin_off, cin_cnt=cin_cnt, cpad=pad)]
+
+
+def spec_pack_upconv2x_dgrad_weight(w, dtype, cin_off=0, cin_cnt=None, pad_to=None):
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
+    pad = cout if pad_to is None else max(cout, int(pad_to))
+    return (cin_cnt, 16, pad), dtype, False, [dict(kind=PACK_UPCONV_DGRAD, src=w, off=0, total=cin_cnt * 16 * pad, cout=cout,
+                                                   cin=cin, taps=9, cin_off=cin_off, cin_cnt=cin_cnt, cpad=pad)]
 
 
 def spec_pack_stem_s2d_weight(w, dtype, cpad=16):

@@ -150,6 +150,34 @@ def test_tma_dgrad_stride2_phases(case):
         assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('case', [(2, 64, 32, 8, 16), (1, 32, 64, 11, 13), (2, 128, 64, 5, 9), (1, 256, 256, 6, 11)])
+def test_upconv2x_dgrad_as_strided_conv(case):
+    """Gradient of `3x3 conv after exact 2x nearest up-sampling` w.r.t. the low-res source as ONE 4x4 / stride-2 conv over
+    dy (rcfd_pack_upconv2x_dgrad_weight) vs autograd through F.interpolate + conv2d; batched pack == single pack."""
+    from rcfd import ops
+    n, cin, cout, h, w = case
+    x = _q(_rand(n, cin, h, w, seed=31)).requires_grad_(True)
+    wt = _q(_rand(cout, cin, 3, 3, seed=32) / (cin * 9) ** 0.5)
+    y = F.conv2d(F.interpolate(x, size=(2 * h, 2 * w), mode='nearest'), wt, None, 1, 1)
+    dy = _q(_rand(*y.shape, seed=33))
+    y.backward(dy)
+    w4 = ops.pack_upconv2x_dgrad_weight(wt.to(DEV), BF)
+    assert w4.shape == (cin, 16, cout)
+    dx = ops.conv2d(_nhwc(dy), w4, cin, 4, 2, pad=1)
+    assert tuple(dx.shape) == (n, h, w, cin)
+    # the packed weights are sums of up to 4 bf16-rounded taps, rounded once more: slightly looser than a plain conv
+    assert relerr(_nchw(dx), x.grad) < 2 * TOL
+    t = ops.PackBatch()
+    shape, dt_, zero, items = ops.spec_pack_upconv2x_dgrad_weight(wt.to(DEV), BF, cin_off=cin // 2, cin_cnt=cin // 2, pad_to=cout + 16)
+    out = torch.full(shape, 3.0, device=DEV, dtype=dt_)
+    for it in items:
+        it = dict(it)
+        t.add(it.pop('kind'), it.pop('src'), out, **it)
+    t.finalize(DEV).run()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ops.pack_upconv2x_dgrad_weight(wt.to(DEV), BF, cin_off=cin // 2, cin_cnt=cin // 2, pad_to=cout + 16))
+
+
 def test_tc_rejects_unsupported():
     from rcfd import ops, _lib
     x = torch.zeros(1, 4, 4, 8, device=DEV)          # fp32 -> not a tcgen05 case

@@ -36,6 +36,9 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
 extern int g_tma_bn_cap;
 extern int g_tma_pair;
+extern int g_wgrad_tma_v2;
+extern int g_wgrad_tma_cs_max;
+extern int g_wgrad_tma_groups;
 extern int g_strip_max_waste;
 extern int g_strip_input_stationary;
 extern int g_strip_up_max_waste;
@@ -104,6 +107,9 @@ int rcfd_set_option(const char* key, int32_t value) {
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
   if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
   if (strcmp(key, "tma_pair") == 0) { g_tma_pair = value; return RCFD_OK; }
+  if (strcmp(key, "wgrad_tma_v2") == 0) { g_wgrad_tma_v2 = value; return RCFD_OK; }
+  if (strcmp(key, "wgrad_tma_cs_max") == 0) { g_wgrad_tma_cs_max = value; return RCFD_OK; }
+  if (strcmp(key, "wgrad_tma_groups") == 0) { g_wgrad_tma_groups = value; return RCFD_OK; }
   if (strcmp(key, "strip_input_stationary") == 0) { g_strip_input_stationary = value; return RCFD_OK; }
   if (strcmp(key, "strip_max_waste") == 0) { g_strip_max_waste = value; return RCFD_OK; }
   if (strcmp(key, "strip_up_max_waste") == 0) { g_strip_up_max_waste = value; return RCFD_OK; }

@@ -319,6 +319,40 @@ def test_tma_wgrad(case):
     assert relerr(gw.cpu(), wt.grad) < 2e-3
 
 
+@pytest.mark.parametrize('case', [(8, 256, 256, 22, 44, 3, 1, 0), (8, 128, 128, 44, 88, 3, 1, 0), (2, 256, 256, 6, 11, 3, 1, 0),
+                                  (4, 128, 256, 22, 44, 3, 2, 0), (2, 128, 512, 22, 44, 1, 1, 0), (2, 256, 256, 11, 22, 3, 1, 256),
+                                  (1, 64, 64, 44, 88, 3, 1, 0), (2, 128, 128, 11, 22, 3, 1, 128), (1, 64, 128, 5, 7, 1, 2, 0),
+                                  (1, 64, 64, 3, 5, 3, 1, 0)])
+def test_tma_wgrad_v2_cluster_reduce(case):
+    """Second-generation TMA weight gradient (several k-tiles per CTA sharing the dY tile, pixel splits merged through
+    distributed shared memory inside a thread-block cluster: no atomics, no memset) vs autograd, at the FusionNet shapes
+    (256 / 128 channels, 22x44 ... 6x11, stride 2, 1x1 stacked fusion pair, decoder concat) and tiny extents (fewer pixel
+    tiles than a cluster); repeatable; agrees with the first-generation kernel."""
+    from rcfd import ops
+    n, cin, cout, h, w, k, s, c1 = case
+    x = _q(_rand(n, cin, h, w, seed=41))
+    x1 = _q(_rand(n, c1, h, w, seed=44)) if c1 else None
+    wt = (_rand(cout, cin + c1, k, k, seed=42) * 0.05).requires_grad_(True)
+    y = F.conv2d(x if x1 is None else torch.cat([x, x1], 1), wt, None, s, k // 2)
+    dy = _q(_rand(*y.shape, seed=43))
+    y.backward(dy)
+    kw = dict(x1=_nhwc(x1)) if c1 else {}
+    dw = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), k, s, engine=ops.ENGINE_TMA, **kw)
+    assert ops._lib.load().rcfd_last_kernel().decode().startswith('wgrad_tma2_kernel')
+    gw = torch.empty(cout, cin + c1, k, k, device=DEV)
+    ops.unpack_wgrad(dw, gw)
+    assert relerr(gw.cpu(), wt.grad) < 2e-3
+    again = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), k, s, engine=ops.ENGINE_TMA, **kw)
+    assert relerr(again.cpu(), dw.cpu()) < 1e-6         # bit identical with one cluster per unit; <= 6 float4 atomics per element otherwise
+    ops.set_option('wgrad_tma_v2', 0)
+    try:
+        old = ops.conv2d_wgrad(_nhwc(x), _nhwc(dy), k, s, engine=ops.ENGINE_TMA, **kw)
+        assert ops._lib.load().rcfd_last_kernel().decode().startswith('wgrad_tma_kernel')
+    finally:
+        ops.set_option('wgrad_tma_v2', 1)
+    assert relerr(dw.cpu(), old.cpu()) < 1e-4
+
+
 def test_tma_wgrad_concat():
     from rcfd import ops
     n, c0, c1, cout = 2, 64, 32, 64

@@ -258,6 +258,18 @@ int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, f
 int rcfd_masked_l1_loss(const float* out, const float* gt, const float* lidar, float w_lidar,
                         double* accum, float* loss, float* dout, int64_t count, void* stream);
 
+/* Edge-aware smoothness losses (src/fusionnet_losses.py:49-74 and :77-125), value + gradient w.r.t. `predict`, sync-free.
+ * predict: float N x 1 x H x W; image: float N x C x H x W (C = 3 for the Sobel form); weights: float N x 1 x H x W;
+ * accum: double[2] scratch (zeroed by the call); loss: float[1]; dpredict: float N x 1 x H x W or NULL.
+ *   smoothness:  mean(exp(-mean_c|dx I|) |dx p|) + mean(exp(-mean_c|dy I|) |dy p|), forward differences (gradient_yx :131-145)
+ *   sobel form:  (mean(w exp(-|Sx gray|) |Gx p|) + mean(w exp(-|Sy gray|) |Gy p|)) / (kh kw), Gx / Gy the reference's kh x kw
+ *                sobel_filter (:147-161) over the replicate-padded prediction, Sx / Sy its 3x3 form over the gray image;
+ *                scratch: 2 * N * H * W floats (needed with dpredict). */
+int rcfd_smoothness_loss(const float* predict, const float* image, int32_t n, int32_t c, int32_t h, int32_t w, double* accum,
+                         float* loss, float* dpredict, void* stream);
+int rcfd_sobel_smoothness_loss(const float* predict, const float* image, const float* weights, int32_t n, int32_t h, int32_t w,
+                               int32_t kh, int32_t kw, double* accum, float* scratch, float* loss, float* dpredict, void* stream);
+
 /* OutlierRemoval.remove_outliers (src/net_utils.py:591-638), float N x 1 x H x W. */
 int rcfd_outlier_removal(const float* depth, float* out, float* scratch_max, int32_t n, int32_t h,
                          int32_t w, int32_t kernel_size, float threshold, void* stream);

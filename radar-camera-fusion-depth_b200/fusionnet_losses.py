@@ -49,8 +49,26 @@ def gradient_yx(T):
     return T[:, :, :-1, :] - T[:, :, 1:, :], T[:, :, :, :-1] - T[:, :, :, 1:]
 
 
+class _KernelLoss(torch.autograd.Function):
+    """A loss whose value and gradient w.r.t. the prediction come out of one fused kernel call."""
+
+    @staticmethod
+    def forward(ctx, predict, fn):
+        loss, grad = fn(predict.detach().float().contiguous(), predict.requires_grad)
+        ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
 def smoothness_loss_func(predict, image):
-    """edge-aware first-order smoothness (reference :49-74)"""
+    """edge-aware first-order smoothness (reference :49-74); CUDA tensors: one fused kernel (rcfd_smoothness_loss)"""
+    if predict.is_cuda and not image.requires_grad:
+        img = image.detach().float().contiguous()
+        return _KernelLoss.apply(predict, lambda p, want: ops.smoothness_loss(p, img, want_grad=want))
     p_dy, p_dx = gradient_yx(predict)
     i_dy, i_dx = gradient_yx(image)
     wx = torch.exp(-i_dx.abs().mean(dim=1, keepdim=True))
@@ -74,9 +92,14 @@ def sobel_filter(filter_size=[1, 1, 3, 3]):
 
 
 def sobel_smoothness_loss_func(predict, image, weights, filter_size=[1, 1, 7, 7]):
-    """Sobel edge-aware smoothness (reference :77-125)"""
+    """Sobel edge-aware smoothness (reference :77-125); CUDA tensors: fused kernels (rcfd_sobel_smoothness_loss)"""
     F = torch.nn.functional
     kh, kw = filter_size[-2], filter_size[-1]
+    if (predict.is_cuda and not image.requires_grad and not weights.requires_grad and kh % 2 == 1 and kw % 2 == 1
+            and 3 <= kh <= 15 and 3 <= kw <= 15 and image.shape[1] == 3):
+        img = image.detach().float().contiguous()
+        wts = weights.detach().float().expand(predict.shape).contiguous()
+        return _KernelLoss.apply(predict, lambda p, want: ops.sobel_smoothness_loss(p, img, wts, kh, kw, want_grad=want))
     predict = F.pad(predict, (kw // 2, kw // 2, kh // 2, kh // 2), mode='replicate')
     gx, gy = [g.to(predict.device) for g in sobel_filter(filter_size)]
     p_dy, p_dx = F.conv2d(predict, gy), F.conv2d(predict, gx)

@@ -531,6 +531,30 @@ def masked_l1_loss(out, gt, lidar, w_lidar, want_grad=True):
     return loss, dout
 
 
+def smoothness_loss(predict, image, want_grad=True):
+    """(loss [1], d loss / d predict or None) of the reference's smoothness_loss_func; float N x 1 x H x W / N x C x H x W."""
+    n, c, h, w = image.shape
+    assert predict.shape == (n, 1, h, w) and predict.dtype == torch.float32 and image.dtype == torch.float32
+    accum = _empty(2, device=predict.device, dtype=torch.float64)
+    loss = _empty(1, device=predict.device, dtype=torch.float32)
+    grad = _empty_like(predict) if want_grad else None
+    _lib.call('rcfd_smoothness_loss', _p(predict), _p(image), n, c, h, w, _p(accum), _p(loss), _p(grad), _stream())
+    return loss, grad
+
+
+def sobel_smoothness_loss(predict, image, weights, kh, kw, want_grad=True):
+    """(loss [1], gradient or None) of the reference's sobel_smoothness_loss_func (kh x kw generalised Sobel filter)."""
+    n, c, h, w = image.shape
+    assert c == 3 and predict.shape == (n, 1, h, w) and weights.shape == (n, 1, h, w)
+    accum = _empty(2, device=predict.device, dtype=torch.float64)
+    loss = _empty(1, device=predict.device, dtype=torch.float32)
+    grad = _empty_like(predict) if want_grad else None
+    scratch = _empty(2 * predict.numel(), device=predict.device, dtype=torch.float32) if want_grad else None
+    _lib.call('rcfd_sobel_smoothness_loss', _p(predict), _p(image), _p(weights), n, h, w, int(kh), int(kw), _p(accum), _p(scratch),
+              _p(loss), _p(grad), _stream())
+    return loss, grad
+
+
 def outlier_removal(depth, kernel_size=7, threshold=1.5):
     depth = depth.contiguous()
     n, _, h, w = depth.shape

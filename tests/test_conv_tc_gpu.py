@@ -178,6 +178,32 @@ def test_upconv2x_dgrad_as_strided_conv(case):
     assert torch.equal(out, ops.pack_upconv2x_dgrad_weight(wt.to(DEV), BF, cin_off=cin // 2, cin_cnt=cin // 2, pad_to=cout + 16))
 
 
+def test_strip_output_stationary_variant_still_correct():
+    """rcfd_set_option('strip_input_stationary', 0) selects the output-stationary single-source row kernels (the default
+    is the input-stationary form): same results on the same layer."""
+    from rcfd import ops
+    n, cin, cout, h, w = 2, 32, 32, 19, 200
+    x = _q(_rand(n, cin, h, w, seed=51))
+    wt = _q(_rand(cout, cin, 3, 3, seed=52) / (cin * 9) ** 0.5)
+    raw = F.conv2d(x, wt, None, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    outs = []
+    for flag in (1, 0):
+        ops.set_option('strip_input_stationary', flag)
+        try:
+            ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+            ssq = torch.zeros_like(ssum)
+            y = ops.conv2d(_nhwc(x), wp, cout, 3, 1, stats=(ssum, ssq), engine=ops.ENGINE_STRIP)
+            name = ops._lib.load().rcfd_last_kernel().decode()
+        finally:
+            ops.set_option('strip_input_stationary', 1)
+        assert relerr(_nchw(y), raw) < TOL
+        assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 1e-2
+        outs.append((name, y))
+    assert outs[0][0] != outs[1][0], outs[0][0]                 # two different kernels really ran
+    assert relerr(_nchw(outs[0][1]), _nchw(outs[1][1])) < 1e-2
+
+
 def test_tc_rejects_unsupported():
     from rcfd import ops, _lib
     x = torch.zeros(1, 4, 4, 8, device=DEV)          # fp32 -> not a tcgen05 case

@@ -212,3 +212,32 @@ def test_padded_pack_unpack_and_fused_adam():
     for q, r in zip(ps, ref):
         assert relerr(q.detach().cpu(), r.detach().cpu()) < 1e-6
         assert q.data_ptr() >= fo_.flat_param.data_ptr()
+
+
+@pytest.mark.parametrize('shape', [(2, 37, 53), (1, 8, 9), (3, 64, 96)])
+def test_smoothness_losses_kernels_vs_formulas(shape):
+    """fusionnet_losses.smoothness_loss_func / sobel_smoothness_loss_func on CUDA tensors (fused value + gradient kernels)
+    == the reference's tensor formulas evaluated on the CPU (the module's own CPU branch, pinned against the reference in
+    tests/test_host_logic.py): value, and gradient w.r.t. the prediction through autograd, odd sizes and borders."""
+    import fusionnet_losses as L
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h * w)
+    image = torch.rand(n, 3, h, w, generator=g)
+    weights = (torch.rand(n, 1, h, w, generator=g) < 0.7).float()
+    for kind in ('first_order', (3, 3), (7, 7), (5, 3)):
+        p_cpu = (torch.rand(n, 1, h, w, generator=torch.Generator().manual_seed(7)) * 40 + 1).requires_grad_(True)
+        p_gpu = p_cpu.detach().clone().to(DEV).requires_grad_(True)
+        if kind == 'first_order':
+            ref = L.smoothness_loss_func(p_cpu, image)
+            got = L.smoothness_loss_func(p_gpu, image.to(DEV))
+        else:
+            fs = [1, 1, kind[0], kind[1]]
+            ref = L.sobel_smoothness_loss_func(p_cpu, image, weights, filter_size=fs)
+            got = L.sobel_smoothness_loss_func(p_gpu, image.to(DEV), weights.to(DEV), filter_size=fs)
+        (3.0 * ref).backward()
+        (3.0 * got).backward()
+        assert abs(float(got) - float(ref)) < 1e-5 * abs(float(ref)), kind
+        assert relerr(p_gpu.grad.cpu(), p_cpu.grad) < 1e-5, kind
+    with torch.no_grad():            # value only (no gradient buffers)
+        v = L.smoothness_loss_func(p_gpu.detach(), image.to(DEV))
+        assert abs(float(v) - float(L.smoothness_loss_func(p_cpu.detach(), image))) < 1e-5 * abs(float(v))

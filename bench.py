@@ -487,8 +487,20 @@ def build_workload(args, mode, batch, dev, rank, world):
 
     def result(out):
         return out.detach().reshape(-1) if not train else out.detach().reshape(1)
-    return dict(step=step, resident=resident, host=host, result=result, model=model, opt=opt,
-                h2d_bytes=sum(t.numel() * t.element_size() for t in host), eager=eager)
+    wl = dict(step=step, resident=resident, host=host, result=result, model=model, opt=opt,
+              h2d_bytes=sum(t.numel() * t.element_size() for t in host), eager=eager)
+    if train and args.graph:
+        # end-to-end arm: the batch crosses PCIe in the reference's ON-DISK sample types (uint8 RGB, uint16 16-bit-PNG maps:
+        # what rcfd.data.FusionNetRawDataset reads, 11 bytes per pixel instead of 28 as float32) and is decoded by
+        # rcfd_decode_crop on the device, the way fusionnet_main.train consumes real data
+        from rcfd import data as rcfd_data
+        image, depth, gt, lidar = host
+        raw = rcfd_data.encode_raw_batch(image * 255.0, depth[:, 0:1], depth[:, 1:2], gt, lidar)[:5]
+        raw = [t.pin_memory() for t in raw]
+        wl['host_raw'] = raw
+        wl['h2d_bytes_raw'] = sum(t.numel() * t.element_size() for t in raw)
+        wl['step_raw'] = lambda inputs: model.train_step_graphed_raw(inputs, opt, 2.0, outlier_removal=outlier)
+    return wl
 
 
 def measure(args, mode, batch, dev, rank, world, peaks, want_census, want_cpu):
@@ -529,6 +541,17 @@ def measure(args, mode, batch, dev, rank, world, peaks, want_census, want_cpu):
         e2e_step()
     reader.drain()
     ms_e2e = timer.timed(e2e_step, args.steps, drain=reader.drain)
+    e2e_inputs, h2d_bytes, e2e_f32 = 'float32 tensors (pinned host)', wl['h2d_bytes'], None
+    if 'step_raw' in wl:
+        def e2e_step_raw():
+            reader.push(wl['result'](wl['step_raw'](wl['host_raw'])))
+        for _ in range(3):
+            e2e_step_raw()
+        reader.drain()
+        e2e_f32 = {'value': world * batch / (ms_e2e * 1e-3), 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': wl['h2d_bytes']}
+        ms_e2e = timer.timed(e2e_step_raw, args.steps, drain=reader.drain)
+        h2d_bytes = wl['h2d_bytes_raw']
+        e2e_inputs = 'on-disk sample types (uint8 RGB + four uint16 maps, pinned host), decoded on the device (rcfd_decode_crop)'
 
     per_unit_gflop = {'train': TRAIN_GFLOP, 'infer': FWD_GFLOP, 'radarnet': RADAR_GFLOP}[mode]
     value = world * batch / (ms * 1e-3)
@@ -542,7 +565,8 @@ def measure(args, mode, batch, dev, rank, world, peaks, want_census, want_cpu):
                    'multistream': bool(args.multistream) and mode != 'radarnet'},
         'clocks': clocks,
         'e2e': {'value': world * batch / (ms_e2e * 1e-3), 'unit': METRIC[mode][1], 'ms_per_step': ms_e2e,
-                'h2d_bytes_per_step': wl['h2d_bytes'], 'd2h_bytes_per_step': reader.bytes},
+                'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': reader.bytes, 'inputs': e2e_inputs,
+                'float32_inputs': e2e_f32},
         'gpu_launches': launches,
         'step_roofline': {'tensor_frac': value / world * per_unit_gflop * 1e9 / (peaks['tc_sustained'] * 1e12),
                           'gflop_per_unit': per_unit_gflop, 'tflops': value / world * per_unit_gflop / 1e3,

@@ -224,11 +224,74 @@ class FusionNetModel(object):
                            outlier_removal=None):
         """One optimisation step of the canonical configuration (reference src/fusionnet_main.py:366-399:
         forward -> ground-truth outlier removal -> masked L1 (+ lidar term) -> backward -> Adam) with the
-        ~700 kernel launches of forward + loss + backward replayed from ONE CUDA graph (captured once per
-        input shape / precision); the gradient all-reduce (data parallel) and the optimiser step follow
-        eagerly, so learning-rate schedules and the Adam step count stay host-side.  Same arithmetic as
-        ``forward`` / ``compute_loss`` / ``loss.backward()`` / ``optimizer.step()``; returns the loss as a
-        0-d tensor owned by the graph (overwritten by the next call)."""
+        ~480 kernel launches of forward + loss + backward replayed from ONE CUDA graph (captured once per
+        input shape / precision); the gradient all-reduce (data parallel), the optimiser step and the batched
+        weight packing of the next step follow eagerly, so learning-rate schedules and the Adam step count stay
+        host-side.  Same arithmetic as ``forward`` / ``compute_loss`` / ``loss.backward()`` / ``optimizer.step()``;
+        returns the loss as a 0-d tensor owned by the graph (overwritten by the next call)."""
+        tensors = (image, input_depth, ground_truth, lidar_map)
+        entry = self._train_graph_entry([tuple(t.shape) for t in tensors], optimizer, w_lidar_loss, outlier_removal,
+                                        fill=lambda static: [s.copy_(t) for s, t in zip(static, tensors)])
+        self._feed(entry, entry['static'], tensors)
+        return self._replay_train(entry, optimizer)
+
+    def train_step_graphed_raw(self, raw, optimizer, w_lidar_loss, outlier_removal=None, response_multiplier=256.0):
+        """The same step fed with a batch in the reference's ON-DISK sample types (what rcfd.data.FusionNetRawDataset
+        yields): ``raw`` = (image uint8 N x H x W x 3, depth / response / ground truth / lidar uint16 N x H x W,
+        int16-viewed tensors are fine), pinned host or device tensors.  11 bytes per pixel cross PCIe instead of the 28
+        of five float32 tensors; the value codec of src/data_utils.py:167-198, 238-318 (/ 255 for the image with
+        normalized_image_range [0, 1], / 256 for the maps, <= 0 -> 0) and the HWC -> CHW change run on the device
+        (rcfd_decode_crop) straight into the graph's input buffers; host copies go through a double-buffered staging
+        set on a copy stream like ``_feed``."""
+        n, h, w, _ = raw[0].shape
+        shapes = [(n, 3, h, w), (n, 2, h, w), (n, 1, h, w), (n, 1, h, w)]
+        dev = next(self.encoder.parameters()).device
+
+        def decode(static, src):
+            ops.decode_crop(src[0], 255.0, out=static[0])
+            ops.decode_crop(src[1], 256.0, out=static[1], out_channel=0)
+            ops.decode_crop(src[2], response_multiplier, out=static[1], out_channel=1)
+            ops.decode_crop(src[3], 256.0, out=static[2])
+            ops.decode_crop(src[4], 256.0, out=static[3])
+        entry = self._train_graph_entry(shapes, optimizer, w_lidar_loss, outlier_removal,
+                                        fill=lambda static: decode(static, [t.to(dev) for t in raw[:5]]))
+        if all(t.is_cuda for t in raw[:5]):
+            decode(entry['static'], raw)
+        else:
+            main = torch.cuda.current_stream()
+            if 'raw_stage' not in entry:
+                entry['raw_stage'] = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in raw[:5]] for _ in range(2)]
+                entry['raw_free'] = [torch.cuda.Event(), torch.cuda.Event()]
+                entry['raw_copy_stream'] = torch.cuda.Stream()
+                entry['raw_n'] = 0
+                for ev in entry['raw_free']:
+                    ev.record(main)
+            slot = entry['raw_n'] % 2
+            entry['raw_n'] += 1
+            cs = entry['raw_copy_stream']
+            cs.wait_event(entry['raw_free'][slot])          # the step that decoded this staging set has read it
+            with torch.cuda.stream(cs):
+                for s_, t in zip(entry['raw_stage'][slot], raw[:5]):
+                    s_.copy_(t, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cs)
+            main.wait_event(ready)
+            decode(entry['static'], entry['raw_stage'][slot])
+            entry['raw_free'][slot].record(main)
+        return self._replay_train(entry, optimizer)
+
+    def _replay_train(self, entry, optimizer):
+        entry['graph'].replay()
+        if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
+            self.grad_hook(entry['grads'])
+        optimizer.step()
+        if entry.get('pack') is not None:
+            entry['pack']['table'].run()            # next step's packed weights (the graph reads the persistent buffers)
+        return entry['loss']
+
+    def _train_graph_entry(self, shapes, optimizer, w_lidar_loss, outlier_removal, fill):
+        """The captured step graph for these input shapes (built on first use; ``fill(static)`` puts a first batch into
+        the graph's input buffers for the warm-up pass)."""
         if not self.encoder.training:
             raise RuntimeError('train_step_graphed needs model.train()')
         if not w_lidar_loss > 0.0:
@@ -237,16 +300,14 @@ class FusionNetModel(object):
             raise RuntimeError('train_step_graphed needs rcfd.optim.FusedAdam (gradients written in place into its flat buffer)')
         if not hasattr(self, '_train_graphs'):
             self._train_graphs = {}
-        key = (tuple(image.shape), tuple(input_depth.shape), self.precision, self.conv_engine, float(w_lidar_loss),
+        key = (tuple(shapes[0]), tuple(shapes[1]), self.precision, self.conv_engine, float(w_lidar_loss),
                None if outlier_removal is None else (outlier_removal.kernel_size, outlier_removal.threshold),
                id(optimizer), self.multistream)
         entry = self._train_graphs.get(key)
         if entry is None:
             dev = next(self.encoder.parameters()).device
-            static = [torch.empty(tuple(t.shape), device=dev, dtype=torch.float32)
-                      for t in (image, input_depth, ground_truth, lidar_map)]
-            for s, t in zip(static, (image, input_depth, ground_truth, lidar_map)):
-                s.copy_(t)
+            static = [torch.empty(tuple(sh), device=dev, dtype=torch.float32) for sh in shapes]
+            fill(static)
 
             def body():
                 out, ectx = self._run(static[0], static[1], record=True)
@@ -289,15 +350,7 @@ class FusionNetModel(object):
                 self.last_capture_launches = _lib.launch_count - l0 + 1 + (1 if pack is not None else 0)      # + Adam (+ pack)
             entry = {'graph': graph, 'static': static, 'loss': loss, 'grads': grads, 'pack': pack}
             self._train_graphs[key] = entry
-        graph, static, loss, grads = entry['graph'], entry['static'], entry['loss'], entry['grads']
-        self._feed(entry, static, (image, input_depth, ground_truth, lidar_map))
-        graph.replay()
-        if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
-            self.grad_hook(grads)
-        optimizer.step()
-        if entry.get('pack') is not None:
-            entry['pack']['table'].run()            # next step's packed weights (the graph reads the persistent buffers)
-        return loss
+        return entry
 
     def _deliver_grads(self, param_grads, hook=True):
         for p, g in param_grads:

@@ -433,3 +433,40 @@ def test_run_entry_point_synthetic(tmp_path):
     back = data.load_png16(os.path.join(out, 'output_depth_fusion', files[-1])).astype(np.float32) / 256.0
     assert np.abs(back - d).max() <= 1.0 / 256.0 + 1e-6
     assert 'Evaluation results' in open(os.path.join(out, 'results.txt')).read()
+
+
+def test_graphed_train_step_raw_inputs():
+    """train_step_graphed_raw (uint8 image + uint16 maps, decoded on the device into the graph's inputs; pinned host
+    batches through the double-buffered staging) == train_step_graphed on the decoded float tensors: same losses over a
+    run of different batches."""
+    from rcfd import optim, data
+    import net_utils
+    cfg = synth.CANONICAL_FUSIONNET
+    p0 = synth_fusionnet_state(cfg, 3)
+    n, h, w = 2, 96, 160
+    raws, floats = [], []
+    for seed in (31, 32, 33, 34):
+        image, depth = synth.fusionnet_inputs(n, h, w, seed, 'quasi_dense')
+        gt, lidar = synth.training_targets(n, h, w, seed)
+        raw = data.encode_raw_batch(image * 255.0, depth[:, 0:1], depth[:, 1:2], gt, lidar)[:5]
+        raws.append([t.pin_memory() for t in raw])
+        dec = data.decode_fusionnet_batch(list(raw) + [torch.zeros(n, 2, dtype=torch.int32)], DEV)
+        floats.append([dec[0] / 255.0, torch.cat([dec[1], dec[2]], 1), dec[3], dec[4]])
+    outlier = net_utils.OutlierRemoval(7, 1.5)
+    losses = []
+    for use_raw in (False, True):
+        m = make_model(cfg, p0, precision='bf16')
+        m.train()
+        opt = optim.FusedAdam(m.parameters(), lr=0.0)          # the weights stay put: every step is comparable
+        cur = []
+        for raw, fl in zip(raws, floats):
+            if use_raw:
+                loss = m.train_step_graphed_raw(raw, opt, 2.0, outlier_removal=outlier)
+            else:
+                loss = m.train_step_graphed(fl[0], fl[1], fl[2], fl[3], opt, 2.0, outlier_removal=outlier)
+            cur.append(loss.clone())
+        torch.cuda.synchronize()
+        losses.append([float(x) for x in cur])
+    for a, b in zip(*losses):
+        assert abs(a - b) < 1e-5 * abs(a), losses
+    assert len(set(losses[0])) == len(losses[0])               # different batches really went through

@@ -48,8 +48,11 @@ def note_params_changed():
 # Most FusionNet layers below 1/4 resolution occupy a fraction of the 148 SMs and are latency bound; the
 # chains are independent between fusion points, so running them side by side (and capturing them as
 # parallel branches of the step's CUDA graph) overlaps those latencies.
-MAIN, DEPTH, FUSE, WG_MAIN, WG_DEPTH, PACK = 0, 1, 2, 3, 4, 5
+MAIN, DEPTH, FUSE, WG_MAIN, WG_DEPTH, PACK, WG_X0, WG_X1 = 0, 1, 2, 3, 4, 5, 6, 7
 _WG_OF = {MAIN: WG_MAIN, DEPTH: WG_DEPTH}
+# weight gradients go round-robin over four streams: the last ones of a step (stems, level-1 / level-2 layers: 80-110 us each)
+# have nothing left to hide behind, so they should at least run side by side instead of queueing on two streams
+_WG_POOL = (WG_MAIN, WG_DEPTH, WG_X0, WG_X1)
 _SIDE_STREAMS = {}
 
 
@@ -62,7 +65,7 @@ def side_streams(device):
         # all 148 SMs in front of a critical-path kernel.  RCFD_STREAM_PRIORITY=0 switches it off.
         import os
         hi = -1 if os.environ.get('RCFD_STREAM_PRIORITY', '1') != '0' else 0
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device, priority=hi if i < 2 else 0) for i in range(5)]
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device, priority=hi if i < 2 else 0) for i in range(7)]
     return _SIDE_STREAMS[key]
 
 
@@ -135,11 +138,11 @@ class Tape(object):
     def side(self, fn):
         """Run ``fn`` (a weight gradient: nothing downstream of it but the optimiser) on the weight-gradient
         stream of the current role, ordered after everything enqueued so far on the current stream."""
-        role = _WG_OF.get(self.sid) if self.streams is not None else None
-        if role is None:
+        if self.streams is None:
             fn()
             return
-        ws = self.streams[role]
+        self.wg_rr = getattr(self, 'wg_rr', 0) + 1
+        ws = self.streams[_WG_POOL[self.wg_rr % len(_WG_POOL)]]
         ws.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(ws):
             fn()

@@ -124,6 +124,7 @@ class FusionNetModel(object):
                                   record=record, engine=self.conv_engine, multistream=self.multistream, x3=self.x3,
                                   external_pack=getattr(self, '_external_pack', False))
             ectx.taps = taps
+            ectx.grad_split = getattr(self, '_grad_split_addr', None) if record else None
             # the layout conversion of each input is issued on its branch's stream
             latent, skips = engine.fusionnet_encoder(ectx, self.encoder, lambda: engine.stem_input(ectx, image),
                                                      lambda: engine.stem_input(ectx, input_depth))
@@ -282,7 +283,15 @@ class FusionNetModel(object):
 
     def _replay_train(self, entry, optimizer):
         entry['graph'].replay()
-        if self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
+        if entry.get('graph_b') is not None:
+            # data parallel: the gradients of encoder levels >= 5 and of the decoder (the tail of the flat buffer, 75 % of
+            # the bytes) are final after the first graph; their all-reduce runs on NCCL's stream while the second graph
+            # computes the rest of the backward
+            self.grad_hook.reduce_slice(entry['split_off'], None)
+            entry['graph_b'].replay()
+            self.grad_hook.reduce_slice(0, entry['split_off'])
+            self.grad_hook.finish()
+        elif self.grad_hook is not None:          # gradients live in the optimiser's flat buffer (written by the graph)
             self.grad_hook(entry['grads'])
         optimizer.step()
         if entry.get('pack') is not None:
@@ -300,23 +309,46 @@ class FusionNetModel(object):
             raise RuntimeError('train_step_graphed needs rcfd.optim.FusedAdam (gradients written in place into its flat buffer)')
         if not hasattr(self, '_train_graphs'):
             self._train_graphs = {}
+        # overlapped gradient all-reduce (rcfd.parallel.use_flat_gradients): split the step into two graphs.  Opt-in
+        # (RCFD_DDP_OVERLAP=1): measured on 2 and 8 B200s it changes nothing (5.867 vs 5.853 ms, 5.967 vs 5.970 ms per step):
+        # the ~0.26 ms an 8-GPU step costs over a 1-GPU step is not hidden by running the all-reduce beside the backward
+        split_off = None
+        hook = self.grad_hook
+        if (hook is not None and getattr(hook, 'flat_grad', None) is not None and hasattr(hook, 'reduce_slice')
+                and self.multistream and not self.x3 and os.environ.get('RCFD_DDP_OVERLAP', '0') == '1'):
+            first = getattr(self.encoder, 'blocks5_image', None)
+            first = next(first.parameters(), None) if first is not None else None
+            if first is not None and getattr(first, '_rcfd_flat', False) and first.grad is not None:
+                split_off = (first.grad.data_ptr() - hook.flat_grad.data_ptr()) // 4
         key = (tuple(shapes[0]), tuple(shapes[1]), self.precision, self.conv_engine, float(w_lidar_loss),
                None if outlier_removal is None else (outlier_removal.kernel_size, outlier_removal.threshold),
-               id(optimizer), self.multistream)
+               id(optimizer), self.multistream, split_off)
         entry = self._train_graphs.get(key)
         if entry is None:
             dev = next(self.encoder.parameters()).device
             static = [torch.empty(tuple(sh), device=dev, dtype=torch.float32) for sh in shapes]
             fill(static)
 
-            def body():
-                out, ectx = self._run(static[0], static[1], record=True)
-                n, h, w, _ = out.shape
-                gt = static[2] if outlier_removal is None else outlier_removal.remove_outliers(static[2])
-                loss, dout = ops.masked_l1_loss(out.view(n, 1, h, w), gt, static[3], float(w_lidar_loss), want_grad=True)
-                tape = ectx.tape
-                tape.set_grad(out, dout.view(out.shape))
-                tape.backward()
+            self._grad_split_addr = None if split_off is None else hook.flat_grad.data_ptr() + 4 * split_off
+            state = {}
+
+            def body(part=None):
+                """part None: the whole step; 0: forward + loss + backward down to the split marker; 1: the rest."""
+                if part in (None, 0):
+                    out, ectx = self._run(static[0], static[1], record=True)
+                    n, h, w, _ = out.shape
+                    gt = static[2] if outlier_removal is None else outlier_removal.remove_outliers(static[2])
+                    loss, dout = ops.masked_l1_loss(out.view(n, 1, h, w), gt, static[3], float(w_lidar_loss), want_grad=True)
+                    tape = ectx.tape
+                    tape.set_grad(out, dout.view(out.shape))
+                    state['tape'], state['loss'] = tape, loss
+                    if part == 0:
+                        tape.backward(part=0)
+                        return
+                    tape.backward()
+                else:
+                    tape, loss = state['tape'], state['loss']
+                    tape.backward(part=1)
                 grads, tape.param_grads = tape.param_grads, []
                 self._deliver_grads(grads, hook=False)       # the few gradients not written in place (captured copies)
                 return loss.view(()), grads
@@ -340,15 +372,31 @@ class FusionNetModel(object):
                 if pack is not None:
                     pack['table'].run()
                 l0 = _lib.launch_count
-                graph = torch.cuda.CUDAGraph()
+                graph, graph_b = torch.cuda.CUDAGraph(), None
                 self._external_pack = pack is not None
                 try:
-                    with torch.cuda.graph(graph, stream=engine.capture_stream(dev)):
-                        loss, grads = body()
+                    if split_off is None:
+                        with torch.cuda.graph(graph, stream=engine.capture_stream(dev)):
+                            loss, grads = body()
+                    else:
+                        with torch.cuda.stream(side):          # the split unpack tables are built by an eager two-part pass
+                            body(0)
+                            body(1)
+                        torch.cuda.current_stream().wait_stream(side)
+                        for b, s in zip(buffers, saved):
+                            b.copy_(s)
+                        l0 = _lib.launch_count
+                        graph_b = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, stream=engine.capture_stream(dev)):
+                            body(0)
+                        with torch.cuda.graph(graph_b, stream=engine.capture_stream(dev), pool=graph.pool()):
+                            loss, grads = body(1)
                 finally:
                     self._external_pack = False
+                    self._grad_split_addr = None
                 self.last_capture_launches = _lib.launch_count - l0 + 1 + (1 if pack is not None else 0)      # + Adam (+ pack)
-            entry = {'graph': graph, 'static': static, 'loss': loss, 'grads': grads, 'pack': pack}
+            entry = {'graph': graph, 'graph_b': graph_b, 'split_off': split_off, 'static': static, 'loss': loss, 'grads': grads,
+                     'pack': pack}
             self._train_graphs[key] = entry
         return entry
 

@@ -95,6 +95,8 @@ class Tape(object):
         self.streams = streams       # None = single stream
         self.sid = MAIN              # role being recorded (forward) / replayed (backward)
         self.finalizers = []         # run on the caller's stream once the backward streams have joined
+        self.split_at = None         # index into steps: backward(part=0) replays steps[split_at:], part=1 the rest
+        self.mid_finalizers = []     # run at the end of part 0
 
     def add_step(self, fn):
         self.steps.append((fn, self.sid))
@@ -147,9 +149,20 @@ class Tape(object):
         with torch.cuda.stream(ws):
             fn()
 
-    def backward(self):
+    def mark_split(self):
+        """Forward-time marker: everything recorded AFTER this call is replayed by backward(part=0), the rest by part=1
+        (data parallel: the gradients of the layers behind the marker are all-reduced while part 1 runs)."""
+        self.split_at = len(self.steps)
+
+    def backward(self, part=None):
+        """part=None: the whole tape.  part=0 / part=1: the two halves around mark_split(); every stream is joined at the
+        end of part 0, so part 1 may be captured into a second CUDA graph."""
+        if part is not None and self.split_at is None:
+            raise RuntimeError('Tape.backward(part): no split marker was recorded')
+        steps = self.steps if part is None else (self.steps[self.split_at:] if part == 0 else self.steps[:self.split_at])
+        last = part is None or part == 1
         if self.streams is None:
-            for fn, _ in reversed(self.steps):
+            for fn, _ in reversed(steps):
                 fn()
         else:
             main = torch.cuda.current_stream()
@@ -157,7 +170,7 @@ class Tape(object):
             with ops.hold_allocations():
                 for s in self.streams[1:]:
                     s.wait_stream(main)
-                for fn, sid in reversed(self.steps):
+                for fn, sid in reversed(steps):
                     self.sid = sid
                     if sid == MAIN:
                         fn()
@@ -167,9 +180,14 @@ class Tape(object):
                 self.sid = MAIN
                 for s in self.streams[1:]:
                     main.wait_stream(s)
-                for fn in self.finalizers:
+                for fn in (self.finalizers if last else self.mid_finalizers):
                     fn()
+        if not last:
+            for e in self.grads.values():          # everything is joined: later waits must not reference this part's events
+                e[2] = None
+            return
         self.finalizers = []
+        self.mid_finalizers = []
         self.steps = []
         self.grads = {}
         self.keep = []
@@ -204,6 +222,9 @@ class Context(object):
         # external_pack: the caller runs the batched pack launch itself before this step (FusionNetModel.train_step_graphed
         # issues it right after the optimiser step, where it overlaps the launch latency of the next graph replay)
         self.external_pack = external_pack
+        # data parallel with an overlapped gradient all-reduce: address in the flat gradient buffer from which on the
+        # gradients belong to the layers behind the tape's split marker (encoder levels >= 5, decoder); None = no split
+        self.grad_split = None
         self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (self.streams is not None and training) else None
         # batched weight (un)packing (training, multi-stream, plain dtypes): ONE rcfd_pack_batch launch per step packs every
         # weight the step uses into persistent buffers, another one unpacks every weight gradient at the end of backward
@@ -211,7 +232,8 @@ class Context(object):
         if self.plan is not None and not self.x3 and self.tape is not None:
             self.unpack = self.cache.setdefault(('unpack_state', dtype), {'bufs': {}, 'items': {}, 'batch': None, 'dirty': False})
             _validate_unpack(self.unpack)
-            self.tape.finalizers.append(lambda: _finish_unpack(self.unpack, self.device))
+            self.tape.finalizers.append(lambda: _finish_unpack(self.unpack, self.device, self.grad_split, 1))
+            self.tape.mid_finalizers.append(lambda: _finish_unpack(self.unpack, self.device, self.grad_split, 0))
             # the pack table of the NEXT step is built here, at the end of the step that recorded the plan (eagerly: a
             # capture that follows, FusionNetModel.train_step_graphed, then already replays the batched form)
             self.tape.finalizers.append(lambda: _pack_batch_for(self.cache, self.plan, self.dtype, self.device))
@@ -433,17 +455,34 @@ def _wgrad_slot(ctx, key, shape, param, gw):
     return buf, batch is not None and key in batch['keys']
 
 
-def _finish_unpack(st, device):
-    """End of backward (streams joined): the one batched unpack; (re)build the table after a recording step."""
-    if st['batch'] is not None:
-        st['batch']['table'].run()
-    if st['dirty'] and not torch.cuda.is_current_stream_capturing():
-        table, checks = ops.PackBatch(), []
+def _finish_unpack(st, device, grad_split=None, part=1):
+    """End of backward (streams joined): the one batched unpack; (re)build the table after a recording step.  With a
+    gradient split (two-part backward) the table exists twice: destinations at / above the split address are unpacked at
+    the end of part 0, the others at the end of part 1."""
+    batch = st['batch']
+    if batch is not None:
+        if grad_split is None:
+            batch['table'].run()
+        else:
+            tables = batch.get(('split', grad_split))
+            if tables is None:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError('the split unpack tables must exist before a capture (run one eager step first)')
+                tables = [ops.PackBatch(), ops.PackBatch()]
+                for kind, src, src_off, dst, f in batch['rows']:
+                    tables[0 if dst.data_ptr() >= grad_split else 1].add(kind, src, dst, src_off=src_off, **f)
+                tables = [t.finalize(device) if t.rows else None for t in tables]
+                batch[('split', grad_split)] = tables
+            if tables[part] is not None:
+                tables[part].run()
+    if part == 1 and st['dirty'] and not torch.cuda.is_current_stream_capturing():
+        table, checks, rows = ops.PackBatch(), [], []
         for key, items in st['items'].items():
             for kind, src, src_off, dst, param, f in items:
                 table.add(kind, src, dst, src_off=src_off, **f)
                 checks.append((param, dst.data_ptr()))
-        st['batch'] = {'table': table.finalize(device), 'keys': set(st['items']), 'checks': checks} if checks else None
+                rows.append((kind, src, src_off, dst, f))
+        st['batch'] = {'table': table.finalize(device), 'keys': set(st['items']), 'checks': checks, 'rows': rows} if checks else None
         st['dirty'] = False
 
 
@@ -831,6 +870,8 @@ def fusionnet_encoder(ctx, enc, image, depth, stem_s2d=False):
         si = getattr(enc, 'blocks%d_image' % level)
         if si is None:
             break
+        if level == 5 and ctx.tape is not None:
+            ctx.tape.mark_split()          # levels 5, 6 and the decoder = the last 75 % of the parameters (registration order)
         with ctx.on(MAIN):
             xi = res_stage(ctx, si, xi)
         with ctx.on(DEPTH):

@@ -78,6 +78,22 @@ class DistributedGradSync(object):
                     p.grad.copy_(g)
                 off += n
 
+    # -- overlapped form (FusionNetModel.train_step_graphed with two graphs): slices of the flat gradient buffer are reduced
+    #    asynchronously on NCCL's stream while the rest of the backward runs; finish() waits and averages
+    def reduce_slice(self, lo, hi):
+        flat = self.flat_grad[lo:hi]
+        if flat.numel() == 0:
+            return
+        if not hasattr(self, '_works'):
+            self._works = []
+        self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in getattr(self, '_works', []):
+            w.wait()
+        self._works = []
+        self.flat_grad.div_(self.world)
+
     def payload_bytes(self):
         return sum(f.numel() * 4 for f in self.flat)
 

@@ -247,8 +247,14 @@ def _ddp_worker(rank, world, port, tmp):
     d = m.forward(image, depth)
     loss, _ = m.compute_loss(image, d, gt, lidar, 'l1', 0.0, -1, torch.ones_like(gt), 2.0)
     loss.backward()
+    # the overlapped form: slices of a flat buffer reduced asynchronously (tail first), finish() waits and averages
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    m.grad_hook.flat_grad = flat
+    m.grad_hook.reduce_slice(6, None)
+    m.grad_hook.reduce_slice(0, 6)
+    m.grad_hook.finish()
     torch.save({'grads': [None if q.grad is None else q.grad.clone() for q in m.parameters()],
-                'params': [q.detach().clone() for q in m.parameters()],
+                'params': [q.detach().clone() for q in m.parameters()], 'sliced': flat.clone(),
                 'payload': m.grad_hook.payload_bytes()}, os.path.join(tmp, 'rank%d.pt' % rank))
     dist.barrier()
     dist.destroy_process_group()
@@ -275,6 +281,38 @@ def test_data_parallel_gradient_sync_gloo(tmp_path):
     assert n_none == 11
     used = sum(p.numel() for p, g in zip(r0['params'], r0['grads']) if g is not None)
     assert r0['payload'] == used * 4
+    assert torch.equal(r0['sliced'], torch.arange(10, dtype=torch.float32) * 1.5) and torch.equal(r0['sliced'], r1['sliced'])
+
+
+def test_two_part_backward_equals_whole_tape(mocked):
+    """Tape.backward(part=0) + backward(part=1) around the split marker (encoder level 5) == one backward(): the same
+    parameter gradients (the data-parallel step captures the two parts as two CUDA graphs and all-reduces the gradients
+    of the first part while the second runs)."""
+    import fusionnet_model
+    from rcfd import engine
+    cfg = dict(synth.SMALL_FUSIONNET)
+    torch.manual_seed(0)
+    m = fusionnet_model.FusionNetModel(device=torch.device('cpu'), **cfg)
+    m.train()
+    image, depth = synth.fusionnet_inputs(1, 64, 64, 3, 'quasi_dense')
+    results = []
+    for two_part in (False, True):
+        out, ectx = m._run(image, depth, record=True)
+        tape = ectx.tape
+        assert tape.split_at is not None and 0 < tape.split_at < len(tape.steps)
+        tape.set_grad(out, torch.ones_like(out))
+        if two_part:
+            tape.backward(part=0)
+            n_first = len(tape.param_grads)
+            assert 0 < n_first and tape.steps            # part 0 delivered the decoder / level >= 5 gradients only
+            tape.backward(part=1)
+            assert len(tape.param_grads) > n_first and not tape.steps
+        else:
+            tape.backward()
+        results.append({id(p): g.clone() for p, g in tape.param_grads})
+    assert set(results[0]) == set(results[1])
+    for k in results[0]:
+        assert torch.allclose(results[0][k], results[1][k], rtol=1e-5, atol=1e-7)
 
 
 def test_batched_transforms_match_reference_fixture():

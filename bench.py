@@ -21,7 +21,7 @@ The default run prints ONE JSON line for the train step; at N = 1 that line also
   `cpu_baseline` the reference's CPU path (oracle port) timed on the box's host cores at the SAME batch;
   `gpu_baseline` PyTorch eager + cuDNN running the reference graph on this GPU (fp32/TF32 and autocast bf16 +
                  channels_last; tools/eager_fusionnet.py) -- the library path the reference itself would use here;
-  `also`         the same measurement object for the other BASELINE configs (infer batch 8, radarnet 16 x 64);
+  `also`         the same measurement object for the other BASELINE configs (infer batch 8, radarnet 16 x 64, and the inference sweep at batch 1 / 32 / 128);
   `parity`       the recorded deviation of this arithmetic from the fp32 oracle (profiles/r2_bf16_deviation.json).
 
 --impl reference times the reference's own CPU path (the oracle port: same algorithm, fp32, torch CPU ops on the host
@@ -655,8 +655,9 @@ def run_ours(args):
     if solo and args.mode == 'train' and not args.no_also:
         # the other BASELINE configs, same measurement object each (driver-visible in the one JSON line)
         also = {}
-        for mode, b in (('infer', 8), ('radarnet', 16)):
-            sub = measure(args, mode, b, dev, rank, world, peaks, want_census=not args.no_census, want_cpu=False)
+        # (BASELINE configs[4]: the inference sweep 1 / 8 / 32 / 128; the roofline census only at batch 8)
+        for mode, b in (('infer', 8), ('radarnet', 16), ('infer', 1), ('infer', 32), ('infer', 128)):
+            sub = measure(args, mode, b, dev, rank, world, peaks, want_census=not args.no_census and b in (8, 16), want_cpu=False)
             sub.pop('parity', None)
             also['%s_b%d' % (mode, b)] = sub
         line['also'] = also

@@ -97,7 +97,8 @@ int64_t rcfd_conv2d_wgrad_workspace(const rcfd_conv_desc* d);
  * mode 0: forward weights, channels [cin_off, cin_off+cin_cnt) of the OIHW tensor, zero-padded to
  *         cin_pad >= cin_cnt channels per tap (the 3- / 2- / 1-channel inputs are stored with 8).
  * mode 1: dgrad weights  out[ci][kh-1-r][kw-1-s][co] = w[co][cin_off+ci][r][s]
- *         (rows = cin_cnt, K = kh*kw*cout_pad with cout zero-padded to `cin_pad` when it is larger). */
+ *         (rows = cin_cnt, K = kh*kw*cout_pad with cout zero-padded to `cin_pad` when it is larger; rows with
+ *         cin_off + ci >= cin, i.e. the zero-padded channels of a padded source, are zero). */
 int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh,
                           int32_t kw, int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t mode,
                           int32_t dtype, void* stream);
@@ -257,6 +258,19 @@ int rcfd_depth_head_bwd(const float* ddepth, const float* depth, void* dlogit, f
  * accum: double[4] scratch (zeroed by the call); loss: float[1]; dout: float grad (may be NULL). */
 int rcfd_masked_l1_loss(const float* out, const float* gt, const float* lidar, float w_lidar,
                         double* accum, float* loss, float* dout, int64_t count, void* stream);
+
+/* Multi-resolution decoder glue (src/networks.py:1595-1642, n_resolution > 1).
+ *   bilinear2x: float N x H x W -> N x 2H x 2W, torch.nn.functional.interpolate(scale_factor=2, mode='bilinear',
+ *               align_corners=True) of the 1-channel logits (:1600-1604); bwd = its transpose.
+ *   concat_logit: out[p][0..c) = skip[p][0..c), out[p][c] = logit[p], out[p][c+1..c_out) = 0: torch.cat([skip, up], 1)
+ *               (:1608, :1624, :1640) with the channel count padded to c_out; skip may be NULL with c = 0.
+ *   split_logit: the transpose (d skip in dtype, d logit float). */
+int rcfd_bilinear2x_fwd(const float* x, float* y, int32_t n, int32_t h, int32_t w, void* stream);
+int rcfd_bilinear2x_bwd(const float* dy, float* dx, int32_t n, int32_t h, int32_t w, void* stream);
+int rcfd_concat_logit(const void* skip, const float* logit, void* out, int64_t pixels, int32_t c, int32_t c_out, int32_t dtype,
+                      void* stream);
+int rcfd_split_logit(const void* dcat, void* dskip, float* dlogit, int64_t pixels, int32_t c, int32_t c_out, int32_t dtype,
+                     void* stream);
 
 /* Edge-aware smoothness losses (src/fusionnet_losses.py:49-74 and :77-125), value + gradient w.r.t. `predict`, sync-free.
  * predict: float N x 1 x H x W; image: float N x C x H x W (C = 3 for the Sobel form); weights: float N x 1 x H x W;

@@ -127,37 +127,51 @@ def decoder_block(p, prefix, x, skip, shape, use_bn, training, new_stats=None):
 
 
 def multiscale_decoder(p, latent, skips, shape, use_bn=True, training=False,
-                       new_stats=None, taps=None, pre='decoder.'):
-    """src/networks.py:1557-1657, n_resolution == 1 path.  Decoder depth follows the
-    number of filters: deconv{len-1} ... deconv0, the last one without a skip
-    (:1647-1652) when there are fewer skips than blocks."""
+                       new_stats=None, taps=None, pre='decoder.', all_outputs=False):
+    """src/networks.py:1557-1657.  Decoder depth follows the number of filters: deconv{len-1} ... deconv0, the last one
+    without a skip (:1647-1652) when there are fewer skips than blocks.  n_resolution > 1 (detected from the output1..3
+    weights): after deconv{b} (b = 3, 2, 1 when n_resolution > b) a 3x3 output conv gives the logits at that resolution
+    (:1595-1598, :1610-1613, :1626-1629), which are up-sampled 2x bilinearly with align_corners=True (:1600-1604, ...) and
+    concatenated BEHIND the next block's skip (:1608, :1624, :1640-1642; alone when that block has no skip).
+    Returns the full-resolution logits, or with all_outputs the list [coarsest ..., output0] (:1656)."""
     n_blocks = 0
     while (pre + 'deconv%d.conv.conv.weight' % n_blocks) in p:
         n_blocks += 1
+    n_resolution = 1 + sum(1 for b in (1, 2, 3) if (pre + 'output%d.conv.weight' % b) in p)
     x = latent
     n = len(skips) - 1
+    outputs, up = [], None
     for b in range(n_blocks - 1, -1, -1):
-        if n >= 0:
-            x = decoder_block(p, pre + 'deconv%d' % b, x, skips[n], None, use_bn, training, new_stats)
-            n -= 1
-        else:
-            x = decoder_block(p, pre + 'deconv%d' % b, x, None, shape, use_bn, training, new_stats)
+        skip = skips[n] if n >= 0 else None
+        n -= 1
+        if up is not None:
+            skip = torch.cat([skip, up], dim=1) if skip is not None else up
+        x = decoder_block(p, pre + 'deconv%d' % b, x, skip, None if skip is not None else shape, use_bn, training, new_stats)
         if taps is not None:
             taps['deconv%d' % b] = x
-    return conv_block(p, pre + 'output0', x, 1, None, False, training)
+        up = None
+        if 1 <= b <= 3 and n_resolution > b:
+            out_b = conv_block(p, pre + 'output%d' % b, x, 1, None, False, training)
+            outputs.append(out_b)
+            up = F.interpolate(out_b, scale_factor=2, mode='bilinear', align_corners=True)
+    outputs.append(conv_block(p, pre + 'output0', x, 1, None, False, training))
+    return outputs if all_outputs else outputs[-1]
 
 
 def fusionnet_forward(p, image, input_depth, min_predict_depth=1.0, max_predict_depth=100.0,
-                      n_levels=6, training=False, new_stats=None, taps=None):
-    """src/fusionnet_model.py:140-170.  Returns (depth, logits)."""
+                      n_levels=6, training=False, new_stats=None, taps=None, return_multiscale=False):
+    """src/fusionnet_model.py:140-170.  Returns (depth, logits); with return_multiscale both are lists over the decoder's
+    output resolutions, coarsest first."""
     latent, skips = fusionnet_encoder(p, image, input_depth, n_levels, True, training, new_stats, taps)
     if taps is not None:
         taps['latent'] = latent
         for i, s in enumerate(skips):
             taps['skip%d' % (i + 1)] = s
-    logits = multiscale_decoder(p, latent, skips, image.shape[-2:], True, training, new_stats, taps)
-    depth = min_predict_depth / (torch.sigmoid(logits) + min_predict_depth / max_predict_depth)
-    return depth, logits
+    logits = multiscale_decoder(p, latent, skips, image.shape[-2:], True, training, new_stats, taps, all_outputs=True)
+    depth = [min_predict_depth / (torch.sigmoid(o) + min_predict_depth / max_predict_depth) for o in logits]
+    if return_multiscale:
+        return depth, logits
+    return depth[-1], logits[-1]
 
 
 def fusionnet_loss(output_depth, ground_truth, lidar_map, w_lidar_loss=2.0, loss_func='l1'):

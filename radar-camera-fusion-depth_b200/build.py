@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'librcfd_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_tma.cu', 'conv_strip.cu', 'wgrad_tc.cu', 'wgrad_tma.cu', 'wgrad_strip.cu', 'elementwise.cu', 'scatter.cu', 'parity.cu', 'dataops.cu', 'radar_train.cu', 'packbatch.cu', 'losses.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_tma.cu', 'conv_strip.cu', 'wgrad_tc.cu', 'wgrad_tma.cu', 'wgrad_strip.cu', 'elementwise.cu', 'scatter.cu', 'parity.cu', 'dataops.cu', 'radar_train.cu', 'packbatch.cu', 'losses.cu', 'multires.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -1033,7 +1033,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       int64_t r = i / copad;
       const int tap = (int)(r % taps);
       const int ci = (int)(r / taps);
-      out[i] = from_f<T>(co < cout ? w[((size_t)co * cin + cin_off + ci) * taps + (taps - 1 - tap)] : 0.f);
+      // rows past the real input channels (a source stored with zero-padded channels) are zero
+      out[i] = from_f<T>((co < cout && cin_off + ci < cin) ? w[((size_t)co * cin + cin_off + ci) * taps + (taps - 1 - tap)] : 0.f);
     }
   }
 }
@@ -1455,7 +1456,8 @@ int rcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 int rcfd_pack_conv_weight(const float* w_oihw, void* packed, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
                           int32_t cin_off, int32_t cin_cnt, int32_t cin_pad, int32_t mode, int32_t dtype, void* stream) {
   RCFD_CHECK_ARG(w_oihw && packed && cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_weight: bad args");
-  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin && (mode == 0 || mode == 1), "pack_weight: range");
+  RCFD_CHECK_ARG(cin_off >= 0 && cin_cnt > 0 && cin_off < cin && (mode == 1 || cin_off + cin_cnt <= cin) && (mode == 0 || mode == 1),
+                 "pack_weight: range");
   RCFD_CHECK_ARG(mode == 1 || cin_pad >= cin_cnt, "pack_weight: cin_pad < cin_cnt");
   const int64_t total = mode == 0 ? (int64_t)cout * kh * kw * cin_pad
                                   : (int64_t)cin_cnt * kh * kw * (cin_pad > cout ? cin_pad : cout);

@@ -19,7 +19,7 @@ constexpr int DG_CO = 128;
 __host__ __device__ inline bool row_path(const rcfd_pack_item& it) {
   switch (it.kind) {
     case RCFD_PACK_FWD: return it.cin_cnt * it.taps <= ROW_FLOATS && it.cpad * it.taps <= 4 * ROW_FLOATS;
-    case RCFD_PACK_DGRAD: return (DG_CI * it.taps + 1) * DG_CO <= ROW_FLOATS;
+    case RCFD_PACK_DGRAD: return (DG_CI * it.taps + 1) * DG_CO <= ROW_FLOATS && it.cin_off + it.cin_cnt <= it.cin;   // padded rows: element-wise path
     case RCFD_PACK_UP2X: return it.cin * 9 <= ROW_FLOATS;
     case RCFD_UNPACK_CONV: return it.cpad * it.taps <= ROW_FLOATS;
     default: return false;
@@ -52,7 +52,7 @@ __device__ __forceinline__ void pack_one(const rcfd_pack_item& it, uint32_t i) {
       const uint32_t co = i % it.cout, r = i / it.cout;
       const uint32_t tap = r % taps, ci = r / taps;
       out[((size_t)ci * taps + tap) * it.dst_cols + it.col_off + co] =
-          from_f<T>(__ldg(w + ((size_t)co * it.cin + it.cin_off + ci) * taps + (taps - 1 - tap)));
+          from_f<T>((int)(it.cin_off + ci) < it.cin ? __ldg(w + ((size_t)co * it.cin + it.cin_off + ci) * taps + (taps - 1 - tap)) : 0.f);
       break;
     }
     case RCFD_PACK_UP2X: {                     // out[phase][co][2x2 tap][ci]: sums of the 3x3 taps hitting one low-res pixel

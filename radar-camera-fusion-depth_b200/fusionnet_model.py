@@ -31,19 +31,23 @@ class _FusionNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(fctx, model, record, image, input_depth, *params):
         out_nhwc, ectx = model._run(image, input_depth, record=record)
-        fctx.model, fctx.ectx, fctx.out_nhwc = model, ectx, out_nhwc
+        # multi-resolution decoder: the coarser outputs first, the full-resolution one last (reference :160-170)
+        outs = list(getattr(ectx, 'multiscale', [])) + [out_nhwc]
+        fctx.model, fctx.ectx, fctx.outs_nhwc = model, ectx, outs
         fctx.set_materialize_grads(False)
-        n, h, w, _ = out_nhwc.shape
-        return out_nhwc.view(n, 1, h, w)        # C == 1: NHWC and NCHW coincide
+        views = tuple(t.view(t.shape[0], 1, t.shape[1], t.shape[2]) for t in outs)        # C == 1: NHWC and NCHW coincide
+        return views if len(views) > 1 else views[0]
 
     @staticmethod
-    def backward(fctx, grad_out):
+    def backward(fctx, *grad_outs):
         ectx = fctx.ectx
         n_in = 4 + len(list(fctx.model.parameters()))
-        if grad_out is None or ectx is None or ectx.tape is None:
+        if all(g is None for g in grad_outs) or ectx is None or ectx.tape is None:
             return (None,) * n_in
         tape = ectx.tape
-        tape.set_grad(fctx.out_nhwc, grad_out.contiguous().float().view(fctx.out_nhwc.shape))
+        for t, g in zip(fctx.outs_nhwc, grad_outs):
+            if g is not None:
+                tape.set_grad(t, g.contiguous().float().view(t.shape))
         tape.backward()
         fctx.model._deliver_grads(tape.param_grads)
         tape.param_grads = []
@@ -142,15 +146,15 @@ class FusionNetModel(object):
         """N x 3 x H x W image, N x 2 x H x W (depth, response) -> N x 1 x H x W depth in
         [min, max] metres (reference src/fusionnet_model.py:140-170)."""
         if return_logits:
-            out, _ = self._run(image, input_depth, return_logits=True)
-            n, h, w, _ = out.shape
-            out = out.view(n, 1, h, w)
+            out, ectx = self._run(image, input_depth, return_logits=True)
+            outs = [t.view(t.shape[0], 1, t.shape[1], t.shape[2]) for t in list(ectx.multiscale) + [out]]
         else:
             params = self.parameters()
             # grad mode is off inside autograd.Function.forward, so decide here whether to tape
             record = torch.is_grad_enabled() and self.encoder.training and any(p.requires_grad for p in params)
-            out = _FusionNetFunction.apply(self, record, image, input_depth, *params)
-        return [out] if return_multiscale else out
+            outs = _FusionNetFunction.apply(self, record, image, input_depth, *params)
+            outs = list(outs) if isinstance(outs, tuple) else [outs]
+        return outs if return_multiscale else outs[-1]
 
     def _feed(self, entry, static, tensors):
         """Bring this step's inputs into the graph's static buffers.  Device tensors: one device copy each.

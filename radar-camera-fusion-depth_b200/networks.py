@@ -144,7 +144,10 @@ class RadarNetV1Encoder(torch.nn.Module):
 
 
 class MultiScaleDecoder(torch.nn.Module):
-    """U-Net decoder (reference src/networks.py:1337-1657), single output resolution."""
+    """U-Net decoder (reference src/networks.py:1337-1657).  n_resolution > 1: output{b} convs after deconv{b} (b = 1..3,
+    present when n_resolution > b) whose logits, up-sampled 2x bilinearly, join the next block's skip (one more skip
+    channel for deconv{b-1}); modules are registered in the reference's order (deconv3, output3, deconv2, output2, ...),
+    which is the order of parameters() and of the optimiser state."""
 
     def __init__(self, input_channels=256, output_channels=1, n_resolution=1, n_filters=[256, 128, 64, 32, 16],
                  n_skips=[256, 128, 64, 32, 0], weight_initializer='kaiming_uniform', activation_func='leaky_relu',
@@ -153,9 +156,8 @@ class MultiScaleDecoder(torch.nn.Module):
         depth = len(n_filters)
         assert depth < 8, 'Does not support network depth of 8 or more'
         assert n_resolution > 0 and n_resolution < depth
-        if n_resolution != 1 or 'upsample' in output_func:
-            raise ValueError('multi-resolution decoder outputs are not on the B200 path '
-                             '(every shipped config uses n_resolutions_decoder 1)')
+        if n_resolution > 4:
+            raise ValueError('n_resolution must be 1 .. 4 (the reference builds output0 .. output3)')
         if output_func != 'linear':
             raise ValueError("output_func must be 'linear' (reference fusionnet_model.py:131, radarnet_model.py:94)")
         self.n_resolution = n_resolution
@@ -165,10 +167,14 @@ class MultiScaleDecoder(torch.nn.Module):
         in_channels = input_channels
         for i in range(depth):
             b = depth - 1 - i                   # deconv{depth-1} ... deconv0
+            extra = output_channels if (b <= 2 and n_resolution > b + 1) else 0      # the up-sampled logits of output{b+1}
             setattr(self, 'deconv%d' % b,
-                    net_utils.DecoderBlock(in_channels, n_skips[i], n_filters[i], weight_initializer, act,
+                    net_utils.DecoderBlock(in_channels, n_skips[i] + extra, n_filters[i], weight_initializer, act,
                                            use_batch_norm, deconv_type))
             in_channels = n_filters[i]
+            if 1 <= b <= 3 and n_resolution > b:
+                setattr(self, 'output%d' % b, net_utils.Conv2d(in_channels, output_channels, 3, 1, weight_initializer,
+                                                               net_utils.activation_func(output_func), False))
         for b in range(depth, 7):
             setattr(self, 'deconv%d' % b, None)
         self.output0 = net_utils.Conv2d(in_channels, output_channels, 3, 1, weight_initializer,

@@ -75,6 +75,10 @@ _SIGS = {
     'rcfd_nhwc_to_nchw': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],
     'rcfd_depth_head_bwd': [_P, _P, _P, c_float, c_float, c_int64, c_int32, c_int32, _P],
     'rcfd_masked_l1_loss': [_P, _P, _P, c_float, _P, _P, _P, c_int64, _P],
+    'rcfd_bilinear2x_fwd': [_P, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_bilinear2x_bwd': [_P, _P, c_int32, c_int32, c_int32, _P],
+    'rcfd_concat_logit': [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_split_logit': [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_smoothness_loss': [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P],
     'rcfd_sobel_smoothness_loss': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P],
     'rcfd_outlier_removal': [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P],

@@ -897,20 +897,76 @@ def resnet_encoder(ctx, enc, x, stem_s2d=False):
     return layers[-1], layers[:-1]
 
 
+def _logit_output(ctx, mod, x, head):
+    """An intermediate output of the multi-resolution decoder: 3x3 conv -> float logits [N, h, w, 1], their depth
+    (bounded head, when ``head`` is given) and the 2x bilinear up-sampling that joins the next skip.  Returns
+    (logits, depth or None, up); with a tape the gradients of depth and up accumulate on the logits."""
+    logits = ops.conv2d(x, ctx.weight(mod), mod.out_channels, 3, 1, out_f32=True, engine=ctx.engine)
+    if ctx.tape is not None:
+        # d(logits): float, 1 channel -> the compute dtype with CPAD_DY channels (rows of >= 32 bytes for the conv engines)
+        to_dy = lambda d: ops.nchw_to_nhwc(d.view(d.shape[0], 1, d.shape[1], d.shape[2]), ctx.dtype,
+                                           cpad=CPAD_DY if (ctx.dtype == torch.bfloat16 or ctx.x3) else 8)
+        _record_conv_backward(ctx, mod, x, None, None, logits, None, True, pre=to_dy)
+    depth = None
+    if head is not None:
+        depth = ops.epilogue_f32(logits, None, None, ACT_DEPTH_HEAD, act_params=head)
+    up = ops.bilinear2x(logits)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            for t, back in ((up, ops.bilinear2x_bwd),
+                            (depth, (lambda d: ops.depth_head_bwd(d, depth, head[0], head[1], torch.float32, cpad=1)))):
+                if t is None:
+                    continue
+                d = tape.grad_of(t)
+                if d is not None:
+                    tape.add_grad(logits, back(d.contiguous()))
+        tape.add_step(bwd)
+    return logits, depth, up
+
+
+def _skip_with_logit(ctx, skip, up):
+    """torch.cat([skip, up], 1) of the reference (src/networks.py:1608, 1624, 1640), channels padded to a multiple of 16."""
+    cat = ops.concat_logit(skip, up, ctx.dtype)
+    if ctx.tape is not None:
+        tape = ctx.tape
+        c = 0 if skip is None else skip.shape[3]
+
+        def bwd():
+            d = tape.grad_of(cat)
+            if d is None:
+                return
+            dskip, dup = ops.split_logit(d, c)
+            if skip is not None:
+                tape.add_grad(skip, dskip)
+            tape.add_grad(up, dup)
+        tape.add_step(bwd)
+    return cat
+
+
 def multiscale_decoder(ctx, dec, latent, skips, shape, head=None):
-    """networks.MultiScaleDecoder.forward, n_resolution == 1 (reference src/networks.py:1557-1657).
-    Returns (output, last feature map)."""
+    """networks.MultiScaleDecoder.forward (reference src/networks.py:1557-1657).  Returns (output, last feature map);
+    with n_resolution > 1 the coarser outputs (depth when ``head`` is given, else logits; float [N, h, w, 1], coarsest
+    first) are left in ``ctx.multiscale``."""
     x = latent
     n = len(skips) - 1
+    up = None
+    ctx.multiscale = []
     for b in range(dec.n_blocks - 1, -1, -1):
         blk = getattr(dec, 'deconv%d' % b)
-        if n >= 0:
-            x = decoder_block(ctx, blk, x, skips[n], None)
-            n -= 1
-        else:
-            x = decoder_block(ctx, blk, x, None, shape)
+        skip = skips[n] if n >= 0 else None
+        n -= 1
+        if up is not None:
+            skip = _skip_with_logit(ctx, skip, up)
+        x = decoder_block(ctx, blk, x, skip, shape if skip is None else None)
+        up = None
         if ctx.taps is not None:
             ctx.taps['deconv%d' % b] = x
+        out_mod = getattr(dec, 'output%d' % b, None) if b >= 1 else None
+        if out_mod is not None:
+            logits, depth, up = _logit_output(ctx, out_mod, x, head)
+            ctx.multiscale.append(depth if head is not None else logits)
     out = conv_unit(ctx, dec.output0, x, head=head) if head is not None else \
         ops.conv2d(x, ctx.weight(dec.output0), dec.output0.out_channels, 3, 1, out_f32=True, engine=ctx.engine)
     return out, x

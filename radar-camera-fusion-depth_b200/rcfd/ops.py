@@ -531,6 +531,42 @@ def masked_l1_loss(out, gt, lidar, w_lidar, want_grad=True):
     return loss, dout
 
 
+def bilinear2x(x):
+    """float [N, H, W, 1] -> [N, 2H, 2W, 1]: bilinear, align_corners=True (multi-resolution decoder)."""
+    n, h, w, c = x.shape
+    assert c == 1 and x.dtype == torch.float32
+    y = _empty((n, 2 * h, 2 * w, 1), device=x.device, dtype=torch.float32)
+    _lib.call('rcfd_bilinear2x_fwd', _p(x), _p(y), n, h, w, _stream())
+    return y
+
+
+def bilinear2x_bwd(dy):
+    n, ho, wo, c = dy.shape
+    assert c == 1 and dy.dtype == torch.float32 and ho % 2 == 0 and wo % 2 == 0
+    dx = _empty((n, ho // 2, wo // 2, 1), device=dy.device, dtype=torch.float32)
+    _lib.call('rcfd_bilinear2x_bwd', _p(dy), _p(dx), n, ho // 2, wo // 2, _stream())
+    return dx
+
+
+def concat_logit(skip, logit, dtype, cpad=16):
+    """NHWC [skip | logit | zeros] with (C + 1) rounded up to a multiple of cpad channels; skip may be None."""
+    n, h, w, _ = logit.shape
+    c = 0 if skip is None else skip.shape[3]
+    co = (c + 1 + cpad - 1) // cpad * cpad
+    out = _empty((n, h, w, co), device=logit.device, dtype=dtype)
+    _lib.call('rcfd_concat_logit', _p(skip), _p(logit), _p(out), n * h * w, c, co, _DT[dtype], _stream())
+    return out
+
+
+def split_logit(dcat, c):
+    """Transpose of concat_logit: (d skip [N, H, W, c] in dcat's dtype or None, d logit float [N, H, W, 1])."""
+    n, h, w, co = dcat.shape
+    dskip = _empty((n, h, w, c), device=dcat.device, dtype=dcat.dtype) if c > 0 else None
+    dlogit = _empty((n, h, w, 1), device=dcat.device, dtype=torch.float32)
+    _lib.call('rcfd_split_logit', _p(dcat), _p(dskip), _p(dlogit), n * h * w, c, co, dt(dcat), _stream())
+    return dskip, dlogit
+
+
 def smoothness_loss(predict, image, want_grad=True):
     """(loss [1], d loss / d predict or None) of the reference's smoothness_loss_func; float N x 1 x H x W / N x C x H x W."""
     n, c, h, w = image.shape

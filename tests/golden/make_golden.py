@@ -543,7 +543,50 @@ def checkpoint_case(name, seed):
     print(name, 'ok: reference checkpoint', os.path.getsize(path), 'bytes, both directions load')
 
 
+def multires_case(name, n_resolution, n, h, w, seed):
+    """Multi-resolution decoder (src/networks.py:1595-1642): every output of forward(return_multiscale=True) in train mode,
+    a loss over ALL scales (so that every output{k} conv and the bilinear / concat path carry gradient) and the
+    gradient fingerprints, written by the reference; the oracle is checked against it on the spot."""
+    cfg = dict(synth.SMALL_FUSIONNET, n_resolution_decoder=n_resolution)
+    model, p = build_fusionnet(cfg, seed)
+    image, depth = synth.fusionnet_inputs(n, h, w, seed, 'quasi_dense')
+    p_before = {k: v.clone() for k, v in p.items()}
+    model.train()
+    outs = model.forward(image, depth, return_multiscale=True)
+    assert len(outs) == n_resolution
+    weights = [float(i + 1) for i in range(n_resolution)]
+    loss = sum(wi * o.mean() for wi, o in zip(weights, outs))
+    loss.backward()
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in p_before.items()}
+    d_or, _ = fo.fusionnet_forward(po, image, depth, training=True, return_multiscale=True)
+    loss_or = sum(wi * o.mean() for wi, o in zip(weights, d_or))
+    loss_or.backward()
+    for a, b in zip(d_or, outs):
+        assert relerr(a.detach(), b.detach()) < 1e-5
+    ref_named = dict(list(('encoder.' + k, v) for k, v in model.encoder.named_parameters()) +
+                     list(('decoder.' + k, v) for k, v in model.decoder.named_parameters()))
+    names, gsum, gabs, gnone = [], [], [], []
+    for k, v in ref_named.items():
+        g_or = po[k].grad
+        assert (v.grad is None) == (g_or is None), k
+        names.append(k)
+        if v.grad is None:
+            gnone.append(1); gsum.append(0.0); gabs.append(0.0)
+            continue
+        assert relerr(g_or, v.grad) < 1e-4, (k, relerr(g_or, v.grad))
+        gnone.append(0); gsum.append(float(v.grad.double().sum())); gabs.append(float(v.grad.double().abs().sum()))
+    out = {'depth%d' % i: o.detach().numpy() for i, o in enumerate(outs)}
+    out.update(meta=np.array([n, h, w, seed, n_resolution]), loss=np.float64(float(loss)), grad_names=np.array(names),
+               grad_sum=np.array(gsum), grad_abs=np.array(gabs), grad_none=np.array(gnone),
+               param_order=np.array([k for k, _ in model.decoder.named_parameters()]))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'ok  loss', float(loss), [tuple(o.shape) for o in outs])
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'multires':
+        multires_case('fusionnet_multires3_2x64x96', 3, 2, 64, 96, 81)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'checkpoint':
         checkpoint_case('reference_checkpoint_tiny', 71)
         sys.exit(0)
@@ -566,4 +609,5 @@ if __name__ == '__main__':
     radarnet_loss_case('radarnet_loss_3x64x64', 61)
     checkpoint_case('reference_checkpoint_tiny', 71)
     crop_case('crop_origins_90x160')
+    multires_case('fusionnet_multires3_2x64x96', 3, 2, 64, 96, 81)
     print('golden fixtures written to', OUT)

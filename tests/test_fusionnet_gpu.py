@@ -526,6 +526,27 @@ def test_multires_graphed_train_step_matches_eager():
     assert relerr(losses[1][1].cpu(), losses[0][1].cpu()) < 1e-3
 
 
+def test_forward_graphed_raw_inputs():
+    """forward_graphed_raw (uint8 image + uint16 depth / response decoded on the device, pinned host batches through the
+    staging sets) == forward on the decoded float tensors."""
+    from rcfd import data
+    cfg = synth.CANONICAL_FUSIONNET
+    m = make_model(cfg, synth_fusionnet_state(cfg, 2), precision='bf16')
+    m.eval()
+    n, h, w = 2, 96, 160
+    outs, refs = [], []
+    for seed in (41, 42, 43):
+        image, depth = synth.fusionnet_inputs(n, h, w, seed, 'quasi_dense')
+        zero = torch.zeros(n, 1, h, w)
+        raw = [t.pin_memory() for t in data.encode_raw_batch(image * 255.0, depth[:, 0:1], depth[:, 1:2], zero, zero)[:3]]
+        dec = data.decode_fusionnet_batch(list(raw) + [raw[1], raw[1], torch.zeros(n, 2, dtype=torch.int32)], DEV)
+        with torch.no_grad():
+            outs.append(m.forward_graphed_raw(raw).clone())
+            refs.append(m.forward(dec[0] / 255.0, torch.cat([dec[1], dec[2]], 1)).clone())
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+
+
 def test_multires_glue_kernels():
     """rcfd_bilinear2x_fwd / bwd == F.interpolate(scale_factor=2, bilinear, align_corners=True) and its autograd;
     rcfd_concat_logit / rcfd_split_logit == torch.cat([skip, up], 1) with zero-padded channels and its transpose."""

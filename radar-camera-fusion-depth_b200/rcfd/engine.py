@@ -164,6 +164,8 @@ class Tape(object):
         if self.streams is None:
             for fn, _ in reversed(steps):
                 fn()
+            for fn in (self.finalizers if last else self.mid_finalizers):
+                fn()
         else:
             main = torch.cuda.current_stream()
             self.streams[MAIN] = main
@@ -225,7 +227,10 @@ class Context(object):
         # data parallel with an overlapped gradient all-reduce: address in the flat gradient buffer from which on the
         # gradients belong to the layers behind the tape's split marker (encoder levels >= 5, decoder); None = no split
         self.grad_split = None
-        self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (self.streams is not None and training) else None
+        # pack plan / batched (un)packing: every training context on the device (also the single-stream schedule, so that
+        # profiles taken on one stream show the kernels the graphed step runs)
+        on_device = torch.device(device).type == 'cuda'
+        self.plan = self.cache.setdefault(('pack_plan', dtype, self.x3), {}) if (on_device and training) else None
         # batched weight (un)packing (training, multi-stream, plain dtypes): ONE rcfd_pack_batch launch per step packs every
         # weight the step uses into persistent buffers, another one unpacks every weight gradient at the end of backward
         self.unpack = None
@@ -324,8 +329,11 @@ class Context(object):
         """Issue every pack call recorded by the previous step on the PACK stream (training, multi-stream)."""
         if self.plan is None or not self.plan:
             return
-        pk, main = self.streams[PACK], self.streams[MAIN]
-        pk.wait_stream(main)
+        if self.streams is not None:
+            pk, main = self.streams[PACK], self.streams[MAIN]
+            pk.wait_stream(main)
+        else:
+            pk = torch.cuda.current_stream()
         with torch.cuda.stream(pk):
             batch = _pack_batch_for(self.cache, self.plan, self.dtype, self.device)
             if batch is not None:

@@ -39,6 +39,29 @@ def forward(model, image, radar_points, bounding_boxes_list, device=torch.device
     return output_depth, output_response
 
 
+def forward_batch(model, images, radar_points, bounding_boxes, device=torch.device('cuda'), compat=None):
+    """``forward`` for N frames in ONE pass (the reference's entry point takes one image: src/radarnet_main.py:534-591):
+    images N x 3 x H x W, radar_points N x K x 3, bounding_boxes N x K x 4.  The image encoder runs once over the N frames
+    and the decoder once over the N * K point columns, then one S2 scatter per frame; same arithmetic, frame by frame
+    identical results.  Returns (depth N x 1 x H x W, response N x 1 x H x W) stacked."""
+    compat = REFERENCE_COMPAT if compat is None else compat
+    patch_size = model.input_patch_size_image
+    pad_size = patch_size[1] // 2
+    n, k = radar_points.shape[0], radar_points.shape[1]
+    padded = torch.nn.functional.pad(images, (pad_size, pad_size, 0, 0), mode='replicate')
+    points = radar_points.reshape(n * k, radar_points.shape[2])
+    crops = model.forward(image=padded, point=points, bounding_boxes=[bounding_boxes[b] for b in range(n)],
+                          return_logits=False)
+    height, width = images.shape[-2], images.shape[-1]
+    depth, resp = [], []
+    pts = radar_points.to(device=crops.device, dtype=torch.float32)
+    for b in range(n):
+        d, r = ops.scatter_tiles_argmax(crops[b * k:(b + 1) * k], pts[b], height, width, compat=compat)
+        depth.append(d)
+        resp.append(r)
+    return torch.stack(depth), torch.stack(resp)
+
+
 def make_labels(ground_truth_depth, radar_depth, max_distance_correspondence, set_invalid_to_negative_class):
     """Ground-truth labels and validity map of the training step (reference :349-378): a pixel of a point's crop is a
     positive when its lidar depth is within ``max_distance_correspondence`` of the radar return's depth; pixels without

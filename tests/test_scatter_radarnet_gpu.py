@@ -274,3 +274,27 @@ def test_radarnet_train_entry_point_synthetic(tmp_path):
     assert set(ck) == {'train_step', 'radarnet_optimizer_state_dict', 'radarnet_encoder_state_dict', 'radarnet_decoder_state_dict'}
     kw.update(restore_path=str(tmp_path / 'model-12.pth'), max_steps=13)
     assert radarnet_main.train(**kw)[2] == 13
+
+
+def test_radarnet_forward_batch_equals_per_image():
+    """radarnet_main.forward_batch (N frames in one pass) == radarnet_main.forward frame by frame (eval mode: folded
+    BatchNorm, so batching changes nothing): bit-identical depth / response maps."""
+    import radarnet_main
+    import radarnet_model
+    torch.manual_seed(5)
+    h, w, k, n = 64, 128, 4, 3
+    m = radarnet_model.RadarNetModel(device=DEV, **dict(synth.CANONICAL_RADARNET, input_patch_size_image=(64, 64)))
+    m.set_precision('bf16')
+    m.eval()
+    images = torch.rand(n, 3, h, w, device=DEV)
+    pts = torch.stack([synth.radar_points(k, h, w, 20 + b) for b in range(n)]).to(DEV)
+    pad = 32
+    shifted = pts.clone()
+    shifted[..., 0] += pad
+    boxes = torch.stack([shifted[..., 0] - pad, torch.zeros(n, k, device=DEV), shifted[..., 0] + pad,
+                         torch.full((n, k), float(h), device=DEV)], dim=-1)
+    with torch.no_grad():
+        d_all, r_all = radarnet_main.forward_batch(m, images, shifted, boxes, device=DEV)
+        for b in range(n):
+            d, r = radarnet_main.forward(m, images[b:b + 1], shifted[b], [boxes[b]], device=DEV)
+            assert torch.equal(d_all[b], d) and torch.equal(r_all[b], r)

@@ -36,6 +36,7 @@ int conv_strip_launch(const ConvKP& p, cudaStream_t st);
 extern int g_strip_desc_mode;
 extern int g_tma_bn_cap;
 extern int g_tma_pair;
+extern int g_tma_split_k;
 extern int g_wgrad_tma_v2;
 extern int g_wgrad_tma_cs_max;
 extern int g_wgrad_tma_groups;
@@ -107,6 +108,7 @@ int rcfd_set_option(const char* key, int32_t value) {
   if (strcmp(key, "strip_desc_mode") == 0) { g_strip_desc_mode = value; return RCFD_OK; }
   if (strcmp(key, "tma_bn_cap") == 0) { g_tma_bn_cap = value; return RCFD_OK; }
   if (strcmp(key, "tma_pair") == 0) { g_tma_pair = value; return RCFD_OK; }
+  if (strcmp(key, "tma_split_k") == 0) { g_tma_split_k = value; return RCFD_OK; }
   if (strcmp(key, "wgrad_tma_v2") == 0) { g_wgrad_tma_v2 = value; return RCFD_OK; }
   if (strcmp(key, "wgrad_tma_cs_max") == 0) { g_wgrad_tma_cs_max = value; return RCFD_OK; }
   if (strcmp(key, "wgrad_tma_groups") == 0) { g_wgrad_tma_groups = value; return RCFD_OK; }

@@ -53,7 +53,21 @@ struct TmaConvP {
   int kpair;                // 1: two 64-channel chunks per k-step (one full barrier / one commit per PAIR of stages)
   int phases;               // 1, or 4 = sub-pixel phases of a 2x nearest up-sampled 3x3 conv (2x2 taps each)
   int out_h, out_w, out_s;  // destination extent and pixel stride (out_s = 2 with phases)
+  int splitk;               // 1, or S = 2 | 4: the k-loop of ONE tile is split over the S CTAs of a cluster (grid = tiles x S), partial
+                            // accumulators merged through distributed shared memory; each CTA runs the epilogue of BN / S columns
 };
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
 
 template <int BN>
 struct TmaCfg {
@@ -67,7 +81,7 @@ struct TmaCfg {
   static_assert(SMEM <= 227 * 1024 && STAGES % 2 == 0, "per-tap engine: stage ring");
 };
 
-template <int BN>
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_w, const TmaConvP p) {
@@ -110,6 +124,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   const int a_bytes = TM * p.bkc * 2, b_bytes = BN * p.bkc * 2;
   const int chunks0 = p.c0 / p.bkc, chunks = (p.c0 + p.c1) / p.bkc;
   const int ctot = p.c0 + p.c1;
+  // k-loop units (a 64-channel chunk of one tap, or a pair of them) and this CTA's share of them (split-K: rank = blockIdx.y)
+  const int upt = p.kpair ? chunks / 2 : chunks;              // units per tap
+  const int units = p.kh * p.kw * upt;
+  const int S = SPLIT ? p.splitk : 1, srank = SPLIT ? (int)blockIdx.y : 0;       // SPLIT = false compiles the cluster paths away
+  const int ubeg = (int)((long long)units * srank / S), uend = (int)((long long)units * (srank + 1) / S);
 
   if (warp == 0) {
     // =========================================================== TMA PRODUCER (one lane)
@@ -132,41 +151,40 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         if (p.kpair) {
           // stages are filled and released in PAIRS (s, s+1): 8 MMAs per barrier round trip / commit instead of 4
           constexpr uint32_t NP = C::STAGES / 2;
-          for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+          for (int u = ubeg; u < uend; ++u, ++it) {
+            const int tap = u / upt, ch = 2 * (u - tap * upt);
             const int tr = tap / p.kw, ts = tap - tr * p.kw;
-            for (int ch = 0; ch < chunks; ch += 2, ++it) {
-              const uint32_t pr = it % NP, s = 2 * pr;
-              if (it >= NP) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / NP) & 1) ^ 1);
-              const uint32_t full = sBar + 8 * s;
-              mbar_expect_tx(full, (uint32_t)(2 * (a_bytes + b_bytes)));
+            const uint32_t pr = it % NP, s = 2 * pr;
+            if (it >= NP) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / NP) & 1) ^ 1);
+            const uint32_t full = sBar + 8 * s;
+            mbar_expect_tx(full, (uint32_t)(2 * (a_bytes + b_bytes)));
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int c = ch + h;
-                const uint32_t a_dst = sStage + (s + h) * C::STAGE, b_dst = a_dst + C::A_BYTES;
-                if (c < chunks0) tma_load_4d(a_dst, &map_a0, full, c * p.bkc, x0 + ts, y0 + tr, img);
-                else tma_load_4d(a_dst, &map_a1, full, (c - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
-                tma_load_2d(b_dst, &map_w, full, tap * ctot + c * p.bkc, n0);
-              }
+            for (int h = 0; h < 2; ++h) {
+              const int c = ch + h;
+              const uint32_t a_dst = sStage + (s + h) * C::STAGE, b_dst = a_dst + C::A_BYTES;
+              if (c < chunks0) tma_load_4d(a_dst, &map_a0, full, c * p.bkc, x0 + ts, y0 + tr, img);
+              else tma_load_4d(a_dst, &map_a1, full, (c - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+              tma_load_2d(b_dst, &map_w, full, tap * ctot + c * p.bkc, n0);
             }
           }
           continue;
         }
-        for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+        for (int u = ubeg; u < uend; ++u, ++it) {
+          const int tap = u / upt, ch = u - tap * upt;
           const int tr = tap / p.kw, ts = tap - tr * p.kw;
-          for (int ch = 0; ch < chunks; ++ch, ++it) {
-            const int s = it % C::STAGES;
-            if (it >= (uint32_t)C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / C::STAGES) & 1) ^ 1);
-            const uint32_t full = sBar + 8 * s;
-            const uint32_t a_dst = sStage + s * C::STAGE, b_dst = a_dst + C::A_BYTES;
-            mbar_expect_tx(full, (uint32_t)(a_bytes + b_bytes));
-            if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
-            else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
-            tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
-          }
+          const int s = it % C::STAGES;
+          if (it >= (uint32_t)C::STAGES) mbar_wait(sBar + 8 * (C::STAGES + s), ((it / C::STAGES) & 1) ^ 1);
+          const uint32_t full = sBar + 8 * s;
+          const uint32_t a_dst = sStage + s * C::STAGE, b_dst = a_dst + C::A_BYTES;
+          mbar_expect_tx(full, (uint32_t)(a_bytes + b_bytes));
+          if (ch < chunks0) tma_load_4d(a_dst, &map_a0, full, ch * p.bkc, x0 + ts, y0 + tr, img);
+          else tma_load_4d(a_dst, &map_a1, full, (ch - chunks0) * p.bkc, x0 + ts, y0 + tr, img);
+          tma_load_2d(b_dst, &map_w, full, tap * ctot + ch * p.bkc, n0);
         }
       }
       TRACE(3);
     }
+    if (SPLIT) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }      // the epilogue's two cluster barriers count every thread
   } else if (warp == 1) {
     // =========================================================== MMA ISSUER
     const uint32_t idesc = umma_idesc(BN);
@@ -181,8 +199,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const uint32_t d_tmem = tmem_base + acc * BN;
       if (p.kpair) {
         constexpr uint32_t NP = C::STAGES / 2;
-        const int npairs = p.ksteps / 2;
-        for (int kp = 0; kp < npairs; ++kp, ++it) {
+        for (int kp = ubeg; kp < uend; ++kp, ++it) {
           const uint32_t pr = it % NP, s = 2 * pr;
           mbar_wait(sBar + 8 * s, (it / NP) & 1);
           tc_fence_after();
@@ -196,17 +213,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
-                         (uint32_t)((kp | h | k) != 0));
+                         (uint32_t)(((kp - ubeg) | h | k) != 0));
             }
             umma_commit(sBar + 8 * (C::STAGES + s));
-            if (kp == npairs - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
-            if (kp == npairs - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
+            if (kp == uend - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+            if (kp == uend - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
           }
           __syncwarp();
         }
         continue;
       }
-      for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+      for (int ks = ubeg; ks < uend; ++ks, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(sBar + 8 * s, (it / C::STAGES) & 1);
         tc_fence_after();
@@ -214,17 +231,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           const uint32_t a_st = sStage + s * C::STAGE, b_st = a_st + C::A_BYTES;
           for (int k = 0; k < p.bkc / 16; ++k) {
             umma_f16(d_tmem, umma_desc(a_st + k * 32, 16, sbo, layout), umma_desc(b_st + k * 32, 16, sbo, layout), idesc,
-                     (uint32_t)((ks | k) != 0));
+                     (uint32_t)(((ks - ubeg) | k) != 0));
           }
           umma_commit(sBar + 8 * (C::STAGES + s));
-          if (ks == p.ksteps - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
+          if (ks == uend - 1) umma_commit(sBar + 8 * (2 * C::STAGES + acc));
           if (it == 0) TRACE(4);
-          if (ks == p.ksteps - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
+          if (ks == uend - 1) { if (tcount == 0) TRACE(5); TRACE(6); }
         }
         __syncwarp();
       }
     }
     tc_fence_before();
+    if (SPLIT) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
   } else {
     // =========================================================== EPILOGUE (warps 2..9)
     // EPI_GROUPS warps per TMEM lane quarter, each taking every EPI_GROUPS-th CW-column chunk of its 32 tile rows; BatchNorm statistics
@@ -261,10 +279,35 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       tc_fence_after();
       if (tid == 64 && tcount == 0) TRACE(7);
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      // split-K: every CTA of the cluster stages its partial accumulator ([column][row] floats in the stage ring, which is
+      // free once the accumulator is ready), then sums ITS column slice over all peers and runs the epilogue on that slice
+      int c_lo = 0, c_hi = BN;
+      if (SPLIT) {
+        float* stg = reinterpret_cast<float*>(gen_base);
 #pragma unroll 1
-      for (int cb = grp * CW; cb < BN; cb += EPI_GROUPS * CW) {
+        for (int cb = grp * CW; cb < BN; cb += EPI_GROUPS * CW) {
+          uint32_t raw[CW];
+#pragma unroll
+          for (int j = 0; j < CW; j += 16) tmem_ld16_nowait(trow + cb + j, raw + j);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < CW; ++i) stg[(cb + i) * TM + r] = __uint_as_float(raw[i]);      // lanes = consecutive rows
+        }
+        cluster_sync_all();
+        c_lo = srank * (BN / S);
+        c_hi = c_lo + BN / S;
+      }
+#pragma unroll 1
+      for (int cb = c_lo + grp * CW; cb < c_hi; cb += EPI_GROUPS * CW) {
         float v[CW];
-        {
+        if (SPLIT) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = 0.f;
+          for (int pr = 0; pr < S; ++pr) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] += ld_dsmem_f32(sStage + (uint32_t)(((cb + i) * TM + r) * 4), (uint32_t)pr);
+          }
+        } else {
           uint32_t raw[CW];
 #pragma unroll
           for (int j = 0; j < CW; j += 16) tmem_ld16_nowait(trow + cb + j, raw + j);
@@ -380,7 +423,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (tid == 64 && tcount == 0) TRACE(8);
       if (want_stats) {
         asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-        for (int c = etid; c < BN; c += NEPI) {
+        for (int c = c_lo + etid; c < c_hi; c += NEPI) {
           if (n0 + c < p.cout) {
             double s = 0.0, qq = 0.0;
 #pragma unroll
@@ -394,6 +437,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         }
       }
       if (tid == 64) { if (tcount == 0) TRACE(9); TRACE(10); TRACE_VAL(12, tcount + 1); TRACE_VAL(13, p.ksteps); }
+      if (SPLIT) cluster_sync_all();            // peers have read this CTA's staging: it may exit
     }
   }
   __syncthreads();
@@ -407,6 +451,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 }  // namespace
 extern int g_tma_bn_cap;
 extern int g_tma_pair;
+extern int g_tma_split_k;
 namespace {
 
 template <int BN>
@@ -416,14 +461,60 @@ int launch_tma(const ConvKP& k, const TmaConvP& tp, const CUtensorMap& a0, const
   typedef TmaCfg<BN> C;
   static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tma_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("conv_tma: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     attr_set = true;
   }
-  int grid = tp.num_tiles < num_sms() ? tp.num_tiles : num_sms();
-  conv_tma_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(a0, a1, w, tp);
-  RCFD_CHECK_LAUNCH("conv_tma");
   (void)k;
+  // split-K over a thread-block cluster for layers with fewer tiles than SMs (every level <= 11x22 at batch 8, everything at
+  // batch 1): there the latency of ONE CTA's k-loop is the kernel's duration, so S CTAs share it and merge their partial
+  // accumulators through distributed shared memory.  S = the largest of 4, 2 that keeps the whole grid resident at once.
+  constexpr int CWh = BN >= 64 ? 32 : 16;
+  TmaConvP t2 = tp;
+  t2.splitk = 1;
+  // Measured: inference batch 1 0.653 -> 0.592 ms, batch 8 1.416 -> 1.392 ms; the training step got slower with it (the extra
+  // CTAs and the all-or-nothing start of a cluster compete with the weight-gradient kernels), so only the eval-mode
+  // epilogue (folded BatchNorm, no statistics) splits; rcfd_set_option("tma_split_k", 2) forces it everywhere (tests).
+  if (g_tma_split_k == 2 || (g_tma_split_k == 1 && tp.ssum == nullptr && tp.scale != nullptr)) {
+    const int units = tp.kh * tp.kw * ((tp.c0 + tp.c1) / tp.bkc) / (tp.kpair ? 2 : 1);
+    static int max_clusters_dev[16][3] = {};
+    for (int sidx = 2; sidx >= 1; --sidx) {
+      const int S = 1 << sidx;
+      if ((BN / S) % CWh != 0 || BN / S < CWh || units < 2 * S || tp.num_tiles * S > num_sms()) continue;
+      int& mc = max_clusters_dev[cur_dev()][sidx];
+      if (mc == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1, S, 1); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = S; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tma_kernel<BN, true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+        mc = n;
+      }
+      if (mc >= tp.num_tiles) { t2.splitk = S; break; }
+    }
+  }
+  if (t2.splitk > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tp.num_tiles, t2.splitk, 1);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = t2.splitk; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<BN, true>, a0, a1, w, t2);
+    if (e != cudaSuccess) { set_error("conv_tma (split-K) launch: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
+    RCFD_CHECK_LAUNCH("conv_tma");
+    return RCFD_OK;
+  }
+  int grid = tp.num_tiles < num_sms() ? tp.num_tiles : num_sms();
+  conv_tma_kernel<BN, false><<<grid, NTHREADS, C::SMEM, st>>>(a0, a1, w, t2);
+  RCFD_CHECK_LAUNCH("conv_tma");
   return RCFD_OK;
 }
 
@@ -439,6 +530,7 @@ extern "C" int rcfd_debug_clear_trace() {
 }
 #endif
 
+int g_tma_split_k = 1;     // rcfd_set_option("tma_split_k"): 0 = never split the k-loop of a tile over a cluster
 int g_tma_pair = 1;        // rcfd_set_option("tma_pair"): 0 = one 64-channel chunk per k-step (4 MMAs per commit)
 int g_tma_bn_cap = -1;    // rcfd_set_option("tma_bn_cap"): -1 = widest tile (default: narrower tiles measured slower, k-steps are latency bound), 0 = occupancy heuristic, n = cap the cout tile at n
 

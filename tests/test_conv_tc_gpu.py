@@ -204,6 +204,41 @@ def test_strip_output_stationary_variant_still_correct():
     assert relerr(_nchw(outs[0][1]), _nchw(outs[1][1])) < 1e-2
 
 
+@pytest.mark.parametrize('case', [(8, 256, 256, 6, 11, 3, 1), (1, 128, 128, 22, 44, 3, 1), (2, 256, 128, 11, 22, 3, 2),
+                                  (1, 128, 512, 11, 22, 1, 1), (1, 64, 64, 44, 88, 3, 1), (2, 128, 64, 7, 9, 3, 1)])
+def test_tma_conv_split_k_cluster(case):
+    """Layers with fewer tiles than SMs split the k-loop of a tile over a 2- / 4-CTA cluster and merge the partial
+    accumulators through distributed shared memory: same results as the unsplit kernel (statistics, folded BN + activation +
+    residual epilogue), and as F.conv2d."""
+    from rcfd import ops
+    n, cin, cout, h, w, k, s_ = case
+    x = _q(_rand(n, cin, h * s_, w * s_, seed=61))
+    wt = _q(_rand(cout, cin, k, k, seed=62) / (cin * k * k) ** 0.5)
+    raw = F.conv2d(x, wt, None, s_, k // 2)
+    scale, shift = torch.rand(cout) + 0.5, _rand(cout, seed=63) * 0.1
+    res = _q(_rand(*raw.shape, seed=64))
+    ref = F.leaky_relu(F.leaky_relu(raw * scale[None, :, None, None] + shift[None, :, None, None], 0.2) + res, 0.2)
+    wp = ops.pack_weight(wt.to(DEV), BF)
+    outs = []
+    for split in (2, 0):
+        ops.set_option('tma_split_k', split)
+        try:
+            ssum = torch.zeros(cout, dtype=torch.float64, device=DEV)
+            ssq = torch.zeros_like(ssum)
+            y = ops.conv2d(_nhwc(x), wp, cout, k, s_, stats=(ssum, ssq), engine=ops.ENGINE_TMA)
+            z = ops.conv2d(_nhwc(x), wp, cout, k, s_, scale=scale.to(DEV), shift=shift.to(DEV), act=ops.ACT_LEAKY,
+                           residual=_nhwc(res), engine=ops.ENGINE_TMA)
+        finally:
+            ops.set_option('tma_split_k', 1)
+        torch.cuda.synchronize()
+        assert relerr(_nchw(y), raw) < TOL and relerr(_nchw(z), ref) < TOL
+        assert relerr(ssum.cpu(), raw.double().sum(dim=(0, 2, 3))) < 2e-3 * max(1.0, float(raw.abs().sum() / raw.double().sum(dim=(0, 2, 3)).abs().max() / raw.shape[1]))
+        assert relerr(ssq.cpu(), (raw.double() ** 2).sum(dim=(0, 2, 3))) < 1e-3
+        outs.append((y, z, ssum, ssq))
+    assert relerr(_nchw(outs[0][0]), _nchw(outs[1][0])) < 1e-2 and relerr(_nchw(outs[0][1]), _nchw(outs[1][1])) < 1e-2
+    assert relerr(outs[0][3].cpu(), outs[1][3].cpu()) < 1e-5
+
+
 def test_tc_rejects_unsupported():
     from rcfd import ops, _lib
     x = torch.zeros(1, 4, 4, 8, device=DEV)          # fp32 -> not a tcgen05 case

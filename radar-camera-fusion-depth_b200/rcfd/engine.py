@@ -416,12 +416,18 @@ def _pack_batch_for(cache, plan, dtype, device):
     per model / dtype outside graph capture and reused while the plan and the parameters' storage stay the same."""
     key = ('pack_batch', dtype)
     batch = cache.get(key)
-    if batch is not None and (batch['n_plan'] != len(plan) or any(t.data_ptr() != ptr for t, ptr in batch['srcs'])):
-        batch = None                     # the plan grew, or a parameter moved (model.to(), a new state_dict storage)
+    if batch is not None:
+        # the plan grew, or a parameter's storage moved (model.to(), rcfd.optim.FusedAdam re-pointing .data into its flat
+        # buffer): the specs are re-evaluated (they take fresh aliases of the parameters) and compared with the table
+        now = [it['src'].data_ptr() for _, (fn, spec) in plan.items() if spec is not None for it in spec()[3]] \
+            if batch['n_plan'] == len(plan) else None
+        if now != batch['src_ptrs']:
+            batch = None
     if batch is None:
         if torch.cuda.is_current_stream_capturing():
             return None                  # table upload and allocations belong outside a capture: per-item path this time
         table, outputs, srcs = ops.PackBatch(), {}, []
+        src_ptrs = []
         for k, (fn, spec) in plan.items():
             if spec is None:
                 continue
@@ -432,10 +438,11 @@ def _pack_batch_for(cache, plan, dtype, device):
                 src = it.pop('src')
                 table.add(it.pop('kind'), src, out, **it)
                 srcs.append((src, src.data_ptr()))
+                src_ptrs.append(src.data_ptr())
             outputs[k] = out
         if not outputs:
             return None
-        batch = {'table': table.finalize(device), 'outputs': outputs, 'srcs': srcs, 'n_plan': len(plan)}
+        batch = {'table': table.finalize(device), 'outputs': outputs, 'srcs': srcs, 'src_ptrs': src_ptrs, 'n_plan': len(plan)}
         cache[key] = batch
     return batch
 

@@ -111,3 +111,43 @@ def test_batched_step_equals_per_layer_step():
     assert relerr(g_b.cpu(), g_a.cpu()) < 1e-4 and relerr(g_c.cpu(), g_a.cpu()) < 1e-4
     assert float(g_a.abs().max()) > 0
     assert n_b == n_c and n_b < n_a - 150, (n_a, n_b, n_c)      # ~140 pack + ~75 unpack launches became two
+
+
+def test_pack_table_follows_parameter_storage():
+    """A model that trained with torch.optim.Adam (parameters in their own storages) and is then handed to FusedAdam (which
+    re-points every parameter into one flat buffer) must rebuild its pack table: the step after the switch uses the CURRENT
+    weights, not the old storages."""
+    from rcfd import optim, synth
+    cfg = synth.SMALL_FUSIONNET
+    p0 = synth_fusionnet_state(cfg, 9)
+    n, h, w = 2, 64, 96
+    image, depth = synth.fusionnet_inputs(n, h, w, 9, 'quasi_dense')
+    gt, lidar = synth.training_targets(n, h, w, 9)
+    image, depth, gt, lidar = [t.to(DEV) for t in (image, depth, gt, lidar)]
+
+    def step(m):
+        d = m.forward(image, depth)
+        loss, _ = m.compute_loss(image, d, gt, lidar, 'l1', 0.0, -1, None, 2.0)
+        loss.backward()
+        return float(loss)
+
+    m = make_model(cfg, p0, precision='bf16')
+    m.train()
+    adam = torch.optim.Adam(m.parameters(), lr=1e-2)
+    for _ in range(2):                          # records the plan, builds the table, takes real steps
+        adam.zero_grad()
+        step(m)
+        adam.step()
+    fused = optim.FusedAdam(m.parameters(), lr=1e-2)          # parameters move into the flat buffer
+    with torch.no_grad():
+        for q in m.parameters():
+            q.mul_(0.5)                          # and change there: the old storages keep the old values
+    from rcfd import engine
+    engine.note_params_changed()
+    got = step(m)
+    ref_model = make_model(cfg, p0, precision='bf16')
+    ref_model.train()
+    ref_model.encoder.load_state_dict(m.encoder.state_dict())
+    ref_model.decoder.load_state_dict(m.decoder.state_dict())
+    want = step(ref_model)
+    assert abs(got - want) < 1e-4 * abs(want), (got, want)

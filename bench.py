@@ -11,7 +11,11 @@ One "step" is one pass of the hot path over one synthetic batch:
   radarnet (configs[2])                  : RadarNet stage-1 forward + S2 scatter, 16 images x 64 radar points / GPU.
 `value` is whole-job throughput with inputs resident in HBM; `e2e` is the same step through the public API with
 pinned-host inputs copied H2D and the result (loss / depth maps / depth + response maps) read back D2H inside the
-timed region.  N > 1: launched by torchrun, one rank per GPU, gradients all-reduced over NCCL (train) or independent
+timed region.  The FusionNet e2e arms are measured with both input forms of the public API -- float32 tensors
+(train_step_graphed / forward_graphed) and the reference's on-disk sample types, uint8 RGB + uint16 maps decoded on
+the device (train_step_graphed_raw / forward_graphed_raw, 2.5x fewer PCIe bytes) -- `e2e` is the float32 form on one GPU
+and the on-disk form when several ranks share the host (measured: 10 468 vs 10 303 maps/s on 8 GPUs); the other one is
+reported under `e2e.other_input_form`.  N > 1: launched by torchrun, one rank per GPU, gradients all-reduced over NCCL (train) or independent
 replicas (infer, radarnet); weak scaling.
 
 The default run prints ONE JSON line for the train step; at N = 1 that line also carries

@@ -14,8 +14,12 @@
 //     using a leading-dimension byte offset of ONE PIXEL between its channel blocks:
 //       CIN = 32:  M = 4 blocks x 32 channels = taps s = 0, 1, 2 (+ one ignored block),
 //       CIN = 64:  M = 2 blocks x 64 channels = taps (0, 1) and (2, ignored);
+//       CIN = 16:  M = 8 blocks x 16 channels = taps s = 0 .. 3 of the 4x4 stems (+ four ignored blocks);
 //   * the accumulators (one per filter row / tap group) stay in TMEM for the whole kernel; the
 //     epilogue warps add them to dW with coalesced fp32 red.global.add once at the end.
+//
+// Variant KS = 4: the 4x4 / stride-1 / pad-2 form of the 7x7 / stride-2 stems on their space-to-depth input (16 channels):
+// four filter-row accumulators, three halo rows, window origin two pixels left of the strip.
 //
 // Variant UP: the convolution sits behind an exact 2x nearest up-sampling (decoder "deconv" convs).
 // Streamed over LOW-RES input rows with the sub-pixel decomposition of conv_strip_up_kernel:
@@ -31,7 +35,6 @@ using namespace tc;
 using namespace tma;
 constexpr int NTHREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int SW = 128;            // strip width in output pixels (= K extent of one row step)
-constexpr int HALO_W = SW + 2;
 
 struct WgStripP {
   int n, h, w, cout;               // h, w: the grid the kernel walks (output grid; low-res grid when UP)
@@ -39,17 +42,22 @@ struct WgStripP {
   int ld_co, ld_tap, coff;         // element strides of the destination: dst[co * ld_co + tap * ld_tap + coff + ci]
 };
 
-template <int BN, int CIN, bool UP>
+template <int BN, int CIN, bool UP, int KS>
 struct WgStripCfg {
   static constexpr int RB = CIN * 2;                                        // bytes per input pixel
-  static constexpr int ROWBUF = (((HALO_W + 1) * RB + 1023) / 1024) * 1024;  // +1: the ignored 4th tap reads pixel 130
+  static constexpr int PAD = KS / 2;                                        // 3x3: 1, 4x4 stem: 2
+  static constexpr int HALO_W = SW + KS - 1;                                // pixels one TMA box of an input row brings
+  static constexpr int G = (KS == 3 && CIN == 64) ? 2 : 1;                  // tap groups per filter row (plain)
+  // pixels the M = 128 window touches: 128 / CIN channel blocks one pixel apart, shifted by 2 (G - 1); the blocks past
+  // tap KS - 1 are ignored but still read (CIN = 32: pixel 130, CIN = 16: pixels 131 .. 134)
+  static constexpr int REACH = SW + 128 / CIN - 1 + 2 * (G - 1);
+  static constexpr int ROWBUF = (((REACH > HALO_W ? REACH : HALO_W) * RB + 1023) / 1024) * 1024;
   static constexpr int DB = BN * 2;                                         // bytes per dY pixel
   static constexpr int DYBUF = SW * DB < 1024 ? 1024 : SW * DB;
   static constexpr int NB = UP ? 4 : 1;                                     // dY buffers per row step (phases)
-  static constexpr int NRX = (UP && BN == 64) ? 4 : 5;                      // ring of input rows
+  static constexpr int NRX = (UP && BN == 64) ? 4 : KS + 2;                 // ring of input rows
   static constexpr int NRD = (UP && BN == 64) ? 2 : 3;                      // ring of dY row steps
-  static constexpr int G = CIN == 64 ? 2 : 1;                               // tap groups per filter row (plain)
-  static constexpr int MT = UP ? 8 : 3 * G;                                 // accumulator tiles
+  static constexpr int MT = UP ? 8 : KS * G;                                // accumulator tiles
   static constexpr int COLS = MT * BN;
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
   static constexpr int SMEM = NRX * ROWBUF + NRD * NB * DYBUF + 1024 + 256;
@@ -57,14 +65,16 @@ struct WgStripCfg {
   static constexpr uint32_t LAYOUT_B = DB == 128 ? 2u : (DB == 64 ? 4u : 6u);
   static_assert(COLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static_assert(!UP || CIN == 64, "the up-sampling variant is instantiated for 64 input channels");
+  static_assert(!UP || (CIN == 64 && KS == 3), "the up-sampling variant is instantiated for 64 input channels, 3x3");
+  static_assert(KS == 3 || (KS == 4 && CIN == 16), "4x4 taps: the 16-channel space-to-depth stems only");
+  static_assert(128 / CIN + 2 * (G - 1) >= KS, "the channel blocks of one filter row must cover its taps");
 };
 
-template <int BN, int CIN, bool UP>
+template <int BN, int CIN, bool UP, int KS>
 __global__ void __launch_bounds__(NTHREADS)
 wgrad_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgStripP p,
                    float* __restrict__ dst) {
-  typedef WgStripCfg<BN, CIN, UP> C;
+  typedef WgStripCfg<BN, CIN, UP, KS> C;
   constexpr int NRX = C::NRX, NRD = C::NRD;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -107,13 +117,13 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int img = col / p.strips;
         const int y0 = ck * p.rows_per_chunk;
         const int rows = min(p.rows_per_chunk, p.h - y0);
-        for (int j = 0; j < rows + 2; ++j, ++L) {
+        for (int j = 0; j < rows + KS - 1; ++j, ++L) {
           const int s = L % NRX;
           if (L >= (uint32_t)NRX) mbar_wait(bXE + 8 * s, ((L / NRX) & 1) ^ 1);
-          mbar_expect_tx(bXF + 8 * s, (uint32_t)(HALO_W * C::RB));
-          tma_load_4d(sRing + s * C::ROWBUF, &map_x, bXF + 8 * s, 0, strip * SW - 1, y0 - 1 + j, img);
-          if (j >= 2) {
-            const int t = j - 2;
+          mbar_expect_tx(bXF + 8 * s, (uint32_t)(C::HALO_W * C::RB));
+          tma_load_4d(sRing + s * C::ROWBUF, &map_x, bXF + 8 * s, 0, strip * SW - C::PAD, y0 - C::PAD + j, img);
+          if (j >= KS - 1) {
+            const int t = j - (KS - 1);
             const int ds = D % NRD;
             if (D >= (uint32_t)NRD) mbar_wait(bDE + 8 * ds, ((D / NRD) & 1) ^ 1);
             mbar_expect_tx(bDF + 8 * ds, (uint32_t)(C::NB * SW * C::DB));
@@ -141,10 +151,10 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int ck = item % p.chunks_per_col;
       const int y0 = ck * p.rows_per_chunk;
       const int rows = min(p.rows_per_chunk, p.h - y0);
-      mbar_wait(bXF + 8 * (L % NRX), (L / NRX) & 1);
-      mbar_wait(bXF + 8 * ((L + 1) % NRX), ((L + 1) / NRX) & 1);
+#pragma unroll
+      for (int i = 0; i < KS - 1; ++i) mbar_wait(bXF + 8 * ((L + i) % NRX), ((L + i) / NRX) & 1);
       for (int t = 0; t < rows; ++t, ++D) {
-        const uint32_t Lnew = L + t + 2;
+        const uint32_t Lnew = L + t + KS - 1;
         mbar_wait(bXF + 8 * (Lnew % NRX), (Lnew / NRX) & 1);
         const int ds = D % NRD;
         mbar_wait(bDF + 8 * ds, (D / NRD) & 1);
@@ -171,14 +181,14 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           umma_commit(bDE + 8 * ds);                         // dY row step consumed
           umma_commit(bXE + 8 * ((L + t) % NRX));            // oldest input row no longer needed
           if (t == rows - 1) {
-            umma_commit(bXE + 8 * ((L + t + 1) % NRX));
-            umma_commit(bXE + 8 * ((L + t + 2) % NRX));
+#pragma unroll
+            for (int i = 1; i < KS; ++i) umma_commit(bXE + 8 * ((L + t + i) % NRX));
           }
         }
         fresh = false;
         __syncwarp();
       }
-      L += rows + 2;
+      L += rows + KS - 1;
     }
     if (lane == 0) umma_commit(bDone);
     __syncwarp();
@@ -200,8 +210,8 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           valid = true;
         } else {
           const int r = mt / C::G, s = 2 * (mt % C::G) + blk;
-          tap = r * 3 + s;
-          valid = s < 3;
+          tap = r * KS + s;
+          valid = s < KS;
         }
         const uint32_t trow = tmem_base + mt * BN + ((uint32_t)(q * 32) << 16);
         float* drow = dst + (size_t)tap * p.ld_tap + p.coff + ci;
@@ -252,10 +262,10 @@ __global__ void wgrad_up_fold_kernel(const float* __restrict__ g, float* __restr
   }
 }
 
-inline bool make_x_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c) {
+inline bool make_x_row_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int halo_w) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)HALO_W, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)halo_w, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(c), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -280,19 +290,19 @@ void plan_items(WgStripP& t, int ctas) {
   t.num_items = cols * t.chunks_per_col;
 }
 
-template <int BN, int CIN, bool UP>
+template <int BN, int CIN, bool UP, int KS = 3>
 int launch_wg_strip(const void* x, int n, int hx, int wx, const void* dy, int hd, int wd, int cout, WgStripP& t, float* dst,
                     cudaStream_t st) {
-  note_kernel("wgrad_strip_kernel<%d,%d,%d>", BN, CIN, (int)UP);
-  typedef WgStripCfg<BN, CIN, UP> C;
+  note_kernel("wgrad_strip_kernel<%d,%d,%d,%d>", BN, CIN, (int)UP, KS);
+  typedef WgStripCfg<BN, CIN, UP, KS> C;
   static bool attr_set_dev[16] = {}; bool& attr_set = attr_set_dev[cur_dev()];   // per device: the attribute belongs to the device's copy of the kernel
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_strip_kernel<BN, CIN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_strip_kernel<BN, CIN, UP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { set_error("wgrad_strip: smem attribute: %s", cudaGetErrorString(e)); return RCFD_ECUDA; }
     attr_set = true;
   }
   alignas(64) CUtensorMap mx, md;
-  if (!make_x_row_map(&mx, x, n, hx, wx, CIN) || !make_dy_row_map(&md, dy, n, hd, wd, cout, BN, UP ? 2 : 1)) {
+  if (!make_x_row_map(&mx, x, n, hx, wx, CIN, C::HALO_W) || !make_dy_row_map(&md, dy, n, hd, wd, cout, BN, UP ? 2 : 1)) {
     set_error("wgrad_strip: cuTensorMapEncodeTiled failed");
     return RCFD_ECUDA;
   }
@@ -301,7 +311,7 @@ int launch_wg_strip(const void* x, int n, int hx, int wx, const void* dy, int hd
   int ctas = num_sms() * per_sm;
   plan_items(t, ctas);
   if (ctas > t.num_items) ctas = t.num_items;
-  wgrad_strip_kernel<BN, CIN, UP><<<ctas, NTHREADS, C::SMEM, st>>>(mx, md, t, dst);
+  wgrad_strip_kernel<BN, CIN, UP, KS><<<ctas, NTHREADS, C::SMEM, st>>>(mx, md, t, dst);
   RCFD_CHECK_LAUNCH("wgrad_strip");
   return RCFD_OK;
 }
@@ -316,7 +326,13 @@ int dispatch_wg_strip(int cin, int bn, const void* x, int n, int hx, int wx, con
       default: return launch_wg_strip<16, 64, UP>(x, n, hx, wx, dy, hd, wd, cout, t, dst, st);
     }
   }
-  if (!UP) {
+  if (!UP && cin == 16) {            // 4x4 space-to-depth stems
+    switch (bn) {
+      case 32: return launch_wg_strip<32, 16, false, 4>(x, n, hx, wx, dy, hd, wd, cout, t, dst, st);
+      case 16: return launch_wg_strip<16, 16, false, 4>(x, n, hx, wx, dy, hd, wd, cout, t, dst, st);
+      default: break;
+    }
+  } else if (!UP) {
     switch (bn) {
       case 64: return launch_wg_strip<64, 32, false>(x, n, hx, wx, dy, hd, wd, cout, t, dst, st);
       case 32: return launch_wg_strip<32, 32, false>(x, n, hx, wx, dy, hd, wd, cout, t, dst, st);
@@ -332,16 +348,19 @@ bool chan_ok(int c) { return c == 32 || c == 64; }
 }  // namespace
 
 // plain: 3x3 / stride 1 / pad 1, one or two sources with 32 or 64 channels each, cout in {16, 32, 64}
+// stem : 4x4 / stride 1 / pad 2 on ONE 16-channel (space-to-depth) source, output cropped to the input grid, cout in {16, 32}
 bool wgrad_strip_supported(const ConvKP& p, int dtype) {
   if (dtype != RCFD_BF16 || p.dil != 1) return false;
-  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
+  const bool stem = p.kh == 4 && p.kw == 4 && p.stride == 1 && p.pad == 2 && !p.up && p.c0 == 16 && p.c1 == 0 &&
+                    (p.cout == 16 || p.cout == 32);
+  if (!stem && (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1)) return false;
   if (p.ho != p.hin || p.wo != p.win) return false;
   if (p.cout != 16 && p.cout != 32 && p.cout != 64) return false;
   if ((reinterpret_cast<uintptr_t>(p.src0) & 15) || (reinterpret_cast<uintptr_t>(p.dst) & 15)) return false;
   if (p.c1 > 0 && (reinterpret_cast<uintptr_t>(p.src1) & 15)) return false;
   if (get_encode() == nullptr) return false;
   if (p.up) return p.c1 == 0 && p.c0 == 64 && p.hin == 2 * p.h0 && p.win == 2 * p.w0;
-  return chan_ok(p.c0) && (p.c1 == 0 || chan_ok(p.c1));
+  return stem || (chan_ok(p.c0) && (p.c1 == 0 || chan_ok(p.c1)));
 }
 
 int64_t wgrad_strip_workspace(const ConvKP& p, int dtype) {

@@ -578,6 +578,32 @@ def test_stem_space_to_depth(cin, cout):
     assert relerr(g.cpu(), wt.grad) < 2e-3
 
 
+@pytest.mark.parametrize('case', [(1, 3, 32, 70, 300), (2, 2, 16, 66, 128), (1, 3, 32, 64, 131)])
+def test_stem_wgrad_strip(case):
+    """Weight gradient of the 4x4 / pad-2 space-to-depth stems on the row-streaming engine (KS = 4, 16-channel pixels:
+    one MMA covers the four taps of a filter row) against the gather engine and autograd of the 7x7 / stride-2 conv."""
+    from rcfd import ops
+    n, cin, cout, hs, ws_ = case
+    h, w = 2 * hs, 2 * ws_
+    x = _q(_rand(n, cin, h, w, seed=71))
+    wt = (_q(_rand(cout, cin, 7, 7, seed=72) / (cin * 49) ** 0.5)).requires_grad_(True)
+    y = F.conv2d(x, wt, None, 2, 3)
+    dyt = _q(_rand(*y.shape, seed=73))
+    y.backward(dyt)
+    xs = ops.nchw_to_s2d(x.to(DEV), BF, 16)
+    dyn = _nhwc(dyt)
+    dw = ops.conv2d_wgrad(xs, dyn, 4, 1, pad=2, engine=ops.ENGINE_STRIP)
+    assert ops._lib.load().rcfd_last_kernel().decode().startswith('wgrad_strip_kernel<%d,16,0,4>' % cout)
+    dw_g = ops.conv2d_wgrad(xs, dyn, 4, 1, pad=2, engine=ops.ENGINE_TCGEN05)
+    assert relerr(dw, dw_g) < 1e-3
+    g = torch.empty(cout, cin, 7, 7, device=DEV)
+    ops.unpack_stem_s2d_wgrad(dw, g)
+    assert relerr(g.cpu(), wt.grad) < 2e-3
+    if hs >= 64 and ws_ >= 256:
+        ops.conv2d_wgrad(xs, dyn, 4, 1, pad=2)
+        assert ops._lib.load().rcfd_last_kernel().decode().startswith('wgrad_strip_kernel')
+
+
 # ----------------------------------------------------------------------------- row-streaming weight gradient
 @pytest.mark.parametrize('case', [(1, 64, 64, 12, 128), (2, 64, 32, 19, 200), (1, 32, 32, 33, 130), (2, 32, 64, 9, 70),
                                   (1, 64, 16, 70, 256), (2, 32, 16, 40, 300)])

@@ -52,6 +52,7 @@ CASES = {
     'wg_b4_img': ('wgrad', 256, 256, 22, 44, dict()),
     'wg_b6_img': ('wgrad', 256, 256, 6, 11, dict()),
     'wg_stem': ('wgrad', 16, 32, 176, 352, dict(k=4, pad=2)),
+    'wg_stem_depth': ('wgrad', 16, 16, 176, 352, dict(k=4, pad=2)),
     'bnbwd_dec0': ('bnbwd', 32, 32, 352, 704, dict()),
     'bnbwd_b2': ('bnbwd', 64, 64, 88, 176, dict()),
     'bnbwd_b4': ('bnbwd', 256, 256, 22, 44, dict()),

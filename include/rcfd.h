@@ -198,6 +198,15 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
                           const float* mean, const float* invstd, const double* sums, void* dy,
                           float* dgamma, float* dbeta, int64_t pixels, int32_t channels, int32_t act,
                           int32_t dtype, void* stream);
+/* reduce + apply of a SMALL map in ONE launch (a CTA owns one 16-byte channel vector over all pixels, so the channel
+ * sums stay inside the CTA; the second read of dz / y hits L1 / L2): the <= 22x44 levels of a batch-8 step, whose
+ * backward chains are bound by kernel count, not bytes.  post_z / dz_masked (both or neither): the gradient first goes
+ * through the LeakyReLU that follows the residual add of a ResNetBlock (src/net_utils.py:253-323: post_z = the block's
+ * output); the masked gradient, which is also the gradient of the shortcut branch, is written to dz_masked.
+ * channels % 8 == 0 (bf16) / % 4 == 0 (float). */
+int rcfd_bn_act_bwd_fused(const void* dz, const void* y, const void* post_z, void* dz_masked, const float* scale,
+                          const float* shift, const float* mean, const float* invstd, void* dy, float* dgamma,
+                          float* dbeta, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream);
 
 /* Gated fusion  fused = sigmoid(a) * b + img  with (a|b) = affine(y[:, :C] | y[:, C:2C])
  * (src/networks.py:864-866 ... :973-975).  y: pixels x 2C; scale/shift: [2C] or NULL. */

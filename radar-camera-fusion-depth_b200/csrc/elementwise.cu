@@ -9,6 +9,11 @@ namespace {
 
 constexpr int NT = 256;
 
+}  // namespace (anonymous)
+// rcfd_set_option("bn_vectors_per_thread"): 16-byte vectors one thread of the wide BatchNorm kernels handles at least
+// (their per-thread parameter prologue is paid once; 1 = one vector per thread until the grid cap, the round-1 sizing)
+int g_bn_vectors_per_thread = 8;
+namespace {
 inline int grid_for(int64_t work, int per_block = NT, int cap = 148 * 16) {
   int64_t g = (work + per_block - 1) / per_block;
   if (g > cap) g = cap;
@@ -184,7 +189,27 @@ __global__ void bn_act_fwd_wide(const T* __restrict__ y, const float* __restrict
   float sc[N], sh[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) { sc[k] = scale ? scale[c + k] : 1.f; sh[k] = scale ? shift[c + k] : 0.f; }
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = i0;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {          // grid sized for >= 4 vectors per thread, all loads in flight
+    float v[4][N], r[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      V16<T>::ld(y + (i + u * stride) * N, v[u]);
+      if (res) V16<T>::ld(res + (i + u * stride) * N, r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float x = apply_act(fmaf(v[u][k], sc[k], sh[k]), act, 0.f, 0.f);
+        if (res) x = leaky(x + r[u][k]);
+        v[u][k] = x;
+      }
+      V16<T>::st(out + (i + u * stride) * N, v[u]);
+    }
+  }
+  for (; i < nvec; i += stride) {
     float v[N], r[N];
     V16<T>::ld(y + i * N, v);
     if (res) V16<T>::ld(res + i * N, r);
@@ -245,7 +270,27 @@ __global__ void bn_train_act_fwd_wide(const T* __restrict__ y, const double* __r
   float sc[N], sh[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) { sc[k] = s_sc[c0 + k]; sh[k] = s_sh[c0 + k]; }
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = i0;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {          // grid sized for >= 4 vectors per thread, all loads in flight
+    float v[4][N], r[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      V16<T>::ld(y + (i + u * stride) * N, v[u]);
+      if (res) V16<T>::ld(res + (i + u * stride) * N, r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float x = apply_act(fmaf(v[u][k], sc[k], sh[k]), act, 0.f, 0.f);
+        if (res) x = leaky(x + r[u][k]);
+        v[u][k] = x;
+      }
+      V16<T>::st(out + (i + u * stride) * N, v[u]);
+    }
+  }
+  for (; i < nvec; i += stride) {
     float v[N], r[N];
     V16<T>::ld(y + i * N, v);
     if (res) V16<T>::ld(res + i * N, r);
@@ -351,7 +396,29 @@ __global__ void bn_bwd_apply_wide(const T* __restrict__ dz, const T* __restrict_
     k1[k] = (float)sums[c + k] * inv_count;                     // mean of dpre
     k2[k] = invstd[c + k] * (float)sums[C + c + k] * inv_count;       // invstd * mean(dpre * xhat)
   }
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  // the grid is sized for >= 4 vectors per thread (the 56 parameter loads above are per thread, not per vector: with one
+  // vector per thread they made a 22x44 x 256 map take 19.6 us on 968 blocks against 5 us of traffic); 8 loads in flight
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = i0;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    float g[4][N], v[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      V16<T>::ld(dz + (i + u * stride) * N, g[u]);
+      V16<T>::ld(y + (i + u * stride) * N, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float d = dact(fmaf(v[u][k], sc[k], sh[k]), g[u][k], act);
+        o[k] = sc[k] * (d - k1[k] - (v[u][k] - mu[k]) * k2[k]);
+      }
+      V16<T>::st(dy + (i + u * stride) * N, o);
+    }
+  }
+  for (; i < nvec; i += stride) {
     float g[N], v[N], o[N];
     V16<T>::ld(dz + i * N, g);
     V16<T>::ld(y + i * N, v);
@@ -364,10 +431,149 @@ __global__ void bn_bwd_apply_wide(const T* __restrict__ dz, const T* __restrict_
   }
 }
 
+// BatchNorm backward of a SMALL map in one launch: a CTA owns one 16-byte channel vector over ALL pixels, so the
+// per-channel sums never leave the CTA (no second kernel, no grid barrier): pass 1 sums, block reduce, pass 2 re-reads the
+// two tensors (L1 / L2 hits at these sizes) and writes dy.  POST: the gradient first goes through the LeakyReLU after a
+// residual add (z = its output); the masked gradient is written to dzm for the shortcut branch.
+constexpr int NT_SLICED = 512;
+template <typename T, bool POST>
+__global__ void __launch_bounds__(NT_SLICED)
+bn_bwd_sliced_kernel(const T* __restrict__ dz, const T* __restrict__ y, const T* __restrict__ zpost, T* dzm,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, T* __restrict__ dy, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int pixels, int C, int act, float inv_count) {
+  constexpr int N = V16<T>::N;
+  constexpr int U = 4;
+  __shared__ double red[NT_SLICED / 32][2 * N];
+  __shared__ float tot[2 * N];
+  const int c = blockIdx.x * N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float sc[N], sh[N], mu[N], is[N], s[N], q[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    sc[k] = scale[c + k]; sh[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k];
+    s[k] = 0.f; q[k] = 0.f;
+  }
+  auto pass1 = [&](const float* g, const float* v) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float d = dact(fmaf(v[k], sc[k], sh[k]), g[k], act);
+      s[k] += d;
+      q[k] += d * (v[k] - mu[k]) * is[k];
+    }
+  };
+  int p = tid;
+  for (; p + (U - 1) * NT_SLICED < pixels; p += U * NT_SLICED) {
+    float g[U][N], v[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t o = (size_t)(p + u * NT_SLICED) * C + c;
+      V16<T>::ld(dz + o, g[u]);
+      V16<T>::ld(y + o, v[u]);
+      if (POST) {
+        float z[N];
+        V16<T>::ld(zpost + o, z);
+#pragma unroll
+        for (int k = 0; k < N; ++k) g[u][k] = to_f<T>(from_f<T>(z[k] > 0.f ? g[u][k] : kLeakySlope * g[u][k]));   // as stored
+        V16<T>::st(dzm + o, g[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) pass1(g[u], v[u]);
+  }
+  for (; p < pixels; p += NT_SLICED) {
+    float g[N], v[N];
+    const size_t o = (size_t)p * C + c;
+    V16<T>::ld(dz + o, g);
+    V16<T>::ld(y + o, v);
+    if (POST) {
+      float z[N];
+      V16<T>::ld(zpost + o, z);
+#pragma unroll
+      for (int k = 0; k < N; ++k) g[k] = to_f<T>(from_f<T>(z[k] > 0.f ? g[k] : kLeakySlope * g[k]));
+      V16<T>::st(dzm + o, g);
+    }
+    pass1(g, v);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], off);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) { red[warp][k] = (double)s[k]; red[warp][N + k] = (double)q[k]; }
+  }
+  __syncthreads();
+  if (tid < 2 * N) {
+    double a = 0.0;
+    for (int w = 0; w < NT_SLICED / 32; ++w) a += red[w][tid];
+    tot[tid] = (float)a;
+    if (tid < N) { if (dbeta) dbeta[c + tid] = (float)a; }
+    else if (dgamma) dgamma[c + tid - N] = (float)a;
+  }
+  __syncthreads();
+  float k1[N], k2[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { k1[k] = tot[k] * inv_count; k2[k] = is[k] * tot[N + k] * inv_count; }
+  // pass 2 (POST: dzm holds this thread's own masked gradients, read back in program order)
+  const T* gsrc = POST ? dzm : dz;
+  auto pass2 = [&](const float* g, const float* v, float* o) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float d = dact(fmaf(v[k], sc[k], sh[k]), g[k], act);
+      o[k] = sc[k] * (d - k1[k] - (v[k] - mu[k]) * k2[k]);
+    }
+  };
+  p = tid;
+  for (; p + (U - 1) * NT_SLICED < pixels; p += U * NT_SLICED) {
+    float g[U][N], v[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t o = (size_t)(p + u * NT_SLICED) * C + c;
+      V16<T>::ld(gsrc + o, g[u]);
+      V16<T>::ld(y + o, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float o[N];
+      pass2(g[u], v[u], o);
+      V16<T>::st(dy + (size_t)(p + u * NT_SLICED) * C + c, o);
+    }
+  }
+  for (; p < pixels; p += NT_SLICED) {
+    float g[N], v[N], o[N];
+    const size_t off = (size_t)p * C + c;
+    V16<T>::ld(gsrc + off, g);
+    V16<T>::ld(y + off, v);
+    pass2(g, v, o);
+    V16<T>::st(dy + off, o);
+  }
+}
+
 template <typename T>
 __global__ void leaky_bwd_wide(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ din, int64_t nvec) {
   constexpr int N = V16<T>::N;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {            // 8 loads in flight per thread
+    float g[4][N], o[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      V16<T>::ld(dout + (i + u * stride) * N, g[u]);
+      V16<T>::ld(out + (i + u * stride) * N, o[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) g[u][k] = o[u][k] > 0.f ? g[u][k] : kLeakySlope * g[u][k];
+      V16<T>::st(din + (i + u * stride) * N, g[u]);
+    }
+  }
+  for (; i < nvec; i += stride) {
     float g[N], o[N];
     V16<T>::ld(dout + i * N, g);
     V16<T>::ld(out + i * N, o);
@@ -379,7 +585,23 @@ __global__ void leaky_bwd_wide(const T* __restrict__ dout, const T* __restrict__
 template <typename T>
 __global__ void add_inplace_wide(T* __restrict__ acc, const T* __restrict__ x, int64_t nvec) {
   constexpr int N = V16<T>::N;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {            // 8 loads in flight per thread
+    float a[4][N], b[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      V16<T>::ld(acc + (i + u * stride) * N, a[u]);
+      V16<T>::ld(x + (i + u * stride) * N, b[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) a[u][k] += b[u][k];
+      V16<T>::st(acc + (i + u * stride) * N, a[u]);
+    }
+  }
+  for (; i < nvec; i += stride) {
     float a[N], b[N];
     V16<T>::ld(acc + i * N, a);
     V16<T>::ld(x + i * N, b);
@@ -1138,7 +1360,7 @@ int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (channels % vw == 0 && NT % (channels / vw) == 0) {
     const int64_t nv = pixels * channels / vw;
-    DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, scale, shift, (const T*)residual, (T*)out, nv, channels, act)));
     RCFD_CHECK_LAUNCH("bn_act_fwd");
     return RCFD_OK;
@@ -1160,7 +1382,7 @@ int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum,
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (channels % vw == 0 && NT % (channels / vw) == 0 && channels <= BN_TRAIN_MAX_C) {
     const int64_t nv = pixels * channels / vw;
-    DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean,
                           save_invstd, (const T*)residual, (T*)out, nv, channels, act, (double)pixels, eps, momentum)));
     RCFD_CHECK_LAUNCH("bn_train_act_fwd");
@@ -1223,7 +1445,7 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (channels % vw == 0 && NT % (channels / vw) == 0) {
     const int64_t nv = pixels * channels / vw;
-    DISPATCH_T(dtype, (bn_bwd_apply_wide<T><<<grid_for(nv, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (bn_bwd_apply_wide<T><<<grid_for(nv, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dz, (const T*)y, scale, shift, mean, invstd, sums, (T*)dy, nv, channels, act,
                           (float)(1.0 / (double)pixels), dgamma, dbeta)));
   } else {
@@ -1233,6 +1455,28 @@ int rcfd_bn_act_bwd_apply(const void* dz, const void* y, const float* scale, con
                           (float)(1.0 / (double)pixels), dgamma, dbeta)));
   }
   RCFD_CHECK_LAUNCH("bn_bwd_apply");
+  return RCFD_OK;
+}
+
+int rcfd_bn_act_bwd_fused(const void* dz, const void* y, const void* post_z, void* dz_masked, const float* scale,
+                          const float* shift, const float* mean, const float* invstd, void* dy, float* dgamma,
+                          float* dbeta, int64_t pixels, int32_t channels, int32_t act, int32_t dtype, void* stream) {
+  RCFD_CHECK_ARG(dz && y && scale && shift && mean && invstd && dy, "bn_bwd_fused: null");
+  RCFD_CHECK_ARG((post_z == nullptr) == (dz_masked == nullptr), "bn_bwd_fused: post_z and dz_masked go together");
+  const int vw = dtype == RCFD_BF16 ? 8 : 4;
+  RCFD_CHECK_ARG(channels > 0 && channels % vw == 0, "bn_bwd_fused: channels must be a multiple of %d", vw);
+  RCFD_CHECK_ARG(pixels > 0 && pixels <= (1 << 20), "bn_bwd_fused: 1 .. 2^20 pixels (small maps; use reduce + apply)");
+  const float inv_count = (float)(1.0 / (double)pixels);
+  if (post_z) {
+    DISPATCH_T(dtype, (bn_bwd_sliced_kernel<T, true><<<channels / vw, NT_SLICED, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, (const T*)post_z, (T*)dz_masked, scale, shift, mean, invstd, (T*)dy,
+                          dgamma, dbeta, (int)pixels, channels, act, inv_count)));
+  } else {
+    DISPATCH_T(dtype, (bn_bwd_sliced_kernel<T, false><<<channels / vw, NT_SLICED, 0, (cudaStream_t)stream>>>(
+                          (const T*)dz, (const T*)y, nullptr, nullptr, scale, shift, mean, invstd, (T*)dy, dgamma, dbeta,
+                          (int)pixels, channels, act, inv_count)));
+  }
+  RCFD_CHECK_LAUNCH("bn_bwd_fused");
   return RCFD_OK;
 }
 
@@ -1333,7 +1577,7 @@ int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, 
   RCFD_CHECK_ARG(dout && out && din && count > 0, "leaky_bwd: bad args");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (count % vw == 0) {
-    DISPATCH_T(dtype, (leaky_bwd_wide<T><<<grid_for(count / vw, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (leaky_bwd_wide<T><<<grid_for(count / vw, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dout, (const T*)out, (T*)din, count / vw)));
   } else {
     DISPATCH_T(dtype, (leaky_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out,
@@ -1347,7 +1591,7 @@ int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, voi
   RCFD_CHECK_ARG(acc && x && count > 0, "add_inplace: bad args");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (count % vw == 0) {
-    DISPATCH_T(dtype, (add_inplace_wide<T><<<grid_for(count / vw, NT, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (add_inplace_wide<T><<<grid_for(count / vw, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (T*)acc, (const T*)x, count / vw)));
   } else {
     DISPATCH_T(dtype, (add_inplace_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((T*)acc, (const T*)x, count)));

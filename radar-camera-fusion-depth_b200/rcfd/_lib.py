@@ -59,6 +59,7 @@ _SIGS = {
     'rcfd_bn_act_bwd_reduce': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_act_bwd_reduce_acc': [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_bn_act_bwd_apply': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
+    'rcfd_bn_act_bwd_fused': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P],
     'rcfd_gate_fuse_fwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
     'rcfd_gate_fuse_bwd': [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P],
     'rcfd_maxpool3x3s2_fwd': [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P],

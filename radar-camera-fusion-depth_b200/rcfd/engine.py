@@ -652,12 +652,14 @@ def _record_conv_backward(ctx, mod, x0, x1, in_size, z, bn_state, want_input_gra
             dz = pre(dz)
         if bn_state is not None:
             y, scale, shift, mean, invstd, act, residual = bn_state
-            if residual is not None:
-                dz = ops.leaky_bwd(dz, z)               # through the post-add activation
             bn = mod.batch_norm
             dgamma = _grad_dst(bn.weight)
             dbeta = _grad_dst(bn.bias)
-            dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=ctx.zeroed_sums(y.shape[3]))
+            if residual is not None:                    # through the post-add activation first (z = its output)
+                dy, dz = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta,
+                                        sums=ctx.zeroed_sums(y.shape[3]), post_z=z)
+            else:
+                dy = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=ctx.zeroed_sums(y.shape[3]))
             if residual is not None:
                 tape.add_grad(residual, dz)             # published after its last read here (Tape.add_grad)
             tape.param_grads.append((bn.weight, dgamma))

@@ -4,6 +4,7 @@ Every function requires CUDA tensors and calls librcfd_b200.so; nothing here com
 PyTorch.  Activations are NHWC tensors [N, H, W, C] (float32 or bfloat16).
 """
 import ctypes
+import os
 import sys
 
 import torch
@@ -392,11 +393,24 @@ def bn_train_act(y, ssum, ssq, bn_weight, bn_bias, running_mean, running_var, sc
     return out
 
 
-def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None):
+# BatchNorm backward of maps up to this many pixels (N * H * W) runs as ONE launch (rcfd_bn_act_bwd_fused); 0 = never
+BN_BWD_FUSED_MAX_PIXELS = int(os.environ.get('RCFD_BN_BWD_FUSED_MAX_PIXELS', '1024'))
+
+
+def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None, post_z=None):
     """sums: optional ZEROED float64 [2c] scratch (a slice of a pool zeroed once per step); default: a fresh buffer
-    zeroed by the call."""
+    zeroed by the call.  post_z: dz is the gradient of the output of a LeakyReLU applied AFTER a residual add (post_z = that
+    output): it is masked first and (dy, masked dz) is returned -- the masked gradient also belongs to the shortcut."""
     c = y.shape[-1]
     pixels = y.numel() // c
+    if pixels <= BN_BWD_FUSED_MAX_PIXELS and c % (8 if y.dtype == torch.bfloat16 else 4) == 0:
+        dy = _empty_like(y)
+        dzm = _empty_like(dz) if post_z is not None else None
+        _lib.call('rcfd_bn_act_bwd_fused', _p(dz), _p(y), _p(post_z), _p(dzm), _p(scale), _p(shift), _p(mean), _p(invstd),
+                  _p(dy), _p(dgamma), _p(dbeta), pixels, c, act, dt(y), _stream())
+        return dy if post_z is None else (dy, dzm)
+    if post_z is not None:
+        dz = leaky_bwd(dz, post_z)
     entry = 'rcfd_bn_act_bwd_reduce_acc'
     if sums is None:
         sums = _empty(2 * c, device=y.device, dtype=torch.float64)
@@ -406,7 +420,7 @@ def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None)
     dy = _empty_like(y)
     _lib.call('rcfd_bn_act_bwd_apply', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), _p(dy),
               _p(dgamma), _p(dbeta), pixels, c, act, dt(y), _stream())
-    return dy
+    return dy if post_z is None else (dy, dz)
 
 
 def gate_fuse(y2c, scale, shift, img):

@@ -215,7 +215,10 @@ def _dact(pre, dz, act):
     return dz
 
 
-def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None):
+def bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=None, post_z=None):
+    if post_z is not None:
+        dzm = leaky_bwd(dz, post_z)
+        return bn_act_bwd(dzm, y, scale, shift, mean, invstd, act, dgamma, dbeta, sums=sums), dzm
     c = y.shape[-1]
     yf, dzf = y.float().reshape(-1, c), dz.float().reshape(-1, c)
     d = _dact(yf * scale + shift, dzf, act)

@@ -63,6 +63,49 @@ def test_batchnorm_train_forward_backward(act, name):
     assert relerr(dg.cpu(), bn.weight.grad) < 1e-4 and relerr(db.cpu(), bn.bias.grad) < 1e-4
 
 
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('pixels,c', [(528, 256), (1936, 128), (7744, 64), (2049, 32), (37, 8)])
+def test_batchnorm_backward_single_launch(dtype, pixels, c, monkeypatch):
+    """rcfd_bn_act_bwd_fused (small maps: one CTA per 16-byte channel vector, reduce + apply in one launch, optionally
+    behind the post-add LeakyReLU of a ResNetBlock) == leaky_bwd + reduce + apply; the float form also against the
+    formulas in float64."""
+    from rcfd import ops
+    g = torch.Generator().manual_seed(pixels + c)
+    y = (torch.randn(1, 1, pixels, c, generator=g) * 1.5 + 0.3).to(DEV, dtype)
+    dz = torch.randn(1, 1, pixels, c, generator=g).to(DEV, dtype)
+    zpost = torch.randn(1, 1, pixels, c, generator=g).to(DEV, dtype)
+    scale = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(c, generator=g) * 0.2).to(DEV)
+    mean = y.float().reshape(-1, c).mean(0)
+    invstd = 1.0 / torch.sqrt(y.float().reshape(-1, c).var(0, unbiased=False) + 1e-5)
+    for act in (ops.ACT_LEAKY, ops.ACT_NONE):
+        for post in (None, zpost):
+            outs = []
+            for limit in (1 << 20, 0):
+                monkeypatch.setattr(ops, 'BN_BWD_FUSED_MAX_PIXELS', limit)
+                dg, db = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+                r = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, act, dg, db, post_z=post)
+                dy, dzm = r if post is not None else (r, None)
+                outs.append((dy, dzm, dg, db))
+            (dy1, dzm1, dg1, db1), (dy0, dzm0, dg0, db0) = outs
+            if post is not None:
+                assert torch.equal(dzm1, dzm0)
+            assert relerr(dg1, dg0) < 5e-5 and relerr(db1, db0) < 5e-5
+            assert relerr(dy1.float(), dy0.float()) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+            if dtype == torch.float32:
+                d = dz.double().reshape(-1, c)
+                if post is not None:
+                    d = torch.where(post.double().reshape(-1, c) > 0, d, 0.2 * d)
+                yd = y.double().reshape(-1, c)
+                pre = yd * scale.double() + shift.double()
+                if act == ops.ACT_LEAKY:
+                    d = torch.where(pre > 0, d, 0.2 * d)
+                xhat = (yd - mean.double()) * invstd.double()
+                ref = scale.double() * (d - d.mean(0) - xhat * (d * xhat).mean(0))
+                assert relerr(dy1.reshape(-1, c), ref.float()) < 1e-5
+                assert relerr(dg1, (d * xhat).sum(0).float()) < 1e-5 and relerr(db1, d.sum(0).float()) < 1e-5
+
+
 def test_bn_fold_and_gate():
     from rcfd import ops
     c, n, h, w = 8, 2, 5, 6

@@ -965,26 +965,48 @@ __global__ void upsample2x_bwd_wide(const T* __restrict__ dup, T* __restrict__ d
   constexpr int NV = V16<T>::N;
   const int CV = C / NV;
   const int64_t total = (int64_t)N * HS * WS * CV;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto src = [&](int64_t i) {
     const int cv = (int)(i % CV);
     int64_t r = i / CV;
     const int sx = (int)(r % WS); r /= WS;
     const int sy = (int)(r % HS);
     const int n = (int)(r / HS);
-    const T* base = dup + (((size_t)(n * 2 * HS + 2 * sy) * (2 * WS) + 2 * sx) * CV + cv) * NV;
+    return dup + (((size_t)(n * 2 * HS + 2 * sy) * (2 * WS) + 2 * sx) * CV + cv) * NV;
+  };
+  auto finish = [&](int64_t i, float* a, const float* b, const float* c, const float* d) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a[k] = ((a[k] + b[k]) + c[k]) + d[k];      // same order as the generic kernel
+    if (accumulate) {
+      float e[NV];
+      V16<T>::ld(dsrc + i * NV, e);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) a[k] += e[k];
+    }
+    V16<T>::st(dsrc + i * NV, a);
+  };
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + stride < total; i += 2 * stride) {               // two source pixels per trip: 8 loads in flight
+    float a[2][NV], b[2][NV], c[2][NV], d[2][NV];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const T* base = src(i + u * stride);
+      V16<T>::ld(base, a[u]);
+      V16<T>::ld(base + C, b[u]);
+      V16<T>::ld(base + (size_t)2 * WS * C, c[u]);
+      V16<T>::ld(base + (size_t)2 * WS * C + C, d[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) finish(i + u * stride, a[u], b[u], c[u], d[u]);
+  }
+  for (; i < total; i += stride) {
+    const T* base = src(i);
     float a[NV], b[NV], c[NV], d[NV];
     V16<T>::ld(base, a);
     V16<T>::ld(base + C, b);
     V16<T>::ld(base + (size_t)2 * WS * C, c);
     V16<T>::ld(base + (size_t)2 * WS * C + C, d);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) a[k] = ((a[k] + b[k]) + c[k]) + d[k];      // same order as the generic kernel
-    if (accumulate) {
-      V16<T>::ld(dsrc + i * NV, b);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) a[k] += b[k];
-    }
-    V16<T>::st(dsrc + i * NV, a);
+    finish(i, a, b, c, d);
   }
 }
 

@@ -13,6 +13,8 @@ constexpr int NT = 256;
 // rcfd_set_option("bn_vectors_per_thread"): 16-byte vectors one thread of the wide BatchNorm kernels handles at least
 // (their per-thread parameter prologue is paid once; 1 = one vector per thread until the grid cap, the round-1 sizing)
 int g_bn_vectors_per_thread = 8;
+int g_bn_fwd_vectors_per_thread = 4;   // bn_act_fwd / bn_train_act_fwd
+int g_ew_vectors_per_thread = 4;       // add_inplace / leaky_bwd (no prologue)
 namespace {
 inline int grid_for(int64_t work, int per_block = NT, int cap = 148 * 16) {
   int64_t g = (work + per_block - 1) / per_block;
@@ -1382,7 +1384,7 @@ int rcfd_bn_act_fwd(const void* y, const float* scale, const float* shift, const
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (channels % vw == 0 && NT % (channels / vw) == 0) {
     const int64_t nv = pixels * channels / vw;
-    DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (bn_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_fwd_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, scale, shift, (const T*)residual, (T*)out, nv, channels, act)));
     RCFD_CHECK_LAUNCH("bn_act_fwd");
     return RCFD_OK;
@@ -1404,7 +1406,7 @@ int rcfd_bn_train_act_fwd(const void* y, const double* sum, const double* sqsum,
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (channels % vw == 0 && NT % (channels / vw) == 0 && channels <= BN_TRAIN_MAX_C) {
     const int64_t nv = pixels * channels / vw;
-    DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (bn_train_act_fwd_wide<T><<<grid_for(nv, NT * g_bn_fwd_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)y, sum, sqsum, gamma, beta, running_mean, running_var, scale, shift, save_mean,
                           save_invstd, (const T*)residual, (T*)out, nv, channels, act, (double)pixels, eps, momentum)));
     RCFD_CHECK_LAUNCH("bn_train_act_fwd");
@@ -1599,7 +1601,7 @@ int rcfd_leaky_bwd(const void* dout, const void* out, void* din, int64_t count, 
   RCFD_CHECK_ARG(dout && out && din && count > 0, "leaky_bwd: bad args");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (count % vw == 0) {
-    DISPATCH_T(dtype, (leaky_bwd_wide<T><<<grid_for(count / vw, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (leaky_bwd_wide<T><<<grid_for(count / vw, NT * g_ew_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (const T*)dout, (const T*)out, (T*)din, count / vw)));
   } else {
     DISPATCH_T(dtype, (leaky_bwd_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)out,
@@ -1613,7 +1615,7 @@ int rcfd_add_inplace(void* acc, const void* x, int64_t count, int32_t dtype, voi
   RCFD_CHECK_ARG(acc && x && count > 0, "add_inplace: bad args");
   const int vw = dtype == RCFD_BF16 ? 8 : 4;
   if (count % vw == 0) {
-    DISPATCH_T(dtype, (add_inplace_wide<T><<<grid_for(count / vw, NT * g_bn_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, (add_inplace_wide<T><<<grid_for(count / vw, NT * g_ew_vectors_per_thread, 148 * 8), NT, 0, (cudaStream_t)stream>>>(
                           (T*)acc, (const T*)x, count / vw)));
   } else {
     DISPATCH_T(dtype, (add_inplace_kernel<T><<<grid_for(count), NT, 0, (cudaStream_t)stream>>>((T*)acc, (const T*)x, count)));

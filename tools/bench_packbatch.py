@@ -56,7 +56,7 @@ def subset(table, kinds):
     return t.finalize(dev) if t.rows else None
 
 
-names = {0: 'fwd', 1: 'dgrad', 2: 'up2x', 3: 'stem', 4: 'unpack', 5: 'unpack_stem', 6: 'copy'}
+names = {0: 'fwd', 1: 'dgrad', 2: 'up2x', 3: 'stem', 4: 'unpack', 5: 'unpack_stem', 6: 'copy', 7: 'dgrad_s2', 8: 'upconv_dgrad'}
 for label, table in (('pack', pack), ('unpack', unpack)):
     elems = sum(it.total for it in table.rows)
     print('%s: %d items, %d blocks, %.1f M elements: cold %.1f us, warm %.1f us' %
@@ -64,4 +64,4 @@ for label, table in (('pack', pack), ('unpack', unpack)):
     for k in sorted(set(it.kind for it in table.rows)):
         sub = subset(table, (k,))
         print('   %-12s %4d items %6d blocks %6.1f M elements: cold %.1f us, warm %.1f us' %
-              (names[k], len(sub.rows), sub.total_blocks, sum(it.total for it in sub.rows) / 1e6, timed(sub, True), timed(sub, False)))
+              (names.get(k, str(k)), len(sub.rows), sub.total_blocks, sum(it.total for it in sub.rows) / 1e6, timed(sub, True), timed(sub, False)))

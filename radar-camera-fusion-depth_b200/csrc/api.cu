@@ -41,6 +41,7 @@ extern int g_wgrad_tma_v2;
 extern int g_wgrad_tma_cs_max;
 extern int g_wgrad_tma_groups;
 extern int g_bn_vectors_per_thread;
+extern int g_bn_reduce_rows_per_thread;
 extern int g_bn_fwd_vectors_per_thread;
 extern int g_ew_vectors_per_thread;
 extern int g_strip_max_waste;
@@ -115,6 +116,7 @@ int rcfd_set_option(const char* key, int32_t value) {
   if (strcmp(key, "wgrad_tma_v2") == 0) { g_wgrad_tma_v2 = value; return RCFD_OK; }
   if (strcmp(key, "wgrad_tma_cs_max") == 0) { g_wgrad_tma_cs_max = value; return RCFD_OK; }
   if (strcmp(key, "wgrad_tma_groups") == 0) { g_wgrad_tma_groups = value; return RCFD_OK; }
+  if (strcmp(key, "bn_reduce_rows_per_thread") == 0) { g_bn_reduce_rows_per_thread = value < 1 ? 1 : value; return RCFD_OK; }
   if (strcmp(key, "bn_vectors_per_thread") == 0) { g_bn_vectors_per_thread = value < 1 ? 1 : value; return RCFD_OK; }
   if (strcmp(key, "bn_fwd_vectors_per_thread") == 0) { g_bn_fwd_vectors_per_thread = value < 1 ? 1 : value; return RCFD_OK; }
   if (strcmp(key, "ew_vectors_per_thread") == 0) { g_ew_vectors_per_thread = value < 1 ? 1 : value; return RCFD_OK; }

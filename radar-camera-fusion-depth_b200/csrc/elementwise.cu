@@ -13,6 +13,7 @@ constexpr int NT = 256;
 // rcfd_set_option("bn_vectors_per_thread"): 16-byte vectors one thread of the wide BatchNorm kernels handles at least
 // (their per-thread parameter prologue is paid once; 1 = one vector per thread until the grid cap, the round-1 sizing)
 int g_bn_vectors_per_thread = 8;
+int g_bn_reduce_rows_per_thread = 16;  // bn_bwd_reduce: rows one thread sums at least (rcfd_set_option)
 int g_bn_fwd_vectors_per_thread = 4;   // bn_act_fwd / bn_train_act_fwd
 int g_ew_vectors_per_thread = 4;       // add_inplace / leaky_bwd (no prologue)
 namespace {
@@ -1433,7 +1434,8 @@ static int bn_bwd_reduce_impl(const void* dz, const void* y, const float* scale,
   const bool wide = channels % vw == 0;
   const int CVP = next_pow2(channels / (wide ? vw : 4));
   const int rstep = NT / CVP;
-  int blocks = (int)((pixels + rstep * 8 - 1) / (rstep * 8));
+  const int rpt = g_bn_reduce_rows_per_thread;
+  int blocks = (int)((pixels + rstep * rpt - 1) / (rstep * rpt));
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   int64_t rpb = (pixels + blocks - 1) / blocks;
